@@ -1,0 +1,135 @@
+/*
+ * mlstm_b200.h — C ABI of the B200-native mLSTM cell (chunkwise matrix-memory LSTM, fwd + bwd).
+ *
+ * This is the drop-in boundary for the ONE hot path of DJT777/xlstm-yolo that this repo
+ * accelerates.  The reference has no native ABI for this path: it reaches the arithmetic
+ * through the Python operator seam
+ *
+ *     mlstm_kernels.torch.backend_module.mLSTMBackend.forward(q, k, v, i, f,
+ *         c_initial=None, n_initial=None, m_initial=None, return_last_states=None, mode=None)
+ *
+ * called at  nn/modules/vision_lstm/vision_lstm2.py:912-948  (MatrixLSTMCell.forward),
+ *            nn/modules/vision_lstm/mlstm_large.py:295-330   (mLSTMLayerVision.forward),
+ *            nn/modules/vision_lstm/xlstm/xlstm_large/model.py:425-434,
+ * and, on CPU, through the in-tree PyTorch functions
+ *            nn/modules/vision_lstm/xlstm/blocks/mlstm/backends.py:149 (chunkwise_simple),
+ *            :93 (recurrent_step_stabilized_simple), :9 (parallel_stabilized_simple).
+ * Each entry point below names the reference call it replaces.  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - Plain C: raw device pointers, element strides, sizes.  No torch / C++ types.
+ *   - The caller (PyTorch) owns every buffer, including the workspace; the library borrows
+ *     pointers for the duration of the launch, allocates nothing persistent on the device
+ *     and keeps no mutable global state except a launch counter and a thread-local error
+ *     string.  All work is enqueued on the CUDA stream passed in; no host synchronisation.
+ *   - Every function returns 0 on success or a negative mlstm_status; no C++ exception
+ *     crosses the ABI.  mlstm_b200_last_error() describes the last failure on this thread.
+ *   - Re-entrant: forward is called from the main thread, backward from autograd's worker
+ *     thread; DDP is one process per GPU.
+ *   - Tensors q,k,v,h,dh,dq,dk,dv are logically (B, NH, S, DH) with arbitrary element
+ *     strides for B, NH, S and unit stride for DH — so the reference's native
+ *     (B, S, NH, DH) storage viewed as (B, NH, S, DH) (vision_lstm2.py:900-902) is consumed
+ *     without a .contiguous() copy.  Gates i,f / di,df are fp32 (B, NH, S) with strides.
+ */
+#ifndef MLSTM_B200_H_
+#define MLSTM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLSTM_B200_ABI_VERSION 1
+
+typedef enum mlstm_status {
+  MLSTM_OK = 0,
+  MLSTM_ERR_INVALID_ARG = -1,   /* null pointer, bad size, misaligned pointer/stride        */
+  MLSTM_ERR_UNSUPPORTED = -2,   /* head dim / dtype combination without a kernel            */
+  MLSTM_ERR_WORKSPACE = -3,     /* workspace missing or too small                            */
+  MLSTM_ERR_CUDA = -4,          /* a CUDA runtime / driver call failed (see last_error)      */
+  MLSTM_ERR_NO_DEVICE = -5      /* no sm_100 device / driver entry points unavailable        */
+} mlstm_status;
+
+typedef enum mlstm_dtype {
+  MLSTM_F32 = 0,   /* fp32 I/O, fp32 SIMT arithmetic ("fp32 mode", tolerance 1e-4)          */
+  MLSTM_BF16 = 1   /* bf16 I/O, tcgen05 bf16 MMAs with fp32 accumulation (tolerance 1e-2)   */
+} mlstm_dtype;
+
+/* One strided (B, NH, S, DH) activation tensor; innermost stride is 1 element. */
+typedef struct mlstm_act {
+  void* ptr;
+  int64_t stride_b, stride_h, stride_s; /* in elements */
+} mlstm_act;
+
+/* One strided fp32 (B, NH, S) per-token scalar tensor (gate pre-activations and their grads). */
+typedef struct mlstm_gate {
+  float* ptr;
+  int64_t stride_b, stride_h, stride_s; /* in elements */
+} mlstm_gate;
+
+typedef struct mlstm_params {
+  int32_t abi_version;  /* must be MLSTM_B200_ABI_VERSION */
+  int32_t B, NH, S;     /* batch, heads, tokens (S = H*W of the feature map) */
+  int32_t DHQK, DHV;    /* head dims of q/k and of v/h */
+  int32_t dtype;        /* mlstm_dtype of q,k,v,h,dh,dq,dk,dv */
+  int32_t reverse;      /* 0: scan from token 0 (ROWWISE_FROM_TOP_LEFT);
+                           1: scan from token S-1 (ROWWISE_FROM_BOT_RIGHT) — replaces the
+                              flip pair at vision_lstm2.py:479-480,505-506 */
+  int32_t chunk_size;   /* the reference's config knob (vision_lstm2.py:823); results do not
+                           depend on it, the kernels pick their own tile */
+  float eps;            /* normaliser epsilon (5e-5 in MatrixLSTMCell, vision_lstm2.py:827) */
+  float qk_scale;       /* 0 -> DHQK^-1/2 (backends.py:168) */
+
+  /* forward inputs */
+  mlstm_act q, k, v;
+  mlstm_gate i, f;                      /* gate pre-activations, fp32 */
+  const float* c_initial;               /* optional (B,NH,DHQK,DHV) contiguous fp32, or NULL */
+  const float* n_initial;               /* optional (B,NH,DHQK)     contiguous fp32, or NULL */
+  const float* m_initial;               /* optional (B,NH)          contiguous fp32, or NULL */
+  /* forward outputs */
+  mlstm_act h;
+  float* n_row;                         /* (B,NH,S) contiguous fp32: signed normaliser sum   */
+  float* m_row;                         /* (B,NH,S) contiguous fp32: stabiliser m_t          */
+                                        /* both may be NULL when no backward will follow     */
+  float* c_last; float* n_last; float* m_last; /* optional last states, shapes as *_initial */
+
+  /* backward inputs (in addition to q,k,v,i,f,h,n_row,m_row and *_initial above) */
+  mlstm_act dh;
+  /* backward outputs */
+  mlstm_act dq, dk, dv;
+  mlstm_gate di, df;
+
+  void* workspace;                      /* device scratch, >= mlstm_b200_workspace_bytes()  */
+  size_t workspace_bytes;
+} mlstm_params;
+
+/* Library / ABI identification. */
+int mlstm_b200_abi_version(void);
+
+/* Scratch bytes the given call needs (0 is possible). is_backward: 0 fwd, 1 bwd. */
+size_t mlstm_b200_workspace_bytes(const mlstm_params* p, int is_backward);
+
+/* Forward: h = mLSTM(q,k,v,i,f[,C0,n0,m0]) (+ n_row, m_row, last states).
+ * Replaces mLSTMBackend.forward at vision_lstm2.py:912-948 / chunkwise_simple backends.py:149. */
+int mlstm_b200_fwd(const mlstm_params* p, void* cuda_stream);
+
+/* Backward: (dq,dk,dv,di,df) from dh, recomputing the gate/decay matrices per chunk.
+ * Replaces the autograd backward of the same backend call (trainer: engine/trainer.py:389). */
+int mlstm_b200_bwd(const mlstm_params* p, void* cuda_stream);
+
+/* Name of the kernel family the call would dispatch to: "tcgen05" or "simt" (or NULL). */
+const char* mlstm_b200_kernel_name(const mlstm_params* p, int is_backward);
+
+/* Kernels launched by this library in this process so far (for bench.py's gpu_launches). */
+uint64_t mlstm_b200_launch_count(void);
+
+/* Human-readable description of the last error on the calling thread ("" if none). */
+const char* mlstm_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLSTM_B200_H_ */

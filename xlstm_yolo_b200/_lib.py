@@ -1,0 +1,105 @@
+"""ctypes binding of ``lib/libmlstm_b200.so`` (C ABI: include/mlstm_b200.h).
+
+There is no fallback: if the library is missing or does not export the expected symbols,
+importing a CUDA op raises.  ``build.build()`` compiles it in-tree.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libmlstm_b200.so")
+
+ABI_VERSION = 1
+MLSTM_F32, MLSTM_BF16 = 0, 1
+
+STATUS = {0: "OK", -1: "INVALID_ARG", -2: "UNSUPPORTED", -3: "WORKSPACE", -4: "CUDA", -5: "NO_DEVICE"}
+
+EXPORTS = (
+    "mlstm_b200_abi_version",
+    "mlstm_b200_workspace_bytes",
+    "mlstm_b200_fwd",
+    "mlstm_b200_bwd",
+    "mlstm_b200_kernel_name",
+    "mlstm_b200_launch_count",
+    "mlstm_b200_last_error",
+)
+
+
+class Act(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("stride_b", C.c_int64), ("stride_h", C.c_int64), ("stride_s", C.c_int64)]
+
+
+class Gate(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("stride_b", C.c_int64), ("stride_h", C.c_int64), ("stride_s", C.c_int64)]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("B", C.c_int32), ("NH", C.c_int32), ("S", C.c_int32),
+        ("DHQK", C.c_int32), ("DHV", C.c_int32),
+        ("dtype", C.c_int32), ("reverse", C.c_int32), ("chunk_size", C.c_int32),
+        ("eps", C.c_float), ("qk_scale", C.c_float),
+        ("q", Act), ("k", Act), ("v", Act),
+        ("i", Gate), ("f", Gate),
+        ("c_initial", C.c_void_p), ("n_initial", C.c_void_p), ("m_initial", C.c_void_p),
+        ("h", Act),
+        ("n_row", C.c_void_p), ("m_row", C.c_void_p),
+        ("c_last", C.c_void_p), ("n_last", C.c_void_p), ("m_last", C.c_void_p),
+        ("dh", Act),
+        ("dq", Act), ("dk", Act), ("dv", Act),
+        ("di", Gate), ("df", Gate),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once). Raises LibraryMissing if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise LibraryMissing(
+                f"{LIB_PATH} not found: build it with `python -m xlstm_yolo_b200.build` "
+                "(there is no CPU or PyTorch fallback for CUDA tensors)")
+        lib = C.CDLL(LIB_PATH)
+        for name in EXPORTS:
+            if not hasattr(lib, name):
+                raise LibraryMissing(f"{LIB_PATH} does not export {name}")
+        lib.mlstm_b200_abi_version.restype = C.c_int
+        lib.mlstm_b200_workspace_bytes.restype = C.c_size_t
+        lib.mlstm_b200_workspace_bytes.argtypes = [C.POINTER(Params), C.c_int]
+        lib.mlstm_b200_fwd.restype = C.c_int
+        lib.mlstm_b200_fwd.argtypes = [C.POINTER(Params), C.c_void_p]
+        lib.mlstm_b200_bwd.restype = C.c_int
+        lib.mlstm_b200_bwd.argtypes = [C.POINTER(Params), C.c_void_p]
+        lib.mlstm_b200_kernel_name.restype = C.c_char_p
+        lib.mlstm_b200_kernel_name.argtypes = [C.POINTER(Params), C.c_int]
+        lib.mlstm_b200_launch_count.restype = C.c_uint64
+        lib.mlstm_b200_last_error.restype = C.c_char_p
+        if lib.mlstm_b200_abi_version() != ABI_VERSION:
+            raise LibraryMissing(f"ABI mismatch: library {lib.mlstm_b200_abi_version()} vs binding {ABI_VERSION}")
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().mlstm_b200_last_error().decode("utf-8", "replace")
+
+
+def launch_count() -> int:
+    return int(load().mlstm_b200_launch_count())

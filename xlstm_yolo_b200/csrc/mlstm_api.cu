@@ -1,0 +1,149 @@
+// extern "C" entry points of libmlstm_b200.so (declared in include/mlstm_b200.h):
+// argument validation, kernel-family dispatch, error reporting.  No torch types.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "mlstm_common.cuh"
+
+namespace mlstm {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+namespace {
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_act(const char* name, const mlstm_act& a, bool required) {
+  if (!a.ptr) {
+    if (required) { set_error("%s: null pointer", name); return MLSTM_ERR_INVALID_ARG; }
+    return MLSTM_OK;
+  }
+  return MLSTM_OK;
+}
+
+int validate(const mlstm_params* p, int is_bwd) {
+  if (!p) { set_error("params is NULL"); return MLSTM_ERR_INVALID_ARG; }
+  if (p->abi_version != MLSTM_B200_ABI_VERSION) {
+    set_error("abi_version %d != %d", p->abi_version, MLSTM_B200_ABI_VERSION);
+    return MLSTM_ERR_INVALID_ARG;
+  }
+  if (p->B < 0 || p->NH <= 0 || p->S < 0 || p->DHQK <= 0 || p->DHV <= 0) {
+    set_error("bad sizes B=%d NH=%d S=%d DHQK=%d DHV=%d", p->B, p->NH, p->S, p->DHQK, p->DHV);
+    return MLSTM_ERR_INVALID_ARG;
+  }
+  if (p->dtype != MLSTM_F32 && p->dtype != MLSTM_BF16) {
+    set_error("unsupported dtype %d", p->dtype);
+    return MLSTM_ERR_UNSUPPORTED;
+  }
+  if (p->B == 0 || p->S == 0) return MLSTM_OK;  // empty input: nothing to do
+  int rc;
+  if ((rc = check_act("q", p->q, true)) || (rc = check_act("k", p->k, true)) || (rc = check_act("v", p->v, true)) ||
+      (rc = check_act("h", p->h, true)))
+    return rc;
+  if (!p->i.ptr || !p->f.ptr) { set_error("gate pre-activations i/f: null pointer"); return MLSTM_ERR_INVALID_ARG; }
+  if ((p->c_last != nullptr) != (p->n_last != nullptr) || (p->c_last != nullptr) != (p->m_last != nullptr)) {
+    set_error("c_last/n_last/m_last must be given together");
+    return MLSTM_ERR_INVALID_ARG;
+  }
+  if ((p->n_row != nullptr) != (p->m_row != nullptr)) {
+    set_error("n_row/m_row must be given together");
+    return MLSTM_ERR_INVALID_ARG;
+  }
+  if (is_bwd) {
+    if ((rc = check_act("dh", p->dh, true)) || (rc = check_act("dq", p->dq, true)) ||
+        (rc = check_act("dk", p->dk, true)) || (rc = check_act("dv", p->dv, true)))
+      return rc;
+    if (!p->di.ptr || !p->df.ptr) { set_error("di/df: null pointer"); return MLSTM_ERR_INVALID_ARG; }
+    if (!p->n_row || !p->m_row) { set_error("backward needs n_row and m_row from the forward"); return MLSTM_ERR_INVALID_ARG; }
+    size_t need = mlstm_b200_workspace_bytes(p, 1);
+    if (need && (!p->workspace || p->workspace_bytes < need)) {
+      set_error("workspace too small: have %zu, need %zu", p->workspace ? p->workspace_bytes : (size_t)0, need);
+      return MLSTM_ERR_WORKSPACE;
+    }
+    if (need && !aligned16(p->workspace)) { set_error("workspace must be 16-byte aligned"); return MLSTM_ERR_INVALID_ARG; }
+  }
+  return MLSTM_OK;
+}
+
+enum Family { FAM_NONE = 0, FAM_SIMT = 1, FAM_TC = 2 };
+
+Family pick(const mlstm_params& p) {
+  if (p.dtype == MLSTM_BF16 && tc_supported(p)) return FAM_TC;
+  if (simt_supported(p)) return FAM_SIMT;
+  return FAM_NONE;
+}
+
+}  // namespace
+}  // namespace mlstm
+
+using namespace mlstm;
+
+extern "C" {
+
+int mlstm_b200_abi_version(void) { return MLSTM_B200_ABI_VERSION; }
+
+size_t mlstm_b200_workspace_bytes(const mlstm_params* p, int is_backward) {
+  if (!p || p->B <= 0 || p->S <= 0) return 0;
+  if (!is_backward) return 0;
+  switch (pick(*p)) {
+    case FAM_TC: return tc_bwd_workspace(*p);
+    case FAM_SIMT: return simt_bwd_workspace(*p);
+    default: return 0;
+  }
+}
+
+const char* mlstm_b200_kernel_name(const mlstm_params* p, int /*is_backward*/) {
+  if (!p) return nullptr;
+  switch (pick(*p)) {
+    case FAM_TC: return "tcgen05";
+    case FAM_SIMT: return "simt";
+    default: return nullptr;
+  }
+}
+
+int mlstm_b200_fwd(const mlstm_params* p, void* cuda_stream) {
+  g_err[0] = 0;
+  int rc = validate(p, 0);
+  if (rc) return rc;
+  if (p->B == 0 || p->S == 0) return MLSTM_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  switch (pick(*p)) {
+    case FAM_TC: return tc_fwd(*p, st);
+    case FAM_SIMT: return simt_fwd(*p, st);
+    default:
+      set_error("no kernel for dtype=%d DHQK=%d DHV=%d", p->dtype, p->DHQK, p->DHV);
+      return MLSTM_ERR_UNSUPPORTED;
+  }
+}
+
+int mlstm_b200_bwd(const mlstm_params* p, void* cuda_stream) {
+  g_err[0] = 0;
+  int rc = validate(p, 1);
+  if (rc) return rc;
+  if (p->B == 0 || p->S == 0) return MLSTM_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  switch (pick(*p)) {
+    case FAM_TC: return tc_bwd(*p, st);
+    case FAM_SIMT: return simt_bwd(*p, st);
+    default:
+      set_error("no kernel for dtype=%d DHQK=%d DHV=%d", p->dtype, p->DHQK, p->DHV);
+      return MLSTM_ERR_UNSUPPORTED;
+  }
+}
+
+uint64_t mlstm_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* mlstm_b200_last_error(void) { return g_err; }
+
+}  // extern "C"
