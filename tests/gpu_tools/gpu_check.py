@@ -60,13 +60,26 @@ def run(B, NH, S, DH, dtype, regime, reverse=False, eps=1e-6, qk_std=1.0, states
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
-    for regime in ["rand", "refinit", "forget"]:
-        run(2, 2, 100, 16, torch.float32, regime)
-    run(2, 4, 400, 64, torch.float32, "rand", reverse=True)
-    run(1, 2, 70, 32, torch.float32, "rand", states=True)
-    run(2, 2, 300, 128, torch.float32, "refinit", eps=5e-5)
-    run(1, 2, 1, 16, torch.float32, "rand")
-    run(2, 4, 400, 64, torch.bfloat16, "rand", qk_std=0.125)
-    run(2, 4, 400, 64, torch.bfloat16, "refinit", qk_std=0.125, eps=5e-5, reverse=True)
-    run(1, 4, 1600, 128, torch.bfloat16, "rand", qk_std=0.09)
-    run(2, 8, 256, 16, torch.bfloat16, "rand", qk_std=0.25)
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "case":  # case B NH S DH dtype regime reverse states qk_std
+        a = sys.argv[2:]
+        run(int(a[0]), int(a[1]), int(a[2]), int(a[3]), getattr(torch, a[4]), a[5], reverse=bool(int(a[6])),
+            states=bool(int(a[7])), qk_std=float(a[8]))
+        sys.exit(0)
+    if which in ("all", "simt"):
+        for regime in ["rand", "refinit", "forget"]:
+            run(2, 2, 100, 16, torch.float32, regime)
+        run(2, 4, 400, 64, torch.float32, "rand", reverse=True)
+        run(1, 2, 70, 32, torch.float32, "rand", states=True)
+        run(2, 2, 300, 128, torch.float32, "refinit", eps=5e-5)
+        run(2, 8, 256, 16, torch.bfloat16, "rand", qk_std=0.25)
+    if which in ("all", "tc"):
+        run(1, 1, 128, 64, torch.bfloat16, "rand", qk_std=0.125)
+        run(1, 1, 128, 128, torch.bfloat16, "rand", qk_std=0.09)
+        run(2, 4, 400, 64, torch.bfloat16, "rand", qk_std=0.125)
+        run(2, 4, 400, 64, torch.bfloat16, "refinit", qk_std=0.125, eps=5e-5, reverse=True)
+        run(2, 4, 400, 128, torch.bfloat16, "forget", qk_std=0.09, reverse=True)
+        run(1, 4, 1600, 128, torch.bfloat16, "rand", qk_std=0.09)
+        run(1, 2, 300, 128, torch.bfloat16, "rand", qk_std=0.09, states=True)
+        run(1, 2, 300, 64, torch.bfloat16, "rand", qk_std=0.125, states=True, reverse=True)
+        run(2, 2, 1, 64, torch.bfloat16, "rand", qk_std=0.125)
