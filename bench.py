@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — mLSTM cell fwd+bwd throughput (BASELINE.json metric) on B200.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...           # reference CPU path (oracle port)
+
+One "step" = one forward + one backward of the mLSTM cell over one synthetic batch of the
+workload (default: BASELINE.json configs[1]: B=32, NH=4, S=400, DH=64, bf16).  Prints ONE JSON
+line (see the repo contract).  Timing: CUDA events on the launching stream, >=3 warm-up
+steps, inputs rotate over enough independent sets that the working set exceeds L2, max over
+ranks for N>1 (one process per GPU, torchrun env).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B, NH, S, DH)  — BASELINE.json configs
+    "cfg2_B32_NH4_S400_DH64": (32, 4, 400, 64),
+    "cfg2alt_B32_NH4_S400_DH128": (32, 4, 400, 128),
+    "cfg3_B32_NH4_S1600_DH128": (32, 4, 1600, 128),
+    "cfg3_B32_NH4_S6400_DH128": (32, 4, 6400, 128),
+    "ddp_B8_NH4_S1600_DH128": (8, 4, 1600, 128),
+}
+DEFAULT_WORKLOAD = "cfg2_B32_NH4_S400_DH64"
+CHUNK = 64          # the config's chunk size (algorithmic FLOP formula; kernels tile on their own)
+L2_BYTES = 126e6
+
+
+def algorithmic(B, NH, S, DH):
+    """per token-head FLOPs and HBM bytes (bf16 I/O, fp32 gates/rows)."""
+    th = B * NH * S
+    flops_fwd = 4 * DH * DH + 2 * (CHUNK + 1) * DH
+    return {
+        "token_heads": th,
+        "flops_fwdbwd": 3 * flops_fwd * th,
+        "bytes_fwd": (8 * DH + 16) * th,
+        "bytes_bwd": (14 * DH + 24) * th,
+        # per-kernel minimal traffic of the two-kernel backward
+        "bytes_bwd_dq": (10 * DH + 24) * th,     # read q,k,v,dh + i,f,n,m ; write dq + dn,R
+        "bytes_bwd_dkv": (12 * DH + 32) * th,    # read q,k,v,dh + i,f,n,m,dn,R ; write dk,dv + di,df
+    }
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def make_inputs(torch, B, NH, S, DH, seed, device, dtype):
+    """SURVEY.md §8(d) synthetic inputs in the reference's memory layout: (B,S,NH,DH) storage
+    viewed as (B,NH,S,DH); gates (B,S,NH) viewed (B,NH,S).  q,k in the post-projection regime."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    std = DH ** -0.5
+    q = (torch.randn(B, S, NH, DH, generator=g) * std).to(dtype)
+    k = (torch.randn(B, S, NH, DH, generator=g) * std).to(dtype)
+    v = torch.randn(B, S, NH, DH, generator=g).to(dtype)
+    dh = torch.randn(B, S, NH, DH, generator=g).to(dtype)
+    i = torch.randn(B, S, NH, generator=g)
+    f = torch.linspace(3.0, 6.0, NH).view(1, 1, NH) + torch.randn(B, S, NH, generator=g)
+    return [t.to(device) if device != "cpu" else t for t in (q, k, v, i, f, dh)]
+
+
+def as_heads(ts):
+    return [t.transpose(1, 2) for t in ts]
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_fwbw_step(torch, O, cpu_inputs):
+    q, k, v, i, f, dh = cpu_inputs
+    return O.mlstm_fwbw(q, k, v, i, f, dh, chunk_size=CHUNK, eps=1e-6)
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (oracle port of
+    backends.py:149-263, torch CPU ops, all host threads), same config/metric/unit."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import mlstm_oracle as O
+    B, NH, S, DH = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # bounded sample: a slice of the batch sized for ~1 s per step on a few cores
+    Bs = max(1, min(B, int(args.cpu_sample_batch)))
+    inputs = as_heads([t.float() for t in make_inputs(torch, Bs, NH, S, DH, 0, "cpu", torch.bfloat16)])
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_fwbw_step(torch, O, inputs)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_fwbw_step(torch, O, inputs)
+    dt = (time.perf_counter() - t0) / steps
+    val = Bs * S / dt
+    sample = f"batch slice {Bs}/{B} of {args.workload}, {steps} steps, fp32 torch CPU ops"
+    out = {
+        "impl": "reference", "metric": "mLSTM fwd+bwd tokens/s/GPU", "value": val, "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "B": B, "NH": NH, "S": S, "DH": DH, "chunk_size": CHUNK},
+        "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--reverse", type=int, default=0)
+    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from xlstm_yolo_b200 import _lib, ops
+    from xlstm_yolo_b200.backend import mLSTMBackend, mLSTMBackendConfig
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    B, NH, S, DH = WORKLOADS[args.workload]
+    alg = algorithmic(B, NH, S, DH)
+    pk = peaks()
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    # ---- device-resident arm ("value"): rotating input sets so the working set exceeds L2 ----
+    set_bytes = alg["bytes_fwd"] + alg["bytes_bwd"]
+    nsets = max(2, int(2.2 * L2_BYTES / set_bytes) + 1)
+    plans = []
+    for s_ in range(nsets):
+        q, k, v, i, f, dh = as_heads(make_inputs(torch, B, NH, S, DH, 1000 * rank + s_, dev, torch.bfloat16))
+        plans.append(ops.MLSTMPlan(q, k, v, i, f, dh, eps=1e-6, chunk_size=CHUNK, reverse=bool(args.reverse)))
+    family = plans[0].family
+
+    def step(pl, evs=None):
+        if evs is not None:
+            evs[0].record()
+        pl.forward()
+        if evs is not None:
+            evs[1].record()
+        pl.backward(0)
+        if evs is not None:
+            evs[2].record()
+        pl.backward(1)
+        if evs is not None:
+            evs[3].record()
+
+    for w in range(W):
+        step(plans[w % nsets])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    launches0 = _lib.launch_count()
+    torch.cuda.synchronize()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s_ in range(K):
+        step(plans[(W + s_) % nsets], evs[s_])
+    t_end.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - launches0
+    if world > 1:
+        dist.barrier()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    # keep the sampler alive long enough for at least a few samples of a very short region
+    t_hold = time.time()
+    while len(sampler.samples) < 3 and time.time() - t_hold < 0.2:
+        step(plans[0])
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / K
+    dq_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / K
+    dkv_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / K
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / K
+    value = world * B * S / (ms_per_step * 1e-3)
+
+    # ---- end-to-end arm: host buffers -> public API (mLSTMBackend + autograd) -> host --------
+    be = mLSTMBackend(mLSTMBackendConfig(chunk_size=CHUNK, eps=1e-6, autocast_kernel_dtype="bfloat16"))
+    host = [t.pin_memory() for t in make_inputs(torch, B, NH, S, DH, 77 + rank, "cpu", torch.bfloat16)]
+    dev_in = [torch.empty_like(t, device=dev) for t in host]
+    res_host = torch.empty(4, dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    d2h = res_host.numel() * 4
+
+    def e2e_step():
+        for d_, h_ in zip(dev_in, host):
+            d_.copy_(h_, non_blocking=True)
+        q, k, v, i, f, dh = as_heads(dev_in)
+        leaves = [t.detach().requires_grad_(True) for t in (q, k, v, i, f)]
+        h = be(*leaves)
+        h.backward(dh)
+        res = torch.stack([h.float().abs().mean(), leaves[0].grad.float().abs().mean(),
+                           leaves[3].grad.abs().mean(), leaves[4].grad.abs().mean()])
+        res_host.copy_(res, non_blocking=True)
+
+    Ke = max(3, min(K, 50))
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(Ke):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / Ke
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_val = world * B * S / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel --------------------------------------------------
+    parts = {"fwd": (fwd_ms, alg["bytes_fwd"]), "bwd_dq": (dq_ms, alg["bytes_bwd_dq"]), "bwd_dkv": (dkv_ms, alg["bytes_bwd_dkv"])}
+    dom = max(parts, key=lambda n: parts[n][0])
+    dom_ms, dom_bytes = parts[dom]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": f"{family}:{dom}", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+        "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+        "per_kernel_ms": {"fwd": fwd_ms, "bwd_dq": dq_ms, "bwd_dkv": dkv_ms},
+        "step_hbm_frac": (alg["bytes_fwd"] + alg["bytes_bwd"]) / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+        "step_tensor_frac": alg["flops_fwdbwd"] / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+    }
+
+    out = {
+        "metric": "mLSTM fwd+bwd tokens/s/GPU", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": args.workload, "B_per_gpu": B, "NH": NH, "S": S, "DH": DH, "chunk_size": CHUNK,
+                   "reverse": int(args.reverse), "kernel_family": family,
+                   "l2": f"inputs rotate over {nsets} sets x {set_bytes / 1e6:.0f} MB > 126 MB L2", "parallelism": f"dp{world}"},
+        "clocks": sampler.result(),
+        "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "api": "xlstm_yolo_b200.mLSTMBackend + autograd"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+
+    # ---- CPU baseline (rank 0, N=1): the oracle port on the host cores, bounded sample ------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import mlstm_oracle as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        Bs = max(1, min(B, int(args.cpu_sample_batch)))
+        cin = as_heads([t.float() for t in make_inputs(torch, Bs, NH, S, DH, 0, "cpu", torch.bfloat16)])
+        cpu_fwbw_step(torch, O, cin)
+        n = 3
+        t0 = time.perf_counter()
+        for _ in range(n):
+            cpu_fwbw_step(torch, O, cin)
+        dt = (time.perf_counter() - t0) / n
+        out["cpu_baseline"] = {"value": Bs * S / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
+                               "sample": f"batch slice {Bs}/{B} of {args.workload}, {n} steps, fp32 torch CPU ops"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

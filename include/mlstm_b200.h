@@ -120,6 +120,12 @@ int mlstm_b200_fwd(const mlstm_params* p, void* cuda_stream);
  * Replaces the autograd backward of the same backend call (trainer: engine/trainer.py:389). */
 int mlstm_b200_bwd(const mlstm_params* p, void* cuda_stream);
 
+/* Profiling aid: run only one kernel of the backward (part 0 = dq / forward-walk kernel,
+ * part 1 = dk,dv,di,df / reverse-walk kernel; part 0 must have run before part 1 on the same
+ * workspace).  mlstm_b200_bwd(p) == part 0 then part 1.  Used by bench.py to time each kernel
+ * with CUDA events. */
+int mlstm_b200_bwd_part(const mlstm_params* p, int part, void* cuda_stream);
+
 /* Name of the kernel family the call would dispatch to: "tcgen05" or "simt" (or NULL). */
 const char* mlstm_b200_kernel_name(const mlstm_params* p, int is_backward);
 

@@ -1,0 +1,189 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, the
+ctypes mirror matches the C struct layout, argument validation works without a GPU, and the
+host-side mirrors of the reference interface (mLSTMBackend seam, MatrixLSTMCell) behave."""
+import copy
+import ctypes as C
+import inspect
+import os
+import pickle
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from oracle import mlstm_oracle as O  # noqa: E402
+from xlstm_yolo_b200 import MatrixLSTMCell, _lib, build, mLSTMBackend, mLSTMBackendConfig  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "mlstm_b200.h")).read()
+    declared = set(re.findall(r"\b(mlstm_b200_\w+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mlstm_b200_abi_version() == _lib.ABI_VERSION
+
+
+def test_ctypes_struct_matches_c_layout(tmp_path):
+    fields = [n for n, _ in _lib.Params._fields_]
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/mlstm_b200.h"', "int main(void){",
+             'printf("%zu\\n", sizeof(mlstm_params));']
+    lines += [f'printf("%zu\\n", offsetof(mlstm_params, {f}));' for f in fields]
+    lines += ["return 0;}"]
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == C.sizeof(_lib.Params)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(_lib.Params, f).offset == int(off), f
+
+
+def _params(**kw):
+    p = _lib.Params()
+    p.abi_version = _lib.ABI_VERSION
+    p.B, p.NH, p.S, p.DHQK, p.DHV = 2, 2, 64, 64, 64
+    p.dtype = _lib.MLSTM_BF16
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def test_validation_errors_need_no_gpu(lib):
+    assert lib.mlstm_b200_fwd(None, None) == -1
+    p = _params()
+    assert lib.mlstm_b200_fwd(C.byref(p), None) == -1 and b"null" in lib.mlstm_b200_last_error()
+    p = _params(abi_version=99)
+    assert lib.mlstm_b200_fwd(C.byref(p), None) == -1 and b"abi_version" in lib.mlstm_b200_last_error()
+    p = _params(dtype=7)
+    assert lib.mlstm_b200_fwd(C.byref(p), None) == -2
+    p = _params(DHQK=0)
+    assert lib.mlstm_b200_bwd(C.byref(p), None) == -1
+    # empty inputs are a successful no-op
+    p = _params(S=0)
+    assert lib.mlstm_b200_fwd(C.byref(p), None) == 0
+    p = _params(B=0)
+    assert lib.mlstm_b200_bwd(C.byref(p), None) == 0
+
+
+def test_kernel_family_and_workspace(lib):
+    p = _params()
+    assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"tcgen05"
+    assert lib.mlstm_b200_workspace_bytes(C.byref(p), 1) == 2 * 4 * 2 * 2 * 64
+    assert lib.mlstm_b200_workspace_bytes(C.byref(p), 0) == 0
+    p = _params(DHQK=16, DHV=16)
+    assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
+    p = _params(dtype=_lib.MLSTM_F32, DHQK=128, DHV=128)
+    assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
+    p = _params(DHQK=256, DHV=256)
+    assert lib.mlstm_b200_kernel_name(C.byref(p), 0) is None
+
+
+def test_cuda_op_refuses_cpu_tensors():
+    from xlstm_yolo_b200 import ops
+    x = torch.randn(1, 2, 8, 16)
+    g = torch.randn(1, 2, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.mlstm(x, x, x, g, g)
+
+
+# ---- MatrixLSTMCell drop-in contract (reference: vision_lstm2.py:802-966) ---------------------
+
+def test_cell_constructor_signature_matches_reference():
+    sig = inspect.signature(MatrixLSTMCell.__init__)
+    names = list(sig.parameters)[1:8]
+    assert names == ["dim", "num_heads", "norm_bias", "eps", "chunk_size", "use_autocast", "autocast_dtype"]
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert d["norm_bias"] is True and d["eps"] == 1e-6 and d["chunk_size"] == 16 and d["use_autocast"] is True
+    assert d["autocast_dtype"] == torch.bfloat16
+    assert list(inspect.signature(MatrixLSTMCell.forward).parameters) == ["self", "q", "k", "v"]
+
+
+def test_cell_state_dict_and_init():
+    cell = MatrixLSTMCell(dim=256, num_heads=4)
+    sd = cell.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        "igate.weight": (4, 768), "igate.bias": (4,), "fgate.weight": (4, 768), "fgate.bias": (4,),
+        "outnorm.weight": (256,), "outnorm.bias": (256,)}
+    assert torch.all(sd["igate.weight"] == 0) and torch.all(sd["fgate.weight"] == 0)
+    assert torch.all(sd["igate.bias"] == -10)                      # vision_lstm2.py:965
+    assert torch.allclose(sd["fgate.bias"], torch.tensor([3.0, 4.0, 5.0, 6.0]))   # :962
+    assert torch.all(sd["outnorm.weight"] == 0) and cell.outnorm.eps == 1e-3       # :812
+    assert "outnorm.bias" not in MatrixLSTMCell(dim=64, num_heads=4, norm_bias=False).state_dict()
+    # no persistent buffers, survives pickle / deepcopy / half / float (EMA + checkpoints)
+    assert len(list(cell.buffers())) == 0
+    c2 = pickle.loads(pickle.dumps(cell))
+    c3 = copy.deepcopy(cell).half().float()
+    for k in sd:
+        assert torch.equal(c2.state_dict()[k], sd[k]) and torch.allclose(c3.state_dict()[k], sd[k], atol=1e-2)
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_cell_cpu_forward_matches_oracle(reverse):
+    torch.manual_seed(0)
+    cell = MatrixLSTMCell(dim=64, num_heads=4, chunk_size=16, reverse=reverse)
+    with torch.no_grad():
+        cell.igate.weight.normal_(0, 0.05)
+        cell.fgate.weight.normal_(0, 0.05)
+        cell.igate.bias.fill_(0.0)
+        cell.outnorm.weight.normal_(0, 0.1)
+    q, k, v = (torch.randn(2, 50, 64) for _ in range(3))
+    y = cell(q, k, v)
+    want = O.cell_forward(q, k, v, 4, cell.igate.weight, cell.igate.bias, cell.fgate.weight, cell.fgate.bias,
+                          cell.outnorm.weight, cell.outnorm.bias, chunk_size=16, eps=5e-5, reverse=reverse)
+    assert y.shape == (2, 50, 64)
+    assert (y - want).abs().max() < 1e-4
+    y.square().mean().backward()
+    assert cell.igate.weight.grad.abs().sum() > 0 and cell.fgate.bias.grad.abs().sum() > 0
+    # HEAD's raw (B,NH,S,DH) output is still reachable
+    assert MatrixLSTMCell(dim=64, num_heads=4, raw_output=True)(q, k, v).shape == (2, 4, 50, 16)
+
+
+def test_backend_seam_cpu():
+    be = mLSTMBackend(mLSTMBackendConfig(chunkwise_kernel="chunkwise--triton_xl_chunk_siging", sequence_kernel="native_sequence__triton",
+                                         step_kernel="triton", chunk_size=16, autocast_kernel_dtype="bfloat16",
+                                         return_last_states=False, mode="train", eps=5e-5))
+    g = torch.Generator().manual_seed(1)
+    q, k, v = (torch.randn(2, 3, 40, 8, generator=g) for _ in range(3))
+    i, f = torch.randn(2, 3, 40, generator=g), 3 + torch.randn(2, 3, 40, generator=g)
+    h = be(q=q, k=k, v=v, i=i, f=f)
+    want = O.mlstm_chunkwise(q, k, v, i, f, chunk_size=16, eps=5e-5)
+    assert (h - want).abs().max() < 1e-5
+    C0, n0, m0 = torch.randn(2, 3, 8, 8, generator=g), torch.randn(2, 3, 8, generator=g), torch.randn(2, 3, 1, generator=g)
+    h2, (C1, n1, m1) = be(q, k, v, i, f, c_initial=C0, n_initial=n0, m_initial=m0, return_last_states=True, mode="inference")
+    w2, (Cw, nw, mw) = O.mlstm_chunkwise(q, k, v, i, f, C0, n0, m0, chunk_size=16, eps=5e-5, return_last_states=True)
+    assert (h2 - w2).abs().max() < 1e-5 and (C1 - Cw).abs().max() < 1e-4 and (m1 - mw).abs().max() < 1e-5
+    assert be.config.mode == "train"          # read by mlstm_large.py:305-306
+    with pytest.raises(ValueError):
+        be(q, k, v, i[:, :, :-1], f)
+    with pytest.raises(ValueError):
+        mLSTMBackendConfig(mode="nope")
+
+
+def test_mlstm_kernels_shim_exports_what_the_reference_imports():
+    from xlstm_yolo_b200 import compat
+    compat.install()
+    from mlstm_kernels.torch.backend_module import (BackendModeType, ChunkwiseKernelType, DtypeType,  # noqa: F401
+                                                    SequenceKernelType, StepKernelType, mLSTMBackend as B2,
+                                                    mLSTMBackendConfig as C2)
+    from mlstm_kernels.torch.chunkwise.triton_xl_chunk import mlstm_chunkwise__xl_chunk  # noqa: F401
+    assert B2 is mLSTMBackend and C2 is mLSTMBackendConfig
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "xlstm_yolo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, fn

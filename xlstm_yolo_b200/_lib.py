@@ -22,6 +22,7 @@ EXPORTS = (
     "mlstm_b200_workspace_bytes",
     "mlstm_b200_fwd",
     "mlstm_b200_bwd",
+    "mlstm_b200_bwd_part",
     "mlstm_b200_kernel_name",
     "mlstm_b200_launch_count",
     "mlstm_b200_last_error",
@@ -87,6 +88,8 @@ def load() -> C.CDLL:
         lib.mlstm_b200_fwd.argtypes = [C.POINTER(Params), C.c_void_p]
         lib.mlstm_b200_bwd.restype = C.c_int
         lib.mlstm_b200_bwd.argtypes = [C.POINTER(Params), C.c_void_p]
+        lib.mlstm_b200_bwd_part.restype = C.c_int
+        lib.mlstm_b200_bwd_part.argtypes = [C.POINTER(Params), C.c_int, C.c_void_p]
         lib.mlstm_b200_kernel_name.restype = C.c_char_p
         lib.mlstm_b200_kernel_name.argtypes = [C.POINTER(Params), C.c_int]
         lib.mlstm_b200_launch_count.restype = C.c_uint64

@@ -76,6 +76,26 @@ int validate(const mlstm_params* p, int is_bwd) {
   return MLSTM_OK;
 }
 
+// Bind the device that owns the buffers to the calling thread.  PyTorch runs the backward on
+// an autograd worker thread that may not have a current CUDA context yet, and the driver-side
+// tensor-map encoder needs one.
+int bind_device(const void* dev_ptr) {
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, dev_ptr);
+  if (e != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+    (void)cudaGetLastError();
+    set_error("q does not point to device memory (%s)", e == cudaSuccess ? "host/unregistered pointer" : cudaGetErrorString(e));
+    return MLSTM_ERR_INVALID_ARG;
+  }
+  e = cudaSetDevice(attr.device);
+  if (e == cudaSuccess) e = cudaFree(nullptr);   // forces the primary context current on this thread
+  if (e != cudaSuccess) {
+    set_error("cudaSetDevice(%d): %s", attr.device, cudaGetErrorString(e));
+    return MLSTM_ERR_CUDA;
+  }
+  return MLSTM_OK;
+}
+
 enum Family { FAM_NONE = 0, FAM_SIMT = 1, FAM_TC = 2 };
 
 Family pick(const mlstm_params& p) {
@@ -117,6 +137,7 @@ int mlstm_b200_fwd(const mlstm_params* p, void* cuda_stream) {
   int rc = validate(p, 0);
   if (rc) return rc;
   if (p->B == 0 || p->S == 0) return MLSTM_OK;
+  if ((rc = bind_device(p->q.ptr))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   switch (pick(*p)) {
     case FAM_TC: return tc_fwd(*p, st);
@@ -127,20 +148,26 @@ int mlstm_b200_fwd(const mlstm_params* p, void* cuda_stream) {
   }
 }
 
-int mlstm_b200_bwd(const mlstm_params* p, void* cuda_stream) {
+static int bwd_impl(const mlstm_params* p, int part, void* cuda_stream) {
   g_err[0] = 0;
   int rc = validate(p, 1);
   if (rc) return rc;
+  if (part < -1 || part > 1) { set_error("bad backward part %d", part); return MLSTM_ERR_INVALID_ARG; }
   if (p->B == 0 || p->S == 0) return MLSTM_OK;
+  if ((rc = bind_device(p->q.ptr))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   switch (pick(*p)) {
-    case FAM_TC: return tc_bwd(*p, st);
-    case FAM_SIMT: return simt_bwd(*p, st);
+    case FAM_TC: return tc_bwd(*p, st, part);
+    case FAM_SIMT: return simt_bwd(*p, st, part);
     default:
       set_error("no kernel for dtype=%d DHQK=%d DHV=%d", p->dtype, p->DHQK, p->DHV);
       return MLSTM_ERR_UNSUPPORTED;
   }
 }
+
+int mlstm_b200_bwd(const mlstm_params* p, void* cuda_stream) { return bwd_impl(p, -1, cuda_stream); }
+
+int mlstm_b200_bwd_part(const mlstm_params* p, int part, void* cuda_stream) { return bwd_impl(p, part, cuda_stream); }
 
 uint64_t mlstm_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

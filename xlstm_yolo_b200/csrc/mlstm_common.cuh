@@ -14,12 +14,12 @@ void count_launch(int n = 1);
 
 // Per-family launchers (each returns an mlstm_status).
 int simt_fwd(const mlstm_params& p, cudaStream_t st);
-int simt_bwd(const mlstm_params& p, cudaStream_t st);
+int simt_bwd(const mlstm_params& p, cudaStream_t st, int part = -1);  // part -1: both kernels
 size_t simt_bwd_workspace(const mlstm_params& p);
 bool simt_supported(const mlstm_params& p);
 
 int tc_fwd(const mlstm_params& p, cudaStream_t st);
-int tc_bwd(const mlstm_params& p, cudaStream_t st);
+int tc_bwd(const mlstm_params& p, cudaStream_t st, int part = -1);
 size_t tc_bwd_workspace(const mlstm_params& p);
 bool tc_supported(const mlstm_params& p);
 

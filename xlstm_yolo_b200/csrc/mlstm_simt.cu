@@ -493,7 +493,7 @@ int simt_fwd(const mlstm_params& p, cudaStream_t st) {
   return check_launch("simt_fwd");
 }
 
-int simt_bwd(const mlstm_params& p, cudaStream_t st) {
+int simt_bwd(const mlstm_params& p, cudaStream_t st, int part) {
   const float scale = resolve_scale(p);
   const size_t rows = (size_t)p.B * p.NH * p.S;
   float* ws_dn = reinterpret_cast<float*>(p.workspace);
@@ -501,21 +501,29 @@ int simt_bwd(const mlstm_params& p, cudaStream_t st) {
   dim3 grid(p.B * p.NH), block(NT);
   const size_t smA = bwd_dq_smem(p.DHQK, p.DHV), smB = bwd_dkv_smem(p.DHQK, p.DHV);
   int rc;
-  if (p.dtype == MLSTM_F32) {
-    if ((rc = set_smem(simt_bwd_dq_kernel<float>, smA))) return rc;
-    if ((rc = set_smem(simt_bwd_dkv_kernel<float>, smB))) return rc;
-    simt_bwd_dq_kernel<float><<<grid, block, smA, st>>>(p, scale, ws_dn, ws_R);
+  if (part != 1) {
+    if (p.dtype == MLSTM_F32) {
+      if ((rc = set_smem(simt_bwd_dq_kernel<float>, smA))) return rc;
+      simt_bwd_dq_kernel<float><<<grid, block, smA, st>>>(p, scale, ws_dn, ws_R);
+    } else {
+      if ((rc = set_smem(simt_bwd_dq_kernel<__nv_bfloat16>, smA))) return rc;
+      simt_bwd_dq_kernel<__nv_bfloat16><<<grid, block, smA, st>>>(p, scale, ws_dn, ws_R);
+    }
+    count_launch();
     if ((rc = check_launch("simt_bwd_dq"))) return rc;
-    simt_bwd_dkv_kernel<float><<<grid, block, smB, st>>>(p, scale, ws_dn, ws_R);
-  } else {
-    if ((rc = set_smem(simt_bwd_dq_kernel<__nv_bfloat16>, smA))) return rc;
-    if ((rc = set_smem(simt_bwd_dkv_kernel<__nv_bfloat16>, smB))) return rc;
-    simt_bwd_dq_kernel<__nv_bfloat16><<<grid, block, smA, st>>>(p, scale, ws_dn, ws_R);
-    if ((rc = check_launch("simt_bwd_dq"))) return rc;
-    simt_bwd_dkv_kernel<__nv_bfloat16><<<grid, block, smB, st>>>(p, scale, ws_dn, ws_R);
   }
-  count_launch(2);
-  return check_launch("simt_bwd_dkv");
+  if (part != 0) {
+    if (p.dtype == MLSTM_F32) {
+      if ((rc = set_smem(simt_bwd_dkv_kernel<float>, smB))) return rc;
+      simt_bwd_dkv_kernel<float><<<grid, block, smB, st>>>(p, scale, ws_dn, ws_R);
+    } else {
+      if ((rc = set_smem(simt_bwd_dkv_kernel<__nv_bfloat16>, smB))) return rc;
+      simt_bwd_dkv_kernel<__nv_bfloat16><<<grid, block, smB, st>>>(p, scale, ws_dn, ws_R);
+    }
+    count_launch();
+    if ((rc = check_launch("simt_bwd_dkv"))) return rc;
+  }
+  return MLSTM_OK;
 }
 
 }  // namespace mlstm

@@ -218,3 +218,49 @@ def mlstm(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, i: torch.Tensor, f:
         h, C, n, m = out
         return h.to(in_dtype), (C, n, m)
     return out.to(in_dtype)
+
+
+class MLSTMPlan:
+    """Pre-bound forward+backward call on fixed device buffers (steady-state / benchmark use).
+
+    All outputs and the workspace are allocated once; ``forward()`` / ``backward()`` are then a
+    single C-ABI call each (plus the host-side TMA descriptor encode inside the library).
+    """
+
+    def __init__(self, q, k, v, i, f, dh, *, eps=1e-6, chunk_size=64, reverse=False):
+        self.lib = _lib.load()
+        B, NH, S, DK = q.shape
+        DV = v.shape[-1]
+        dev = q.device
+        self.inputs = (q, k, v, i, f, dh)
+        self.h = _empty_act(B, NH, S, DV, q.dtype, dev)
+        self.n_row = torch.empty((B, NH, S), dtype=torch.float32, device=dev)
+        self.m_row = torch.empty((B, NH, S), dtype=torch.float32, device=dev)
+        self.dq = _empty_act(B, NH, S, DK, q.dtype, dev)
+        self.dk = _empty_act(B, NH, S, DK, q.dtype, dev)
+        self.dv = _empty_act(B, NH, S, DV, q.dtype, dev)
+        self.di = torch.empty((B, S, NH), dtype=torch.float32, device=dev).transpose(1, 2)
+        self.df = torch.empty((B, S, NH), dtype=torch.float32, device=dev).transpose(1, 2)
+        p = _base_params(q, k, v, i, f, eps, chunk_size, reverse, None)
+        p.h = _act(self.h)
+        p.n_row, p.m_row = _ptr(self.n_row), _ptr(self.m_row)
+        p.dh = _act(dh)
+        p.dq, p.dk, p.dv = _act(self.dq), _act(self.dk), _act(self.dv)
+        p.di, p.df = _gate(self.di), _gate(self.df)
+        need = self.lib.mlstm_b200_workspace_bytes(C.byref(p), 1)
+        self.ws = torch.empty(max(1, (need + 3) // 4), dtype=torch.float32, device=dev)
+        p.workspace, p.workspace_bytes = self.ws.data_ptr(), self.ws.numel() * 4
+        self.p = p
+        self.family = self.lib.mlstm_b200_kernel_name(C.byref(p), 0).decode()
+
+    def forward(self):
+        rc = self.lib.mlstm_b200_fwd(C.byref(self.p), _stream())
+        if rc:
+            _fail(rc, "forward")
+        return self.h
+
+    def backward(self, part: int = -1):
+        rc = self.lib.mlstm_b200_bwd_part(C.byref(self.p), part, _stream())
+        if rc:
+            _fail(rc, "backward")
+        return self.dq, self.dk, self.dv, self.di, self.df
