@@ -240,8 +240,9 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_dq_kernel(const __grid_constant_
   constexpr int TILE_C = DH * 128;
   constexpr uint32_t A_LBO_STATE = (DH == 128) ? TILE : 0;
   using SM = SmemB<DH, 4>;
-  extern __shared__ uint8_t smem_raw[];
-  SM& sm = *reinterpret_cast<SM*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   uint8_t *sq = sm.in[0], *sk = sm.in[1], *sv = sm.in[2], *sdh = sm.in[3];
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -490,8 +491,9 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_dkv_kernel(const __grid_constant
   constexpr int TILE_C = DH * 128;
   constexpr uint32_t A_LBO_STATE = (DH == 128) ? TILE : 0;
   using SM = SmemB<DH, 3>;
-  extern __shared__ uint8_t smem_raw[];
-  SM& sm = *reinterpret_cast<SM*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   uint8_t *sq = sm.in[0], *skv = sm.in[1], *sdh = sm.in[2];
   __shared__ __align__(16) float colv[3][L];     // per-query-row vectors: [0] exponent offset, [1] 1/N, [2] dn
   __shared__ __align__(16) float rowscale[L];    // (w s / N)_t for the dC update operand

@@ -1,7 +1,12 @@
 // tcgen05 / TMEM / TMA forward kernel of the mLSTM cell for bf16 I/O, DH in {64, 128}.
 //
-// One CTA (128 threads, thread t <-> tile row t <-> TMEM lane t) per (batch, head) walks the
-// sequence in chunks of L = 128 tokens with the (C, n, m) state resident on chip:
+// One CTA per (batch, head) walks the sequence in chunks of L = 128 tokens with the (C, n, m)
+// state resident on chip.  21 warps in three roles:
+//   16 compute warps  warp w owns tile rows / TMEM lanes 32*(w%4)..+31 and the 32-column block
+//                     w/4 of every 128-wide matrix (one 32x32 block of S, H, G, C per warp)
+//    1 control warp   lane 0 issues every TMA load/store and every tcgen05.mma (pre-built
+//                     descriptors), so no compute warp ever sits in an issue loop
+//    1 gate warp      log-sigmoid cumsum / running-max scans of the gates, two chunks ahead
 //   C  : fp32 accumulator in TMEM, updated by an accumulating MMA  C += Kbar^T V
 //   Cb : bf16 copy of C in shared memory (MN-major B operand of  G = Q Cb)
 //   n  : fp32 in TMEM (MMA against a ones tile) + an fp32 copy in shared memory
@@ -26,11 +31,22 @@ namespace {
 using namespace ptx;
 
 constexpr int L = 128;                 // chunk rows
-constexpr int NT = 128;                // threads per CTA
+constexpr int CT = 512;                // compute threads (16 warps: 4 row groups x 4 column blocks)
+constexpr int GT0 = CT + 32;           // first gate thread (after the control warp)
+constexpr int NT = GT0 + 32;           // 576 threads = 18 warps
 constexpr int TILE = L * 128;          // bytes of one [128 rows][64 bf16] swizzled tile
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct FwdMaps { CUtensorMap q, k, v, h; };
+
+// Developer aid: -DMLSTM_TIMELINE makes CTA 0 dump clock64() stamps of every phase of every
+// chunk (compute thread 0 and the issuer) into p.workspace (tests/gpu_tools/timeline.py).
+#ifdef MLSTM_TIMELINE
+#define TL_STAMP(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) tl_buf[(c) * 32 + (k)] = clock64(); \
+                          if (blockIdx.x == 0 && threadIdx.x == CT) tl_buf[(c) * 32 + 16 + (k)] = clock64(); } while (0)
+#else
+#define TL_STAMP(k) do { } while (0)
+#endif
 
 struct alignas(16) GateBuf {       // indexed by tile row
   float u2[L];         // u * log2e + log2(scale)   (exponent of P, scale folded in)
@@ -40,6 +56,7 @@ struct alignas(16) GateBuf {       // indexed by tile row
   float kw[L];         // exp(u - M_L)              (key weight for the state update)
   float decay;         // exp(m_prev - M_L)
   float m_next;        // g + M_L
+  float pad[2];
 };
 
 template <int DH>
@@ -47,15 +64,16 @@ struct Smem {
   static constexpr int KT = DH / 64;               // 64-wide tiles per operand
   static constexpr int TILE_C = DH * 128;          // bytes of one [DH rows][64] Cb tile
   alignas(1024) uint8_t q[KT * TILE];
-  alignas(1024) uint8_t k[KT * TILE];
+  alignas(1024) uint8_t k[2][KT * TILE];           // double buffered: K(c+1) streams in during chunk c
   alignas(1024) uint8_t v[KT * TILE];
   alignas(1024) uint8_t p[2 * TILE];               // P (K-major, 2 tiles over j); h staging reuses it
   alignas(1024) uint8_t cb[KT * TILE_C];           // bf16 C, MN-major [dk][dv]
   alignas(1024) uint8_t ones[2048];                // bf16 1.0 (B operand of n += Kbar^T 1)
-  GateBuf g[2];
+  GateBuf g[3];                                    // ring: chunk c uses g[c % 3]
   float n_prev[DH];
-  float scan_a[4], scan_b[4];
-  uint64_t bar_q, bar_k, bar_v, bar_m1, bar_kv, bar_m2;
+  float part_qn[4][L];                             // per column-block partials of q . n_prev
+  float part_rs[4][L];                             // per column-block partials of the row sums of P
+  uint64_t bar_q, bar_k[2], bar_v, bar_m1, bar_kv, bar_m2;
   uint32_t tmem_base;
 };
 
@@ -64,59 +82,74 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// log(sigmoid(x)) with fast intrinsics (abs error < 1e-7, enough for the bf16 path)
+__device__ __forceinline__ float log_sigmoid_fast(float x) {
+  return fminf(x, 0.f) - __logf(1.f + __expf(-fabsf(x)));
+}
 
-// Gate vectors of chunk `c` into `G` (all 128 threads; thread t = scan-local index t).
+// Gate vectors of chunk `c` into `G`, computed by ONE warp (lane l owns scan-local indices
+// 4l..4l+3), off the other warps' path.  Chunks are anchored at token 0 in both directions, so a
+// partial chunk always has its invalid rows at the tile's end (TMA zero-fills / clips them); in
+// reverse mode the partial chunk is simply the first one processed.
 template <int DH>
-__device__ __forceinline__ void compute_gates(Smem<DH>& sm, GateBuf& G, const mlstm_params& p, int b, int h, int c,
+__device__ __forceinline__ void compute_gates(GateBuf& G, const mlstm_params& p, int b, int h, int c, int lane,
                                               float m_prev, float scale) {
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  // Memory chunk and its valid rows.  Chunks are anchored at token 0 in both directions, so a
-  // partial chunk always has its invalid rows at the tile's end (TMA zero-fills / clips them);
-  // in reverse mode the partial chunk is simply the first one processed.
   const int NCc = (p.S + L - 1) / L;
   const int mc = p.reverse ? (NCc - 1 - c) : c;
   const int tok0 = mc * L;
   const int nvalid = min(L, p.S - tok0);
-  const bool valid = t < nvalid;
-  const int r = (p.reverse && valid) ? (nvalid - 1 - t) : t;   // tile row of scan-local index t
-  float ii = -INFINITY, logf = 0.f;
-  if (valid) {
-    const int tok = tok0 + r;
-    const int64_t off = (int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s;
-    const int64_t offi = (int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s;
-    logf = log_sigmoid(p.f.ptr[off]);
-    ii = p.i.ptr[offi];
-  }
-  float bs = warp_scan_add(logf, lane);
-  if (lane == 31) sm.scan_a[warp] = bs;
-  __syncthreads();
-  float pre = 0.f;
+  float ii[4], bs[4];
+  int r[4];
+  float run = 0.f;
 #pragma unroll
-  for (int w = 0; w < 4; ++w) pre += (w < warp) ? sm.scan_a[w] : 0.f;
-  bs += pre;
-  const float g_tot = sm.scan_a[0] + sm.scan_a[1] + sm.scan_a[2] + sm.scan_a[3];
-  const float u = ii - bs;
-  float cm = warp_scan_max(u, lane);
-  if (lane == 31) sm.scan_b[warp] = cm;
-  __syncthreads();
-  float cmax_all = -INFINITY;
-#pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    if (w < warp) cm = fmaxf(cm, sm.scan_b[w]);
-    cmax_all = fmaxf(cmax_all, sm.scan_b[w]);
+  for (int e = 0; e < 4; ++e) {
+    const int t = lane * 4 + e;
+    const bool valid = t < nvalid;
+    r[e] = (p.reverse && valid) ? (nvalid - 1 - t) : t;   // tile row of scan-local index t
+    ii[e] = -INFINITY;
+    float logf = 0.f;
+    if (valid) {
+      const int tok = tok0 + r[e];
+      logf = log_sigmoid_fast(p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s]);
+      ii[e] = p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s];
+    }
+    run += logf;
+    bs[e] = run;
   }
-  const float M = fmaxf(m_prev, cm);
-  const float ML = fmaxf(m_prev, cmax_all);
-  G.u2[r] = u * LOG2E + log2f(scale);
-  G.M2[r] = M * LOG2E;
-  G.wq[r] = __expf(m_prev - M) * scale;
-  G.mrow[r] = bs + M;
-  G.kw[r] = __expf(u - ML);
-  if (t == 0) {
+  const float incl = warp_scan_add(run, lane);
+  const float excl = incl - run;
+  const float g_tot = __shfl_sync(0xffffffffu, incl, 31);
+  float u[4], cm[4];
+  float lmax = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    bs[e] += excl;
+    u[e] = ii[e] - bs[e];
+    lmax = fmaxf(lmax, u[e]);
+    cm[e] = lmax;
+  }
+  const float imax = warp_scan_max(lmax, lane);
+  float emax = __shfl_up_sync(0xffffffffu, imax, 1);
+  if (lane == 0) emax = -INFINITY;
+  const float ML = fmaxf(m_prev, __shfl_sync(0xffffffffu, imax, 31));
+  const float l2s = log2f(scale);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float M = fmaxf(m_prev, fmaxf(emax, cm[e]));
+    G.u2[r[e]] = u[e] * LOG2E + l2s;
+    G.M2[r[e]] = M * LOG2E;
+    G.wq[r[e]] = __expf(m_prev - M) * scale;
+    G.mrow[r[e]] = bs[e] + M;
+    G.kw[r[e]] = __expf(u[e] - ML);
+  }
+  if (lane == 0) {
     G.decay = __expf(m_prev - ML);
     G.m_next = g_tot + ML;
   }
-  __syncthreads();
+  __syncwarp();
 }
 
 template <int DH>
@@ -124,24 +157,32 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
                                                        const float scale) {
   constexpr int KT = DH / 64;
   constexpr int TILE_C = Smem<DH>::TILE_C;
+  constexpr int NB = DH / 32;                                // 32-column blocks of a DH-wide matrix
   constexpr uint32_t A_LBO_STATE = (DH == 128) ? TILE : 0;  // DH=64: the 2nd 64-row M block aliases the 1st
-  extern __shared__ uint8_t smem_raw[];
-  Smem<DH>& sm = *reinterpret_cast<Smem<DH>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled tiles need 1024-byte alignment
+  Smem<DH>& sm = *reinterpret_cast<Smem<DH>*>(smem_raw);       // no pointer arithmetic: keeps the shared address space (LDS/STS)
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool compute = tid < CT;
+  const bool issuer = tid == CT;       // lane 0 of the control warp
+  const bool gatew = tid >= GT0;       // gate warps
+  const int rg = warp & 3;             // row group: tile rows / TMEM lanes 32*rg .. 32*rg+31
+  const int cq = compute ? (warp >> 2) : 4;   // column block: columns 32*cq .. 32*cq+31 (4 = none)
+  const int row = rg * 32 + lane;      // this thread's tile row
   const int bh = blockIdx.x, b = bh / p.NH, h = bh % p.NH;
   const int S = p.S, NC = (S + L - 1) / L;
   const bool has_init = p.c_initial != nullptr;
   const bool rev = p.reverse != 0;
 
-  if (tid == 0) {
+  if (issuer) {
     tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.v); tma_prefetch_desc(&maps.h);
-    mbar_init(&sm.bar_q, 1); mbar_init(&sm.bar_k, 1); mbar_init(&sm.bar_v, 1);
+    mbar_init(&sm.bar_q, 1); mbar_init(&sm.bar_k[0], 1); mbar_init(&sm.bar_k[1], 1); mbar_init(&sm.bar_v, 1);
     mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_kv, 1); mbar_init(&sm.bar_m2, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
-  // ones tile, zero Cb / n_prev when there is no initial state
+  // ones tile; zero Cb / n_prev when there is no initial state
   for (int e = tid; e < 2048 / 4; e += NT) reinterpret_cast<uint32_t*>(sm.ones)[e] = 0x3F803F80u;
   if (!has_init) {
     for (int e = tid; e < KT * TILE_C / 16; e += NT) reinterpret_cast<uint4*>(sm.cb)[e] = make_uint4(0, 0, 0, 0);
@@ -152,47 +193,69 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
   tc_fence_after();
   const uint32_t tm = sm.tmem_base;
   const uint32_t tS = tm, tG = tm + 128, tC = tm + 128 + DH, tN = tm + 128 + 2 * DH;
-  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_sel = (uint32_t)(rg * 32) << 16;
 
   auto tok0_of = [&](int c) { return (rev ? (NC - 1 - c) : c) * L; };
   auto issue_loads = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int c) {
     mbar_arrive_expect_tx(bar, KT * TILE);
     for (int kt = 0; kt < KT; ++kt) tma_load_4d(dst + kt * TILE, map, bar, kt * 64, tok0_of(c), h, b);
   };
+  // UMMA shared-memory descriptors are loop invariant: build them once, advance per k-step by
+  // adding a constant to the start-address field (issue cost: a couple of instructions per MMA).
+  const uint64_t dQ = make_sdesc(smem_u32(sm.q), 16, 1024);
+  const uint64_t dCbmn = make_sdesc(smem_u32(sm.cb), TILE_C, 1024), dVmn = make_sdesc(smem_u32(sm.v), TILE, 1024);
+  const uint64_t dP = make_sdesc(smem_u32(sm.p), 16, 1024), dOnes = make_sdesc(smem_u32(sm.ones), 1024, 1024);
+  const uint64_t dKk0 = make_sdesc(smem_u32(sm.k[0]), 16, 1024), dKmn0 = make_sdesc(smem_u32(sm.k[0]), A_LBO_STATE, 1024);
+  constexpr uint64_t KBUF_STEP = (uint64_t)(KT * TILE) >> 4;     // descriptor distance between the two K buffers
+  auto kstep = [](int ks) { return (uint64_t)((((ks >> 2) * TILE) + (ks & 3) * 32) >> 4); };   // K-major advance
+  auto mnstep = [](int ks) { return (uint64_t)((ks * 2048) >> 4); };                             // MN-major advance
+  auto issue_mma1 = [&](int c) {   // S = Q K^T, G = Q Cb   (chunk c)
+    const uint64_t dKk = dKk0 + (c & 1) * KBUF_STEP;
+    constexpr uint32_t idS = make_idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tS, dQ + kstep(ks), dKk + kstep(ks), idS, ks > 0);
+    constexpr uint32_t idG = make_idesc_bf16(128, DH, 0, 1);
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tG, dQ + kstep(ks), dCbmn + mnstep(ks), idG, ks > 0);
+    umma_commit(&sm.bar_m1);
+  };
 
-  float m_prev = p.m_initial ? p.m_initial[bh] : 0.f;
-  if (tid == 0) {
+  // ---- prologue: first loads, gates of chunks 0 and 1, initial state -----------------------
+  if (issuer) {
     issue_loads(sm.q, &maps.q, &sm.bar_q, 0);
-    issue_loads(sm.k, &maps.k, &sm.bar_k, 0);
+    issue_loads(sm.k[0], &maps.k, &sm.bar_k[0], 0);
     issue_loads(sm.v, &maps.v, &sm.bar_v, 0);
   }
-  compute_gates<DH>(sm, sm.g[0], p, b, h, 0, m_prev, scale);
+  if (gatew) {
+    compute_gates<DH>(sm.g[0], p, b, h, 0, lane, p.m_initial ? p.m_initial[bh] : 0.f, scale);
+    if (NC > 1) compute_gates<DH>(sm.g[1], p, b, h, 1, lane, sm.g[0].m_next, scale);
+  }
+  __syncthreads();
 
-  if (has_init) {  // TMEM C <- decay_0 * C_0 ; Cb <- bf16(C_0) ; n likewise
+  if (has_init) {  // TMEM C <- decay_0 * C_0 ; Cb <- bf16(C_0) ; n likewise  (thread: state row `row`, block cq)
     const float d0 = sm.g[0].decay;
-    if (tid < DH) {
-      const float* crow = p.c_initial + ((int64_t)bh * DH + tid) * DH;
-      for (int cbk = 0; cbk < DH / 32; ++cbk) {
-        float r[32];
+    if (row < DH && cq < NB) {
+      const float* crow = p.c_initial + ((int64_t)bh * DH + row) * DH + cq * 32;
+      float r[32];
 #pragma unroll
-        for (int x = 0; x < 32; ++x) r[x] = crow[cbk * 32 + x];
+      for (int x = 0; x < 32; ++x) r[x] = crow[x];
 #pragma unroll
-        for (int x = 0; x < 32; x += 8) {
-          const int dv = cbk * 32 + x;
-          *reinterpret_cast<uint4*>(sm.cb + (dv >> 6) * TILE_C + swz128(tid, dv & 63)) =
-              make_uint4(pack_bf16x2(r[x], r[x + 1]), pack_bf16x2(r[x + 2], r[x + 3]), pack_bf16x2(r[x + 4], r[x + 5]),
-                         pack_bf16x2(r[x + 6], r[x + 7]));
-        }
-#pragma unroll
-        for (int x = 0; x < 32; ++x) r[x] *= d0;
-        tmem_st32(tC + lane_sel + cbk * 32, r);
+      for (int x = 0; x < 32; x += 8) {
+        const int dv = cq * 32 + x;
+        *reinterpret_cast<uint4*>(sm.cb + (dv >> 6) * TILE_C + swz128(row, dv & 63)) =
+            make_uint4(pack_bf16x2(r[x], r[x + 1]), pack_bf16x2(r[x + 2], r[x + 3]), pack_bf16x2(r[x + 4], r[x + 5]),
+                       pack_bf16x2(r[x + 6], r[x + 7]));
       }
-      const float n0 = p.n_initial[(int64_t)bh * DH + tid];
-      sm.n_prev[tid] = n0;
-      float r16[32];
 #pragma unroll
-      for (int x = 0; x < 32; ++x) r16[x] = n0 * d0;
-      tmem_st32(tN + lane_sel, r16);  // tN occupies 16 columns; the next 16 are unused scratch
+      for (int x = 0; x < 32; ++x) r[x] *= d0;
+      tmem_st32(tC + lane_sel + cq * 32, r);
+      if (cq == 0) {
+        const float n0 = p.n_initial[(int64_t)bh * DH + row];
+        sm.n_prev[row] = n0;
+#pragma unroll
+        for (int x = 0; x < 32; ++x) r[x] = n0 * d0;
+        tmem_st32(tN + lane_sel, r);   // tN occupies 16 columns; the next 16 are unused scratch
+      }
       tmem_st_wait();
     }
     fence_proxy_async_smem();
@@ -200,106 +263,82 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
     __syncthreads();
     tc_fence_after();
   }
-
-  for (int c = 0; c < NC; ++c) {
-    GateBuf& G = sm.g[c & 1];
-    GateBuf& Gn = sm.g[(c + 1) & 1];
-    const uint32_t ph = c & 1;
-    const int tok0 = tok0_of(c);
-
-    // ---- MMA1: S = Q K^T, G = Q Cb ------------------------------------------------------
-    mbar_wait(&sm.bar_q, ph);
-    mbar_wait(&sm.bar_k, ph);
-    if (tid == 0) {
-      tc_fence_after();
-      constexpr uint32_t idS = make_idesc_bf16(128, 128, 0, 0);
-      for (int ks = 0; ks < DH / 16; ++ks) {
-        const uint32_t off = (ks >> 2) * TILE + (ks & 3) * 32;
-        umma_bf16_ss(tS, make_sdesc(smem_u32(sm.q) + off, 16, 1024), make_sdesc(smem_u32(sm.k) + off, 16, 1024), idS, ks > 0);
-      }
-      constexpr uint32_t idG = make_idesc_bf16(128, DH, 0, 1);
-      for (int ks = 0; ks < DH / 16; ++ks) {
-        const uint32_t off = (ks >> 2) * TILE + (ks & 3) * 32;
-        umma_bf16_ss(tG, make_sdesc(smem_u32(sm.q) + off, 16, 1024),
-                     make_sdesc(smem_u32(sm.cb) + ks * 2048, TILE_C, 1024), idG, ks > 0);
-      }
-      umma_commit(&sm.bar_m1);
-    }
-    // ---- in the MMA shadow: gates of the next chunk, q . n_prev --------------------------
-    if (c + 1 < NC) compute_gates<DH>(sm, Gn, p, b, h, c + 1, G.m_next, scale);
-    float qn = 0.f;
-    for (int kt = 0; kt < KT; ++kt) {
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        const uint4 w = *reinterpret_cast<const uint4*>(sm.q + kt * TILE + swz128(tid, c8 * 8));
-        const float4 n0 = *reinterpret_cast<const float4*>(&sm.n_prev[kt * 64 + c8 * 8]);
-        const float4 n1 = *reinterpret_cast<const float4*>(&sm.n_prev[kt * 64 + c8 * 8 + 4]);
-        const __nv_bfloat162* qq = reinterpret_cast<const __nv_bfloat162*>(&w);
-        float2 a = __bfloat1622float2(qq[0]), bq = __bfloat1622float2(qq[1]), cq = __bfloat1622float2(qq[2]),
-               dq = __bfloat1622float2(qq[3]);
-        qn += a.x * n0.x + a.y * n0.y + bq.x * n0.z + bq.y * n0.w + cq.x * n1.x + cq.y * n1.y + dq.x * n1.z + dq.y * n1.w;
-      }
-    }
-    mbar_wait(&sm.bar_m1, ph);
+  if (issuer) {   // MMA1 of chunk 0 (later chunks: issued while the previous epilogue finishes)
+    mbar_wait(&sm.bar_q, 0);
+    mbar_wait(&sm.bar_k[0], 0);
     tc_fence_after();
+    issue_mma1(0);
+  }
 
-    // ---- Kbar = kw * K, in place ---------------------------------------------------------
-    for (int it = 0; it < KT * TILE / 16 / NT; ++it) {
-      const uint32_t o = (uint32_t)(tid + it * NT) * 16u;
-      const int row = (o >> 7) & (L - 1);
-      const float s = G.kw[row];
-      uint4 w = *reinterpret_cast<uint4*>(sm.k + o);
-      __nv_bfloat162* kk = reinterpret_cast<__nv_bfloat162*>(&w);
+#ifdef MLSTM_TIMELINE
+  long long* tl_buf = reinterpret_cast<long long*>(p.workspace);
+#endif
+  for (int c = 0; c < NC; ++c) {
+    TL_STAMP(0);
+    const uint32_t ph = c & 1;
+    const bool last = (c + 1 == NC);
+    if (gatew) {
+      // two chunks ahead, into the ring slot chunk c-1 just released
+      if (c + 2 < NC) compute_gates<DH>(sm.g[(c + 2) % 3], p, b, h, c + 2, lane, sm.g[(c + 1) % 3].m_next, scale);
+      __syncthreads();   // the end-of-chunk barrier is the only one the gate warp takes part in
+      continue;
+    }
+    GateBuf& G = sm.g[c % 3];
+    const int tok0 = tok0_of(c);
+    uint8_t* sk = sm.k[c & 1];
+
+    // ---- top: K(c+1) streams into the other buffer (once the h(c-1) staged there has been read)
+    if (issuer && !last) {
+      tma_store_wait_read<0>();
+      issue_loads(sm.k[(c + 1) & 1], &maps.k, &sm.bar_k[(c + 1) & 1], c + 1);
+    }
+    mbar_wait(&sm.bar_q, ph);
+    mbar_wait(&sm.bar_k[c & 1], (c >> 1) & 1);
+    TL_STAMP(1);
+    // partial q . n_prev in the MMA1 shadow: this thread: row `row`, dk in [32 cq, 32 cq + 32)
+    if (cq < NB) {
+      float qn = 0.f;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f2 = __bfloat1622float2(kk[e]);
-        kk[e] = __floats2bfloat162_rn(f2.x * s, f2.y * s);
+      for (int x = 0; x < 32; x += 8) {
+        const int col = cq * 32 + x;
+        const uint4 w = *reinterpret_cast<const uint4*>(sm.q + (col >> 6) * TILE + swz128(row, col & 63));
+        const float4 n0 = *reinterpret_cast<const float4*>(&sm.n_prev[col]);
+        const float4 n1 = *reinterpret_cast<const float4*>(&sm.n_prev[col + 4]);
+        const __nv_bfloat162* qq = reinterpret_cast<const __nv_bfloat162*>(&w);
+        float2 a = __bfloat1622float2(qq[0]), bq = __bfloat1622float2(qq[1]), cq_ = __bfloat1622float2(qq[2]),
+               dq = __bfloat1622float2(qq[3]);
+        qn += a.x * n0.x + a.y * n0.y + bq.x * n0.z + bq.y * n0.w + cq_.x * n1.x + cq_.y * n1.y + dq.x * n1.z + dq.y * n1.w;
       }
-      *reinterpret_cast<uint4*>(sm.k + o) = w;
+      sm.part_qn[cq][row] = qn;
+    } else if (compute) {
+      sm.part_qn[cq][row] = 0.f;
     }
-    fence_proxy_async_smem();
-    if (tid == 0) tma_store_wait_read<0>();   // the previous chunk's h staging (= P tile) has been read
-    tc_fence_before();
-    __syncthreads();
+    TL_STAMP(2);
+    mbar_wait(&sm.bar_m1, ph);     // S(c) and G(c) are in TMEM
+    tc_fence_after();
+    TL_STAMP(3);
 
-    // ---- state MMAs: C += Kbar^T V, n += Kbar^T 1 ; prefetch Q(c+1) ----------------------
-    if (tid == 0) {
-      if (c + 1 < NC) issue_loads(sm.q, &maps.q, &sm.bar_q, c + 1);
-      mbar_wait(&sm.bar_v, ph);
-      tc_fence_after();
-      constexpr uint32_t idC = make_idesc_bf16(128, DH, 1, 1);
-      constexpr uint32_t idN = make_idesc_bf16(128, 16, 1, 1);
-      const uint32_t acc0 = (c > 0 || has_init) ? 1u : 0u;
-      for (int ks = 0; ks < L / 16; ++ks) {
-        const uint64_t a = make_sdesc(smem_u32(sm.k) + ks * 2048, A_LBO_STATE, 1024);
-        umma_bf16_ss(tC, a, make_sdesc(smem_u32(sm.v) + ks * 2048, TILE, 1024), idC, (ks > 0) ? 1u : acc0);
-        umma_bf16_ss(tN, a, make_sdesc(smem_u32(sm.ones), 1024, 1024), idN, (ks > 0) ? 1u : acc0);
-      }
-      umma_commit(&sm.bar_kv);
-    }
-
-    // ---- P = S * exp2(u2_j - M2_t), causal; row sums -------------------------------------
-    const float M2t = G.M2[tid];
-    float rowsum = 0.f;
-#pragma unroll 1
-    for (int cbk = 0; cbk < 4; ++cbk) {
-      // forward: keys j <= t ; reverse: keys j >= t   (tile rows; warp w owns rows 32w..32w+31)
-      const bool full = rev ? (cbk > warp) : (cbk < warp);
-      const bool diag = (cbk == warp);
+    // ---- P = S * exp2(u2_j - M2_t), causal: one 32x32 block per warp; partial row sums ----
+    if (compute) {
+      const float M2t = G.M2[row];
+      // forward: keys j <= t ; reverse: keys j >= t   (tile rows)
+      const bool full = rev ? (cq > rg) : (cq < rg);
+      const bool diag = (cq == rg);
       uint32_t packed[16];
+      float rowsum = 0.f;
       if (full || diag) {
         float s[32];
-        tmem_ld32(tS + lane_sel + cbk * 32, s);
+        tmem_ld32(tS + lane_sel + cq * 32, s);
         tmem_ld_wait();
 #pragma unroll
         for (int x = 0; x < 32; x += 4) {
-          const float4 u4 = *reinterpret_cast<const float4*>(&G.u2[cbk * 32 + x]);
+          const float4 u4 = *reinterpret_cast<const float4*>(&G.u2[cq * 32 + x]);
           const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
           float pv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int j = cbk * 32 + x + e;
-            const bool keep = full || (rev ? (j >= tid) : (j <= tid));
+            const int j = cq * 32 + x + e;
+            const bool keep = full || (rev ? (j >= row) : (j <= row));
             pv[e] = keep ? s[x + e] * ex2(uu[e] - M2t) : 0.f;
             rowsum += pv[e];
           }
@@ -310,114 +349,161 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
 #pragma unroll
         for (int x = 0; x < 16; ++x) packed[x] = 0u;
       }
+      sm.part_rs[cq][row] = rowsum;
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
-        const int j = cbk * 32 + x * 8;
-        *reinterpret_cast<uint4*>(sm.p + (j >> 6) * TILE + swz128(tid, j & 63)) =
+        const int j = cq * 32 + x * 8;
+        *reinterpret_cast<uint4*>(sm.p + (j >> 6) * TILE + swz128(row, j & 63)) =
             make_uint4(packed[4 * x], packed[4 * x + 1], packed[4 * x + 2], packed[4 * x + 3]);
       }
     }
+    TL_STAMP(4);
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();
+    named_sync(2, GT0);
+    TL_STAMP(5);
 
-    // ---- MMA2: H = P V (into the S columns) ; prefetch K(c+1) ----------------------------
-    if (tid == 0) {
+    // ---- MMA2: H = P V (into the S columns); Q(c+1) prefetch (Q(c) is dead) ----------------
+    if (issuer) {
+      if (!last) issue_loads(sm.q, &maps.q, &sm.bar_q, c + 1);
+      mbar_wait(&sm.bar_v, ph);
       tc_fence_after();
       constexpr uint32_t idH = make_idesc_bf16(128, DH, 0, 1);
-      for (int ks = 0; ks < L / 16; ++ks) {
-        umma_bf16_ss(tS, make_sdesc(smem_u32(sm.p) + (ks >> 2) * TILE + (ks & 3) * 32, 16, 1024),
-                     make_sdesc(smem_u32(sm.v) + ks * 2048, TILE, 1024), idH, ks > 0);
-      }
+#pragma unroll
+      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tS, dP + kstep(ks), dVmn + mnstep(ks), idH, ks > 0);
       umma_commit(&sm.bar_m2);
-      mbar_wait(&sm.bar_kv, ph);
-      if (c + 1 < NC) issue_loads(sm.k, &maps.k, &sm.bar_k, c + 1);
     }
-    // row normaliser (backends.py:249-252)
-    const float wq = G.wq[tid];
-    const float mrow = G.mrow[tid];
-    const float nr = rowsum + wq * qn;
-    const float Nrow = fmaxf(fabsf(nr), __expf(-mrow)) + p.eps;
-    const float inv = 1.f / Nrow;
-    {
-      const int tok = tok0 + tid;
-      if (p.n_row && tok >= 0 && tok < S) {
+    // ---- in the MMA2 shadow: normaliser, n-state partials, Kbar = kw * K in place ------------
+    const float wq = G.wq[row];
+    const float mrow = G.mrow[row];
+    const float nr = (sm.part_rs[0][row] + sm.part_rs[1][row] + sm.part_rs[2][row] + sm.part_rs[3][row]) +
+                     wq * (sm.part_qn[0][row] + sm.part_qn[1][row] + sm.part_qn[2][row] + sm.part_qn[3][row]);
+    const float inv = 1.f / (fmaxf(fabsf(nr), __expf(-mrow)) + p.eps);   // backends.py:249-252
+    if (cq == 0) {
+      const int tok = tok0 + row;
+      if (p.n_row && tok < S) {
         p.n_row[(int64_t)bh * S + tok] = nr;
         p.m_row[(int64_t)bh * S + tok] = mrow;
       }
     }
+#pragma unroll
+    for (int it = 0; it < (compute ? KT * TILE / 16 / CT : 0); ++it) {
+      const uint32_t o = (uint32_t)(tid + it * CT) * 16u;
+      const int krow = (o >> 7) & (L - 1);
+      const float s = G.kw[krow];
+      uint4 w = *reinterpret_cast<uint4*>(sk + o);
+      __nv_bfloat162* kk = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f2 = __bfloat1622float2(kk[e]);
+        kk[e] = __floats2bfloat162_rn(f2.x * s, f2.y * s);
+      }
+      *reinterpret_cast<uint4*>(sk + o) = w;
+    }
+    TL_STAMP(6);
+    fence_proxy_async_smem();
+    named_sync(2, GT0);
+    TL_STAMP(7);
+
+    // ---- state MMA: C += Kbar^T V ------------------------------------------------------------
+    if (issuer) {
+      tc_fence_after();
+      const uint64_t dKmn = dKmn0 + (c & 1) * KBUF_STEP;
+      constexpr uint32_t idC = make_idesc_bf16(128, DH, 1, 1);
+      constexpr uint32_t idN = make_idesc_bf16(128, 16, 1, 1);
+      const uint32_t acc0 = (c > 0 || has_init) ? 1u : 0u;
+#pragma unroll
+      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tC, dKmn + mnstep(ks), dVmn + mnstep(ks), idC, (ks > 0) ? 1u : acc0);
+#pragma unroll
+      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tN, dKmn + mnstep(ks), dOnes, idN, (ks > 0) ? 1u : acc0);
+      umma_commit(&sm.bar_kv);
+    }
     mbar_wait(&sm.bar_m2, ph);
     tc_fence_after();
-    if (tid == 0 && c + 1 < NC) issue_loads(sm.v, &maps.v, &sm.bar_v, c + 1);
+    TL_STAMP(8);
 
-    // ---- epilogue: h = (H + wq G) / N -> bf16 staging (P tile) ---------------------------
-#pragma unroll 1
-    for (int cbk = 0; cbk < DH / 32; ++cbk) {
+    // ---- epilogue part 1 (in the state-MMA shadow): h = (H + wq G) / N, packed bf16 in registers
+    uint32_t hpk[16];
+    if (cq < NB) {
       float hi[32], gg[32];
-      tmem_ld32(tS + lane_sel + cbk * 32, hi);
-      tmem_ld32(tG + lane_sel + cbk * 32, gg);
+      tmem_ld32(tS + lane_sel + cq * 32, hi);
+      tmem_ld32(tG + lane_sel + cq * 32, gg);
       tmem_ld_wait();
 #pragma unroll
-      for (int x = 0; x < 32; x += 8) {
-        float o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = (hi[x + e] + wq * gg[x + e]) * inv;
-        const int dv = cbk * 32 + x;
-        *reinterpret_cast<uint4*>(sm.p + (dv >> 6) * TILE + swz128(tid, dv & 63)) =
-            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-      }
+      for (int x = 0; x < 32; x += 2)
+        hpk[x / 2] = pack_bf16x2((hi[x] + wq * gg[x]) * inv, (hi[x + 1] + wq * gg[x + 1]) * inv);
     }
-    // ---- state pass: Cb <- bf16(C); C <- decay_next C; n likewise ------------------------
-    const bool last = (c + 1 == NC);
-    const float dnext = last ? 1.f : Gn.decay;
-    if (warp < DH / 32) {
-#pragma unroll 1
-      for (int cbk = 0; cbk < DH / 32; ++cbk) {
+    TL_STAMP(9);
+    mbar_wait(&sm.bar_kv, ph);   // state update complete: C final, Kbar and V dead
+    tc_fence_after();
+    TL_STAMP(10);
+    if (issuer && !last) issue_loads(sm.v, &maps.v, &sm.bar_v, c + 1);
+
+    // ---- state pass: Cb <- bf16(C); C <- decay_next C (state row `row`, block cq); n in smem ----
+    const float dnext = last ? 1.f : sm.g[(c + 1) % 3].decay;
+    if (cq < NB) {
+      if (row < DH) {
         float r[32];
-        tmem_ld32(tC + lane_sel + cbk * 32, r);
+        tmem_ld32(tC + lane_sel + cq * 32, r);
         tmem_ld_wait();
         if (last && p.c_last) {
-          float* dst = p.c_last + ((int64_t)bh * DH + tid) * DH + cbk * 32;
+          float* dst = p.c_last + ((int64_t)bh * DH + row) * DH + cq * 32;
 #pragma unroll
           for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4*>(dst + x) = make_float4(r[x], r[x + 1], r[x + 2], r[x + 3]);
         }
 #pragma unroll
         for (int x = 0; x < 32; x += 8) {
-          const int dv = cbk * 32 + x;
-          *reinterpret_cast<uint4*>(sm.cb + (dv >> 6) * TILE_C + swz128(tid, dv & 63)) =
+          const int dv = cq * 32 + x;
+          *reinterpret_cast<uint4*>(sm.cb + (dv >> 6) * TILE_C + swz128(row, dv & 63)) =
               make_uint4(pack_bf16x2(r[x], r[x + 1]), pack_bf16x2(r[x + 2], r[x + 3]), pack_bf16x2(r[x + 4], r[x + 5]),
                          pack_bf16x2(r[x + 6], r[x + 7]));
         }
         if (!last) {
 #pragma unroll
           for (int x = 0; x < 32; ++x) r[x] *= dnext;
-          tmem_st32(tC + lane_sel + cbk * 32, r);
+          tmem_st32(tC + lane_sel + cq * 32, r);
         }
-      }
-      float rn[16];
-      tmem_ld16(tN + lane_sel, rn);
-      tmem_ld_wait();
-      sm.n_prev[tid] = rn[0];
-      if (last && p.n_last) p.n_last[(int64_t)bh * DH + tid] = rn[0];
-      if (!last) {
-        float r32[32];
+        if (cq == 0) {
+          float rn[16];
+          tmem_ld16(tN + lane_sel, rn);
+          tmem_ld_wait();
+          sm.n_prev[row] = rn[0];
+          if (last && p.n_last) p.n_last[(int64_t)bh * DH + row] = rn[0];
+          if (!last) {
 #pragma unroll
-        for (int x = 0; x < 32; ++x) r32[x] = rn[0] * dnext;
-        tmem_st32(tN + lane_sel, r32);
-        tmem_st_wait();
+            for (int x = 0; x < 32; ++x) r[x] = rn[0] * dnext;
+            tmem_st32(tN + lane_sel, r);
+          }
+        }
+        if (!last) tmem_st_wait();
+      }
+      // ---- epilogue part 2: stage h in the (now dead) K buffer of this chunk for the TMA store ----
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int dv = cq * 32 + x * 8;
+        *reinterpret_cast<uint4*>(sk + (dv >> 6) * TILE + swz128(row, dv & 63)) =
+            make_uint4(hpk[4 * x], hpk[4 * x + 1], hpk[4 * x + 2], hpk[4 * x + 3]);
       }
     }
-    if (last && p.m_last && tid == 0) p.m_last[bh] = G.m_next;
+    if (last && p.m_last && issuer) p.m_last[bh] = G.m_next;
+    TL_STAMP(11);
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      for (int kt = 0; kt < KT; ++kt) tma_store_4d(&maps.h, sm.p + kt * TILE, kt * 64, tok0, h, b);
+    __syncthreads();   // end of chunk: everybody, including the gate warp
+    TL_STAMP(12);
+    if (issuer) {
+      for (int kt = 0; kt < KT; ++kt) tma_store_4d(&maps.h, sk + kt * TILE, kt * 64, tok0, h, b);
       tma_store_commit();
+      if (!last) {   // MMA1 of the next chunk: nobody waits for this issue loop
+        mbar_wait(&sm.bar_q, ph ^ 1);
+        mbar_wait(&sm.bar_k[(c + 1) & 1], ((c + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_mma1(c + 1);
+      }
     }
   }
 
-  if (tid == 0) tma_store_wait_all<0>();
+  if (issuer) tma_store_wait_all<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tm, 512);
