@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MLSTM_B200_ABI_VERSION 1
+#define MLSTM_B200_ABI_VERSION 2
 
 typedef enum mlstm_status {
   MLSTM_OK = 0,
@@ -104,6 +104,13 @@ typedef struct mlstm_params {
 
   void* workspace;                      /* device scratch, >= mlstm_b200_workspace_bytes()  */
   size_t workspace_bytes;
+
+  /* Per-chunk entry states (bf16 C, fp32 n, m for every 128-token chunk), written by the
+   * forward's state kernel and read by its chunk-parallel kernel and by the backward.  Size
+   * mlstm_b200_state_bytes(); keep it with q,k,v,i,f,h,n_row,m_row until the backward has run.
+   * 0 bytes (NULL allowed) for the SIMT kernel family. */
+  void* states;
+  size_t states_bytes;
 } mlstm_params;
 
 /* Library / ABI identification. */
@@ -111,6 +118,9 @@ int mlstm_b200_abi_version(void);
 
 /* Scratch bytes the given call needs (0 is possible). is_backward: 0 fwd, 1 bwd. */
 size_t mlstm_b200_workspace_bytes(const mlstm_params* p, int is_backward);
+
+/* Bytes of the per-chunk state buffer `states` the given call needs (0 for the SIMT family). */
+size_t mlstm_b200_state_bytes(const mlstm_params* p);
 
 /* Forward: h = mLSTM(q,k,v,i,f[,C0,n0,m0]) (+ n_row, m_row, last states).
  * Replaces mLSTMBackend.forward at vision_lstm2.py:912-948 / chunkwise_simple backends.py:149. */

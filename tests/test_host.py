@@ -81,8 +81,10 @@ def test_kernel_family_and_workspace(lib):
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"tcgen05"
     assert lib.mlstm_b200_workspace_bytes(C.byref(p), 1) == 2 * 4 * 2 * 2 * 64
     assert lib.mlstm_b200_workspace_bytes(C.byref(p), 0) == 0
+    assert lib.mlstm_b200_state_bytes(C.byref(p)) >= 2 * 2 * 1 * (64 * 64 * 2 + 64 * 4 + 4)   # per-chunk entry states
     p = _params(DHQK=16, DHV=16)
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
+    assert lib.mlstm_b200_state_bytes(C.byref(p)) == 0
     p = _params(dtype=_lib.MLSTM_F32, DHQK=128, DHV=128)
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
     p = _params(DHQK=256, DHV=256)

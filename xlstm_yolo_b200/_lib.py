@@ -12,7 +12,7 @@ import threading
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libmlstm_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MLSTM_F32, MLSTM_BF16 = 0, 1
 
 STATUS = {0: "OK", -1: "INVALID_ARG", -2: "UNSUPPORTED", -3: "WORKSPACE", -4: "CUDA", -5: "NO_DEVICE"}
@@ -20,6 +20,7 @@ STATUS = {0: "OK", -1: "INVALID_ARG", -2: "UNSUPPORTED", -3: "WORKSPACE", -4: "C
 EXPORTS = (
     "mlstm_b200_abi_version",
     "mlstm_b200_workspace_bytes",
+    "mlstm_b200_state_bytes",
     "mlstm_b200_fwd",
     "mlstm_b200_bwd",
     "mlstm_b200_bwd_part",
@@ -54,6 +55,7 @@ class Params(C.Structure):
         ("dq", Act), ("dk", Act), ("dv", Act),
         ("di", Gate), ("df", Gate),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("states", C.c_void_p), ("states_bytes", C.c_size_t),
     ]
 
 
@@ -84,6 +86,8 @@ def load() -> C.CDLL:
         lib.mlstm_b200_abi_version.restype = C.c_int
         lib.mlstm_b200_workspace_bytes.restype = C.c_size_t
         lib.mlstm_b200_workspace_bytes.argtypes = [C.POINTER(Params), C.c_int]
+        lib.mlstm_b200_state_bytes.restype = C.c_size_t
+        lib.mlstm_b200_state_bytes.argtypes = [C.POINTER(Params)]
         lib.mlstm_b200_fwd.restype = C.c_int
         lib.mlstm_b200_fwd.argtypes = [C.POINTER(Params), C.c_void_p]
         lib.mlstm_b200_bwd.restype = C.c_int

@@ -123,6 +123,11 @@ size_t mlstm_b200_workspace_bytes(const mlstm_params* p, int is_backward) {
   }
 }
 
+size_t mlstm_b200_state_bytes(const mlstm_params* p) {
+  if (!p || p->B <= 0 || p->S <= 0) return 0;
+  return pick(*p) == FAM_TC ? tc_state_bytes(*p) : 0;
+}
+
 const char* mlstm_b200_kernel_name(const mlstm_params* p, int /*is_backward*/) {
   if (!p) return nullptr;
   switch (pick(*p)) {

@@ -539,7 +539,11 @@ int launch_fwd(const mlstm_params& p, cudaStream_t st) {
 
 }  // namespace
 
+bool tc_use_two_phase(const mlstm_params& p);
+int tc_fwd_two_phase(const mlstm_params& p, cudaStream_t st);
+
 int tc_fwd(const mlstm_params& p, cudaStream_t st) {
+  if (tc_use_two_phase(p)) return tc_fwd_two_phase(p, st);
   if (p.DHQK == 64) return launch_fwd<64>(p, st);
   return launch_fwd<128>(p, st);
 }

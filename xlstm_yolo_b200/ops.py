@@ -96,10 +96,20 @@ def kernel_family(q: torch.Tensor, v: torch.Tensor) -> str:
     return name.decode() if name else "none"
 
 
+def _alloc_states(lib, p, dev):
+    """Per-chunk entry-state buffer of the tcgen05 family (None for SIMT); attaches it to p."""
+    need = lib.mlstm_b200_state_bytes(C.byref(p))
+    if not need:
+        return None
+    states = torch.empty(need, dtype=torch.uint8, device=dev)
+    p.states, p.states_bytes = states.data_ptr(), need
+    return states
+
+
 def mlstm_fwd_raw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None, *, eps=1e-6, chunk_size=64,
                   reverse=False, save_rows=True, return_last_states=False, qk_scale=None):
     """One forward launch through the C ABI.  Inputs must already be CUDA, fp32 or bf16
-    (q,k,v same dtype), gates fp32.  Returns (h, n_row, m_row, last_states_or_None)."""
+    (q,k,v same dtype), gates fp32.  Returns (h, n_row, m_row, last_states_or_None, chunk_states)."""
     lib = _lib.load()
     B, NH, S, DK = q.shape
     DV = v.shape[-1]
@@ -120,15 +130,16 @@ def mlstm_fwd_raw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None,
     p.n_row, p.m_row = _ptr(n_row), _ptr(m_row)
     if last is not None:
         p.c_last, p.n_last, p.m_last = (_ptr(t) for t in last)
+    states = _alloc_states(lib, p, dev)
     with torch.cuda.device(dev):
         rc = lib.mlstm_b200_fwd(C.byref(p), _stream())
     if rc:
         _fail(rc, "forward")
-    return h, n_row, m_row, last
+    return h, n_row, m_row, last, states
 
 
 def mlstm_bwd_raw(q, k, v, i, f, h, n_row, m_row, dh, c_initial=None, n_initial=None, m_initial=None, *, eps=1e-6,
-                  chunk_size=64, reverse=False, qk_scale=None):
+                  chunk_size=64, reverse=False, qk_scale=None, states=None):
     """One backward call through the C ABI.  Returns (dq, dk, dv, di, df) — dq,dk,dv in the
     layout/dtype of q,k,v; di,df fp32 (B,NH,S)."""
     lib = _lib.load()
@@ -147,6 +158,8 @@ def mlstm_bwd_raw(q, k, v, i, f, h, n_row, m_row, dh, c_initial=None, n_initial=
     p.dh = _act(dh)
     p.dq, p.dk, p.dv = _act(dq), _act(dk), _act(dv)
     p.di, p.df = _gate(di), _gate(df)
+    if states is not None:
+        p.states, p.states_bytes = states.data_ptr(), states.numel()
     need = lib.mlstm_b200_workspace_bytes(C.byref(p), 1)
     ws = None
     if need:
@@ -166,11 +179,11 @@ class _MLSTMCellFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, i, f, c_initial, n_initial, m_initial, eps, chunk_size, reverse, return_last_states):
         need_grad = any(t.requires_grad for t in (q, k, v, i, f))
-        h, n_row, m_row, last = mlstm_fwd_raw(
+        h, n_row, m_row, last, states = mlstm_fwd_raw(
             q, k, v, i, f, c_initial, n_initial, m_initial, eps=eps, chunk_size=chunk_size, reverse=reverse,
             save_rows=need_grad, return_last_states=return_last_states)
         if need_grad:
-            ctx.save_for_backward(q, k, v, i, f, h, n_row, m_row, c_initial, n_initial, m_initial)
+            ctx.save_for_backward(q, k, v, i, f, h, n_row, m_row, c_initial, n_initial, m_initial, states)
         ctx.cfg = (eps, chunk_size, reverse)
         if return_last_states:
             ctx.mark_non_differentiable(*last)
@@ -179,13 +192,13 @@ class _MLSTMCellFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dh, *dstates):
-        q, k, v, i, f, h, n_row, m_row, c0, n0, m0 = ctx.saved_tensors
+        q, k, v, i, f, h, n_row, m_row, c0, n0, m0, states = ctx.saved_tensors
         eps, chunk_size, reverse = ctx.cfg
         if dh.dtype != q.dtype:
             dh = dh.to(q.dtype)  # e.g. loss-scaled fp16 -> bf16: no clamping, inf/NaN propagate
         dh = _prep_act(dh)
         dq, dk, dv, di, df = mlstm_bwd_raw(q, k, v, i, f, h, n_row, m_row, dh, c0, n0, m0, eps=eps,
-                                           chunk_size=chunk_size, reverse=reverse)
+                                           chunk_size=chunk_size, reverse=reverse, states=states)
         return dq, dk, dv, di, df, None, None, None, None, None, None, None
 
 
@@ -247,6 +260,7 @@ class MLSTMPlan:
         p.dh = _act(dh)
         p.dq, p.dk, p.dv = _act(self.dq), _act(self.dk), _act(self.dv)
         p.di, p.df = _gate(self.di), _gate(self.df)
+        self.states = _alloc_states(self.lib, p, dev)
         need = self.lib.mlstm_b200_workspace_bytes(C.byref(p), 1)
         self.ws = torch.empty(max(1, (need + 3) // 4), dtype=torch.float32, device=dev)
         p.workspace, p.workspace_bytes = self.ws.data_ptr(), self.ws.numel() * 4
