@@ -1,635 +1,265 @@
-// tcgen05 / TMEM / TMA backward kernels of the mLSTM cell for bf16 I/O, DH in {64, 128}.
+// tcgen05 / TMEM / TMA backward of the mLSTM cell for bf16 I/O, DH in {64, 128}.
 //
-// The backward recomputes every gate/decay matrix per chunk from q,k,v,i,f and the per-row
-// (n_t, m_t) the forward saved; nothing of size S x S or S x DH x DH is ever stored.  The
-// adjoint (derived in tests/emu_kernel_dataflow.py, checked there against autograd through
-// the oracle) splits into three chunk walks, each with one DH x DH state resident in TMEM:
+// Everything of size S x S (gate/decay matrices, dS, E) is recomputed per 128-token chunk from
+// q,k,v,i,f and the per-row (n_t, m_t) saved by the forward; the only stored intermediates are the
+// per-chunk states: the forward's entry states Cs/ns (DH^2/128 bf16 per token-head) and their
+// adjoints dCs/dns produced here.  With the states in HBM every chunk is independent, so all heavy
+// kernels are chunk-parallel persistent kernels that fill the GPU whatever the batch size:
 //
-//   kernel A  (scan order)      carries C (recomputed like the forward)        -> dq, dn_t, R_t
-//   kernel B1 (reverse order)   carries dC                                     -> dv
-//   kernel B2 (reverse order)   carries dC and dn                              -> dk, di, df
+//   A   (par)  dn_t, dS = (dH V^T / N + dn) * D,  dq = s [ dS K + w (dH Cs^T / N + dn ns) ],  R_t = q.dq
+//   SB  (seq)  dC <- decay dC + ((w s / N) Q)^T dH ;  dn_state <- decay dn_state + Q^T (w s dn)
+//              one CTA per (batch, head), reverse chunk order, one MMA + one TMEM pass per chunk
+//   B1  (par)  dv = (s S^T D / N) dH + kw (K dCs)
+//   B2  (par)  dk = s [ dS^T Q + (kw/s) V dCs^T ] + kw dns ;  K_j = k_j . dk_j
+//   DF  (seq)  di = K ;  df = sigmoid(-f) * suffix_sum(R - K)        (tiny scan kernel)
 //
-// with (s = qk scale, N_t = max(|n_t|, e^-m_t) + eps, D_tj = exp(u_j - M_t) causal):
-//   dn_t = -[|n_t| >= e^-m_t] sign(n_t) (dh_t . h_t) / N_t
-//   dS   = (dH V^T / N + dn) * D            dq = s [ dS K + w (dH C^T / N + dn n) ]
-//   dv   = (s S^T D / N) dH + kw (K dC)     dk = s dS^T Q + kw (V dC^T + dn_state)
-//   dC  <- decay dC + (w s / N  Q)^T dH     dn_state <- decay dn_state + Q^T (w s dn)
-//   di_j = k_j . dk_j ;  df = sigmoid(-f) * suffix_sum(q . dq - k . dk)
-// All contractions are tcgen05 MMAs (bf16 operands from 128B-swizzled shared memory tiles,
-// fp32 accumulators in TMEM); gating / masks / normalisers are fused SIMT between them.
-#include "mlstm_common.cuh"
-#include "tc_ptx.cuh"
-#include "tc_tmap.cuh"
+// (s = qk scale, N_t = max(|n_t|, e^-m_t) + eps, D_tj = exp(u_j - M_t) causal; derivation and
+// CPU emulation in tests/emu_kernel_dataflow.py.)  The parallel kernels share one skeleton:
+// MMA1 (128x128 tile product) -> SIMT gating into a bf16 tile -> MMA2, with 16 compute warps,
+// one control warp issuing all TMA / tcgen05.mma, one gate warp preparing the next item.
+#include "tc_common.cuh"
 
 namespace mlstm {
 namespace {
 
-using namespace ptx;
+using namespace tc;
 
-constexpr int L = 128;
-constexpr int NT = 128;
-constexpr int TILE = L * 128;
-constexpr float LOG2E = 1.4426950408889634f;
+enum { MODE_A = 0, MODE_B1 = 1, MODE_B2 = 2 };
 
-struct BwdMaps { CUtensorMap q, k, v, dh, out0, out1; };  // out0/out1: dq | dv | dk
+struct BwdMaps { CUtensorMap t0, t1, t2, st; };
 
-struct alignas(16) GateBufB {   // all indexed by tile row
-  float u2[L];      // u * log2e
-  float M2[L];      // M * log2e
-  float w[L];       // exp(m_prev - M)
-  float invN[L];    // 1 / N_t
-  float dn[L];      // dn_t
-  float kw[L];      // exp(u - M_L)
-  float R[L];       // q . dq   (kernel B2)
-  float sig[L];     // sigmoid(-f)
-  float decay;
-  float pad[3];
+// backward scratch (p.workspace)
+struct BwdLayout {
+  size_t dn_off, rpart_off, kpart_off, dcs_off, dns_off, total;
+  __host__ __device__ BwdLayout(int B, int NH, int S, int DH) {
+    const size_t rows = (size_t)B * NH * S, items = (size_t)B * NH * num_chunks(S);
+    dn_off = 0;
+    rpart_off = dn_off + rows * 4;
+    kpart_off = rpart_off + 4 * rows * 4;
+    dcs_off = (kpart_off + 4 * rows * 4 + 255) & ~(size_t)255;
+    dns_off = dcs_off + items * DH * DH * 2;
+    total = (dns_off + items * DH * 4 + 255) & ~(size_t)255;
+  }
 };
 
-template <int DH, int NIN>
+// =============================================================================================
+// Chunk-parallel kernels A / B1 / B2
+//   tiles:  A : t0 = dH, t1 = V, t2 = K, st = Cs     thread row = query t
+//           B1: t0 = K,  t1 = Q, t2 = dH, st = dCs   thread row = key j
+//           B2: t0 = V,  t1 = dH, t2 = Q, st = dCs   thread row = key j
+// =============================================================================================
+template <int DH>
 struct SmemB {
   static constexpr int KT = DH / 64;
   static constexpr int TILE_C = DH * 128;
-  alignas(1024) uint8_t in[NIN][KT * TILE];      // TMA-loaded operand tiles
-  alignas(1024) uint8_t x[2 * TILE];             // dS / E^T / dS^T tile (K-major), then staging
-  alignas(1024) uint8_t cb[KT * TILE_C];         // bf16 state (C or dC), [dk][dv]
-  alignas(1024) uint8_t vec[2 * 2048];           // K-major [16][128] bf16 vector tile (kw or w s dn)
-  GateBufB g[2];
-  float nvec[DH];                                // n_prev (A) / dn_state (B2), fp32
-  float scan[8];
-  uint64_t bar_in[NIN], bar_m1, bar_s, bar_m2;
+  alignas(1024) uint8_t t0[KT * TILE];
+  alignas(1024) uint8_t t1[KT * TILE];
+  alignas(1024) uint8_t t2[KT * TILE];
+  alignas(1024) uint8_t st[KT * TILE_C];
+  alignas(1024) uint8_t x[2 * TILE];               // gated bf16 tile (K-major, 2 tiles over the column index)
+  GateBuf g[2];
+  alignas(16) float vecf[2][DH];                   // ns (A) / dns (B2) of the item
+  float part[4][L];
+  uint64_t bar_t0, bar_t1, bar_t2, bar_st, bar_m1, bar_i, bar_m2;
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__device__ __forceinline__ uint64_t dK(uint32_t base, int ks, uint32_t atom_stride) {  // K-major operand, k-step ks
-  return make_sdesc(base + (ks >> 2) * atom_stride + (ks & 3) * 32, 16, 1024);
-}
-__device__ __forceinline__ uint64_t dMN(uint32_t base, int ks, uint32_t lbo) {         // MN-major operand
-  return make_sdesc(base + ks * 2048, lbo, 1024);
-}
-
-struct ChunkGeom { int mc, tok0, nvalid; };
-__device__ __forceinline__ ChunkGeom geom(int mc, int S) {
-  ChunkGeom g;
-  g.mc = mc; g.tok0 = mc * L; g.nvalid = min(L, S - g.tok0);
-  return g;
-}
-
-// Gate vectors of memory chunk `mc`, rebuilt from i, f and the saved rows (n_t, m_t).
-// Thread t = scan-local index t.  `need_dn`: also load dn_t and R_t from the workspace.
-template <class SM>
-__device__ __forceinline__ void gates_from_rows(SM& sm, GateBufB& G, const mlstm_params& p, int b, int h, int bh, int mc,
-                                                const float* ws_dn, const float* ws_R) {
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const ChunkGeom cg = geom(mc, p.S);
-  const bool rev = p.reverse != 0;
-  const bool valid = t < cg.nvalid;
-  const int r = (rev && valid) ? (cg.nvalid - 1 - t) : t;
-  float ii = -INFINITY, logf = 0.f, fi = 0.f, mrow = 0.f, nrow = 0.f, dn = 0.f, R = 0.f;
-  if (valid) {
-    const int tok = cg.tok0 + r;
-    fi = p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s];
-    ii = p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s];
-    logf = log_sigmoid(fi);
-    mrow = p.m_row[(int64_t)bh * p.S + tok];
-    nrow = p.n_row[(int64_t)bh * p.S + tok];
-    if (ws_dn) { dn = ws_dn[(int64_t)bh * p.S + tok]; R = ws_R[(int64_t)bh * p.S + tok]; }
-  }
-  float bs = warp_scan_add(logf, lane);
-  if (lane == 31) sm.scan[warp] = bs;
-  __syncthreads();
-  float pre = 0.f;
-#pragma unroll
-  for (int w = 0; w < 4; ++w) pre += (w < warp) ? sm.scan[w] : 0.f;
-  bs += pre;
-  const float u = ii - bs;
-  float M = mrow - bs;
-  if (t == cg.nvalid - 1) sm.scan[4] = M;        // M_L: M at the last valid scan index
-  // m of the row that precedes this chunk in scan order (or the initial m)
-  float m_prev;
-  {
-    const int ptok = rev ? (cg.tok0 + cg.nvalid) : (cg.tok0 - 1);
-    m_prev = (ptok >= 0 && ptok < p.S) ? p.m_row[(int64_t)bh * p.S + ptok] : (p.m_initial ? p.m_initial[bh] : 0.f);
-  }
-  __syncthreads();
-  const float ML = sm.scan[4];
-  if (!valid) M = ML;
-  G.u2[r] = u * LOG2E;
-  G.M2[r] = M * LOG2E;
-  G.w[r] = __expf(m_prev - M);
-  G.invN[r] = valid ? 1.f / (fmaxf(fabsf(nrow), __expf(-mrow)) + p.eps) : 0.f;
-  G.dn[r] = dn;
-  G.kw[r] = __expf(u - ML);
-  G.R[r] = R;
-  G.sig[r] = 1.f / (1.f + __expf(fi));
-  if (t == 0) G.decay = __expf(m_prev - ML);
-  __syncthreads();
-}
-
-// rows of a [128][DH] swizzled bf16 tile set scaled in place by rowscale[row]
-template <int DH>
-__device__ __forceinline__ void scale_rows(uint8_t* tile, const float* rowscale) {
+template <int DH, int MODE>
+__global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant__ BwdMaps maps, const mlstm_params p,
+                                                           const float scale, const int n_items) {
   constexpr int KT = DH / 64;
-  for (int it = 0; it < KT * TILE / 16 / NT; ++it) {
-    const uint32_t o = (uint32_t)(threadIdx.x + it * NT) * 16u;
-    const float s = rowscale[(o >> 7) & (L - 1)];
-    uint4 w = *reinterpret_cast<uint4*>(tile + o);
-    __nv_bfloat162* kk = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 f2 = __bfloat1622float2(kk[e]);
-      kk[e] = __floats2bfloat162_rn(f2.x * s, f2.y * s);
-    }
-    *reinterpret_cast<uint4*>(tile + o) = w;
-  }
-}
+  constexpr int TILE_C = SmemB<DH>::TILE_C;
+  constexpr int NB = DH / 32;
+  constexpr bool IS_A = (MODE == MODE_A);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SmemB<DH>& sm = *reinterpret_cast<SmemB<DH>*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
 
-// K-major [16 rows][128] bf16 tile whose every row is the vector val[0..127] (thread j writes val_j)
-__device__ __forceinline__ void write_vec_tile(uint8_t* vec, float val) {
-  const int j = threadIdx.x;
-  const __nv_bfloat16 bv = __float2bfloat16_rn(val);
-#pragma unroll
-  for (int row = 0; row < 16; ++row)
-    *reinterpret_cast<__nv_bfloat16*>(vec + (j >> 6) * 2048 + swz128(row, j & 63)) = bv;
-}
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool compute = tid < CT, issuer = tid == CT, gatew = tid >= GT0;
+  const int rg = warp & 3, cq = compute ? (warp >> 2) : 4, row = rg * 32 + lane;
+  const int S = p.S, NC = num_chunks(S);
+  const bool rev = p.reverse != 0;
+  const size_t rows_total = (size_t)p.B * p.NH * S;
+  const StateLayout slay(p.B, p.NH, S, DH);
+  const BwdLayout blay(p.B, p.NH, S, DH);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(p.workspace);
+  float* ws_dn = reinterpret_cast<float*>(ws + blay.dn_off);
+  float* ws_rpart = reinterpret_cast<float*>(ws + blay.rpart_off);
+  float* ws_kpart = reinterpret_cast<float*>(ws + blay.kpart_off);
+  const float* ns_all = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.states) + slay.ns_off);
+  const float* dns_all = reinterpret_cast<const float*>(ws + blay.dns_off);
+  const float l2s = log2f(scale);
 
-// dot of this thread's row of a swizzled [128][DH] bf16 tile with 32-float blocks held in regs is done inline.
-template <int DH>
-__device__ __forceinline__ void load_row_f32(const uint8_t* tile, int row, int cb32, float (&out)[32]) {
-  // columns [cb32*32, cb32*32+32) of `row`
-#pragma unroll
-  for (int x = 0; x < 32; x += 8) {
-    const int col = cb32 * 32 + x;
-    const uint4 w = *reinterpret_cast<const uint4*>(tile + (col >> 6) * TILE + swz128(row, col & 63));
-    const __nv_bfloat162* qq = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 f2 = __bfloat1622float2(qq[e]);
-      out[x + 2 * e] = f2.x;
-      out[x + 2 * e + 1] = f2.y;
-    }
-  }
-}
-
-// state pass: cb <- bf16(T), T <- dnext * T (skipped when last); nvec <- n column
-template <int DH, class SM>
-__device__ __forceinline__ void state_pass(SM& sm, uint32_t tC, uint32_t tN, bool has_n, float dnext, bool last,
-                                           uint32_t lane_sel) {
-  constexpr int TILE_C = DH * 128;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  if (warp < DH / 32) {
-#pragma unroll 1
-    for (int cbk = 0; cbk < DH / 32; ++cbk) {
-      float r[32];
-      tmem_ld32(tC + lane_sel + cbk * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int x = 0; x < 32; x += 8) {
-        const int dv = cbk * 32 + x;
-        *reinterpret_cast<uint4*>(sm.cb + (dv >> 6) * TILE_C + swz128(tid, dv & 63)) =
-            make_uint4(pack_bf16x2(r[x], r[x + 1]), pack_bf16x2(r[x + 2], r[x + 3]), pack_bf16x2(r[x + 4], r[x + 5]),
-                       pack_bf16x2(r[x + 6], r[x + 7]));
-      }
-      if (!last) {
-#pragma unroll
-        for (int x = 0; x < 32; ++x) r[x] *= dnext;
-        tmem_st32(tC + lane_sel + cbk * 32, r);
-      }
-    }
-    if (has_n) {
-      float rn[16];
-      tmem_ld16(tN + lane_sel, rn);
-      tmem_ld_wait();
-      sm.nvec[tid] = rn[0];
-      if (!last) {
-        float r32[32];
-#pragma unroll
-        for (int x = 0; x < 32; ++x) r32[x] = rn[0] * dnext;
-        tmem_st32(tN + lane_sel, r32);
-      }
-    }
-    if (!last) tmem_st_wait();
-  }
-}
-
-template <class SM>
-__device__ __forceinline__ void setup(SM& sm, int nbar_in) {
-  const int tid = threadIdx.x, warp = tid >> 5;
-  if (tid == 0) {
-    for (int i = 0; i < nbar_in; ++i) mbar_init(&sm.bar_in[i], 1);
-    mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_s, 1); mbar_init(&sm.bar_m2, 1);
+  if (issuer) {
+    tma_prefetch_desc(&maps.t0); tma_prefetch_desc(&maps.t1); tma_prefetch_desc(&maps.t2); tma_prefetch_desc(&maps.st);
+    mbar_init(&sm.bar_t0, 1); mbar_init(&sm.bar_t1, 1); mbar_init(&sm.bar_t2, 1); mbar_init(&sm.bar_st, 1);
+    mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_i, 1); mbar_init(&sm.bar_m2, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
-}
-
-// ======================================================================================
-// Kernel A: scan-order walk, carries C and n.  Tiles: in[0]=q in[1]=k in[2]=v in[3]=dh.
-// ======================================================================================
-template <int DH>
-__global__ void __launch_bounds__(NT, 1) tc_bwd_dq_kernel(const __grid_constant__ BwdMaps maps, const mlstm_params p,
-                                                          const float scale, float* __restrict__ ws_dn,
-                                                          float* __restrict__ ws_R) {
-  constexpr int KT = DH / 64;
-  constexpr int TILE_C = DH * 128;
-  constexpr uint32_t A_LBO_STATE = (DH == 128) ? TILE : 0;
-  using SM = SmemB<DH, 4>;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  SM& sm = *reinterpret_cast<SM*>(smem_raw);
-  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-  uint8_t *sq = sm.in[0], *sk = sm.in[1], *sv = sm.in[2], *sdh = sm.in[3];
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int bh = blockIdx.x, b = bh / p.NH, h = bh % p.NH;
-  const int S = p.S, NC = (S + L - 1) / L;
-  const bool has_init = p.c_initial != nullptr;
-  const bool rev = p.reverse != 0;
-
-  setup(sm, 4);
-  if (tid == 0) { tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.v); tma_prefetch_desc(&maps.dh); tma_prefetch_desc(&maps.out0); }
-  if (!has_init) {
-    for (int e = tid; e < KT * TILE_C / 16; e += NT) reinterpret_cast<uint4*>(sm.cb)[e] = make_uint4(0, 0, 0, 0);
-    for (int e = tid; e < DH; e += NT) sm.nvec[e] = 0.f;
-  }
+  if (warp == 0) tmem_alloc(&sm.tmem_base, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tm = sm.tmem_base;
-  const uint32_t tZ = tm, tG = tm + 128, tC = tm + 128 + DH, tN = tm + 128 + 2 * DH;
-  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+  const uint32_t tm = sm.tmem_base, tS = tm, tO = tm + 128;   // tO: G (A) or the dv / dk accumulator (B)
+  const uint32_t lane_sel = (uint32_t)(rg * 32) << 16;
 
-  auto mc_of = [&](int c) { return rev ? (NC - 1 - c) : c; };
-  auto load = [&](int slot, const CUtensorMap* map, int c) {
-    mbar_arrive_expect_tx(&sm.bar_in[slot], KT * TILE);
-    for (int kt = 0; kt < KT; ++kt) tma_load_4d(sm.in[slot] + kt * TILE, map, &sm.bar_in[slot], kt * 64, mc_of(c) * L, h, b);
+  const uint64_t d0k = make_sdesc(smem_u32(sm.t0), 16, 1024), d1k = make_sdesc(smem_u32(sm.t1), 16, 1024);
+  const uint64_t d2mn = make_sdesc(smem_u32(sm.t2), TILE, 1024), dXk = make_sdesc(smem_u32(sm.x), 16, 1024);
+  const uint64_t dStk = make_sdesc(smem_u32(sm.st), 16, 1024), dStmn = make_sdesc(smem_u32(sm.st), TILE_C, 1024);
+
+  auto coords = [&](int item, int& b, int& h, int& tok0) {
+    const int bh = item / NC, sc = item % NC;
+    b = bh / p.NH; h = bh % p.NH; tok0 = mem_chunk(sc, NC, rev) * L;
   };
-  if (tid == 0) { load(3, &maps.dh, 0); load(2, &maps.v, 0); load(1, &maps.k, 0); load(0, &maps.q, 0); }
-  gates_from_rows(sm, sm.g[0], p, b, h, bh, mc_of(0), nullptr, nullptr);
-
-  if (has_init) {
-    const float d0 = sm.g[0].decay;
-    if (tid < DH) {
-      const float* crow = p.c_initial + ((int64_t)bh * DH + tid) * DH;
-      for (int cbk = 0; cbk < DH / 32; ++cbk) {
-        float r[32];
+  auto load_act = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int item) {
+    int b, h, tok0; coords(item, b, h, tok0);
+    mbar_arrive_expect_tx(bar, KT * TILE);
+    for (int kt = 0; kt < KT; ++kt) tma_load_4d(dst + kt * TILE, map, bar, kt * 64, tok0, h, b);
+  };
+  auto load_st = [&](int item) {
+    mbar_arrive_expect_tx(&sm.bar_st, KT * TILE_C);
+    for (int kt = 0; kt < KT; ++kt) tma_load_2d(sm.st + kt * TILE_C, &maps.st, &sm.bar_st, kt * 64, item * DH);
+  };
+  auto issue_mma1 = [&]() {   // tS = t0 t1^T  (+ A: tO = G = dH Cs^T, Cs read as a K-major operand)
+    constexpr uint32_t id1 = make_idesc_bf16(128, 128, 0, 0);
 #pragma unroll
-        for (int x = 0; x < 32; ++x) r[x] = crow[cbk * 32 + x];
-#pragma unroll
-        for (int x = 0; x < 32; x += 8) {
-          const int dv = cbk * 32 + x;
-          *reinterpret_cast<uint4*>(sm.cb + (dv >> 6) * TILE_C + swz128(tid, dv & 63)) =
-              make_uint4(pack_bf16x2(r[x], r[x + 1]), pack_bf16x2(r[x + 2], r[x + 3]), pack_bf16x2(r[x + 4], r[x + 5]),
-                         pack_bf16x2(r[x + 6], r[x + 7]));
-        }
-#pragma unroll
-        for (int x = 0; x < 32; ++x) r[x] *= d0;
-        tmem_st32(tC + lane_sel + cbk * 32, r);
-      }
-      const float n0 = p.n_initial[(int64_t)bh * DH + tid];
-      sm.nvec[tid] = n0;
-      float r32[32];
-#pragma unroll
-      for (int x = 0; x < 32; ++x) r32[x] = n0 * d0;
-      tmem_st32(tN + lane_sel, r32);
-      tmem_st_wait();
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-  }
-
-  for (int c = 0; c < NC; ++c) {
-    GateBufB& G = sm.g[c & 1];
-    GateBufB& Gn = sm.g[(c + 1) & 1];
-    const uint32_t ph = c & 1;
-    const ChunkGeom cg = geom(mc_of(c), S);
-    const int tok = cg.tok0 + tid;
-    const bool row_ok = tid < cg.nvalid;
-
-    // ---- MMA1: Z = dH V^T, G = dH Cb^T ---------------------------------------------------
-    mbar_wait(&sm.bar_in[3], ph);
-    mbar_wait(&sm.bar_in[2], ph);
-    if (tid == 0) {
-      tc_fence_after();
-      constexpr uint32_t idZ = make_idesc_bf16(128, 128, 0, 0);
-      for (int ks = 0; ks < DH / 16; ++ks)
-        umma_bf16_ss(tZ, dK(smem_u32(sdh), ks, TILE), dK(smem_u32(sv), ks, TILE), idZ, ks > 0);
+    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tS, d0k + kstep(ks), d1k + kstep(ks), id1, ks > 0);
+    if (IS_A) {
       constexpr uint32_t idG = make_idesc_bf16(128, DH, 0, 0);
-      for (int ks = 0; ks < DH / 16; ++ks)
-        umma_bf16_ss(tG, dK(smem_u32(sdh), ks, TILE), dK(smem_u32(sm.cb), ks, TILE_C), idG, ks > 0);
-      umma_commit(&sm.bar_m1);
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tO, d0k + kstep(ks), dStk + kstep(ks, TILE_C), idG, ks > 0);
     }
-    // ---- shadow: next gates; dn_t = -[active] sign(n) (dh . h) / N ------------------------
-    if (c + 1 < NC) gates_from_rows(sm, Gn, p, b, h, bh, mc_of(c + 1), nullptr, nullptr);
-    float dn = 0.f;
-    const float invN = G.invN[tid];
-    if (row_ok) {
-      const __nv_bfloat16* hrow = reinterpret_cast<const __nv_bfloat16*>(p.h.ptr) + (int64_t)b * p.h.stride_b +
-                                  (int64_t)h * p.h.stride_h + (int64_t)tok * p.h.stride_s;
-      float hd = 0.f;
-#pragma unroll 1
-      for (int cbk = 0; cbk < DH / 32; ++cbk) {
-        float dhr[32];
-        load_row_f32<DH>(sdh, tid, cbk, dhr);
-#pragma unroll
-        for (int x = 0; x < 32; x += 8) {
-          const uint4 w = *reinterpret_cast<const uint4*>(hrow + cbk * 32 + x);
-          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float2 f2 = __bfloat1622float2(hh[e]);
-            hd += dhr[x + 2 * e] * f2.x + dhr[x + 2 * e + 1] * f2.y;
-          }
-        }
-      }
-      const float nr = p.n_row[(int64_t)bh * S + tok];
-      const float mr = p.m_row[(int64_t)bh * S + tok];
-      dn = (fabsf(nr) >= __expf(-mr)) ? -copysignf(1.f, nr) * hd * invN : 0.f;
-      ws_dn[(int64_t)bh * S + tok] = dn;
-    }
-    mbar_wait(&sm.bar_m1, ph);
-    tc_fence_after();
-
-    // ---- Vbar = kw * V in place; kw vector tile -------------------------------------------
-    scale_rows<DH>(sv, G.kw);
-    write_vec_tile(sm.vec, G.kw[tid]);
-    fence_proxy_async_smem();
-    if (tid == 0) tma_store_wait_read<0>();
-    tc_fence_before();
-    __syncthreads();
-
-    // ---- state MMAs: C += K^T Vbar, n += K^T kw ; prefetch dH(c+1) -------------------------
-    if (tid == 0) {
-      if (c + 1 < NC) load(3, &maps.dh, c + 1);
-      mbar_wait(&sm.bar_in[1], ph);
-      tc_fence_after();
-      constexpr uint32_t idC = make_idesc_bf16(128, DH, 1, 1);
-      constexpr uint32_t idN = make_idesc_bf16(128, 16, 1, 0);
-      const uint32_t acc0 = (c > 0 || has_init) ? 1u : 0u;
-      for (int ks = 0; ks < L / 16; ++ks) {
-        const uint64_t a = dMN(smem_u32(sk), ks, A_LBO_STATE);
-        umma_bf16_ss(tC, a, dMN(smem_u32(sv), ks, TILE), idC, (ks > 0) ? 1u : acc0);
-        umma_bf16_ss(tN, a, dK(smem_u32(sm.vec), ks, 2048), idN, (ks > 0) ? 1u : acc0);
-      }
-      umma_commit(&sm.bar_s);
-    }
-
-    // ---- dS = (Z / N + dn) * exp2(u2_j - M2_t), causal -> bf16 tile -----------------------
-    const float M2t = G.M2[tid];
-#pragma unroll 1
-    for (int cbk = 0; cbk < 4; ++cbk) {
-      const bool full = rev ? (cbk > warp) : (cbk < warp);
-      const bool diag = (cbk == warp);
-      uint32_t packed[16];
-      if (full || diag) {
-        float z[32];
-        tmem_ld32(tZ + lane_sel + cbk * 32, z);
-        tmem_ld_wait();
-#pragma unroll
-        for (int x = 0; x < 32; x += 4) {
-          const float4 u4 = *reinterpret_cast<const float4*>(&G.u2[cbk * 32 + x]);
-          const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
-          float pv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = cbk * 32 + x + e;
-            const bool keep = full || (rev ? (j >= tid) : (j <= tid));
-            pv[e] = keep ? fmaf(z[x + e], invN, dn) * ex2(uu[e] - M2t) : 0.f;
-          }
-          packed[x / 2] = pack_bf16x2(pv[0], pv[1]);
-          packed[x / 2 + 1] = pack_bf16x2(pv[2], pv[3]);
-        }
-      } else {
-#pragma unroll
-        for (int x = 0; x < 16; ++x) packed[x] = 0u;
-      }
-#pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        const int j = cbk * 32 + x * 8;
-        *reinterpret_cast<uint4*>(sm.x + (j >> 6) * TILE + swz128(tid, j & 63)) =
-            make_uint4(packed[4 * x], packed[4 * x + 1], packed[4 * x + 2], packed[4 * x + 3]);
-      }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-
-    // ---- MMA2: dQ = dS K (into the Z columns) ; prefetch V(c+1) ---------------------------
-    if (tid == 0) {
-      tc_fence_after();
-      constexpr uint32_t idQ = make_idesc_bf16(128, DH, 0, 1);
-      for (int ks = 0; ks < L / 16; ++ks)
-        umma_bf16_ss(tZ, dK(smem_u32(sm.x), ks, TILE), dMN(smem_u32(sk), ks, TILE), idQ, ks > 0);
-      umma_commit(&sm.bar_m2);
-      mbar_wait(&sm.bar_s, ph);
-      if (c + 1 < NC) load(2, &maps.v, c + 1);
-    }
-    mbar_wait(&sm.bar_in[0], ph);
-    mbar_wait(&sm.bar_m2, ph);
-    tc_fence_after();
-    if (tid == 0 && c + 1 < NC) load(1, &maps.k, c + 1);
-
-    // ---- epilogue: dq = s [ dQ + w (G / N + dn n_prev) ]; R = q . dq ----------------------
-    const float wt = G.w[tid];
-    float Rt = 0.f;
-#pragma unroll 1
-    for (int cbk = 0; cbk < DH / 32; ++cbk) {
-      float dq_[32], gg[32], qr[32];
-      tmem_ld32(tZ + lane_sel + cbk * 32, dq_);
-      tmem_ld32(tG + lane_sel + cbk * 32, gg);
-      tmem_ld_wait();
-      load_row_f32<DH>(sq, tid, cbk, qr);
-#pragma unroll
-      for (int x = 0; x < 32; x += 8) {
-        float o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          o[e] = scale * (dq_[x + e] + wt * fmaf(gg[x + e], invN, dn * sm.nvec[cbk * 32 + x + e]));
-          Rt = fmaf(qr[x + e], o[e], Rt);
-        }
-        const int dk_ = cbk * 32 + x;
-        *reinterpret_cast<uint4*>(sm.x + (dk_ >> 6) * TILE + swz128(tid, dk_ & 63)) =
-            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-      }
-    }
-    if (row_ok) ws_R[(int64_t)bh * S + tok] = Rt;
-    __syncthreads();   // every thread is done with nvec (n_prev) before the state pass rewrites it
-    const bool last = (c + 1 == NC);
-    state_pass<DH>(sm, tC, tN, true, last ? 1.f : Gn.decay, last, lane_sel);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      for (int kt = 0; kt < KT; ++kt) tma_store_4d(&maps.out0, sm.x + kt * TILE, kt * 64, cg.tok0, h, b);
-      tma_store_commit();
-      if (c + 1 < NC) load(0, &maps.q, c + 1);
-    }
-  }
-  if (tid == 0) tma_store_wait_all<0>();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, 512);
-}
-
-// ======================================================================================
-// Kernels B1 / B2: reverse-order walk carrying dC.  Thread j <-> key row j.
-//   MODE 1 (dv): tiles in[0]=q in[1]=k  in[2]=dh ; out0 = dv
-//   MODE 2 (dk): tiles in[0]=q in[1]=v  in[2]=dh ; out0 = dk ; also di, df, carries dn_state
-// ======================================================================================
-template <int DH, int MODE>
-__global__ void __launch_bounds__(NT, 1) tc_bwd_dkv_kernel(const __grid_constant__ BwdMaps maps, const mlstm_params p,
-                                                           const float scale, const float* __restrict__ ws_dn,
-                                                           const float* __restrict__ ws_R) {
-  constexpr int KT = DH / 64;
-  constexpr int TILE_C = DH * 128;
-  constexpr uint32_t A_LBO_STATE = (DH == 128) ? TILE : 0;
-  using SM = SmemB<DH, 3>;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  SM& sm = *reinterpret_cast<SM*>(smem_raw);
-  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-  uint8_t *sq = sm.in[0], *skv = sm.in[1], *sdh = sm.in[2];
-  __shared__ __align__(16) float colv[3][L];     // per-query-row vectors: [0] exponent offset, [1] 1/N, [2] dn
-  __shared__ __align__(16) float rowscale[L];    // (w s / N)_t for the dC update operand
-  __shared__ __align__(16) float kwos[L];        // kw_j / s
-  __shared__ float df_carry;
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int bh = blockIdx.x, b = bh / p.NH, h = bh % p.NH;
-  const int S = p.S, NC = (S + L - 1) / L;
-  const bool rev = p.reverse != 0;
-  const CUtensorMap* map_kv = (MODE == 1) ? &maps.k : &maps.v;
-
-  setup(sm, 3);
-  if (tid == 0) { tma_prefetch_desc(&maps.q); tma_prefetch_desc(map_kv); tma_prefetch_desc(&maps.dh); tma_prefetch_desc(&maps.out0); df_carry = 0.f; }
-  for (int e = tid; e < KT * TILE_C / 16; e += NT) reinterpret_cast<uint4*>(sm.cb)[e] = make_uint4(0, 0, 0, 0);
-  for (int e = tid; e < DH; e += NT) sm.nvec[e] = 0.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tm = sm.tmem_base;
-  const uint32_t tS = tm, tO = tm + 128, tC = tm + 128 + DH, tN = tm + 128 + 2 * DH;
-  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-
-  // processing step c (0 = scan-last chunk) -> memory chunk
-  auto mc_of = [&](int c) { return rev ? c : (NC - 1 - c); };
-  auto load = [&](int slot, const CUtensorMap* map, int c) {
-    mbar_arrive_expect_tx(&sm.bar_in[slot], KT * TILE);
-    for (int kt = 0; kt < KT; ++kt) tma_load_4d(sm.in[slot] + kt * TILE, map, &sm.bar_in[slot], kt * 64, mc_of(c) * L, h, b);
+    umma_commit(&sm.bar_m1);
   };
-  if (tid == 0) { load(1, map_kv, 0); load(2, &maps.dh, 0); load(0, &maps.q, 0); }
-  gates_from_rows(sm, sm.g[0], p, b, h, bh, mc_of(0), MODE == 2 ? ws_dn : nullptr, ws_R);
-
-  for (int c = 0; c < NC; ++c) {
-    GateBufB& G = sm.g[c & 1];
-    GateBufB& Gn = sm.g[(c + 1) & 1];
-    const uint32_t ph = c & 1;
-    const ChunkGeom cg = geom(mc_of(c), S);
-    const int tok = cg.tok0 + tid;
-    const bool row_ok = tid < cg.nvalid;
-
-    // ---- MMA1: S^T = K Q^T (dv)  |  Z^T = V dH^T (dk) -------------------------------------
-    mbar_wait(&sm.bar_in[1], ph);
-    mbar_wait(&sm.bar_in[MODE == 1 ? 0 : 2], ph);
-    if (tid == 0) {
-      tc_fence_after();
-      constexpr uint32_t id1 = make_idesc_bf16(128, 128, 0, 0);
-      const uint32_t bb = smem_u32(MODE == 1 ? sq : sdh);
-      for (int ks = 0; ks < DH / 16; ++ks)
-        umma_bf16_ss(tS, dK(smem_u32(skv), ks, TILE), dK(bb, ks, TILE), id1, ks > 0);
-      umma_commit(&sm.bar_m1);
+  auto prep_item = [&](int item, int slot) {   // gate warp
+    int b, h, tok0; coords(item, b, h, tok0);
+    const int bh = item / NC, sc = item % NC;
+    GateBuf& G = sm.g[slot];
+    gates_warp_bwd(G, p, b, h, bh, mem_chunk(sc, NC, rev), lane, MODE == MODE_B2 ? ws_dn : nullptr);
+    if (MODE == MODE_B2) {   // row scale of the V tile: kw / s  (s is applied in the epilogue)
+      for (int r = lane; r < L; r += 32) G.w[r] = G.kw[r] / scale;
     }
-    // ---- shadow: next gates; per-query-row vectors ---------------------------------------
-    if (c + 1 < NC) gates_from_rows(sm, Gn, p, b, h, bh, mc_of(c + 1), MODE == 2 ? ws_dn : nullptr, ws_R);
-    {
-      const float inv = G.invN[tid];
-      // dv: E^T = S^T * exp2(u2_j + log2 s - (M2_t - log2(invN_t)))   (1/N folded into the exponent)
-      // dk: dS^T = (Z^T invN_t + dn_t) * exp2(u2_j + log2 s - M2_t)
-      colv[0][tid] = (MODE == 1) ? (G.M2[tid] - ((inv > 0.f) ? log2f(inv) : -INFINITY)) : G.M2[tid];
-      colv[1][tid] = inv;
-      colv[2][tid] = G.dn[tid];
-      rowscale[tid] = G.w[tid] * scale * inv;
-      kwos[tid] = G.kw[tid] / scale;
+    for (int d = lane; d < DH; d += 32)
+      sm.vecf[slot][d] = IS_A ? ns_all[(size_t)item * DH + d] : (MODE == MODE_B2 ? dns_all[(size_t)item * DH + d] : 0.f);
+    __syncwarp();
+  };
+
+  const int item0 = blockIdx.x;   // the grid is never larger than n_items
+  if (issuer) {
+    load_act(sm.t0, &maps.t0, &sm.bar_t0, item0); load_act(sm.t1, &maps.t1, &sm.bar_t1, item0);
+    load_st(item0); load_act(sm.t2, &maps.t2, &sm.bar_t2, item0);
+  }
+  if (gatew) prep_item(item0, 0);
+  __syncthreads();
+  if (issuer) {
+    mbar_wait(&sm.bar_t0, 0); mbar_wait(&sm.bar_t1, 0);
+    if (IS_A) mbar_wait(&sm.bar_st, 0);
+    tc_fence_after();
+    issue_mma1();
+  }
+
+  int n = 0;
+  for (int item = item0; item < n_items; item += gridDim.x, ++n) {
+    const uint32_t ph = n & 1;
+    const int next = item + gridDim.x;
+    const bool has_next = next < n_items;
+    if (gatew) {
+      if (has_next) prep_item(next, (n + 1) & 1);
+      __syncthreads();
+      continue;
     }
-    mbar_wait(&sm.bar_in[MODE == 1 ? 2 : 0], ph);   // third tile (needed by the state MMAs)
+    const GateBuf& G = sm.g[n & 1];
+    const float* vecf = sm.vecf[n & 1];
+    int b, h, tok0; coords(item, b, h, tok0);
+    const int bh = item / NC;
+    const int tok = tok0 + row;
+    const bool row_ok = compute && tok < S;
+    const size_t grow = (size_t)bh * S + tok;          // index into the per-row workspace arrays
+
+    // ---- A: dn_t = dnf_t (dh_t . h_t), block partials straight from global memory (MMA1 shadow)
+    float dn_row = 0.f;
+    if (IS_A) {
+      float part = 0.f;
+      if (row_ok && cq < NB) {
+        const int64_t off_h = (int64_t)b * p.h.stride_b + (int64_t)h * p.h.stride_h + (int64_t)tok * p.h.stride_s + cq * 32;
+        const int64_t off_d = (int64_t)b * p.dh.stride_b + (int64_t)h * p.dh.stride_h + (int64_t)tok * p.dh.stride_s + cq * 32;
+        float hv[32], dv_[32];
+        load_row32(reinterpret_cast<const __nv_bfloat16*>(p.h.ptr) + off_h, hv);
+        load_row32(reinterpret_cast<const __nv_bfloat16*>(p.dh.ptr) + off_d, dv_);
+#pragma unroll
+        for (int x = 0; x < 32; ++x) part = fmaf(hv[x], dv_[x], part);
+      }
+      if (compute) sm.part[cq][row] = part;
+      if (compute) named_sync(3, CT);
+      if (compute) {
+        dn_row = G.dnf[row] * ((sm.part[0][row] + sm.part[1][row]) + (sm.part[2][row] + sm.part[3][row]));
+        if (cq == 0 && row_ok) ws_dn[grow] = dn_row;
+      }
+    }
     mbar_wait(&sm.bar_m1, ph);
     tc_fence_after();
-    __syncthreads();   // colv / rowscale visible
-
-    // ---- in-place operand scaling ---------------------------------------------------------
-    if (MODE == 1) scale_rows<DH>(skv, G.kw);                   // Kbar = kw_j k_j
-    else scale_rows<DH>(skv, kwos);                             // Vbar = (kw_j / s) v_j  (s applied in the epilogue)
-    if (MODE == 1) scale_rows<DH>(sq, rowscale);                // Qtilde = (w s / N)_t q_t
-    else {
-      scale_rows<DH>(sdh, rowscale);                            // dHtilde = (w s / N)_t dh_t
-      write_vec_tile(sm.vec, G.w[tid] * scale * G.dn[tid]);     // (w s dn)_t for dn_state += Q^T (.)
-    }
-    fence_proxy_async_smem();
-    if (tid == 0) tma_store_wait_read<0>();
-    tc_fence_before();
-    __syncthreads();
-
-    // ---- inter-chunk MMA (overwrites tO) and the dC / dn_state updates ---------------------
-    if (tid == 0) {
-      tc_fence_after();
-      if (MODE == 1) {   // dV = Kbar dCb : A K-major [j][dk], B MN-major [dk][dv]
-        constexpr uint32_t idI = make_idesc_bf16(128, DH, 0, 1);
-        for (int ks = 0; ks < DH / 16; ++ks)
-          umma_bf16_ss(tO, dK(smem_u32(skv), ks, TILE), dMN(smem_u32(sm.cb), ks, TILE_C), idI, ks > 0);
-      } else {           // dK = Vbar dCb^T : A K-major [j][dv], B K-major view of dCb (rows dk)
-        constexpr uint32_t idI = make_idesc_bf16(128, DH, 0, 0);
-        for (int ks = 0; ks < DH / 16; ++ks)
-          umma_bf16_ss(tO, dK(smem_u32(skv), ks, TILE), dK(smem_u32(sm.cb), ks, TILE_C), idI, ks > 0);
-      }
-      constexpr uint32_t idC = make_idesc_bf16(128, DH, 1, 1);
-      constexpr uint32_t idN = make_idesc_bf16(128, 16, 1, 0);
-      const uint32_t acc0 = (c > 0) ? 1u : 0u;
-      for (int ks = 0; ks < L / 16; ++ks) {
-        const uint64_t a = dMN(smem_u32(sq), ks, A_LBO_STATE);
-        umma_bf16_ss(tC, a, dMN(smem_u32(sdh), ks, TILE), idC, (ks > 0) ? 1u : acc0);
-        if (MODE == 2) umma_bf16_ss(tN, a, dK(smem_u32(sm.vec), ks, 2048), idN, (ks > 0) ? 1u : acc0);
-      }
-      umma_commit(&sm.bar_s);
+    if (issuer && has_next) {   // tiles MMA1 (and A's G) read are dead
+      load_act(sm.t1, &maps.t1, &sm.bar_t1, next);
+      if (IS_A) { load_act(sm.t0, &maps.t0, &sm.bar_t0, next); load_st(next); }
     }
 
-    // ---- E^T / dS^T tile: thread j owns key row j, columns t -------------------------------
-    // dv: s folded into the exponent.  dk: NOT folded — kernel A rounds the same un-scaled dS to
-    // bf16, so the rounding noise of R = q.dq and K = k.dk stays correlated and cancels in df.
-    const float u2j = G.u2[tid] + ((MODE == 1) ? log2f(scale) : 0.f);
-#pragma unroll 1
-    for (int cbk = 0; cbk < 4; ++cbk) {
-      // key j contributes to query t iff t is at/after j in scan order: forward t >= j, reverse t <= j
-      const bool full = rev ? (cbk < warp) : (cbk > warp);
-      const bool diag = (cbk == warp);
+    // ---- B: scale the rows of t0 in place (Kbar = kw K | Vbar = kw/s V), then the inter-chunk MMA
+    if (!IS_A) {
+      if (compute) scale_rows<DH>(sm.t0, MODE == MODE_B1 ? G.kw : G.w, tid);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_sync(2, GT0);
+      if (issuer) {
+        mbar_wait(&sm.bar_st, ph);
+        tc_fence_after();
+        if (MODE == MODE_B1) {   // dV = Kbar dCs : dCs as MN-major B operand [dk][dv]
+          constexpr uint32_t idI = make_idesc_bf16(128, DH, 0, 1);
+#pragma unroll
+          for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tO, d0k + kstep(ks), dStmn + mnstep(ks), idI, ks > 0);
+        } else {                 // dK = Vbar dCs^T : dCs as K-major B operand (rows dk)
+          constexpr uint32_t idI = make_idesc_bf16(128, DH, 0, 0);
+#pragma unroll
+          for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tO, d0k + kstep(ks), dStk + kstep(ks, TILE_C), idI, ks > 0);
+        }
+        umma_commit(&sm.bar_i);
+      }
+    }
+
+    // ---- gated bf16 tile: one 32x32 block per warp ----------------------------------------------
+    if (compute) {
+      // A : row = query t, col = key j   : keep j <= t (forward) / j >= t (reverse)
+      // B : row = key j,   col = query t : keep t >= j (forward) / t <= j (reverse)
+      const bool full = IS_A ? (rev ? (cq > rg) : (cq < rg)) : (rev ? (cq < rg) : (cq > rg));
+      const bool diag = (cq == rg);
       uint32_t packed[16];
       if (full || diag) {
-        float s_[32];
-        tmem_ld32(tS + lane_sel + cbk * 32, s_);
+        float a[32];
+        tmem_ld32(tS + lane_sel + cq * 32, a);
         tmem_ld_wait();
+        const float r0 = IS_A ? G.M2[row] : (MODE == MODE_B1 ? G.u2[row] + l2s : G.u2[row]);
+        const float r1 = IS_A ? G.invN[row] : 0.f;
 #pragma unroll
         for (int x = 0; x < 32; x += 4) {
-          const float4 c4 = *reinterpret_cast<const float4*>(&colv[0][cbk * 32 + x]);
-          const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+          const int c0 = cq * 32 + x;
+          const float4 e4 = *reinterpret_cast<const float4*>(IS_A ? &G.u2[c0] : (MODE == MODE_B1 ? &G.c2[c0] : &G.M2[c0]));
+          const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
           float in4[4] = {0.f, 0.f, 0.f, 0.f}, dn4[4] = {0.f, 0.f, 0.f, 0.f};
-          if (MODE == 2) {
-            const float4 i4 = *reinterpret_cast<const float4*>(&colv[1][cbk * 32 + x]);
-            const float4 d4 = *reinterpret_cast<const float4*>(&colv[2][cbk * 32 + x]);
+          if (MODE == MODE_B2) {
+            const float4 i4 = *reinterpret_cast<const float4*>(&G.invN[c0]);
+            const float4 d4 = *reinterpret_cast<const float4*>(&G.dn[c0]);
             in4[0] = i4.x; in4[1] = i4.y; in4[2] = i4.z; in4[3] = i4.w;
             dn4[0] = d4.x; dn4[1] = d4.y; dn4[2] = d4.z; dn4[3] = d4.w;
           }
           float pv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int t = cbk * 32 + x + e;
-            const bool keep = full || (rev ? (t <= tid) : (t >= tid));
-            const float dd = ex2(u2j - cc[e]);
-            const float val = (MODE == 1) ? s_[x + e] * dd : fmaf(s_[x + e], in4[e], dn4[e]) * dd;
+            const int col = c0 + e;
+            const bool keep = full || (IS_A ? (rev ? (col >= row) : (col <= row)) : (rev ? (col <= row) : (col >= row)));
+            float val;
+            if (IS_A) val = fmaf(a[x + e], r1, dn_row) * ex2(ee[e] - r0);
+            else if (MODE == MODE_B1) val = a[x + e] * ex2(r0 - ee[e]);
+            else val = fmaf(a[x + e], in4[e], dn4[e]) * ex2(r0 - ee[e]);
             pv[e] = keep ? val : 0.f;
           }
           packed[x / 2] = pack_bf16x2(pv[0], pv[1]);
@@ -641,104 +271,306 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_dkv_kernel(const __grid_constant
       }
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
-        const int t = cbk * 32 + x * 8;
-        *reinterpret_cast<uint4*>(sm.x + (t >> 6) * TILE + swz128(tid, t & 63)) =
+        const int col = cq * 32 + x * 8;
+        *reinterpret_cast<uint4*>(sm.x + (col >> 6) * TILE + swz128(row, col & 63)) =
             make_uint4(packed[4 * x], packed[4 * x + 1], packed[4 * x + 2], packed[4 * x + 3]);
       }
     }
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();
+    named_sync(2, GT0);
 
-    // ---- MMA2: dV += E^T dH  |  dK += dS^T Q ----------------------------------------------
-    if (tid == 0) {
+    // ---- MMA2: A: dQ = dS K (into tS) | B: tO += X t2 -------------------------------------------
+    if (issuer) {
+      mbar_wait(&sm.bar_t2, ph);
       tc_fence_after();
-      mbar_wait(&sm.bar_s, ph);   // dv: dH must not be... (dH unscaled is read here; dk: Q unscaled) and tO complete
       constexpr uint32_t id2 = make_idesc_bf16(128, DH, 0, 1);
-      const uint32_t bb = smem_u32(MODE == 1 ? sdh : sq);
-      for (int ks = 0; ks < L / 16; ++ks)
-        umma_bf16_ss(tO, dK(smem_u32(sm.x), ks, TILE), dMN(bb, ks, TILE), id2, 1u);
+#pragma unroll
+      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(IS_A ? tS : tO, dXk + kstep(ks), d2mn + mnstep(ks), id2, IS_A ? (ks > 0) : 1u);
       umma_commit(&sm.bar_m2);
-      if (c + 1 < NC) load(1, map_kv, c + 1);   // K/V tile free (inter MMA done)
-      if (c + 1 < NC) load(MODE == 1 ? 0 : 2, MODE == 1 ? &maps.q : &maps.dh, c + 1);  // scaled tile free (dC MMA done)
+      if (!IS_A) {   // the inter-chunk MMA is complete by now: its operands can be refilled
+        mbar_wait(&sm.bar_i, ph);
+        if (has_next) { load_act(sm.t0, &maps.t0, &sm.bar_t0, next); load_st(next); }
+      }
     }
     mbar_wait(&sm.bar_m2, ph);
     tc_fence_after();
-    if (tid == 0 && c + 1 < NC) load(MODE == 1 ? 2 : 0, MODE == 1 ? &maps.dh : &maps.q, c + 1);
+    if (issuer && has_next) load_act(sm.t2, &maps.t2, &sm.bar_t2, next);
 
-    // ---- epilogue --------------------------------------------------------------------------
-    float Kj = 0.f;
-    const float kwj = G.kw[tid];
-    const __nv_bfloat16* krow = nullptr;
-    if (MODE == 2 && row_ok)
-      krow = reinterpret_cast<const __nv_bfloat16*>(p.k.ptr) + (int64_t)b * p.k.stride_b + (int64_t)h * p.k.stride_h +
-             (int64_t)tok * p.k.stride_s;
-#pragma unroll 1
-    for (int cbk = 0; cbk < DH / 32; ++cbk) {
-      float o_[32];
-      tmem_ld32(tO + lane_sel + cbk * 32, o_);
-      tmem_ld_wait();
+    // ---- epilogue: outputs packed in registers --------------------------------------------------
+    uint32_t opk[16];
+    float psum = 0.f;
+    if (cq < NB) {
+      float acc[32];
+      tmem_ld32((IS_A ? tS : tO) + lane_sel + cq * 32, acc);
+      if (IS_A) {
+        float gg[32];
+        tmem_ld32(tO + lane_sel + cq * 32, gg);
+        tmem_ld_wait();
+        const float wt = G.w[row], invN = G.invN[row];
+        float qr[32];
+        if (row_ok) load_row32(reinterpret_cast<const __nv_bfloat16*>(p.q.ptr) + (int64_t)b * p.q.stride_b +
+                               (int64_t)h * p.q.stride_h + (int64_t)tok * p.q.stride_s + cq * 32, qr);
 #pragma unroll
-      for (int x = 0; x < 32; x += 8) {
-        float o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = (MODE == 2) ? fmaf(kwj, sm.nvec[cbk * 32 + x + e], scale * o_[x + e]) : o_[x + e];
-        if (MODE == 2 && row_ok) {
-          const uint4 w = *reinterpret_cast<const uint4*>(krow + cbk * 32 + x);
-          const __nv_bfloat162* kk = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float2 f2 = __bfloat1622float2(kk[e]);
-            Kj = fmaf(f2.x, o[2 * e], Kj);
-            Kj = fmaf(f2.y, o[2 * e + 1], Kj);
-          }
+        for (int x = 0; x < 32; x += 2) {
+          const float o0 = scale * (acc[x] + wt * fmaf(gg[x], invN, dn_row * vecf[cq * 32 + x]));
+          const float o1 = scale * (acc[x + 1] + wt * fmaf(gg[x + 1], invN, dn_row * vecf[cq * 32 + x + 1]));
+          if (row_ok) psum = fmaf(qr[x], o0, fmaf(qr[x + 1], o1, psum));
+          opk[x / 2] = pack_bf16x2(o0, o1);
         }
-        const int d_ = cbk * 32 + x;
-        *reinterpret_cast<uint4*>(sm.x + (d_ >> 6) * TILE + swz128(tid, d_ & 63)) =
-            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-      }
-    }
-    if (MODE == 2) {
-      // di_j = K_j ; df_j = sigmoid(-f_j) * (sum over scan positions >= j of (R - K) + carry)
-      const float dB = row_ok ? (G.R[tid] - Kj) : 0.f;
-      const int lane = tid & 31;
-      float pre = warp_scan_add(dB, lane);
-      if (lane == 31) sm.scan[warp] = pre;
-      __syncthreads();
-      float off = 0.f, tot = 0.f;
+      } else if (MODE == MODE_B1) {
+        tmem_ld_wait();
 #pragma unroll
-      for (int w = 0; w < 4; ++w) { off += (w < warp) ? sm.scan[w] : 0.f; tot += sm.scan[w]; }
-      pre += off;
-      const float carry = df_carry;
-      const float suf = rev ? pre : (tot - pre + dB);
-      if (row_ok) {
-        p.di.ptr[(int64_t)b * p.di.stride_b + (int64_t)h * p.di.stride_h + (int64_t)tok * p.di.stride_s] = Kj;
-        p.df.ptr[(int64_t)b * p.df.stride_b + (int64_t)h * p.df.stride_h + (int64_t)tok * p.df.stride_s] =
-            (suf + carry) * G.sig[tid];
+        for (int x = 0; x < 32; x += 2) opk[x / 2] = pack_bf16x2(acc[x], acc[x + 1]);
+      } else {
+        tmem_ld_wait();
+        const float kwj = G.kw[row];
+        float kr[32];
+        if (row_ok) load_row32(reinterpret_cast<const __nv_bfloat16*>(p.k.ptr) + (int64_t)b * p.k.stride_b +
+                               (int64_t)h * p.k.stride_h + (int64_t)tok * p.k.stride_s + cq * 32, kr);
+#pragma unroll
+        for (int x = 0; x < 32; x += 2) {
+          const float o0 = fmaf(kwj, vecf[cq * 32 + x], scale * acc[x]);
+          const float o1 = fmaf(kwj, vecf[cq * 32 + x + 1], scale * acc[x + 1]);
+          if (row_ok) psum = fmaf(kr[x], o0, fmaf(kr[x + 1], o1, psum));
+          opk[x / 2] = pack_bf16x2(o0, o1);
+        }
       }
-      __syncthreads();
-      if (tid == 0) df_carry = carry + tot;
-    } else {
-      __syncthreads();   // nvec readers / uniform barrier count
     }
-    const bool last = (c + 1 == NC);
-    state_pass<DH>(sm, tC, tN, MODE == 2, last ? 1.f : Gn.decay, last, lane_sel);
-    fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      for (int kt = 0; kt < KT; ++kt) tma_store_4d(&maps.out0, sm.x + kt * TILE, kt * 64, cg.tok0, h, b);
-      tma_store_commit();
+    __syncthreads();   // end of item: TMEM free, next gates published (the gate warp joins here)
+    if (issuer && has_next) {
+      mbar_wait(&sm.bar_t0, ph ^ 1); mbar_wait(&sm.bar_t1, ph ^ 1);
+      if (IS_A) mbar_wait(&sm.bar_st, ph ^ 1);
+      tc_fence_after();
+      issue_mma1();
+    }
+    if (row_ok) {
+      const mlstm_act& out = IS_A ? p.dq : (MODE == MODE_B1 ? p.dv : p.dk);
+      if (cq < NB)
+        store_row32(reinterpret_cast<__nv_bfloat16*>(out.ptr) + (int64_t)b * out.stride_b + (int64_t)h * out.stride_h +
+                    (int64_t)tok * out.stride_s + cq * 32, opk);
+      if (IS_A) ws_rpart[(size_t)cq * rows_total + grow] = psum;
+      if (MODE == MODE_B2) ws_kpart[(size_t)cq * rows_total + grow] = psum;
     }
   }
-  if (tid == 0) tma_store_wait_all<0>();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, 512);
+  if (warp == 0) tmem_dealloc(tm, 256);
+}
+
+// =============================================================================================
+// SB: sequential adjoint-state kernel (reverse chunk order), one CTA per (batch, head)
+// =============================================================================================
+template <int DH>
+struct SmemSB {
+  static constexpr int KT = DH / 64;
+  alignas(1024) uint8_t q[2][KT * TILE];
+  alignas(1024) uint8_t dh[2][KT * TILE];
+  alignas(1024) uint8_t vec[2][2 * 2048];          // K-major [16][128 t] bf16: (dn N)_t in every row
+  GateBuf g[3];
+  uint64_t bar_q[2], bar_dh[2], bar_mma;
+  uint32_t tmem_base;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_constant__ BwdMaps maps, const mlstm_params p,
+                                                             const float scale) {
+  constexpr int KT = DH / 64;
+  constexpr int NB = DH / 32;
+  constexpr uint32_t A_LBO = (DH == 128) ? TILE : 0;
+  constexpr uint32_t TCOLS = 256;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SmemSB<DH>& sm = *reinterpret_cast<SmemSB<DH>*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool compute = tid < CT, issuer = tid == CT, gatew = tid >= GT0;
+  const int rg = warp & 3, cq = compute ? (warp >> 2) : 4, row = rg * 32 + lane;
+  const int bh = blockIdx.x, b = bh / p.NH, h = bh % p.NH;
+  const int S = p.S, NC = num_chunks(S);
+  const bool rev = p.reverse != 0;
+  const BwdLayout blay(p.B, p.NH, S, DH);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(p.workspace);
+  const float* ws_dn = reinterpret_cast<const float*>(ws + blay.dn_off);
+  __nv_bfloat16* dCs = reinterpret_cast<__nv_bfloat16*>(ws + blay.dcs_off) + (size_t)bh * NC * DH * DH;
+  float* dns = reinterpret_cast<float*>(ws + blay.dns_off) + (size_t)bh * NC * DH;
+
+  if (issuer) {
+    tma_prefetch_desc(&maps.t0); tma_prefetch_desc(&maps.t1);
+    mbar_init(&sm.bar_q[0], 1); mbar_init(&sm.bar_q[1], 1); mbar_init(&sm.bar_dh[0], 1); mbar_init(&sm.bar_dh[1], 1);
+    mbar_init(&sm.bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&sm.tmem_base, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = sm.tmem_base, tC = tm, tN = tm + DH;
+  const uint32_t lane_sel = (uint32_t)(rg * 32) << 16;
+
+  // processing step pc = 0..NC-1 handles scan chunk sc = NC-1-pc
+  auto sc_of = [&](int pc) { return NC - 1 - pc; };
+  auto load_qd = [&](int pc) {
+    const int buf = pc & 1, tok0 = mem_chunk(sc_of(pc), NC, rev) * L;
+    mbar_arrive_expect_tx(&sm.bar_q[buf], KT * TILE);
+    for (int kt = 0; kt < KT; ++kt) tma_load_4d(sm.q[buf] + kt * TILE, &maps.t0, &sm.bar_q[buf], kt * 64, tok0, h, b);
+    mbar_arrive_expect_tx(&sm.bar_dh[buf], KT * TILE);
+    for (int kt = 0; kt < KT; ++kt) tma_load_4d(sm.dh[buf] + kt * TILE, &maps.t1, &sm.bar_dh[buf], kt * 64, tok0, h, b);
+  };
+  auto gates_of = [&](int pc) {   // gate warp: G.w <- (w s / N)_t, row scale of the Q tile
+    GateBuf& G = sm.g[pc % 3];
+    gates_warp_bwd(G, p, b, h, bh, mem_chunk(sc_of(pc), NC, rev), lane, ws_dn);
+    for (int r = lane; r < L; r += 32) G.w[r] = G.w[r] * scale * G.invN[r];
+    __syncwarp();
+  };
+  // Qtilde = (w s / N) Q in place and the (dn N) vector tile of step pc
+  auto prep_operands = [&](int pc) {
+    const GateBuf& G = sm.g[pc % 3];
+    scale_rows<DH>(sm.q[pc & 1], G.w, tid);
+    if (tid < L) {
+      const float inv = G.invN[tid];
+      const __nv_bfloat16 bv = __float2bfloat16_rn(inv > 0.f ? G.dn[tid] / inv : 0.f);
+      uint8_t* base = sm.vec[pc & 1] + (tid >> 6) * 2048;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) *reinterpret_cast<__nv_bfloat16*>(base + swz128(r, tid & 63)) = bv;
+    }
+  };
+  const uint64_t dQ0 = make_sdesc(smem_u32(sm.q[0]), A_LBO, 1024), dH0 = make_sdesc(smem_u32(sm.dh[0]), TILE, 1024);
+  const uint64_t dVec0 = make_sdesc(smem_u32(sm.vec[0]), 16, 1024);
+  constexpr uint64_t BUF_STEP = (uint64_t)(KT * TILE) >> 4, VEC_STEP = (uint64_t)(2 * 2048) >> 4;
+
+  if (issuer) { load_qd(0); if (NC > 1) load_qd(1); }
+  if (gatew) { gates_of(0); if (NC > 1) gates_of(1); }
+  // adjoint state leaving the last chunk is zero (the last states carry no gradient)
+  if (row < DH && cq < NB) {
+    uint32_t z[16];
+#pragma unroll
+    for (int x = 0; x < 16; ++x) z[x] = 0u;
+    store_row32(dCs + ((size_t)(NC - 1) * DH + row) * DH + cq * 32, z);
+    if (cq == 0) dns[(size_t)(NC - 1) * DH + row] = 0.f;
+  }
+  __syncthreads();
+  if (!gatew) mbar_wait(&sm.bar_q[0], 0);
+  if (compute) prep_operands(0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  for (int pc = 0; pc < NC; ++pc) {
+    const bool last = (pc + 1 == NC);
+    const int buf = pc & 1, sc = sc_of(pc);
+    if (gatew) {
+      if (pc + 2 < NC) gates_of(pc + 2);
+      __syncthreads();
+      continue;
+    }
+    if (last) break;   // the state leaving chunk -1 is not needed (initial states carry no gradient)
+    if (issuer) {
+      mbar_wait(&sm.bar_dh[buf], (pc >> 1) & 1);
+      tc_fence_after();
+      const uint64_t dQ = dQ0 + buf * BUF_STEP, dH_ = dH0 + buf * BUF_STEP, dVec = dVec0 + buf * VEC_STEP;
+      constexpr uint32_t idC = make_idesc_bf16(128, DH, 1, 1), idN = make_idesc_bf16(128, 16, 1, 0);
+      const uint32_t acc0 = (pc > 0) ? 1u : 0u;
+#pragma unroll
+      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tC, dQ + mnstep(ks), dH_ + mnstep(ks), idC, (ks > 0) ? 1u : acc0);
+#pragma unroll
+      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tN, dQ + mnstep(ks), dVec + kstep(ks, 2048), idN, (ks > 0) ? 1u : acc0);
+      umma_commit(&sm.bar_mma);
+    }
+    if (pc + 1 < NC) {   // operands of the next step, in the MMA shadow
+      mbar_wait(&sm.bar_q[buf ^ 1], ((pc + 1) >> 1) & 1);
+      if (compute) prep_operands(pc + 1);
+      fence_proxy_async_smem();
+    }
+    mbar_wait(&sm.bar_mma, pc & 1);
+    tc_fence_after();
+    if (issuer && pc + 2 < NC) load_qd(pc + 2);
+
+    // state pass: dC_{sc-1} -> workspace (bf16), then TMEM <- decay_{sc-1} dC_{sc-1}
+    const float dnext = sm.g[(pc + 1) % 3].decay;
+    if (row < DH && cq < NB) {
+      float r[32];
+      tmem_ld32(tC + lane_sel + cq * 32, r);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int x = 0; x < 32; x += 2) pk[x / 2] = pack_bf16x2(r[x], r[x + 1]);
+      store_row32(dCs + ((size_t)(sc - 1) * DH + row) * DH + cq * 32, pk);
+#pragma unroll
+      for (int x = 0; x < 32; ++x) r[x] *= dnext;
+      tmem_st32(tC + lane_sel + cq * 32, r);
+      if (cq == 0) {
+        float rn[16];
+        tmem_ld16(tN + lane_sel, rn);
+        tmem_ld_wait();
+        dns[(size_t)(sc - 1) * DH + row] = rn[0];
+#pragma unroll
+        for (int x = 0; x < 32; ++x) r[x] = rn[0] * dnext;
+        tmem_st32(tN + lane_sel, r);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (!gatew) { tc_fence_before(); __syncthreads(); }   // matches the gate warp's last in-loop barrier
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, TCOLS);
+}
+
+// =============================================================================================
+// DF: di = K, df = sigmoid(-f) * suffix_sum(R - K) in scan order.  One CTA per (batch, head).
+// =============================================================================================
+__global__ void __launch_bounds__(128) tc_dfscan_kernel(const mlstm_params p, const int DH) {
+  __shared__ float sc_part[4];
+  __shared__ float carry_s;
+  const int bh = blockIdx.x, b = bh / p.NH, h = bh % p.NH;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int S = p.S, NC = num_chunks(S);
+  const bool rev = p.reverse != 0;
+  const size_t rows_total = (size_t)p.B * p.NH * S;
+  const BwdLayout blay(p.B, p.NH, S, DH);
+  const uint8_t* ws = reinterpret_cast<const uint8_t*>(p.workspace);
+  const float* rp = reinterpret_cast<const float*>(ws + blay.rpart_off);
+  const float* kp = reinterpret_cast<const float*>(ws + blay.kpart_off);
+  const int nb = DH / 32;
+  if (t == 0) carry_s = 0.f;
+  __syncthreads();
+  for (int sc = NC - 1; sc >= 0; --sc) {
+    const int tok0 = mem_chunk(sc, NC, rev) * L;
+    const int nvalid = min(L, S - tok0);
+    const bool valid = t < nvalid;
+    const int tok = tok0 + (rev ? (nvalid - 1 - t) : t);   // thread t = scan-local index t
+    float R = 0.f, K = 0.f, fi = 0.f;
+    if (valid) {
+      const size_t g = (size_t)bh * S + tok;
+      for (int c = 0; c < nb; ++c) { R += rp[(size_t)c * rows_total + g]; K += kp[(size_t)c * rows_total + g]; }
+      fi = p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s];
+    }
+    const float dB = R - K;
+    float pre = warp_scan_add(dB, lane);
+    if (lane == 31) sc_part[warp] = pre;
+    __syncthreads();
+    float off = 0.f, tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { off += (w < warp) ? sc_part[w] : 0.f; tot += sc_part[w]; }
+    pre += off;
+    const float carry = carry_s;
+    if (valid) {
+      p.di.ptr[(int64_t)b * p.di.stride_b + (int64_t)h * p.di.stride_h + (int64_t)tok * p.di.stride_s] = K;
+      p.df.ptr[(int64_t)b * p.df.stride_b + (int64_t)h * p.df.stride_h + (int64_t)tok * p.df.stride_s] =
+          (tot - pre + dB + carry) / (1.f + __expf(fi));
+    }
+    __syncthreads();
+    if (t == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
 }
 
 template <class K>
-int prep_kernel(K kernel, size_t smem, const char* name) {
+int prep(K kernel, size_t smem, const char* name) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(%s, %zu B): %s", name, smem, cudaGetErrorString(e));
@@ -758,46 +590,60 @@ int launched(const char* name) {
 
 template <int DH>
 int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
-  BwdMaps m;
+  const StateLayout slay(p.B, p.NH, p.S, DH);
+  const BwdLayout blay(p.B, p.NH, p.S, DH);
+  if (!p.states || p.states_bytes < slay.total) {
+    set_error("backward needs the forward's chunk-state buffer (%zu bytes)", slay.total);
+    return MLSTM_ERR_WORKSPACE;
+  }
+  const int NC = num_chunks(p.S), n_items = p.B * p.NH * NC;
+  CUtensorMap mq, mk, mv, mdh, mcs, mdcs;
   int r = 0;
-  r |= make_act_tmap(&m.q, p.q.ptr, p.B, p.NH, p.S, DH, p.q.stride_b, p.q.stride_h, p.q.stride_s, L);
-  r |= make_act_tmap(&m.k, p.k.ptr, p.B, p.NH, p.S, DH, p.k.stride_b, p.k.stride_h, p.k.stride_s, L);
-  r |= make_act_tmap(&m.v, p.v.ptr, p.B, p.NH, p.S, DH, p.v.stride_b, p.v.stride_h, p.v.stride_s, L);
-  r |= make_act_tmap(&m.dh, p.dh.ptr, p.B, p.NH, p.S, DH, p.dh.stride_b, p.dh.stride_h, p.dh.stride_s, L);
-  m.out1 = m.q;
-  const size_t rows = (size_t)p.B * p.NH * p.S;
-  float* ws_dn = reinterpret_cast<float*>(p.workspace);
-  float* ws_R = ws_dn + rows;
+  r |= make_act_tmap(&mq, p.q.ptr, p.B, p.NH, p.S, DH, p.q.stride_b, p.q.stride_h, p.q.stride_s, L);
+  r |= make_act_tmap(&mk, p.k.ptr, p.B, p.NH, p.S, DH, p.k.stride_b, p.k.stride_h, p.k.stride_s, L);
+  r |= make_act_tmap(&mv, p.v.ptr, p.B, p.NH, p.S, DH, p.v.stride_b, p.v.stride_h, p.v.stride_s, L);
+  r |= make_act_tmap(&mdh, p.dh.ptr, p.B, p.NH, p.S, DH, p.dh.stride_b, p.dh.stride_h, p.dh.stride_s, L);
+  r |= make_state_tmap(&mcs, reinterpret_cast<uint8_t*>(p.states) + slay.cs_off, (size_t)n_items * DH, DH);
+  r |= make_state_tmap(&mdcs, reinterpret_cast<uint8_t*>(p.workspace) + blay.dcs_off, (size_t)n_items * DH, DH);
+  if (r) {
+    set_error("cuTensorMapEncodeTiled failed (%d)", r);
+    return r == -1 ? MLSTM_ERR_NO_DEVICE : MLSTM_ERR_INVALID_ARG;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = n_items < sms ? n_items : sms;
   const float scale = resolve_scale(p);
-  dim3 grid(p.B * p.NH), block(NT);
+  const size_t smB = sizeof(SmemB<DH>), smSB = sizeof(SmemSB<DH>);
   int rc;
   if (part != 1) {
-    r |= make_act_tmap(&m.out0, p.dq.ptr, p.B, p.NH, p.S, DH, p.dq.stride_b, p.dq.stride_h, p.dq.stride_s, L);
-    if (r) { set_error("cuTensorMapEncodeTiled failed (%d)", r); return r == -1 ? MLSTM_ERR_NO_DEVICE : MLSTM_ERR_INVALID_ARG; }
-    const size_t smA = sizeof(SmemB<DH, 4>) + 1024;
-    if ((rc = prep_kernel(tc_bwd_dq_kernel<DH>, smA, "tc_bwd_dq"))) return rc;
-    tc_bwd_dq_kernel<DH><<<grid, block, smA, st>>>(m, p, scale, ws_dn, ws_R);
+    BwdMaps m{mdh, mv, mk, mcs};
+    if ((rc = prep(tc_bwd_par_kernel<DH, MODE_A>, smB, "tc_bwd_dq"))) return rc;
+    tc_bwd_par_kernel<DH, MODE_A><<<dim3(grid), dim3(NT), smB, st>>>(m, p, scale, n_items);
     if ((rc = launched("tc_bwd_dq"))) return rc;
   }
   if (part != 0) {
-    const size_t smB = sizeof(SmemB<DH, 3>) + 1024;
-    BwdMaps mv = m, mk = m;
-    r |= make_act_tmap(&mv.out0, p.dv.ptr, p.B, p.NH, p.S, DH, p.dv.stride_b, p.dv.stride_h, p.dv.stride_s, L);
-    r |= make_act_tmap(&mk.out0, p.dk.ptr, p.B, p.NH, p.S, DH, p.dk.stride_b, p.dk.stride_h, p.dk.stride_s, L);
-    if (r) { set_error("cuTensorMapEncodeTiled failed (%d)", r); return r == -1 ? MLSTM_ERR_NO_DEVICE : MLSTM_ERR_INVALID_ARG; }
-    if ((rc = prep_kernel(tc_bwd_dkv_kernel<DH, 1>, smB, "tc_bwd_dv"))) return rc;
-    if ((rc = prep_kernel(tc_bwd_dkv_kernel<DH, 2>, smB, "tc_bwd_dk"))) return rc;
-    tc_bwd_dkv_kernel<DH, 1><<<grid, block, smB, st>>>(mv, p, scale, ws_dn, ws_R);
+    BwdMaps ms{mq, mdh, mq, mdcs};
+    if ((rc = prep(tc_state_bwd_kernel<DH>, smSB, "tc_state_bwd"))) return rc;
+    tc_state_bwd_kernel<DH><<<dim3(p.B * p.NH), dim3(NT), smSB, st>>>(ms, p, scale);
+    if ((rc = launched("tc_state_bwd"))) return rc;
+    BwdMaps m1{mk, mq, mdh, mdcs};
+    if ((rc = prep(tc_bwd_par_kernel<DH, MODE_B1>, smB, "tc_bwd_dv"))) return rc;
+    tc_bwd_par_kernel<DH, MODE_B1><<<dim3(grid), dim3(NT), smB, st>>>(m1, p, scale, n_items);
     if ((rc = launched("tc_bwd_dv"))) return rc;
-    tc_bwd_dkv_kernel<DH, 2><<<grid, block, smB, st>>>(mk, p, scale, ws_dn, ws_R);
+    BwdMaps m2{mv, mdh, mq, mdcs};
+    if ((rc = prep(tc_bwd_par_kernel<DH, MODE_B2>, smB, "tc_bwd_dk"))) return rc;
+    tc_bwd_par_kernel<DH, MODE_B2><<<dim3(grid), dim3(NT), smB, st>>>(m2, p, scale, n_items);
     if ((rc = launched("tc_bwd_dk"))) return rc;
+    tc_dfscan_kernel<<<dim3(p.B * p.NH), dim3(128), 0, st>>>(p, DH);
+    if ((rc = launched("tc_dfscan"))) return rc;
   }
   return MLSTM_OK;
 }
 
 }  // namespace
 
-size_t tc_bwd_workspace(const mlstm_params& p) { return sizeof(float) * 2 * (size_t)p.B * p.NH * p.S; }
+size_t tc_bwd_workspace(const mlstm_params& p) { return BwdLayout(p.B, p.NH, p.S, p.DHQK).total; }
 
 int tc_bwd(const mlstm_params& p, cudaStream_t st, int part) {
   if (p.DHQK == 64) return launch_bwd<64>(p, st, part);

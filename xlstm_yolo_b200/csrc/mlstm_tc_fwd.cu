@@ -21,9 +21,7 @@
 //   SIMT  Cb <- bf16(C),  C <- decay_next * C   (one TMEM pass per chunk)
 // No intermediate (D matrix, gates, P) ever reaches HBM.  `reverse` walks the tokens from
 // the end: tiles stay in memory order, the causal mask and the gate scans flip.
-#include "mlstm_common.cuh"
-#include "tc_ptx.cuh"
-#include "tc_tmap.cuh"
+#include "tc_common.cuh"   // StateLayout / store_row32 (the per-chunk state buffer shared with the backward)
 
 namespace mlstm {
 namespace {
@@ -174,6 +172,12 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
   const int S = p.S, NC = (S + L - 1) / L;
   const bool has_init = p.c_initial != nullptr;
   const bool rev = p.reverse != 0;
+  // per-chunk entry states for the backward (only when a backward will follow: n_row given)
+  const bool save_states = p.states != nullptr && p.n_row != nullptr;
+  const tc::StateLayout slay(p.B, p.NH, S, DH);
+  __nv_bfloat16* Cs_g = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(p.states) + slay.cs_off) + (size_t)bh * NC * DH * DH;
+  float* ns_g = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.states) + slay.ns_off) + (size_t)bh * NC * DH;
+  float* ms_g = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.states) + slay.ms_off) + (size_t)bh * NC;
 
   if (issuer) {
     tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.v); tma_prefetch_desc(&maps.h);
@@ -263,6 +267,15 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
     __syncthreads();
     tc_fence_after();
   }
+  if (save_states && row < DH && cq < NB) {   // entry state of chunk 0
+    uint32_t pk[16];
+    const float* crow = has_init ? p.c_initial + ((int64_t)bh * DH + row) * DH + cq * 32 : nullptr;
+#pragma unroll
+    for (int x = 0; x < 32; x += 2) pk[x / 2] = has_init ? pack_bf16x2(crow[x], crow[x + 1]) : 0u;
+    tc::store_row32(Cs_g + (size_t)row * DH + cq * 32, pk);
+    if (cq == 0) ns_g[row] = has_init ? p.n_initial[(int64_t)bh * DH + row] : 0.f;
+  }
+  if (save_states && issuer) ms_g[0] = p.m_initial ? p.m_initial[bh] : 0.f;
   if (issuer) {   // MMA1 of chunk 0 (later chunks: issued while the previous epilogue finishes)
     mbar_wait(&sm.bar_q, 0);
     mbar_wait(&sm.bar_k[0], 0);
@@ -451,12 +464,17 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
 #pragma unroll
           for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4*>(dst + x) = make_float4(r[x], r[x + 1], r[x + 2], r[x + 3]);
         }
+        {
+          uint32_t pk[16];
 #pragma unroll
-        for (int x = 0; x < 32; x += 8) {
-          const int dv = cq * 32 + x;
-          *reinterpret_cast<uint4*>(sm.cb + (dv >> 6) * TILE_C + swz128(row, dv & 63)) =
-              make_uint4(pack_bf16x2(r[x], r[x + 1]), pack_bf16x2(r[x + 2], r[x + 3]), pack_bf16x2(r[x + 4], r[x + 5]),
-                         pack_bf16x2(r[x + 6], r[x + 7]));
+          for (int x = 0; x < 32; x += 2) pk[x / 2] = pack_bf16x2(r[x], r[x + 1]);
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const int dv = cq * 32 + x * 8;
+            *reinterpret_cast<uint4*>(sm.cb + (dv >> 6) * TILE_C + swz128(row, dv & 63)) =
+                make_uint4(pk[4 * x], pk[4 * x + 1], pk[4 * x + 2], pk[4 * x + 3]);
+          }
+          if (save_states && !last) tc::store_row32(Cs_g + ((size_t)(c + 1) * DH + row) * DH + cq * 32, pk);
         }
         if (!last) {
 #pragma unroll
@@ -468,6 +486,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
           tmem_ld16(tN + lane_sel, rn);
           tmem_ld_wait();
           sm.n_prev[row] = rn[0];
+          if (save_states && !last) ns_g[(size_t)(c + 1) * DH + row] = rn[0];
           if (last && p.n_last) p.n_last[(int64_t)bh * DH + row] = rn[0];
           if (!last) {
 #pragma unroll
@@ -486,6 +505,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
       }
     }
     if (last && p.m_last && issuer) p.m_last[bh] = G.m_next;
+    if (save_states && !last && issuer) ms_g[c + 1] = G.m_next;
     TL_STAMP(11);
     fence_proxy_async_smem();
     tc_fence_before();

@@ -500,9 +500,9 @@ bool tc_use_two_phase(const mlstm_params& p) {
   return p.B * p.NH * 2 <= sms && tc::num_chunks(p.S) >= 4;
 }
 
-size_t tc_state_bytes(const mlstm_params& p) {
-  return tc_use_two_phase(p) ? tc::StateLayout(p.B, p.NH, p.S, p.DHQK).total : 0;
-}
+// The chunk-state buffer is needed by the two-phase forward itself and, for training, by the
+// backward whichever forward variant ran.
+size_t tc_state_bytes(const mlstm_params& p) { return tc::StateLayout(p.B, p.NH, p.S, p.DHQK).total; }
 
 int tc_fwd_two_phase(const mlstm_params& p, cudaStream_t st) {
   if (p.DHQK == 64) return launch_fwd<64>(p, st);

@@ -69,6 +69,8 @@ struct alignas(16) GateBuf {
   float invN[L];    // 1 / (max(|n_t|, e^-m_t) + eps)          (backward only)
   float dnf[L];     // -[|n_t| >= e^-m_t] sign(n_t) / N_t      (backward only: dn_t = dnf_t (dh_t . h_t))
   float sig[L];     // sigmoid(-f_t)                           (backward only)
+  float dn[L];      // dn_t                                    (backward only)
+  float c2[L];      // M2_t - log2(invN_t)  (+inf for invalid rows)   (backward only)
   float decay;      // exp(m_prev - M_L)
   float m_next;     // b_L + M_L
   float m_prev;
@@ -131,11 +133,12 @@ __device__ __forceinline__ void gates_warp_fwd(GateBuf& G, const mlstm_params& p
 }
 
 // Backward-style gates: everything rebuilt from i, f and the saved rows (n_t, m_t); no carry.
-__device__ __forceinline__ void gates_warp_bwd(GateBuf& G, const mlstm_params& p, int b, int h, int bh, int mc, int lane) {
+__device__ __forceinline__ void gates_warp_bwd(GateBuf& G, const mlstm_params& p, int b, int h, int bh, int mc, int lane,
+                                               const float* ws_dn = nullptr) {
   const int tok0 = mc * L;
   const int nvalid = min(L, p.S - tok0);
   const bool rev = p.reverse != 0;
-  float ii[4], bs[4], mr[4], nr[4], fi[4];
+  float ii[4], bs[4], mr[4], nr[4], fi[4], dnv[4];
   int r[4];
   float run = 0.f;
 #pragma unroll
@@ -143,7 +146,7 @@ __device__ __forceinline__ void gates_warp_bwd(GateBuf& G, const mlstm_params& p
     const int t = lane * 4 + e;
     const bool valid = t < nvalid;
     r[e] = (rev && valid) ? (nvalid - 1 - t) : t;
-    ii[e] = -INFINITY; mr[e] = 0.f; nr[e] = 0.f; fi[e] = 0.f;
+    ii[e] = -INFINITY; mr[e] = 0.f; nr[e] = 0.f; fi[e] = 0.f; dnv[e] = 0.f;
     float logf = 0.f;
     if (valid) {
       const int tok = tok0 + r[e];
@@ -152,6 +155,7 @@ __device__ __forceinline__ void gates_warp_bwd(GateBuf& G, const mlstm_params& p
       logf = log_sigmoid_fast(fi[e]);
       mr[e] = p.m_row[(int64_t)bh * p.S + tok];
       nr[e] = p.n_row[(int64_t)bh * p.S + tok];
+      if (ws_dn) dnv[e] = ws_dn[(int64_t)bh * p.S + tok];
     }
     run += logf;
     bs[e] = run;
@@ -185,6 +189,8 @@ __device__ __forceinline__ void gates_warp_bwd(GateBuf& G, const mlstm_params& p
     G.invN[r[e]] = valid ? 1.f / N : 0.f;
     G.dnf[r[e]] = (valid && fabsf(nr[e]) >= floor_) ? -copysignf(1.f, nr[e]) / N : 0.f;
     G.sig[r[e]] = 1.f / (1.f + __expf(fi[e]));
+    G.dn[r[e]] = dnv[e];
+    G.c2[r[e]] = valid ? (Me * LOG2E + log2f(N)) : INFINITY;
   }
   if (lane == 0) {
     G.decay = __expf(m_prev - ML);
