@@ -26,7 +26,17 @@ using namespace tc;
 
 enum { MODE_A = 0, MODE_B1 = 1, MODE_B2 = 2 };
 
-struct BwdMaps { CUtensorMap t0, t1, t2, st; };
+// Developer aid (-DMLSTM_TIMELINE): CTA 0 of kernel A dumps clock64() stamps per item into the
+// (otherwise unused by A) K-partials region of the workspace; see tests/gpu_tools/timeline_bwd.py.
+#ifdef MLSTM_TIMELINE
+#define TLB(k) do { if (IS_A && blockIdx.x == 0 && n < 8) { \
+    if (threadIdx.x == 0) tlb[n * 32 + (k)] = clock64(); \
+    if (threadIdx.x == CT) tlb[n * 32 + 16 + (k)] = clock64(); } } while (0)
+#else
+#define TLB(k) do { } while (0)
+#endif
+
+struct BwdMaps { CUtensorMap t0, t1, t2, st, t3, h, out; };   // t3: q (A) / k (B2) rows for R and K; h: A only
 
 // backward scratch (p.workspace)
 struct BwdLayout {
@@ -42,6 +52,23 @@ struct BwdLayout {
   }
 };
 
+// 32 columns [32 cb, 32 cb + 32) of row `row` of a swizzled [128][DH] bf16 tile set -> fp32
+template <int DH>
+__device__ __forceinline__ void tile_row32(const uint8_t* tile, int row, int cb, float (&out)[32]) {
+#pragma unroll
+  for (int x = 0; x < 32; x += 8) {
+    const int col = cb * 32 + x;
+    const uint4 w = *reinterpret_cast<const uint4*>(tile + (col >> 6) * TILE + swz128(row, col & 63));
+    const __nv_bfloat162* qq = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f2 = __bfloat1622float2(qq[e]);
+      out[x + 2 * e] = f2.x;
+      out[x + 2 * e + 1] = f2.y;
+    }
+  }
+}
+
 // =============================================================================================
 // Chunk-parallel kernels A / B1 / B2
 //   tiles:  A : t0 = dH, t1 = V, t2 = K, st = Cs     thread row = query t
@@ -56,11 +83,12 @@ struct SmemB {
   alignas(1024) uint8_t t1[KT * TILE];
   alignas(1024) uint8_t t2[KT * TILE];
   alignas(1024) uint8_t st[KT * TILE_C];
-  alignas(1024) uint8_t x[2 * TILE];               // gated bf16 tile (K-major, 2 tiles over the column index)
-  GateBuf g[2];
-  alignas(16) float vecf[2][DH];                   // ns (A) / dns (B2) of the item
+  alignas(1024) uint8_t x[2 * TILE];               // h tile (A) -> gated bf16 tile (K-major) -> output staging
+  alignas(1024) uint8_t t3[KT * TILE];             // q (A) / k (B2): rows for R = q.dq / K = k.dk
+  GateBuf g[3];                                    // ring: the gate warp runs two items ahead
+  alignas(16) float vecf[3][DH];                   // ns (A) / dns (B2) of the item
   float part[4][L];
-  uint64_t bar_t0, bar_t1, bar_t2, bar_st, bar_m1, bar_i, bar_m2;
+  uint64_t bar_t0, bar_t1, bar_t2, bar_st, bar_t3, bar_h, bar_m1, bar_i, bar_m2;
   uint32_t tmem_base;
 };
 
@@ -94,6 +122,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
   if (issuer) {
     tma_prefetch_desc(&maps.t0); tma_prefetch_desc(&maps.t1); tma_prefetch_desc(&maps.t2); tma_prefetch_desc(&maps.st);
     mbar_init(&sm.bar_t0, 1); mbar_init(&sm.bar_t1, 1); mbar_init(&sm.bar_t2, 1); mbar_init(&sm.bar_st, 1);
+    mbar_init(&sm.bar_t3, 1); mbar_init(&sm.bar_h, 1);
     mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_i, 1); mbar_init(&sm.bar_m2, 1);
     fence_mbar_init();
   }
@@ -149,8 +178,13 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
   if (issuer) {
     load_act(sm.t0, &maps.t0, &sm.bar_t0, item0); load_act(sm.t1, &maps.t1, &sm.bar_t1, item0);
     load_st(item0); load_act(sm.t2, &maps.t2, &sm.bar_t2, item0);
+    if (MODE != MODE_B1) load_act(sm.t3, &maps.t3, &sm.bar_t3, item0);
+    if (IS_A) load_act(sm.x, &maps.h, &sm.bar_h, item0);
   }
-  if (gatew) prep_item(item0, 0);
+  if (gatew) {
+    prep_item(item0, 0);
+    if (item0 + (int)gridDim.x < n_items) prep_item(item0 + gridDim.x, 1);
+  }
   __syncthreads();
   if (issuer) {
     mbar_wait(&sm.bar_t0, 0); mbar_wait(&sm.bar_t1, 0);
@@ -159,36 +193,48 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
     issue_mma1();
   }
 
+#ifdef MLSTM_TIMELINE
+  long long* tlb = reinterpret_cast<long long*>(ws_kpart);
+#endif
   int n = 0;
   for (int item = item0; item < n_items; item += gridDim.x, ++n) {
+    TLB(0);
     const uint32_t ph = n & 1;
     const int next = item + gridDim.x;
     const bool has_next = next < n_items;
     if (gatew) {
-      if (has_next) prep_item(next, (n + 1) & 1);
+      if (next + (int)gridDim.x < n_items) prep_item(next + gridDim.x, (n + 2) % 3);
       __syncthreads();
       continue;
     }
-    const GateBuf& G = sm.g[n & 1];
-    const float* vecf = sm.vecf[n & 1];
+    const GateBuf& G = sm.g[n % 3];
+    const float* vecf = sm.vecf[n % 3];
     int b, h, tok0; coords(item, b, h, tok0);
     const int bh = item / NC;
     const int tok = tok0 + row;
     const bool row_ok = compute && tok < S;
     const size_t grow = (size_t)bh * S + tok;          // index into the per-row workspace arrays
 
-    // ---- A: dn_t = dnf_t (dh_t . h_t), block partials straight from global memory (MMA1 shadow)
+    // ---- A: dn_t = dnf_t (dh_t . h_t): block partials from the h tile (parked in x) and the dH tile
     float dn_row = 0.f;
     if (IS_A) {
+      mbar_wait(&sm.bar_h, ph);
       float part = 0.f;
-      if (row_ok && cq < NB) {
-        const int64_t off_h = (int64_t)b * p.h.stride_b + (int64_t)h * p.h.stride_h + (int64_t)tok * p.h.stride_s + cq * 32;
-        const int64_t off_d = (int64_t)b * p.dh.stride_b + (int64_t)h * p.dh.stride_h + (int64_t)tok * p.dh.stride_s + cq * 32;
-        float hv[32], dv_[32];
-        load_row32(reinterpret_cast<const __nv_bfloat16*>(p.h.ptr) + off_h, hv);
-        load_row32(reinterpret_cast<const __nv_bfloat16*>(p.dh.ptr) + off_d, dv_);
+      if (cq < NB) {
 #pragma unroll
-        for (int x = 0; x < 32; ++x) part = fmaf(hv[x], dv_[x], part);
+        for (int x8 = 0; x8 < 32; x8 += 8) {
+          const int col = cq * 32 + x8;
+          const uint32_t off = (col >> 6) * TILE + swz128(row, col & 63);
+          const uint4 wh = *reinterpret_cast<const uint4*>(sm.x + off);
+          const uint4 wd = *reinterpret_cast<const uint4*>(sm.t0 + off);
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&wh);
+          const __nv_bfloat162* dd = reinterpret_cast<const __nv_bfloat162*>(&wd);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = __bfloat1622float2(hh[e]), c2 = __bfloat1622float2(dd[e]);
+            part = fmaf(a.x, c2.x, fmaf(a.y, c2.y, part));
+          }
+        }
       }
       if (compute) sm.part[cq][row] = part;
       if (compute) named_sync(3, CT);
@@ -197,8 +243,10 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
         if (cq == 0 && row_ok) ws_dn[grow] = dn_row;
       }
     }
+    TLB(1);
     mbar_wait(&sm.bar_m1, ph);
     tc_fence_after();
+    TLB(2);
     if (issuer && has_next) {   // tiles MMA1 (and A's G) read are dead
       load_act(sm.t1, &maps.t1, &sm.bar_t1, next);
       if (IS_A) { load_act(sm.t0, &maps.t0, &sm.bar_t0, next); load_st(next); }
@@ -208,6 +256,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
     if (!IS_A) {
       if (compute) scale_rows<DH>(sm.t0, MODE == MODE_B1 ? G.kw : G.w, tid);
       fence_proxy_async_smem();
+      if (issuer) tma_store_wait_read<0>();   // previous item's staged output (in x) has been read
       tc_fence_before();
       named_sync(2, GT0);
       if (issuer) {
@@ -226,6 +275,10 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
       }
     }
 
+    // x is rewritten next: in A every warp must be done with the h tile parked there (B: the issuer
+    // waited for the previous output store before the barrier above)
+    if (IS_A) named_sync(2, GT0);
+    TLB(3);
     // ---- gated bf16 tile: one 32x32 block per warp ----------------------------------------------
     if (compute) {
       // A : row = query t, col = key j   : keep j <= t (forward) / j >= t (reverse)
@@ -276,9 +329,11 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
             make_uint4(packed[4 * x], packed[4 * x + 1], packed[4 * x + 2], packed[4 * x + 3]);
       }
     }
+    TLB(4);
     fence_proxy_async_smem();
     tc_fence_before();
     named_sync(2, GT0);
+    TLB(5);
 
     // ---- MMA2: A: dQ = dS K (into tS) | B: tO += X t2 -------------------------------------------
     if (issuer) {
@@ -293,9 +348,16 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
         if (has_next) { load_act(sm.t0, &maps.t0, &sm.bar_t0, next); load_st(next); }
       }
     }
+    TLB(6);
     mbar_wait(&sm.bar_m2, ph);
     tc_fence_after();
-    if (issuer && has_next) load_act(sm.t2, &maps.t2, &sm.bar_t2, next);
+    TLB(7);
+    // A stages its output in the (now dead) t2 tile so that x is free for the next h tile at once;
+    // B stages in x and refills t2 now
+    if (issuer && has_next) {
+      if (IS_A) load_act(sm.x, &maps.h, &sm.bar_h, next);
+      else load_act(sm.t2, &maps.t2, &sm.bar_t2, next);
+    }
 
     // ---- epilogue: outputs packed in registers --------------------------------------------------
     uint32_t opk[16];
@@ -309,8 +371,8 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
         tmem_ld_wait();
         const float wt = G.w[row], invN = G.invN[row];
         float qr[32];
-        if (row_ok) load_row32(reinterpret_cast<const __nv_bfloat16*>(p.q.ptr) + (int64_t)b * p.q.stride_b +
-                               (int64_t)h * p.q.stride_h + (int64_t)tok * p.q.stride_s + cq * 32, qr);
+        mbar_wait(&sm.bar_t3, ph);
+        tile_row32<DH>(sm.t3, row, cq, qr);
 #pragma unroll
         for (int x = 0; x < 32; x += 2) {
           const float o0 = scale * (acc[x] + wt * fmaf(gg[x], invN, dn_row * vecf[cq * 32 + x]));
@@ -326,8 +388,8 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
         tmem_ld_wait();
         const float kwj = G.kw[row];
         float kr[32];
-        if (row_ok) load_row32(reinterpret_cast<const __nv_bfloat16*>(p.k.ptr) + (int64_t)b * p.k.stride_b +
-                               (int64_t)h * p.k.stride_h + (int64_t)tok * p.k.stride_s + cq * 32, kr);
+        mbar_wait(&sm.bar_t3, ph);
+        tile_row32<DH>(sm.t3, row, cq, kr);
 #pragma unroll
         for (int x = 0; x < 32; x += 2) {
           const float o0 = fmaf(kwj, vecf[cq * 32 + x], scale * acc[x]);
@@ -337,23 +399,43 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
         }
       }
     }
-    tc_fence_before();
-    __syncthreads();   // end of item: TMEM free, next gates published (the gate warp joins here)
-    if (issuer && has_next) {
-      mbar_wait(&sm.bar_t0, ph ^ 1); mbar_wait(&sm.bar_t1, ph ^ 1);
-      if (IS_A) mbar_wait(&sm.bar_st, ph ^ 1);
-      tc_fence_after();
-      issue_mma1();
+    // stage the output rows (A: in t2, B: in x — both dead after MMA2) for one coalesced TMA store
+    uint8_t* stage = IS_A ? sm.t2 : sm.x;
+    if (cq < NB) {
+#pragma unroll
+      for (int x4 = 0; x4 < 4; ++x4) {
+        const int col = cq * 32 + x4 * 8;
+        *reinterpret_cast<uint4*>(stage + (col >> 6) * TILE + swz128(row, col & 63)) =
+            make_uint4(opk[4 * x4], opk[4 * x4 + 1], opk[4 * x4 + 2], opk[4 * x4 + 3]);
+      }
     }
     if (row_ok) {
-      const mlstm_act& out = IS_A ? p.dq : (MODE == MODE_B1 ? p.dv : p.dk);
-      if (cq < NB)
-        store_row32(reinterpret_cast<__nv_bfloat16*>(out.ptr) + (int64_t)b * out.stride_b + (int64_t)h * out.stride_h +
-                    (int64_t)tok * out.stride_s + cq * 32, opk);
       if (IS_A) ws_rpart[(size_t)cq * rows_total + grow] = psum;
       if (MODE == MODE_B2) ws_kpart[(size_t)cq * rows_total + grow] = psum;
     }
+    TLB(8);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();   // end of item: TMEM free, next gates published (the gate warp joins here)
+    TLB(9);
+    if (issuer) {
+      for (int kt = 0; kt < KT; ++kt) tma_store_4d(&maps.out, stage + kt * TILE, kt * 64, tok0, h, b);
+      tma_store_commit();
+      if (has_next) {
+        if (MODE != MODE_B1) load_act(sm.t3, &maps.t3, &sm.bar_t3, next);   // t3 rows were consumed in the epilogue
+        mbar_wait(&sm.bar_t0, ph ^ 1); mbar_wait(&sm.bar_t1, ph ^ 1);
+        if (IS_A) mbar_wait(&sm.bar_st, ph ^ 1);
+        tc_fence_after();
+        issue_mma1();
+        if (IS_A) {   // refill t2 once the store above has read the staged rows
+          tma_store_wait_read<0>();
+          load_act(sm.t2, &maps.t2, &sm.bar_t2, next);
+        }
+      }
+    }
+    TLB(10);
   }
+  if (issuer) tma_store_wait_all<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tm, 256);
@@ -368,6 +450,7 @@ struct SmemSB {
   alignas(1024) uint8_t q[2][KT * TILE];
   alignas(1024) uint8_t dh[2][KT * TILE];
   alignas(1024) uint8_t vec[2][2 * 2048];          // K-major [16][128 t] bf16: (dn N)_t in every row
+  alignas(1024) uint8_t stage[KT * DH * 128];      // bf16 dC tile staged for the TMA store
   GateBuf g[3];
   uint64_t bar_q[2], bar_dh[2], bar_mma;
   uint32_t tmem_base;
@@ -493,10 +576,13 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
       float r[32];
       tmem_ld32(tC + lane_sel + cq * 32, r);
       tmem_ld_wait();
-      uint32_t pk[16];
 #pragma unroll
-      for (int x = 0; x < 32; x += 2) pk[x / 2] = pack_bf16x2(r[x], r[x + 1]);
-      store_row32(dCs + ((size_t)(sc - 1) * DH + row) * DH + cq * 32, pk);
+      for (int x = 0; x < 32; x += 8) {
+        const int dv = cq * 32 + x;
+        *reinterpret_cast<uint4*>(sm.stage + (dv >> 6) * (DH * 128) + swz128(row, dv & 63)) =
+            make_uint4(pack_bf16x2(r[x], r[x + 1]), pack_bf16x2(r[x + 2], r[x + 3]), pack_bf16x2(r[x + 4], r[x + 5]),
+                       pack_bf16x2(r[x + 6], r[x + 7]));
+      }
 #pragma unroll
       for (int x = 0; x < 32; ++x) r[x] *= dnext;
       tmem_st32(tC + lane_sel + cq * 32, r);
@@ -511,9 +597,17 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
       }
       tmem_st_wait();
     }
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (issuer) {   // dC_{sc-1} tile -> workspace; the staging tile is rewritten one step later
+      for (int kt = 0; kt < KT; ++kt)
+        tma_store_2d(&maps.st, sm.stage + kt * (DH * 128), kt * 64, (bh * NC + (sc - 1)) * DH);
+      tma_store_commit();
+      tma_store_wait_read<0>();
+    }
   }
+  if (issuer) tma_store_wait_all<0>();
   if (!gatew) { tc_fence_before(); __syncthreads(); }   // matches the gate warp's last in-loop barrier
   tc_fence_before();
   __syncthreads();
@@ -521,14 +615,16 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
 }
 
 // =============================================================================================
-// DF: di = K, df = sigmoid(-f) * suffix_sum(R - K) in scan order.  One CTA per (batch, head).
+// DF: di = K, df = sigmoid(-f) * suffix_sum(R - K) in scan order.  One 1024-thread CTA per
+// (batch, head): thread i owns a contiguous run of scan positions (position P <-> token P, or
+// S-1-P in reverse mode), block-wide suffix scan over the per-thread totals.
 // =============================================================================================
-__global__ void __launch_bounds__(128) tc_dfscan_kernel(const mlstm_params p, const int DH) {
-  __shared__ float sc_part[4];
-  __shared__ float carry_s;
+constexpr int DF_MAXSEG = 32;   // S <= 32768
+__global__ void __launch_bounds__(1024) tc_dfscan_kernel(const mlstm_params p, const int DH) {
+  __shared__ float wsum[32];
   const int bh = blockIdx.x, b = bh / p.NH, h = bh % p.NH;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int S = p.S, NC = num_chunks(S);
+  const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
+  const int S = p.S;
   const bool rev = p.reverse != 0;
   const size_t rows_total = (size_t)p.B * p.NH * S;
   const BwdLayout blay(p.B, p.NH, S, DH);
@@ -536,36 +632,40 @@ __global__ void __launch_bounds__(128) tc_dfscan_kernel(const mlstm_params p, co
   const float* rp = reinterpret_cast<const float*>(ws + blay.rpart_off);
   const float* kp = reinterpret_cast<const float*>(ws + blay.kpart_off);
   const int nb = DH / 32;
-  if (t == 0) carry_s = 0.f;
-  __syncthreads();
-  for (int sc = NC - 1; sc >= 0; --sc) {
-    const int tok0 = mem_chunk(sc, NC, rev) * L;
-    const int nvalid = min(L, S - tok0);
-    const bool valid = t < nvalid;
-    const int tok = tok0 + (rev ? (nvalid - 1 - t) : t);   // thread t = scan-local index t
-    float R = 0.f, K = 0.f, fi = 0.f;
-    if (valid) {
+  const int seg = (S + 1023) / 1024;
+  float dB[DF_MAXSEG];
+  float tot = 0.f;
+#pragma unroll 4
+  for (int e = 0; e < DF_MAXSEG; ++e) {
+    dB[e] = 0.f;
+    const int P = i * seg + e;
+    if (e < seg && P < S) {
+      const int tok = rev ? (S - 1 - P) : P;
       const size_t g = (size_t)bh * S + tok;
+      float R = 0.f, K = 0.f;
       for (int c = 0; c < nb; ++c) { R += rp[(size_t)c * rows_total + g]; K += kp[(size_t)c * rows_total + g]; }
-      fi = p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s];
-    }
-    const float dB = R - K;
-    float pre = warp_scan_add(dB, lane);
-    if (lane == 31) sc_part[warp] = pre;
-    __syncthreads();
-    float off = 0.f, tot = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) { off += (w < warp) ? sc_part[w] : 0.f; tot += sc_part[w]; }
-    pre += off;
-    const float carry = carry_s;
-    if (valid) {
       p.di.ptr[(int64_t)b * p.di.stride_b + (int64_t)h * p.di.stride_h + (int64_t)tok * p.di.stride_s] = K;
-      p.df.ptr[(int64_t)b * p.df.stride_b + (int64_t)h * p.df.stride_h + (int64_t)tok * p.df.stride_s] =
-          (tot - pre + dB + carry) / (1.f + __expf(fi));
+      dB[e] = R - K;
+      tot += dB[e];
     }
-    __syncthreads();
-    if (t == 0) carry_s = carry + tot;
-    __syncthreads();
+  }
+  // exclusive suffix sum of `tot` over the threads of the block
+  float incl = warp_scan_add(tot, lane);
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  float before = 0.f, all = 0.f;
+#pragma unroll
+  for (int w = 0; w < 32; ++w) { before += (w < warp) ? wsum[w] : 0.f; all += wsum[w]; }
+  float run = all - (incl + before);   // sum over all later threads
+#pragma unroll 4
+  for (int e = DF_MAXSEG - 1; e >= 0; --e) {
+    const int P = i * seg + e;
+    if (e < seg && P < S) {
+      run += dB[e];
+      const int tok = rev ? (S - 1 - P) : P;
+      const float fi = p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s];
+      p.df.ptr[(int64_t)b * p.df.stride_b + (int64_t)h * p.df.stride_h + (int64_t)tok * p.df.stride_s] = run / (1.f + __expf(fi));
+    }
   }
 }
 
@@ -597,8 +697,12 @@ int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
     return MLSTM_ERR_WORKSPACE;
   }
   const int NC = num_chunks(p.S), n_items = p.B * p.NH * NC;
-  CUtensorMap mq, mk, mv, mdh, mcs, mdcs;
+  CUtensorMap mq, mk, mv, mdh, mcs, mdcs, mh, mdq, mdk, mdv;
   int r = 0;
+  r |= make_act_tmap(&mh, p.h.ptr, p.B, p.NH, p.S, DH, p.h.stride_b, p.h.stride_h, p.h.stride_s, L);
+  r |= make_act_tmap(&mdq, p.dq.ptr, p.B, p.NH, p.S, DH, p.dq.stride_b, p.dq.stride_h, p.dq.stride_s, L);
+  r |= make_act_tmap(&mdk, p.dk.ptr, p.B, p.NH, p.S, DH, p.dk.stride_b, p.dk.stride_h, p.dk.stride_s, L);
+  r |= make_act_tmap(&mdv, p.dv.ptr, p.B, p.NH, p.S, DH, p.dv.stride_b, p.dv.stride_h, p.dv.stride_s, L);
   r |= make_act_tmap(&mq, p.q.ptr, p.B, p.NH, p.S, DH, p.q.stride_b, p.q.stride_h, p.q.stride_s, L);
   r |= make_act_tmap(&mk, p.k.ptr, p.B, p.NH, p.S, DH, p.k.stride_b, p.k.stride_h, p.k.stride_s, L);
   r |= make_act_tmap(&mv, p.v.ptr, p.B, p.NH, p.S, DH, p.v.stride_b, p.v.stride_h, p.v.stride_s, L);
@@ -617,25 +721,26 @@ int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
   const size_t smB = sizeof(SmemB<DH>), smSB = sizeof(SmemSB<DH>);
   int rc;
   if (part != 1) {
-    BwdMaps m{mdh, mv, mk, mcs};
+    BwdMaps m{mdh, mv, mk, mcs, mq, mh, mdq};
     if ((rc = prep(tc_bwd_par_kernel<DH, MODE_A>, smB, "tc_bwd_dq"))) return rc;
     tc_bwd_par_kernel<DH, MODE_A><<<dim3(grid), dim3(NT), smB, st>>>(m, p, scale, n_items);
     if ((rc = launched("tc_bwd_dq"))) return rc;
   }
   if (part != 0) {
-    BwdMaps ms{mq, mdh, mq, mdcs};
+    BwdMaps ms{mq, mdh, mq, mdcs, mq, mh, mdq};
     if ((rc = prep(tc_state_bwd_kernel<DH>, smSB, "tc_state_bwd"))) return rc;
     tc_state_bwd_kernel<DH><<<dim3(p.B * p.NH), dim3(NT), smSB, st>>>(ms, p, scale);
     if ((rc = launched("tc_state_bwd"))) return rc;
-    BwdMaps m1{mk, mq, mdh, mdcs};
+    BwdMaps m1{mk, mq, mdh, mdcs, mq, mh, mdv};
     if ((rc = prep(tc_bwd_par_kernel<DH, MODE_B1>, smB, "tc_bwd_dv"))) return rc;
     tc_bwd_par_kernel<DH, MODE_B1><<<dim3(grid), dim3(NT), smB, st>>>(m1, p, scale, n_items);
     if ((rc = launched("tc_bwd_dv"))) return rc;
-    BwdMaps m2{mv, mdh, mq, mdcs};
+    BwdMaps m2{mv, mdh, mq, mdcs, mk, mh, mdk};
     if ((rc = prep(tc_bwd_par_kernel<DH, MODE_B2>, smB, "tc_bwd_dk"))) return rc;
     tc_bwd_par_kernel<DH, MODE_B2><<<dim3(grid), dim3(NT), smB, st>>>(m2, p, scale, n_items);
     if ((rc = launched("tc_bwd_dk"))) return rc;
-    tc_dfscan_kernel<<<dim3(p.B * p.NH), dim3(128), 0, st>>>(p, DH);
+    if (p.S > 1024 * DF_MAXSEG) { set_error("S = %d exceeds the df-scan limit %d", p.S, 1024 * DF_MAXSEG); return MLSTM_ERR_UNSUPPORTED; }
+    tc_dfscan_kernel<<<dim3(p.B * p.NH), dim3(1024), 0, st>>>(p, DH);
     if ((rc = launched("tc_dfscan"))) return rc;
   }
   return MLSTM_OK;

@@ -35,7 +35,7 @@ constexpr int NT = GT0 + 32;           // 576 threads = 18 warps
 constexpr int TILE = L * 128;          // bytes of one [128 rows][64 bf16] swizzled tile
 constexpr float LOG2E = 1.4426950408889634f;
 
-struct FwdMaps { CUtensorMap q, k, v, h; };
+struct FwdMaps { CUtensorMap q, k, v, h, cs; };   // cs: the per-chunk state buffer (2-D, rows of DH)
 
 // Developer aid: -DMLSTM_TIMELINE makes CTA 0 dump clock64() stamps of every phase of every
 // chunk (compute thread 0 and the issuer) into p.workspace (tests/gpu_tools/timeline.py).
@@ -474,7 +474,6 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
             *reinterpret_cast<uint4*>(sm.cb + (dv >> 6) * TILE_C + swz128(row, dv & 63)) =
                 make_uint4(pk[4 * x], pk[4 * x + 1], pk[4 * x + 2], pk[4 * x + 3]);
           }
-          if (save_states && !last) tc::store_row32(Cs_g + ((size_t)(c + 1) * DH + row) * DH + cq * 32, pk);
         }
         if (!last) {
 #pragma unroll
@@ -513,6 +512,8 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
     TL_STAMP(12);
     if (issuer) {
       for (int kt = 0; kt < KT; ++kt) tma_store_4d(&maps.h, sk + kt * TILE, kt * 64, tok0, h, b);
+      if (save_states && !last)   // entry state of chunk c+1 = the bf16 C tile just written (read again by the next state pass only)
+        for (int kt = 0; kt < KT; ++kt) tma_store_2d(&maps.cs, sm.cb + kt * TILE_C, kt * 64, (bh * NC + c + 1) * DH);
       tma_store_commit();
       if (!last) {   // MMA1 of the next chunk: nobody waits for this issue loop
         mbar_wait(&sm.bar_q, ph ^ 1);
@@ -537,6 +538,16 @@ int launch_fwd(const mlstm_params& p, cudaStream_t st) {
   r |= make_act_tmap(&maps.k, p.k.ptr, p.B, p.NH, p.S, DH, p.k.stride_b, p.k.stride_h, p.k.stride_s, L);
   r |= make_act_tmap(&maps.v, p.v.ptr, p.B, p.NH, p.S, DH, p.v.stride_b, p.v.stride_h, p.v.stride_s, L);
   r |= make_act_tmap(&maps.h, p.h.ptr, p.B, p.NH, p.S, DH, p.h.stride_b, p.h.stride_h, p.h.stride_s, L);
+  maps.cs = maps.h;   // placeholder when no state buffer is given (never dereferenced then)
+  if (p.states) {
+    const tc::StateLayout slay(p.B, p.NH, p.S, DH);
+    if (p.states_bytes < slay.total) {
+      set_error("chunk-state buffer too small: %zu < %zu bytes", p.states_bytes, slay.total);
+      return MLSTM_ERR_WORKSPACE;
+    }
+    r |= tc::make_state_tmap(&maps.cs, reinterpret_cast<uint8_t*>(p.states) + slay.cs_off,
+                             (size_t)p.B * p.NH * tc::num_chunks(p.S) * DH, DH);
+  }
   if (r) {
     set_error("cuTensorMapEncodeTiled failed (%d): pointers must be 16-byte aligned, strides multiples of 8 elements", r);
     return r == -1 ? MLSTM_ERR_NO_DEVICE : MLSTM_ERR_INVALID_ARG;

@@ -217,8 +217,8 @@ struct SmemP {
   alignas(1024) uint8_t v[KT * TILE];
   alignas(1024) uint8_t cs[KT * TILE_C];           // bf16 entry state, [dk][dv]
   alignas(1024) uint8_t p[2 * TILE];               // P (K-major, 2 tiles over j)
-  alignas(1024) uint8_t nvec[2][KT * 2048];        // K-major [16][DH]: row 0 = hi(n), row 1 = lo(n)
-  GateBuf g[2];
+  alignas(1024) uint8_t nvec[3][KT * 2048];        // K-major [16][DH]: row 0 = hi(n), row 1 = lo(n); ring of 3
+  GateBuf g[3];                                    // the gate warp runs two items ahead
   float part_rs[4][L];
   uint64_t bar_q, bar_k, bar_v, bar_cs, bar_m1, bar_m2;
   uint32_t tmem_base;
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_par_kernel(const __grid_constant
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
-  for (int e = tid; e < 2 * KT * 2048 / 16; e += NT) reinterpret_cast<uint4*>(sm.nvec)[e] = make_uint4(0, 0, 0, 0);
+  for (int e = tid; e < 3 * KT * 2048 / 16; e += NT) reinterpret_cast<uint4*>(sm.nvec)[e] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_par_kernel(const __grid_constant
   auto issue_mma1 = [&](int n) {   // S = Q K^T, G = Q Cs, qn = Q [n_hi n_lo]
     constexpr uint32_t idS = make_idesc_bf16(128, 128, 0, 0), idG = make_idesc_bf16(128, DH, 0, 1);
     constexpr uint32_t idN = make_idesc_bf16(128, 16, 0, 0);
-    const uint64_t dNv = dNv0 + (n & 1) * NV_STEP;
+    const uint64_t dNv = dNv0 + (n % 3) * NV_STEP;
 #pragma unroll
     for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tS, dQ + kstep(ks), dKk + kstep(ks), idS, ks > 0);
 #pragma unroll
@@ -306,7 +306,10 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_par_kernel(const __grid_constant
 
   const int item0 = blockIdx.x;   // the grid is never larger than n_items
   if (issuer) { load_qkc(item0); load_v(item0); }
-  if (gatew) prep_item(item0, 0);
+  if (gatew) {
+    prep_item(item0, 0);
+    if (item0 + (int)gridDim.x < n_items) prep_item(item0 + gridDim.x, 1);
+  }
   __syncthreads();
   if (issuer) {
     mbar_wait(&sm.bar_q, 0); mbar_wait(&sm.bar_k, 0); mbar_wait(&sm.bar_cs, 0);
@@ -320,11 +323,11 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_par_kernel(const __grid_constant
     const int next = item + gridDim.x;
     const bool has_next = next < n_items;
     if (gatew) {
-      if (has_next) prep_item(next, (n + 1) & 1);
+      if (next + (int)gridDim.x < n_items) prep_item(next + gridDim.x, (n + 2) % 3);
       __syncthreads();
       continue;
     }
-    const GateBuf& G = sm.g[n & 1];
+    const GateBuf& G = sm.g[n % 3];
     const int bh = item / NC, sc = item % NC, b = bh / p.NH, h = bh % p.NH;
     const int tok0 = mem_chunk(sc, NC, rev) * L;
 

@@ -81,22 +81,26 @@ struct alignas(16) GateBuf {
 __device__ __forceinline__ void gates_warp_fwd(GateBuf& G, const mlstm_params& p, int b, int h, int mc, int lane, float m_prev) {
   const int tok0 = mc * L;
   const int nvalid = min(L, p.S - tok0);
-  float ii[4], bs[4];
+  float ii[4], bs[4], fraw[4];
   int r[4];
-  float run = 0.f;
+  // all global loads first (independent), then the dependent math: one memory latency, not eight
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int t = lane * 4 + e;
     const bool valid = t < nvalid;
     r[e] = (p.reverse && valid) ? (nvalid - 1 - t) : t;   // tile row of scan-local index t
     ii[e] = -INFINITY;
-    float logf = 0.f;
+    fraw[e] = INFINITY;                                     // logsigmoid(+inf) = 0
     if (valid) {
       const int tok = tok0 + r[e];
-      logf = log_sigmoid_fast(p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s]);
+      fraw[e] = p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s];
       ii[e] = p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s];
     }
-    run += logf;
+  }
+  float run = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    run += (lane * 4 + e < nvalid) ? log_sigmoid_fast(fraw[e]) : 0.f;
     bs[e] = run;
   }
   const float incl = warp_scan_add(run, lane);
@@ -140,31 +144,32 @@ __device__ __forceinline__ void gates_warp_bwd(GateBuf& G, const mlstm_params& p
   const bool rev = p.reverse != 0;
   float ii[4], bs[4], mr[4], nr[4], fi[4], dnv[4];
   int r[4];
-  float run = 0.f;
+  // all global loads first (independent), then the dependent math
+  const int ptok = rev ? (tok0 + nvalid) : (tok0 - 1);
+  const float m_prev = (ptok >= 0 && ptok < p.S) ? p.m_row[(int64_t)bh * p.S + ptok] : (p.m_initial ? p.m_initial[bh] : 0.f);
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int t = lane * 4 + e;
     const bool valid = t < nvalid;
     r[e] = (rev && valid) ? (nvalid - 1 - t) : t;
     ii[e] = -INFINITY; mr[e] = 0.f; nr[e] = 0.f; fi[e] = 0.f; dnv[e] = 0.f;
-    float logf = 0.f;
     if (valid) {
       const int tok = tok0 + r[e];
       fi[e] = p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s];
       ii[e] = p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s];
-      logf = log_sigmoid_fast(fi[e]);
       mr[e] = p.m_row[(int64_t)bh * p.S + tok];
       nr[e] = p.n_row[(int64_t)bh * p.S + tok];
       if (ws_dn) dnv[e] = ws_dn[(int64_t)bh * p.S + tok];
     }
-    run += logf;
+  }
+  float run = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    run += (lane * 4 + e < nvalid) ? log_sigmoid_fast(fi[e]) : 0.f;
     bs[e] = run;
   }
   const float incl = warp_scan_add(run, lane);
   const float excl = incl - run;
-  // m of the row that precedes this chunk in scan order (or the initial m)
-  const int ptok = rev ? (tok0 + nvalid) : (tok0 - 1);
-  const float m_prev = (ptok >= 0 && ptok < p.S) ? p.m_row[(int64_t)bh * p.S + ptok] : (p.m_initial ? p.m_initial[bh] : 0.f);
   float M[4], u[4];
   float cand = 0.f;
 #pragma unroll
