@@ -40,7 +40,7 @@ struct BwdMaps { CUtensorMap t0, t1, t2, st, t3, h, out; };   // t3: q (A) / k (
 
 // backward scratch (p.workspace)
 struct BwdLayout {
-  size_t dn_off, rpart_off, kpart_off, dcs_off, dns_off, total;
+  size_t dn_off, rpart_off, kpart_off, dcs_off, dns_off, flow_off, total;
   __host__ __device__ BwdLayout(int B, int NH, int S, int DH) {
     const size_t rows = (size_t)B * NH * S, items = (size_t)B * NH * num_chunks(S);
     dn_off = 0;
@@ -48,7 +48,8 @@ struct BwdLayout {
     kpart_off = rpart_off + 4 * rows * 4;
     dcs_off = (kpart_off + 4 * rows * 4 + 255) & ~(size_t)255;
     dns_off = dcs_off + items * DH * DH * 2;
-    total = (dns_off + items * DH * 4 + 255) & ~(size_t)255;
+    flow_off = (dns_off + items * DH * 4 + 255) & ~(size_t)255;   // fp32 per chunk: <dC, C> + <dn, n> across its entry boundary
+    total = (flow_off + items * 4 + 255) & ~(size_t)255;
   }
 };
 
@@ -451,8 +452,10 @@ struct SmemSB {
   alignas(1024) uint8_t dh[2][KT * TILE];
   alignas(1024) uint8_t vec[2][2 * 2048];          // K-major [16][128 t] bf16: (dn N)_t in every row
   alignas(1024) uint8_t stage[KT * DH * 128];      // bf16 dC tile staged for the TMA store
+  alignas(1024) uint8_t cst[KT * DH * 128];        // forward entry state Cs[sc] (bf16), for the boundary flow <dC, C>
   GateBuf g[3];
-  uint64_t bar_q[2], bar_dh[2], bar_mma;
+  float fpart[16];
+  uint64_t bar_q[2], bar_dh[2], bar_mma, bar_cs;
   uint32_t tmem_base;
 };
 
@@ -482,7 +485,7 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
   if (issuer) {
     tma_prefetch_desc(&maps.t0); tma_prefetch_desc(&maps.t1);
     mbar_init(&sm.bar_q[0], 1); mbar_init(&sm.bar_q[1], 1); mbar_init(&sm.bar_dh[0], 1); mbar_init(&sm.bar_dh[1], 1);
-    mbar_init(&sm.bar_mma, 1);
+    mbar_init(&sm.bar_mma, 1); mbar_init(&sm.bar_cs, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&sm.tmem_base, TCOLS);
@@ -491,6 +494,13 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tm = sm.tmem_base, tC = tm, tN = tm + DH;
   const uint32_t lane_sel = (uint32_t)(rg * 32) << 16;
+  const StateLayout slay(p.B, p.NH, S, DH);
+  const float* ns_f = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.states) + slay.ns_off) + (size_t)bh * NC * DH;
+  float* flow = reinterpret_cast<float*>(ws + blay.flow_off) + (size_t)bh * NC;
+  auto load_cs = [&](int sc) {   // forward entry state of chunk sc (t2 map = the Cs buffer)
+    mbar_arrive_expect_tx(&sm.bar_cs, KT * DH * 128);
+    for (int kt = 0; kt < KT; ++kt) tma_load_2d(sm.cst + kt * (DH * 128), &maps.t2, &sm.bar_cs, kt * 64, (bh * NC + sc) * DH);
+  };
 
   // processing step pc = 0..NC-1 handles scan chunk sc = NC-1-pc
   auto sc_of = [&](int pc) { return NC - 1 - pc; };
@@ -523,7 +533,7 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
   const uint64_t dVec0 = make_sdesc(smem_u32(sm.vec[0]), 16, 1024);
   constexpr uint64_t BUF_STEP = (uint64_t)(KT * TILE) >> 4, VEC_STEP = (uint64_t)(2 * 2048) >> 4;
 
-  if (issuer) { load_qd(0); if (NC > 1) load_qd(1); }
+  if (issuer) { load_qd(0); if (NC > 1) { load_qd(1); load_cs(NC - 1); } }
   if (gatew) { gates_of(0); if (NC > 1) gates_of(1); }
   // adjoint state leaving the last chunk is zero (the last states carry no gradient)
   if (row < DH && cq < NB) {
@@ -572,10 +582,23 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
 
     // state pass: dC_{sc-1} -> workspace (bf16), then TMEM <- decay_{sc-1} dC_{sc-1}
     const float dnext = sm.g[(pc + 1) % 3].decay;
+    float fl = 0.f;   // partial of the boundary flow <dC_{sc-1}, Cs[sc]> + <dn_{sc-1}, ns[sc]>
+    mbar_wait(&sm.bar_cs, pc & 1);
     if (row < DH && cq < NB) {
       float r[32];
       tmem_ld32(tC + lane_sel + cq * 32, r);
       tmem_ld_wait();
+#pragma unroll
+      for (int x = 0; x < 32; x += 8) {
+        const int dv = cq * 32 + x;
+        const uint4 wc = *reinterpret_cast<const uint4*>(sm.cst + (dv >> 6) * (DH * 128) + swz128(row, dv & 63));
+        const __nv_bfloat162* cc = reinterpret_cast<const __nv_bfloat162*>(&wc);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 c2 = __bfloat1622float2(cc[e]);
+          fl = fmaf(r[x + 2 * e], c2.x, fmaf(r[x + 2 * e + 1], c2.y, fl));
+        }
+      }
 #pragma unroll
       for (int x = 0; x < 32; x += 8) {
         const int dv = cq * 32 + x;
@@ -591,15 +614,27 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
         tmem_ld16(tN + lane_sel, rn);
         tmem_ld_wait();
         dns[(size_t)(sc - 1) * DH + row] = rn[0];
+        fl = fmaf(rn[0], ns_f[(size_t)sc * DH + row], fl);
 #pragma unroll
         for (int x = 0; x < 32; ++x) r[x] = rn[0] * dnext;
         tmem_st32(tN + lane_sel, r);
       }
       tmem_st_wait();
     }
+    if (compute) {
+      fl = warp_sum(fl);
+      if (lane == 0) sm.fpart[warp] = fl;
+    }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) {
+      float f_ = 0.f;
+#pragma unroll
+      for (int w = 0; w < 16; ++w) f_ += sm.fpart[w];
+      flow[sc] = f_;
+    }
+    if (issuer && sc - 1 > 0) load_cs(sc - 1);   // (the boundary before chunk 0 is the initial state: not needed)
     if (issuer) {   // dC_{sc-1} tile -> workspace; the staging tile is rewritten one step later
       for (int kt = 0; kt < KT; ++kt)
         tma_store_2d(&maps.st, sm.stage + kt * (DH * 128), kt * 64, (bh * NC + (sc - 1)) * DH);
@@ -615,15 +650,17 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
 }
 
 // =============================================================================================
-// DF: di = K, df = sigmoid(-f) * suffix_sum(R - K) in scan order.  One 1024-thread CTA per
-// (batch, head): thread i owns a contiguous run of scan positions (position P <-> token P, or
-// S-1-P in reverse mode), block-wide suffix scan over the per-thread totals.
+// DF: di = K, df = sigmoid(-f) * suffix_sum(R - K) in scan order.  One 128-thread CTA per chunk:
+// the suffix sum inside the chunk is re-anchored on flow[sc+1] = <dC, C> + <dn, n> across the
+// boundary to the next chunk (written by SB).  In exact arithmetic that flow equals the sum of
+// R - K over all later chunks; taking it from the states keeps the rounding noise of a long
+// sequence from accumulating in df.
 // =============================================================================================
-constexpr int DF_MAXSEG = 32;   // S <= 32768
-__global__ void __launch_bounds__(1024) tc_dfscan_kernel(const mlstm_params p, const int DH) {
-  __shared__ float wsum[32];
-  const int bh = blockIdx.x, b = bh / p.NH, h = bh % p.NH;
-  const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
+__global__ void __launch_bounds__(L) tc_dfscan_kernel(const mlstm_params p, const int DH) {
+  __shared__ float wsum[L / 32];
+  const int NC = num_chunks(p.S);
+  const int bh = blockIdx.x / NC, sc = blockIdx.x % NC, b = bh / p.NH, h = bh % p.NH;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int S = p.S;
   const bool rev = p.reverse != 0;
   const size_t rows_total = (size_t)p.B * p.NH * S;
@@ -631,41 +668,30 @@ __global__ void __launch_bounds__(1024) tc_dfscan_kernel(const mlstm_params p, c
   const uint8_t* ws = reinterpret_cast<const uint8_t*>(p.workspace);
   const float* rp = reinterpret_cast<const float*>(ws + blay.rpart_off);
   const float* kp = reinterpret_cast<const float*>(ws + blay.kpart_off);
+  const float* flow = reinterpret_cast<const float*>(ws + blay.flow_off) + (size_t)bh * NC;
   const int nb = DH / 32;
-  const int seg = (S + 1023) / 1024;
-  float dB[DF_MAXSEG];
-  float tot = 0.f;
-#pragma unroll 4
-  for (int e = 0; e < DF_MAXSEG; ++e) {
-    dB[e] = 0.f;
-    const int P = i * seg + e;
-    if (e < seg && P < S) {
-      const int tok = rev ? (S - 1 - P) : P;
-      const size_t g = (size_t)bh * S + tok;
-      float R = 0.f, K = 0.f;
-      for (int c = 0; c < nb; ++c) { R += rp[(size_t)c * rows_total + g]; K += kp[(size_t)c * rows_total + g]; }
-      p.di.ptr[(int64_t)b * p.di.stride_b + (int64_t)h * p.di.stride_h + (int64_t)tok * p.di.stride_s] = K;
-      dB[e] = R - K;
-      tot += dB[e];
-    }
+  const int tok0 = mem_chunk(sc, NC, rev) * L, nvalid = min(L, S - tok0);
+  const bool valid = t < nvalid;
+  const int tok = tok0 + (rev ? (nvalid - 1 - t) : t);
+  float dB = 0.f;
+  if (valid) {
+    const size_t g = (size_t)bh * S + tok;
+    float R = 0.f, K = 0.f;
+    for (int c = 0; c < nb; ++c) { R += rp[(size_t)c * rows_total + g]; K += kp[(size_t)c * rows_total + g]; }
+    p.di.ptr[(int64_t)b * p.di.stride_b + (int64_t)h * p.di.stride_h + (int64_t)tok * p.di.stride_s] = K;
+    dB = R - K;
   }
-  // exclusive suffix sum of `tot` over the threads of the block
-  float incl = warp_scan_add(tot, lane);
+  const float incl = warp_scan_add(dB, lane);
   if (lane == 31) wsum[warp] = incl;
   __syncthreads();
   float before = 0.f, all = 0.f;
 #pragma unroll
-  for (int w = 0; w < 32; ++w) { before += (w < warp) ? wsum[w] : 0.f; all += wsum[w]; }
-  float run = all - (incl + before);   // sum over all later threads
-#pragma unroll 4
-  for (int e = DF_MAXSEG - 1; e >= 0; --e) {
-    const int P = i * seg + e;
-    if (e < seg && P < S) {
-      run += dB[e];
-      const int tok = rev ? (S - 1 - P) : P;
-      const float fi = p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s];
-      p.df.ptr[(int64_t)b * p.df.stride_b + (int64_t)h * p.df.stride_h + (int64_t)tok * p.df.stride_s] = run / (1.f + __expf(fi));
-    }
+  for (int w = 0; w < L / 32; ++w) { before += (w < warp) ? wsum[w] : 0.f; all += wsum[w]; }
+  // inclusive suffix sum inside the chunk + the exact flow across the boundary to the next chunk
+  const float suffix = all - (incl + before) + dB + ((sc + 1 < NC) ? flow[sc + 1] : 0.f);
+  if (valid) {
+    const float fi = p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s];
+    p.df.ptr[(int64_t)b * p.df.stride_b + (int64_t)h * p.df.stride_h + (int64_t)tok * p.df.stride_s] = suffix / (1.f + __expf(fi));
   }
 }
 
@@ -727,7 +753,7 @@ int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
     if ((rc = launched("tc_bwd_dq"))) return rc;
   }
   if (part != 0) {
-    BwdMaps ms{mq, mdh, mq, mdcs, mq, mh, mdq};
+    BwdMaps ms{mq, mdh, mcs, mdcs, mq, mh, mdq};
     if ((rc = prep(tc_state_bwd_kernel<DH>, smSB, "tc_state_bwd"))) return rc;
     tc_state_bwd_kernel<DH><<<dim3(p.B * p.NH), dim3(NT), smSB, st>>>(ms, p, scale);
     if ((rc = launched("tc_state_bwd"))) return rc;
@@ -739,8 +765,7 @@ int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
     if ((rc = prep(tc_bwd_par_kernel<DH, MODE_B2>, smB, "tc_bwd_dk"))) return rc;
     tc_bwd_par_kernel<DH, MODE_B2><<<dim3(grid), dim3(NT), smB, st>>>(m2, p, scale, n_items);
     if ((rc = launched("tc_bwd_dk"))) return rc;
-    if (p.S > 1024 * DF_MAXSEG) { set_error("S = %d exceeds the df-scan limit %d", p.S, 1024 * DF_MAXSEG); return MLSTM_ERR_UNSUPPORTED; }
-    tc_dfscan_kernel<<<dim3(p.B * p.NH), dim3(1024), 0, st>>>(p, DH);
+    tc_dfscan_kernel<<<dim3(n_items), dim3(L), 0, st>>>(p, DH);
     if ((rc = launched("tc_dfscan"))) return rc;
   }
   return MLSTM_OK;
@@ -748,9 +773,19 @@ int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
 
 }  // namespace
 
-size_t tc_bwd_workspace(const mlstm_params& p) { return BwdLayout(p.B, p.NH, p.S, p.DHQK).total; }
+// Short sequences with enough (batch, head) pairs to fill the GPU keep the single-pass kernels
+// (mlstm_tc_bwd1p.cu): with <= 4 chunks per head the serial chain is short and the chunk-state
+// round trip through HBM does not pay.
+size_t tc_bwd1p_workspace(const mlstm_params& p);
+int tc_bwd1p(const mlstm_params& p, cudaStream_t st, int part);
+bool tc_use_single_pass_bwd(const mlstm_params& p);
+
+size_t tc_bwd_workspace(const mlstm_params& p) {
+  return tc_use_single_pass_bwd(p) ? tc_bwd1p_workspace(p) : BwdLayout(p.B, p.NH, p.S, p.DHQK).total;
+}
 
 int tc_bwd(const mlstm_params& p, cudaStream_t st, int part) {
+  if (tc_use_single_pass_bwd(p)) return tc_bwd1p(p, st, part);
   if (p.DHQK == 64) return launch_bwd<64>(p, st, part);
   return launch_bwd<128>(p, st, part);
 }

@@ -1,7 +1,35 @@
-// Shape/dtype gate of the tcgen05 family (forward: mlstm_tc_fwd.cu, backward: mlstm_tc_bwd.cu).
-#include "mlstm_common.cuh"
+// Shape/dtype gate and kernel-variant selection of the tcgen05 family.
+//   forward : single pass (mlstm_tc_fwd.cu)   | two-phase (mlstm_tc_fwd2p.cu)
+//   backward: single pass (mlstm_tc_bwd1p.cu) | chunk-parallel two-phase (mlstm_tc_bwd.cu)
+// Single-pass kernels run one CTA per (batch, head) with the state on chip: best when there are
+// enough heads to fill the GPU and the per-head chunk chain is short.  The two-phase kernels
+// spill per-chunk states to HBM and are chunk-parallel: best for long sequences / small batches.
+#include "tc_common.cuh"
 namespace mlstm {
+
 bool tc_supported(const mlstm_params& p) {
   return p.dtype == MLSTM_BF16 && p.DHQK == p.DHV && (p.DHQK == 64 || p.DHQK == 128);
 }
+
+static int sm_count() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+bool tc_use_two_phase(const mlstm_params& p) {          // forward
+  return p.B * p.NH * 2 <= sm_count() && tc::num_chunks(p.S) >= 4;
+}
+bool tc_use_single_pass_bwd(const mlstm_params& p) {    // backward
+  return tc::num_chunks(p.S) <= 4 && p.B * p.NH * 2 > sm_count();
+}
+
+// The chunk-state buffer is needed by the two-phase forward itself and by the chunk-parallel
+// backward whichever forward variant ran.
+size_t tc_state_bytes(const mlstm_params& p) {
+  if (!tc_use_two_phase(p) && tc_use_single_pass_bwd(p)) return 0;
+  return tc::StateLayout(p.B, p.NH, p.S, p.DHQK).total;
+}
+
 }  // namespace mlstm

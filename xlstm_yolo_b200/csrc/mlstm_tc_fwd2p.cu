@@ -493,20 +493,6 @@ int launch_fwd(const mlstm_params& p, cudaStream_t st) {
 
 }  // namespace
 
-// The two-phase forward pays an extra HBM round trip of the chunk states and a second read of
-// K,V, but its chunk-parallel kernel fills every SM whatever the batch: it wins when there are
-// too few (batch, head) pairs for the single-pass kernel (one CTA each) to occupy the GPU.
-bool tc_use_two_phase(const mlstm_params& p) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return p.B * p.NH * 2 <= sms && tc::num_chunks(p.S) >= 4;
-}
-
-// The chunk-state buffer is needed by the two-phase forward itself and, for training, by the
-// backward whichever forward variant ran.
-size_t tc_state_bytes(const mlstm_params& p) { return tc::StateLayout(p.B, p.NH, p.S, p.DHQK).total; }
-
 int tc_fwd_two_phase(const mlstm_params& p, cudaStream_t st) {
   if (p.DHQK == 64) return launch_fwd<64>(p, st);
   return launch_fwd<128>(p, st);
