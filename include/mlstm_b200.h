@@ -139,6 +139,11 @@ int mlstm_b200_bwd_part(const mlstm_params* p, int part, void* cuda_stream);
 /* Name of the kernel family the call would dispatch to: "tcgen05" or "simt" (or NULL). */
 const char* mlstm_b200_kernel_name(const mlstm_params* p, int is_backward);
 
+/* Variant inside the family for this shape on the current device: "single_pass" (one CTA walks all
+ * chunks of a (batch, head) pair, state on chip), "two_phase" / "chunk_parallel" (light sequential
+ * state kernel + persistent chunk-parallel kernels, chunk states in `states`), or "simt". */
+const char* mlstm_b200_kernel_variant(const mlstm_params* p, int is_backward);
+
 /* Kernels launched by this library in this process so far (for bench.py's gpu_launches). */
 uint64_t mlstm_b200_launch_count(void);
 

@@ -25,6 +25,7 @@ EXPORTS = (
     "mlstm_b200_bwd",
     "mlstm_b200_bwd_part",
     "mlstm_b200_kernel_name",
+    "mlstm_b200_kernel_variant",
     "mlstm_b200_launch_count",
     "mlstm_b200_last_error",
 )
@@ -95,6 +96,8 @@ def load() -> C.CDLL:
         lib.mlstm_b200_bwd_part.restype = C.c_int
         lib.mlstm_b200_bwd_part.argtypes = [C.POINTER(Params), C.c_int, C.c_void_p]
         lib.mlstm_b200_kernel_name.restype = C.c_char_p
+        lib.mlstm_b200_kernel_variant.restype = C.c_char_p
+        lib.mlstm_b200_kernel_variant.argtypes = [C.POINTER(Params), C.c_int]
         lib.mlstm_b200_kernel_name.argtypes = [C.POINTER(Params), C.c_int]
         lib.mlstm_b200_launch_count.restype = C.c_uint64
         lib.mlstm_b200_last_error.restype = C.c_char_p

@@ -137,6 +137,17 @@ const char* mlstm_b200_kernel_name(const mlstm_params* p, int /*is_backward*/) {
   }
 }
 
+const char* mlstm_b200_kernel_variant(const mlstm_params* p, int is_backward) {
+  if (!p) return nullptr;
+  switch (pick(*p)) {
+    case FAM_TC:
+      if (is_backward) return tc_use_single_pass_bwd(*p) ? "single_pass" : "chunk_parallel";
+      return tc_use_two_phase(*p) ? "two_phase" : "single_pass";
+    case FAM_SIMT: return "simt";
+    default: return nullptr;
+  }
+}
+
 int mlstm_b200_fwd(const mlstm_params* p, void* cuda_stream) {
   g_err[0] = 0;
   int rc = validate(p, 0);

@@ -266,6 +266,8 @@ class MLSTMPlan:
         p.workspace, p.workspace_bytes = self.ws.data_ptr(), self.ws.numel() * 4
         self.p = p
         self.family = self.lib.mlstm_b200_kernel_name(C.byref(p), 0).decode()
+        self.variant_fwd = self.lib.mlstm_b200_kernel_variant(C.byref(p), 0).decode()
+        self.variant_bwd = self.lib.mlstm_b200_kernel_variant(C.byref(p), 1).decode()
 
     def forward(self):
         rc = self.lib.mlstm_b200_fwd(C.byref(self.p), _stream())
