@@ -108,6 +108,10 @@ CASES = [
     (3, 2, 127, 128, torch.bfloat16, "rand", True, 1e-6),
     (2, 2, 1, 64, torch.bfloat16, "rand", False, 1e-6),
     (2, 2, 1, 16, torch.float32, "rand", False, 1e-6),
+    (1, 2, 200, 256, torch.bfloat16, "rand", False, 1e-6),      # secondary-reading head dim: value-sliced SIMT
+    (1, 2, 200, 256, torch.bfloat16, "refinit", True, 5e-5),
+    (1, 2, 70, 256, torch.float32, "rand", True, 1e-6),
+    (1, 2, 96, 192, torch.float32, "forget", False, 1e-6),      # three slices
 ]
 
 
@@ -127,9 +131,11 @@ def test_kernel_family_dispatch():
     assert ops.kernel_family(bf(128), bf(128)) == "tcgen05"
     assert ops.kernel_family(bf(16), bf(16)) == "simt"
     assert ops.kernel_family(bf(128).float(), bf(128).float()) == "simt"
+    assert ops.kernel_family(bf(256), bf(256)) == "simt"
 
 
-@pytest.mark.parametrize("dtype,DH", [(torch.float32, 32), (torch.bfloat16, 64), (torch.bfloat16, 128)])
+@pytest.mark.parametrize("dtype,DH", [(torch.float32, 32), (torch.bfloat16, 64), (torch.bfloat16, 128),
+                                      (torch.float32, 256)])
 @pytest.mark.parametrize("reverse", [False, True])
 def test_initial_and_last_states(dtype, DH, reverse):
     B, NH, S = 2, 2, 300
@@ -284,7 +290,7 @@ def test_empty_and_unaligned_inputs():
 
 def test_unsupported_head_dim_fails_loudly():
     from xlstm_yolo_b200 import ops
-    x = torch.zeros(1, 1, 8, 256, dtype=torch.bfloat16, device="cuda")
+    x = torch.zeros(1, 1, 8, 512, dtype=torch.bfloat16, device="cuda")
     g = torch.zeros(1, 1, 8, device="cuda")
     with pytest.raises(RuntimeError, match="UNSUPPORTED"):
         ops.mlstm(x, x, x, g, g)

@@ -88,8 +88,13 @@ def test_kernel_family_and_workspace(lib):
     assert lib.mlstm_b200_state_bytes(C.byref(p)) == 0
     p = _params(dtype=_lib.MLSTM_F32, DHQK=128, DHV=128)
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
-    p = _params(DHQK=256, DHV=256)
+    p = _params(DHQK=256, DHV=256)   # value-sliced SIMT kernels: dn per slice + R + fp32 dq/dk accumulators
+    assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
+    assert lib.mlstm_b200_workspace_bytes(C.byref(p), 1) == 4 * (rows * 5 + 2 * rows * 256)
+    p = _params(DHQK=512, DHV=512)
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) is None
+    assert lib.mlstm_b200_kernel_variant(C.byref(p), 1) is None
+    assert lib.mlstm_b200_kernel_variant(C.byref(_params()), 0) in (b"single_pass", b"two_phase")
 
 
 def test_cuda_op_refuses_cpu_tensors():

@@ -19,6 +19,19 @@ constexpr int L = 32;     // chunk tile (rows per step)
 constexpr int NT = 256;   // threads per CTA
 constexpr int LP = L + 1; // padded row of the L x L matrices
 
+// Value-dimension slicing.  The state C [DK][DV] must fit in shared memory; beyond DH = 128 the
+// launcher runs the kernels once per DV slice (<= 64 columns) on offset v/h/dh/dv pointers.  The
+// forward is independent per slice.  The backward is linear in the slices: with
+// dn_s = -coef (dh_s . h_s), every slice yields its share of dq, dk, R, di and df; the shares are
+// summed in fp32 (workspace accumulators for dq/dk, the fp32 outputs for di/df) and the last slice
+// rounds once to the output dtype.
+struct Slice {
+  int cld;          // leading dimension (full DV) of c_initial / c_last
+  int first, last;  // first / last slice of the launch sequence
+  float* dq_acc;    // fp32 [B*NH*S][DK] accumulators (nullptr when there is a single slice)
+  float* dk_acc;
+};
+
 struct Gates {  // per-chunk gate-derived vectors, filled by warp 0
   float u[L], M[L], w[L], mrow[L], kw[L], N[L], dn[L], fpre[L], aux[L];
   float decay, m_next;
@@ -82,7 +95,7 @@ __device__ __forceinline__ void gates_forward(Gates& G, const mlstm_params& p, i
 // Forward
 // ---------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(NT) simt_fwd_kernel(const mlstm_params p, const float scale) {
+__global__ void __launch_bounds__(NT) simt_fwd_kernel(const mlstm_params p, const float scale, const Slice sl) {
   extern __shared__ float sm[];
   const int DK = p.DHQK, DV = p.DHV, LQ = DK + 1, LV = DV + 1, LC = DV + 1;
   float* Cs = sm;                  // [DK][LC]
@@ -100,7 +113,7 @@ __global__ void __launch_bounds__(NT) simt_fwd_kernel(const mlstm_params p, cons
 
   for (int e = tid; e < DK * DV; e += NT) {
     int dk = e / DV, dv = e - dk * DV;
-    Cs[dk * LC + dv] = p.c_initial ? p.c_initial[((int64_t)bh * DK + dk) * DV + dv] : 0.f;
+    Cs[dk * LC + dv] = p.c_initial ? p.c_initial[((int64_t)bh * DK + dk) * sl.cld + dv] : 0.f;
   }
   for (int e = tid; e < DK; e += NT) ns[e] = p.n_initial ? p.n_initial[(int64_t)bh * DK + e] : 0.f;
   if (tid == 0) m_carry = p.m_initial ? p.m_initial[bh] : 0.f;
@@ -176,7 +189,7 @@ __global__ void __launch_bounds__(NT) simt_fwd_kernel(const mlstm_params p, cons
   if (p.c_last) {
     for (int e = tid; e < DK * DV; e += NT) {
       int dk = e / DV, dv = e - dk * DV;
-      p.c_last[((int64_t)bh * DK + dk) * DV + dv] = Cs[dk * LC + dv];
+      p.c_last[((int64_t)bh * DK + dk) * sl.cld + dv] = Cs[dk * LC + dv];
     }
     for (int e = tid; e < DK; e += NT) p.n_last[(int64_t)bh * DK + e] = ns[e];
     if (tid == 0) p.m_last[bh] = m_carry;
@@ -188,7 +201,7 @@ __global__ void __launch_bounds__(NT) simt_fwd_kernel(const mlstm_params p, cons
 // ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(NT) simt_bwd_dq_kernel(const mlstm_params p, const float scale, float* __restrict__ ws_dn,
-                                                         float* __restrict__ ws_R) {
+                                                         float* __restrict__ ws_R, const Slice sl) {
   extern __shared__ float sm[];
   const int DK = p.DHQK, DV = p.DHV, LQ = DK + 1, LV = DV + 1, LC = DV + 1;
   float* Cs = sm;
@@ -208,7 +221,7 @@ __global__ void __launch_bounds__(NT) simt_bwd_dq_kernel(const mlstm_params p, c
 
   for (int e = tid; e < DK * DV; e += NT) {
     int dk = e / DV, dv = e - dk * DV;
-    Cs[dk * LC + dv] = p.c_initial ? p.c_initial[((int64_t)bh * DK + dk) * DV + dv] : 0.f;
+    Cs[dk * LC + dv] = p.c_initial ? p.c_initial[((int64_t)bh * DK + dk) * sl.cld + dv] : 0.f;
   }
   for (int e = tid; e < DK; e += NT) ns[e] = p.n_initial ? p.n_initial[(int64_t)bh * DK + e] : 0.f;
   if (tid == 0) m_carry = p.m_initial ? p.m_initial[bh] : 0.f;
@@ -260,8 +273,17 @@ __global__ void __launch_bounds__(NT) simt_bwd_dq_kernel(const mlstm_params p, c
       float acc = 0.f;
       for (int j = 0; j <= t; ++j) acc = fmaf(dSs[t * LP + j], ks[j * LQ + dk], acc);
       float dqv = scale * (acc + G.w[t] * (Gs[t * LQ + dk] / G.N[t] + G.dn[t] * ns[dk]));
-      Gs[t * LQ + dk] = dqv;
-      if (t < nvalid) act_ptr_w<T>(p.dq, b, h, tok_of(pos0 + t, S, p.reverse))[dk] = from_f32<T>(dqv);
+      Gs[t * LQ + dk] = dqv;   // this slice's share (R below is linear in it)
+      if (t < nvalid) {
+        const int tok = tok_of(pos0 + t, S, p.reverse);
+        float out = dqv;
+        if (sl.dq_acc) {
+          float* a = sl.dq_acc + ((int64_t)bh * S + tok) * DK + dk;
+          if (!sl.first) out += *a;
+          if (!sl.last) *a = out;
+        }
+        if (sl.last) act_ptr_w<T>(p.dq, b, h, tok)[dk] = from_f32<T>(out);
+      }
     }
     __syncthreads();
 
@@ -270,7 +292,10 @@ __global__ void __launch_bounds__(NT) simt_bwd_dq_kernel(const mlstm_params p, c
       float r = 0.f;
       for (int d = lane; d < DK; d += 32) r = fmaf(qs[t * LQ + d], Gs[t * LQ + d], r);
       r = warp_sum(r);
-      if (lane == 0 && t < nvalid) ws_R[(int64_t)bh * S + tok_of(pos0 + t, S, p.reverse)] = r / scale;
+      if (lane == 0 && t < nvalid) {
+        float* R = ws_R + (int64_t)bh * S + tok_of(pos0 + t, S, p.reverse);
+        *R = (sl.first ? 0.f : *R) + r / scale;
+      }
     }
     for (int e = tid; e < L * DK; e += NT) {
       int j = e / DK, d = e - j * DK;
@@ -301,7 +326,8 @@ __global__ void __launch_bounds__(NT) simt_bwd_dq_kernel(const mlstm_params p, c
 // ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(NT) simt_bwd_dkv_kernel(const mlstm_params p, const float scale,
-                                                          const float* __restrict__ ws_dn, const float* __restrict__ ws_R) {
+                                                          const float* __restrict__ ws_dn, const float* __restrict__ ws_R,
+                                                          const Slice sl) {
   extern __shared__ float sm[];
   const int DK = p.DHQK, DV = p.DHV, LQ = DK + 1, LV = DV + 1, LC = DV + 1;
   float* dCs = sm;                 // [DK][LC]
@@ -343,7 +369,7 @@ __global__ void __launch_bounds__(NT) simt_bwd_dkv_kernel(const mlstm_params p, 
         mrow = p.m_row[(int64_t)bh * S + tok];
         nr = p.n_row[(int64_t)bh * S + tok];
         dn = ws_dn[(int64_t)bh * S + tok];
-        R = ws_R[(int64_t)bh * S + tok];
+        R = sl.first ? ws_R[(int64_t)bh * S + tok] : 0.f;   // the complete R enters df once
       }
       float bsum = warp_scan_add(logf, lane);
       float u = ii - bsum;
@@ -392,8 +418,17 @@ __global__ void __launch_bounds__(NT) simt_bwd_dkv_kernel(const mlstm_params p, 
       for (int t = j; t < L; ++t) a1 = fmaf(dSts[j * LP + t], qs[t * LQ + dk], a1);
       for (int d = 0; d < DV; ++d) a2 = fmaf(dCs[dk * LC + d], vs[j * LV + d], a2);
       float dkv = a1 + G.kw[j] * (a2 + dnv[dk]);
-      dks[j * LQ + dk] = dkv;
-      if (j < nvalid) act_ptr_w<T>(p.dk, b, h, tok_of(pos0 + j, S, p.reverse))[dk] = from_f32<T>(dkv);
+      dks[j * LQ + dk] = dkv;   // this slice's share (K_j below is linear in it)
+      if (j < nvalid) {
+        const int tok = tok_of(pos0 + j, S, p.reverse);
+        float out = dkv;
+        if (sl.dk_acc) {
+          float* a = sl.dk_acc + ((int64_t)bh * S + tok) * DK + dk;
+          if (!sl.first) out += *a;
+          if (!sl.last) *a = out;
+        }
+        if (sl.last) act_ptr_w<T>(p.dk, b, h, tok)[dk] = from_f32<T>(out);
+      }
     }
     __syncthreads();
 
@@ -430,8 +465,11 @@ __global__ void __launch_bounds__(NT) simt_bwd_dkv_kernel(const mlstm_params p, 
       if (valid) {
         int tok = tok_of(pos0 + lane, S, p.reverse);
         float fi = G.fpre[lane];
-        *gate_ptr(p.di, b, h, tok) = Kj;
-        *gate_ptr(p.df, b, h, tok) = rc / (1.f + __expf(fi));  // sigmoid(-f)
+        float* di = gate_ptr(p.di, b, h, tok);
+        float* df = gate_ptr(p.df, b, h, tok);
+        const float dfv = rc / (1.f + __expf(fi));  // sigmoid(-f)
+        *di = (sl.first ? 0.f : *di) + Kj;
+        *df = (sl.first ? 0.f : *df) + dfv;
       }
       float c0 = __shfl_sync(0xffffffffu, rc, 0);
       if (lane == 0) df_carry = c0;
@@ -469,59 +507,112 @@ int check_launch(const char* what) {
   return MLSTM_OK;
 }
 
+constexpr int SLICE_DV = 64;       // value columns per launch once the state no longer fits
+constexpr size_t SMEM_MAX = 227 * 1024;
+
+int slice_width(const mlstm_params& p) {
+  return (p.DHQK <= 128 && p.DHV <= 128) ? p.DHV : (p.DHV < SLICE_DV ? p.DHV : SLICE_DV);
+}
+int num_slices(const mlstm_params& p) {
+  const int w = slice_width(p);
+  return (p.DHV + w - 1) / w;
+}
+size_t elem_bytes(const mlstm_params& p) { return p.dtype == MLSTM_F32 ? 4 : 2; }
+
+// params of value-slice s: v, h, dh, dv advanced to its first column, DHV = its width
+mlstm_params slice_params(const mlstm_params& p, int s, Slice* sl, float* dq_acc, float* dk_acc) {
+  mlstm_params q = p;
+  const int w = slice_width(p), dv0 = s * w, ns = num_slices(p);
+  q.DHV = (dv0 + w <= p.DHV) ? w : (p.DHV - dv0);
+  const size_t off = (size_t)dv0 * elem_bytes(p);
+  auto adv = [&](mlstm_act& a) { if (a.ptr) a.ptr = reinterpret_cast<uint8_t*>(a.ptr) + off; };
+  adv(q.v); adv(q.h); adv(q.dh); adv(q.dv);
+  if (q.c_initial) q.c_initial += dv0;
+  if (q.c_last) q.c_last += dv0;
+  sl->cld = p.DHV;
+  sl->first = (s == 0);
+  sl->last = (s == ns - 1);
+  sl->dq_acc = ns > 1 ? dq_acc : nullptr;
+  sl->dk_acc = ns > 1 ? dk_acc : nullptr;
+  return q;
+}
+
 }  // namespace
 
 bool simt_supported(const mlstm_params& p) {
-  return p.DHQK >= 1 && p.DHV >= 1 && p.DHQK <= 128 && p.DHV <= 128;
+  if (p.DHQK < 1 || p.DHV < 1 || p.DHQK > 256 || p.DHV > 256) return false;
+  return bwd_dkv_smem(p.DHQK, slice_width(p)) <= SMEM_MAX;
 }
 
-size_t simt_bwd_workspace(const mlstm_params& p) { return sizeof(float) * 2 * (size_t)p.B * p.NH * p.S; }
+// dn per slice, R, and (sliced shapes) the fp32 dq / dk accumulators
+size_t simt_bwd_workspace(const mlstm_params& p) {
+  const size_t rows = (size_t)p.B * p.NH * p.S;
+  const int ns = num_slices(p);
+  return sizeof(float) * (rows * (ns + 1) + (ns > 1 ? 2 * rows * p.DHQK : 0));
+}
 
 int simt_fwd(const mlstm_params& p, cudaStream_t st) {
   const float scale = resolve_scale(p);
-  const size_t smem = fwd_smem(p.DHQK, p.DHV);
   dim3 grid(p.B * p.NH), block(NT);
   int rc;
-  if (p.dtype == MLSTM_F32) {
-    if ((rc = set_smem(simt_fwd_kernel<float>, smem))) return rc;
-    simt_fwd_kernel<float><<<grid, block, smem, st>>>(p, scale);
-  } else {
-    if ((rc = set_smem(simt_fwd_kernel<__nv_bfloat16>, smem))) return rc;
-    simt_fwd_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(p, scale);
+  for (int s = 0; s < num_slices(p); ++s) {
+    Slice sl;
+    const mlstm_params ps = slice_params(p, s, &sl, nullptr, nullptr);
+    const size_t smem = fwd_smem(ps.DHQK, ps.DHV);
+    if (p.dtype == MLSTM_F32) {
+      if ((rc = set_smem(simt_fwd_kernel<float>, smem))) return rc;
+      simt_fwd_kernel<float><<<grid, block, smem, st>>>(ps, scale, sl);
+    } else {
+      if ((rc = set_smem(simt_fwd_kernel<__nv_bfloat16>, smem))) return rc;
+      simt_fwd_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(ps, scale, sl);
+    }
+    count_launch();
+    if ((rc = check_launch("simt_fwd"))) return rc;
   }
-  count_launch();
-  return check_launch("simt_fwd");
+  return MLSTM_OK;
 }
 
 int simt_bwd(const mlstm_params& p, cudaStream_t st, int part) {
   const float scale = resolve_scale(p);
   const size_t rows = (size_t)p.B * p.NH * p.S;
-  float* ws_dn = reinterpret_cast<float*>(p.workspace);
-  float* ws_R = ws_dn + rows;
+  const int ns = num_slices(p);
+  float* ws_dn = reinterpret_cast<float*>(p.workspace);   // [ns][rows]
+  float* ws_R = ws_dn + (size_t)ns * rows;
+  float* dq_acc = ws_R + rows;
+  float* dk_acc = dq_acc + rows * p.DHQK;
   dim3 grid(p.B * p.NH), block(NT);
-  const size_t smA = bwd_dq_smem(p.DHQK, p.DHV), smB = bwd_dkv_smem(p.DHQK, p.DHV);
   int rc;
   if (part != 1) {
-    if (p.dtype == MLSTM_F32) {
-      if ((rc = set_smem(simt_bwd_dq_kernel<float>, smA))) return rc;
-      simt_bwd_dq_kernel<float><<<grid, block, smA, st>>>(p, scale, ws_dn, ws_R);
-    } else {
-      if ((rc = set_smem(simt_bwd_dq_kernel<__nv_bfloat16>, smA))) return rc;
-      simt_bwd_dq_kernel<__nv_bfloat16><<<grid, block, smA, st>>>(p, scale, ws_dn, ws_R);
+    for (int s = 0; s < ns; ++s) {
+      Slice sl;
+      const mlstm_params ps = slice_params(p, s, &sl, dq_acc, dk_acc);
+      const size_t smA = bwd_dq_smem(ps.DHQK, ps.DHV);
+      if (p.dtype == MLSTM_F32) {
+        if ((rc = set_smem(simt_bwd_dq_kernel<float>, smA))) return rc;
+        simt_bwd_dq_kernel<float><<<grid, block, smA, st>>>(ps, scale, ws_dn + (size_t)s * rows, ws_R, sl);
+      } else {
+        if ((rc = set_smem(simt_bwd_dq_kernel<__nv_bfloat16>, smA))) return rc;
+        simt_bwd_dq_kernel<__nv_bfloat16><<<grid, block, smA, st>>>(ps, scale, ws_dn + (size_t)s * rows, ws_R, sl);
+      }
+      count_launch();
+      if ((rc = check_launch("simt_bwd_dq"))) return rc;
     }
-    count_launch();
-    if ((rc = check_launch("simt_bwd_dq"))) return rc;
   }
   if (part != 0) {
-    if (p.dtype == MLSTM_F32) {
-      if ((rc = set_smem(simt_bwd_dkv_kernel<float>, smB))) return rc;
-      simt_bwd_dkv_kernel<float><<<grid, block, smB, st>>>(p, scale, ws_dn, ws_R);
-    } else {
-      if ((rc = set_smem(simt_bwd_dkv_kernel<__nv_bfloat16>, smB))) return rc;
-      simt_bwd_dkv_kernel<__nv_bfloat16><<<grid, block, smB, st>>>(p, scale, ws_dn, ws_R);
+    for (int s = 0; s < ns; ++s) {
+      Slice sl;
+      const mlstm_params ps = slice_params(p, s, &sl, dq_acc, dk_acc);
+      const size_t smB = bwd_dkv_smem(ps.DHQK, ps.DHV);
+      if (p.dtype == MLSTM_F32) {
+        if ((rc = set_smem(simt_bwd_dkv_kernel<float>, smB))) return rc;
+        simt_bwd_dkv_kernel<float><<<grid, block, smB, st>>>(ps, scale, ws_dn + (size_t)s * rows, ws_R, sl);
+      } else {
+        if ((rc = set_smem(simt_bwd_dkv_kernel<__nv_bfloat16>, smB))) return rc;
+        simt_bwd_dkv_kernel<__nv_bfloat16><<<grid, block, smB, st>>>(ps, scale, ws_dn + (size_t)s * rows, ws_R, sl);
+      }
+      count_launch();
+      if ((rc = check_launch("simt_bwd_dkv"))) return rc;
     }
-    count_launch();
-    if ((rc = check_launch("simt_bwd_dkv"))) return rc;
   }
   return MLSTM_OK;
 }
