@@ -268,10 +268,13 @@ def main():
     NBUF = 2
     dev_in = [[torch.empty_like(t, device=dev) for t in host] for _ in range(NBUF)]
     res_host = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(NBUF)]
+    # static device-side result slots: a non_blocking D2H copy from a freshly allocated tensor makes the
+    # caching allocator cudaMalloc every step (measured: 2.7 mallocs/step, 1.4-35 ms of host time)
+    res_dev = [torch.zeros(4, dtype=torch.float32, device=dev) for _ in range(NBUF)]
     h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = res_host[0].numel() * 4
-    copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
+    copy_stream = main_stream if os.environ.get("BENCH_E2E_SERIAL") else torch.cuda.Stream(device=dev)
     ready = [torch.cuda.Event() for _ in range(NBUF)]
     freed = [torch.cuda.Event() for _ in range(NBUF)]
     for ev in freed:
@@ -292,9 +295,10 @@ def main():
         leaves = [t.detach().requires_grad_(True) for t in (q, k, v, i, f)]
         h = be(*leaves)
         h.backward(dh)
-        res = torch.stack([h.float().abs().mean(), leaves[0].grad.float().abs().mean(),
-                           leaves[3].grad.abs().mean(), leaves[4].grad.abs().mean()])
-        res_host[b_].copy_(res, non_blocking=True)
+        with torch.no_grad():
+            torch.stack([h.abs().mean(dtype=torch.float32), leaves[0].grad.abs().mean(dtype=torch.float32),
+                         leaves[3].grad.abs().mean(), leaves[4].grad.abs().mean()], out=res_dev[b_])
+        res_host[b_].copy_(res_dev[b_], non_blocking=True)
         freed[b_].record(main_stream)
 
     def e2e_run(n):
@@ -320,6 +324,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_val = world * B * S / (e2e_ms * 1e-3)
+    if os.environ.get("BENCH_E2E_DEBUG"):
+        def timed(fn, n=20):
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a_.record()
+            for j in range(n):
+                fn(j)
+            th = (time.perf_counter() - t0) / n * 1e3
+            b_.record()
+            torch.cuda.synchronize()
+            return th, a_.elapsed_time(b_) / n
+        print("debug copies  host/dev ms", timed(lambda j: e2e_copy(j)), file=sys.stderr)
+        print("debug compute host/dev ms", timed(lambda j: e2e_compute(j)), file=sys.stderr)
+        print("debug both    host/dev ms", timed(lambda j: (e2e_copy(j), e2e_compute(j))), file=sys.stderr)
+        print("debug run(20) host/dev ms", timed(lambda j: e2e_run(20), 1), file=sys.stderr)
 
     # ---- roofline of the dominant kernel --------------------------------------------------
     parts = {"fwd": (fwd_ms, alg["bytes_fwd"]), "bwd_dq": (dq_ms, alg["bytes_bwd_dq"]), "bwd_dkv": (dkv_ms, alg["bytes_bwd_dkv"])}
