@@ -50,6 +50,16 @@ def algorithmic(B, NH, S, DH):
     }
 
 
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the kernels behind each timed
+# part, from the round-1 `ncu --set full` captures (profiles/r01_ncu_full_*_summary.csv).  Writes that
+# stay in the 126 MB L2 until after the kernel are not counted by ncu.
+NCU_TRAFFIC_BYTES = {
+    "cfg2_B32_NH4_S400_DH64": {"fwd": 20.14e6, "bwd_dq": 33.65e6, "bwd_dkv": 20.53e6 + 27.50e6},
+    "cfg3_B32_NH4_S1600_DH128": {"fwd": 159.13e6 + 70.44e6, "bwd_dq": 321.57e6 + 42.79e6,
+                                 "bwd_dkv": (160.54e6 + 34.42e6) + (215.18e6 + 34.46e6) + (269.97e6 + 40.74e6) + 7.39e6},
+}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -359,7 +369,9 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": f"{family}:{dom}", "launches": launches_of[dom],
         "variants": {"fwd": pl0.variant_fwd, "bwd": pl0.variant_bwd}, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-        "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+        "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_BYTES.get(args.workload, {}).get(dom),
+        "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_full_*_summary.csv)",
+        "algorithmic_bytes": dom_bytes, "peak_source": pk["source"],
         "per_kernel_ms": {"fwd": fwd_ms, "bwd_dq": dq_ms, "bwd_dkv": dkv_ms},
         "step_hbm_frac": (alg["bytes_fwd"] + alg["bytes_bwd"]) / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
         "step_tensor_frac": alg["flops_fwdbwd"] / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
