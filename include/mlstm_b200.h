@@ -113,6 +113,38 @@ typedef struct mlstm_params {
   size_t states_bytes;
 } mlstm_params;
 
+/* ---------------------------------------------------------------------------------------------
+ * Gate projection of the cell (reference: vision_lstm2.py:895-897 -- cat[q,k,v] followed by the two
+ * nn.Linear(3*dim, NH) `igate` / `fgate`).  Forward reads q, k, v in place (no concatenation) and
+ * writes both gate pre-activations; backward adds the gates' contribution to the cell's dq, dk, dv
+ * IN PLACE and produces the weight / bias gradients (deterministic two-stage reduction).
+ * Rows are tokens: q, k, v (and dq, dk, dv) are (T, D) with row stride `ld` elements, D % 8 == 0,
+ * 16-byte aligned; weights fp32 (NH, 3*D) row-major exactly as nn.Linear stores them (columns
+ * [q | k | v]); i, f, di, df fp32 (T, NH) row-major, i.e. (B,S,NH) storage that the cell kernels
+ * read as (B,NH,S) strided views. */
+typedef struct mlstm_gate_proj_params {
+  int32_t abi_version;                  /* MLSTM_B200_ABI_VERSION */
+  int32_t T;                            /* tokens (B * S) */
+  int32_t D;                            /* cell dim = NH * DH */
+  int32_t NH;
+  int32_t dtype;                        /* mlstm_dtype of q,k,v,dq,dk,dv */
+  int64_t ld;                           /* row stride of q,k,v,dq,dk,dv (elements) */
+  const void *q, *k, *v;
+  const float *w_i, *w_f;               /* (NH, 3*D) */
+  const float *b_i, *b_f;               /* (NH) or NULL */
+  float *i, *f;                         /* forward outputs (T, NH) */
+  const float *di, *df;                 /* backward inputs (T, NH) */
+  void *dq, *dk, *dv;                   /* backward in/out (T, D): dx += di W_i[:, x] + df W_f[:, x] */
+  float *dw_i, *dw_f;                   /* backward outputs (NH, 3*D), overwritten */
+  float *db_i, *db_f;                   /* backward outputs (NH), overwritten; NULL allowed */
+  void* workspace;                      /* >= mlstm_b200_gates_workspace_bytes() (backward only) */
+  size_t workspace_bytes;
+} mlstm_gate_proj_params;
+
+size_t mlstm_b200_gates_workspace_bytes(const mlstm_gate_proj_params* p);
+int mlstm_b200_gates_fwd(const mlstm_gate_proj_params* p, void* cuda_stream);
+int mlstm_b200_gates_bwd(const mlstm_gate_proj_params* p, void* cuda_stream);
+
 /* Library / ABI identification. */
 int mlstm_b200_abi_version(void);
 

@@ -33,20 +33,36 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.mlstm_b200_abi_version() == _lib.ABI_VERSION
 
 
-def test_ctypes_struct_matches_c_layout(tmp_path):
-    fields = [n for n, _ in _lib.Params._fields_]
+@pytest.mark.parametrize("cname,ctype", [("mlstm_params", _lib.Params), ("mlstm_gate_proj_params", _lib.GateProjParams)])
+def test_ctypes_struct_matches_c_layout(tmp_path, cname, ctype):
+    fields = [n for n, _ in ctype._fields_]
     src = tmp_path / "layout.c"
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/mlstm_b200.h"', "int main(void){",
-             'printf("%zu\\n", sizeof(mlstm_params));']
-    lines += [f'printf("%zu\\n", offsetof(mlstm_params, {f}));' for f in fields]
+             f'printf("%zu\\n", sizeof({cname}));']
+    lines += [f'printf("%zu\\n", offsetof({cname}, {f}));' for f in fields]
     lines += ["return 0;}"]
     src.write_text("\n".join(lines))
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    assert int(out[0]) == C.sizeof(_lib.Params)
+    assert int(out[0]) == C.sizeof(ctype)
     for f, off in zip(fields, out[1:]):
-        assert getattr(_lib.Params, f).offset == int(off), f
+        assert getattr(ctype, f).offset == int(off), f
+
+
+def test_gate_projection_validation_needs_no_gpu(lib):
+    g = _lib.GateProjParams()
+    assert lib.mlstm_b200_gates_fwd(None, None) == -1
+    g.abi_version, g.T, g.D, g.NH, g.dtype, g.ld = _lib.ABI_VERSION, 16, 60, 4, _lib.MLSTM_BF16, 60
+    assert lib.mlstm_b200_gates_fwd(C.byref(g), None) == -2 and b"multiples of 8" in lib.mlstm_b200_last_error()
+    g.D = g.ld = 64
+    assert lib.mlstm_b200_gates_fwd(C.byref(g), None) == -1          # null pointers
+    assert lib.mlstm_b200_gates_workspace_bytes(C.byref(g)) == 4 * 1 * (8 * 192 + 8)   # one token range of 16
+    g.T = 51200
+    slabs = 1
+    assert lib.mlstm_b200_gates_workspace_bytes(C.byref(g)) == 4 * (4 * 148 // slabs) * (8 * 192 + 8)
+    g.T = 0
+    assert lib.mlstm_b200_gates_fwd(C.byref(g), None) == 0           # empty input: nothing to do
 
 
 def _params(**kw):

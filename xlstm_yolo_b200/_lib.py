@@ -26,6 +26,9 @@ EXPORTS = (
     "mlstm_b200_bwd_part",
     "mlstm_b200_kernel_name",
     "mlstm_b200_kernel_variant",
+    "mlstm_b200_gates_workspace_bytes",
+    "mlstm_b200_gates_fwd",
+    "mlstm_b200_gates_bwd",
     "mlstm_b200_launch_count",
     "mlstm_b200_last_error",
 )
@@ -57,6 +60,21 @@ class Params(C.Structure):
         ("di", Gate), ("df", Gate),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("states", C.c_void_p), ("states_bytes", C.c_size_t),
+    ]
+
+
+class GateProjParams(C.Structure):
+    """ctypes mirror of ``mlstm_gate_proj_params`` (include/mlstm_b200.h)."""
+    _fields_ = [
+        ("abi_version", C.c_int32), ("T", C.c_int32), ("D", C.c_int32), ("NH", C.c_int32), ("dtype", C.c_int32),
+        ("ld", C.c_int64),
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+        ("w_i", C.c_void_p), ("w_f", C.c_void_p), ("b_i", C.c_void_p), ("b_f", C.c_void_p),
+        ("i", C.c_void_p), ("f", C.c_void_p),
+        ("di", C.c_void_p), ("df", C.c_void_p),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("dw_i", C.c_void_p), ("dw_f", C.c_void_p), ("db_i", C.c_void_p), ("db_f", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -99,6 +117,12 @@ def load() -> C.CDLL:
         lib.mlstm_b200_kernel_variant.restype = C.c_char_p
         lib.mlstm_b200_kernel_variant.argtypes = [C.POINTER(Params), C.c_int]
         lib.mlstm_b200_kernel_name.argtypes = [C.POINTER(Params), C.c_int]
+        lib.mlstm_b200_gates_workspace_bytes.restype = C.c_size_t
+        lib.mlstm_b200_gates_workspace_bytes.argtypes = [C.POINTER(GateProjParams)]
+        lib.mlstm_b200_gates_fwd.restype = C.c_int
+        lib.mlstm_b200_gates_fwd.argtypes = [C.POINTER(GateProjParams), C.c_void_p]
+        lib.mlstm_b200_gates_bwd.restype = C.c_int
+        lib.mlstm_b200_gates_bwd.argtypes = [C.POINTER(GateProjParams), C.c_void_p]
         lib.mlstm_b200_launch_count.restype = C.c_uint64
         lib.mlstm_b200_last_error.restype = C.c_char_p
         if lib.mlstm_b200_abi_version() != ABI_VERSION:

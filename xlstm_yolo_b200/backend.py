@@ -95,5 +95,15 @@ class mLSTMBackend(nn.Module):
             return out[0].to(in_dtype), out[1]
         return out.to(in_dtype)
 
+    def fused_cell(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, igate: nn.Linear, fgate: nn.Linear,
+                   num_heads: int, reverse: bool = False) -> torch.Tensor:
+        """CUDA only: gate projection (vision_lstm2.py:895-897) + cell in one autograd node.
+        q,k,v (B,S,dim) -> h (B,NH,S,DH).  Not part of the reference seam; ``MatrixLSTMCell`` uses it."""
+        cfg = self.config
+        from . import ops
+        return ops.fused_cell(q, k, v, igate.weight, igate.bias, fgate.weight, fgate.bias, num_heads, eps=cfg.eps,
+                              chunk_size=cfg.chunk_size, reverse=reverse,
+                              kernel_dtype=_TORCH_DTYPE[cfg.autocast_kernel_dtype])
+
     def extra_repr(self) -> str:
         return f"{self.config}"

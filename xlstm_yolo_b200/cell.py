@@ -8,8 +8,9 @@ Differences, all deliberate:
   * returns the *intended* ``(B, S, dim)`` (outnorm, heads merged — vision_lstm2.py:950-952,
     commented out at HEAD, which makes ViLLayer.forward fail at :498); ``raw_output=True``
     reproduces HEAD's raw ``(B, NH, S, DH)`` for forensic comparison;
-  * the gate projection reads q,k,v through weight slices instead of materialising
-    ``cat[q,k,v]`` (:895) — same arithmetic, one (B,S,3*dim) HBM round trip fewer;
+  * the gate projection reads q,k,v in place instead of materialising ``cat[q,k,v]`` (:895): on
+    CUDA a hand-written streaming kernel fused with the cell into one autograd node (its backward
+    adds the gate path into dq,dk,dv in place), on CPU through weight slices;
   * ``reverse=True`` scans from the last token, replacing the flip pair around the layer
     (:479-480,505-506);
   * on CUDA the arithmetic is the sm_100a kernel library, not Triton.
@@ -77,6 +78,7 @@ class MatrixLSTMCell(nn.Module):
         self.autocast_dtype = autocast_dtype
         self.reverse = reverse
         self.raw_output = raw_output
+        self.fused_gates = True   # CUDA: csrc/mlstm_gates.cu instead of three cuBLAS skinny GEMMs
 
         self.igate = nn.Linear(3 * dim, num_heads)
         self.fgate = nn.Linear(3 * dim, num_heads)
@@ -114,11 +116,15 @@ class MatrixLSTMCell(nn.Module):
             raise ValueError("All input tensors (q, k, v) must be on the same device.")
         backend = self.gpu_backend if self.training else self.gpu_backend_infer
         with torch.autograd.profiler.record_function("ViLLayer::mlstm_cell"):
-            i, f = self._gates(q, k, v)
-            qh = q.view(B, S, self.num_heads, -1).transpose(1, 2)
-            kh = k.view(B, S, self.num_heads, -1).transpose(1, 2)
-            vh = v.view(B, S, self.num_heads, -1).transpose(1, 2)
-            h = backend(q=qh, k=kh, v=vh, i=i, f=f, reverse=self.reverse)  # (B,NH,S,DH)
+            if q.is_cuda and getattr(self, "fused_gates", True) and H % 8 == 0:
+                # hand-written gate projection fused with the cell into one autograd node
+                h = backend.fused_cell(q, k, v, self.igate, self.fgate, self.num_heads, reverse=self.reverse)
+            else:
+                i, f = self._gates(q, k, v)
+                qh = q.view(B, S, self.num_heads, -1).transpose(1, 2)
+                kh = k.view(B, S, self.num_heads, -1).transpose(1, 2)
+                vh = v.view(B, S, self.num_heads, -1).transpose(1, 2)
+                h = backend(q=qh, k=kh, v=vh, i=i, f=f, reverse=self.reverse)  # (B,NH,S,DH)
             if self.raw_output:
                 return h
             h = self.outnorm(h)

@@ -19,6 +19,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+void clear_error() { g_err[0] = 0; }
 
 namespace {
 
@@ -76,6 +77,8 @@ int validate(const mlstm_params* p, int is_bwd) {
   return MLSTM_OK;
 }
 
+}  // namespace
+
 // Bind the device that owns the buffers to the calling thread.  PyTorch runs the backward on
 // an autograd worker thread that may not have a current CUDA context yet, and the driver-side
 // tensor-map encoder needs one.
@@ -95,6 +98,8 @@ int bind_device(const void* dev_ptr) {
   }
   return MLSTM_OK;
 }
+
+namespace {
 
 enum Family { FAM_NONE = 0, FAM_SIMT = 1, FAM_TC = 2 };
 

@@ -11,6 +11,8 @@ namespace mlstm {
 // Host-side launch bookkeeping, defined in mlstm_api.cu.
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void clear_error();
+int bind_device(const void* dev_ptr);   // make the device owning dev_ptr current on this thread
 
 // Per-family launchers (each returns an mlstm_status).
 int simt_fwd(const mlstm_params& p, cudaStream_t st);

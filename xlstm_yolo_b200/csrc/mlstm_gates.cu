@@ -1,0 +1,364 @@
+// Gate projection of the mLSTM cell, forward and backward, as two streaming kernels.
+//
+// Reference (nn/modules/vision_lstm/vision_lstm2.py:895-897):
+//     if_gate_input = torch.cat([q, k, v], dim=-1)            # (B, S, 3*dim) copy
+//     i = self.igate(if_gate_input) ; f = self.fgate(if_gate_input)   # two nn.Linear(3*dim, NH)
+// i.e. two skinny GEMMs (N = NH) over a materialised concatenation.  Here q, k, v are read once in
+// place (no cat), both gates come out of one pass, and the backward updates the cell's dq, dk, dv
+// IN PLACE (dx += di W_i + df W_f) while accumulating dW / db, so autograd never materialises three
+// extra (B,S,dim) gradients.  Pure HBM-bound row work: plain coalesced loads, fp32 FMAs, no tensor
+// cores (2*NH outputs per token is far below any MMA tile).
+//
+// Determinism: the dW / db reduction over tokens goes through per-CTA partials in the workspace and a
+// fixed-order second kernel; no atomics (cfg/default.yaml: deterministic: True).
+#include "mlstm_common.cuh"
+
+namespace mlstm {
+namespace {
+
+constexpr int OG = 8;            // gate outputs per pass (i_0..i_{NH-1}, f_0..f_{NH-1} in groups of 8)
+constexpr int FW_NT = 256;       // forward: 8 warps, each warp a tile of TT tokens
+constexpr int TT = 4;
+constexpr int BW_NT = 256;       // backward: each thread owns column pairs 2*(tid + BW_NT*j), j < BW_J
+constexpr int BW_J = 3;
+constexpr int BW_SLAB = 2 * BW_NT * BW_J;   // 1536 columns of the 3*D concatenated row per CTA column slab
+constexpr int BW_TU = 4;         // tokens in flight per thread
+
+// weight row / bias of gate output o (o < NH: input gate head o; else forget gate head o-NH)
+__device__ __forceinline__ const float* w_row(const mlstm_gate_proj_params& p, int o) {
+  return (o < p.NH ? p.w_i + (size_t)o * 3 * p.D : p.w_f + (size_t)(o - p.NH) * 3 * p.D);
+}
+__device__ __forceinline__ float bias_of(const mlstm_gate_proj_params& p, int o) {
+  const float* b = o < p.NH ? p.b_i : p.b_f;
+  return b ? b[o < p.NH ? o : o - p.NH] : 0.f;
+}
+
+template <typename T> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const void* ptr, float* x) {
+    const uint4 w = *reinterpret_cast<const uint4*>(ptr);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f2 = __bfloat1622float2(h[e]); x[2 * e] = f2.x; x[2 * e + 1] = f2.y; }
+  }
+};
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const void* ptr, float* x) {
+    const float4 a = reinterpret_cast<const float4*>(ptr)[0], b = reinterpret_cast<const float4*>(ptr)[1];
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  }
+};
+
+template <typename T> struct Pair;
+template <> struct Pair<__nv_bfloat16> {
+  static __device__ __forceinline__ float2 load(const void* base, size_t idx) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
+  }
+  static __device__ __forceinline__ void store(void* base, size_t idx, float2 v) {
+    *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = __floats2bfloat162_rn(v.x, v.y);
+  }
+};
+template <> struct Pair<float> {
+  static __device__ __forceinline__ float2 load(const void* base, size_t idx) {
+    return *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(base) + idx);
+  }
+  static __device__ __forceinline__ void store(void* base, size_t idx, float2 v) {
+    *reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + idx) = v;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Forward: i[t, h], f[t, h] = [q_t | k_t | v_t] . W[h] + b[h]
+// Weights of the current output group live in shared memory (fp32, [OG][3D]); a warp owns TT tokens,
+// its lanes stride the 3D columns in 8-element (16/32-byte) chunks, then a butterfly reduction.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(FW_NT) gates_fwd_kernel(const mlstm_gate_proj_params p) {
+  extern __shared__ float wsm[];   // [OG][3D]
+  const int D = p.D, C3 = 3 * D, NO = 2 * p.NH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warps = FW_NT / 32;
+  const void* src[3] = {p.q, p.k, p.v};
+  for (int g0 = 0; g0 < NO; g0 += OG) {
+    __syncthreads();
+    for (int e = tid; e < OG * C3; e += FW_NT) {
+      const int o = g0 + e / C3;
+      wsm[e] = o < NO ? w_row(p, o)[e % C3] : 0.f;
+    }
+    __syncthreads();
+    for (int tile = blockIdx.x * warps + warp; tile * TT < p.T; tile += gridDim.x * warps) {
+      const int t0 = tile * TT;
+      float acc[TT][OG];
+#pragma unroll
+      for (int tt = 0; tt < TT; ++tt)
+#pragma unroll
+        for (int o = 0; o < OG; ++o) acc[tt][o] = 0.f;
+      for (int c = lane * 8; c < C3; c += 256) {
+        const int s = c / D, col = c - s * D;   // D % 8 == 0: a chunk never straddles two sources
+        float x[TT][8];
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) {
+          const int t = min(t0 + tt, p.T - 1);
+          Vec8<T>::load(reinterpret_cast<const T*>(src[s]) + (size_t)t * p.ld + col, x[tt]);
+        }
+#pragma unroll
+        for (int o = 0; o < OG; ++o) {
+          const float4 wa = *reinterpret_cast<const float4*>(&wsm[o * C3 + c]);
+          const float4 wb = *reinterpret_cast<const float4*>(&wsm[o * C3 + c + 4]);
+          const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+          for (int tt = 0; tt < TT; ++tt)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[tt][o] = fmaf(x[tt][e], w[e], acc[tt][o]);
+        }
+      }
+#pragma unroll
+      for (int tt = 0; tt < TT; ++tt)
+#pragma unroll
+        for (int o = 0; o < OG; ++o) acc[tt][o] = warp_sum(acc[tt][o]);
+      if (lane < TT * OG) {
+        const int tt = lane / OG, o = g0 + lane % OG, t = t0 + tt;
+        float val = 0.f;
+#pragma unroll
+        for (int a = 0; a < TT; ++a)
+#pragma unroll
+          for (int b = 0; b < OG; ++b) val = (a == tt && b == lane % OG) ? acc[a][b] : val;
+        if (t < p.T && o < NO) {
+          float* out = o < p.NH ? p.i + (size_t)t * p.NH + o : p.f + (size_t)t * p.NH + (o - p.NH);
+          *out = val + bias_of(p, o);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward: dx[t, c] += sum_o dg[t, o] W[o, c]   (in place on dq | dk | dv)
+//           dW[o, c]  = sum_t dg[t, o] x[t, c] ,  db[o] = sum_t dg[t, o]
+// grid = (token ranges, column slabs, output groups); a thread owns BW_J column pairs with their
+// weights and dW accumulators in registers and streams over the tokens of its range.
+// Partials: ws_w[range][NO][3D], ws_b[range][NO].
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(BW_NT) gates_bwd_kernel(const mlstm_gate_proj_params p, float* __restrict__ ws_w,
+                                                          float* __restrict__ ws_b, const int g0) {
+  const int D = p.D, C3 = 3 * D, NO = 2 * p.NH;
+  const int tid = threadIdx.x;
+  const int c_base = blockIdx.y * BW_SLAB;
+  const int per = (p.T + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * per, t_end = min(p.T, t_begin + per);
+  const void* src[3] = {p.q, p.k, p.v};
+  void* dst[3] = {p.dq, p.dk, p.dv};
+
+  int col[BW_J], sidx[BW_J];
+  bool ok[BW_J];
+  float2 w[BW_J][OG], dw[BW_J][OG];
+#pragma unroll
+  for (int j = 0; j < BW_J; ++j) {
+    const int c = c_base + 2 * (tid + BW_NT * j);
+    ok[j] = c < C3;
+    const int cc = ok[j] ? c : 0;
+    sidx[j] = cc / D;
+    col[j] = cc - sidx[j] * D;
+#pragma unroll
+    for (int o = 0; o < OG; ++o) {
+      const bool oo = ok[j] && (g0 + o < NO);
+      w[j][o] = oo ? *reinterpret_cast<const float2*>(w_row(p, g0 + o) + cc) : make_float2(0.f, 0.f);
+      dw[j][o] = make_float2(0.f, 0.f);
+    }
+  }
+  float dbs[OG];
+#pragma unroll
+  for (int o = 0; o < OG; ++o) dbs[o] = 0.f;
+
+  for (int t0 = t_begin; t0 < t_end; t0 += BW_TU) {
+    float dg[BW_TU][OG];
+    float2 x[BW_TU][BW_J], d[BW_TU][BW_J];
+#pragma unroll
+    for (int u = 0; u < BW_TU; ++u) {
+      const int t = t0 + u;
+      const bool tv = t < t_end;
+#pragma unroll
+      for (int o = 0; o < OG; ++o) {
+        const int oo = g0 + o;
+        dg[u][o] = (tv && oo < NO) ? (oo < p.NH ? p.di[(size_t)t * p.NH + oo] : p.df[(size_t)t * p.NH + (oo - p.NH)]) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < BW_J; ++j) {
+        const bool v = tv && ok[j];
+        // the three sources are selected with a short branch-free chain (pointer arrays indexed by a
+        // runtime value would be spilled to local memory)
+        const void* sp = sidx[j] == 0 ? src[0] : (sidx[j] == 1 ? src[1] : src[2]);
+        const void* dp = sidx[j] == 0 ? dst[0] : (sidx[j] == 1 ? dst[1] : dst[2]);
+        const size_t idx = (size_t)(tv ? t : t_begin) * p.ld + col[j];
+        x[u][j] = v ? Pair<T>::load(sp, idx) : make_float2(0.f, 0.f);
+        d[u][j] = v ? Pair<T>::load(dp, idx) : make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BW_TU; ++u) {
+#pragma unroll
+      for (int o = 0; o < OG; ++o) dbs[o] += dg[u][o];
+#pragma unroll
+      for (int j = 0; j < BW_J; ++j) {
+#pragma unroll
+        for (int o = 0; o < OG; ++o) {
+          dw[j][o].x = fmaf(dg[u][o], x[u][j].x, dw[j][o].x);
+          dw[j][o].y = fmaf(dg[u][o], x[u][j].y, dw[j][o].y);
+          d[u][j].x = fmaf(dg[u][o], w[j][o].x, d[u][j].x);
+          d[u][j].y = fmaf(dg[u][o], w[j][o].y, d[u][j].y);
+        }
+        const int t = t0 + u;
+        if (t < t_end && ok[j]) {
+          void* dp = sidx[j] == 0 ? dst[0] : (sidx[j] == 1 ? dst[1] : dst[2]);
+          Pair<T>::store(dp, (size_t)t * p.ld + col[j], d[u][j]);
+        }
+      }
+    }
+  }
+  float* out_w = ws_w + (size_t)blockIdx.x * NO * C3;
+#pragma unroll
+  for (int j = 0; j < BW_J; ++j) {
+    if (!ok[j]) continue;
+    const int c = c_base + 2 * (tid + BW_NT * j);
+#pragma unroll
+    for (int o = 0; o < OG; ++o)
+      if (g0 + o < NO) *reinterpret_cast<float2*>(out_w + (size_t)(g0 + o) * C3 + c) = dw[j][o];
+  }
+  if (blockIdx.y == 0 && tid == 0) {
+#pragma unroll
+    for (int o = 0; o < OG; ++o)
+      if (g0 + o < NO) ws_b[(size_t)blockIdx.x * NO + g0 + o] = dbs[o];
+  }
+}
+
+// fixed-order sum of the per-range partials
+__global__ void gates_reduce_kernel(const mlstm_gate_proj_params p, const float* __restrict__ ws_w,
+                                    const float* __restrict__ ws_b, const int ranges) {
+  const int C3 = 3 * p.D, NO = 2 * p.NH;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < NO * C3) {
+    float acc = 0.f;
+    for (int r = 0; r < ranges; ++r) acc += ws_w[(size_t)r * NO * C3 + e];
+    const int o = e / C3, c = e - o * C3;
+    float* out = o < p.NH ? p.dw_i + (size_t)o * C3 + c : p.dw_f + (size_t)(o - p.NH) * C3 + c;
+    *out = acc;
+  }
+  if (e < NO) {
+    float acc = 0.f;
+    for (int r = 0; r < ranges; ++r) acc += ws_b[(size_t)r * NO + e];
+    float* out = e < p.NH ? (p.db_i ? p.db_i + e : nullptr) : (p.db_f ? p.db_f + (e - p.NH) : nullptr);
+    if (out) *out = acc;
+  }
+}
+
+int sm_count() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms > 0 ? sms : 148;
+}
+
+int bwd_ranges(const mlstm_gate_proj_params& p) {
+  const int slabs = (3 * p.D + BW_SLAB - 1) / BW_SLAB;
+  int r = (4 * 148 + slabs - 1) / slabs;          // ~4 CTAs per SM over the whole grid (fixed: keeps the
+  const int max_r = (p.T + 4 * BW_TU - 1) / (4 * BW_TU);   // workspace size independent of the device)
+  if (r > max_r) r = max_r;
+  return r < 1 ? 1 : r;
+}
+
+int validate(const mlstm_gate_proj_params* p, bool bwd) {
+  if (!p) { set_error("params is NULL"); return MLSTM_ERR_INVALID_ARG; }
+  if (p->abi_version != MLSTM_B200_ABI_VERSION) {
+    set_error("ABI version mismatch: caller %d, library %d", p->abi_version, MLSTM_B200_ABI_VERSION);
+    return MLSTM_ERR_INVALID_ARG;
+  }
+  if (p->T < 0 || p->D < 1 || p->NH < 1) { set_error("bad sizes T=%d D=%d NH=%d", p->T, p->D, p->NH); return MLSTM_ERR_INVALID_ARG; }
+  if (p->dtype != MLSTM_F32 && p->dtype != MLSTM_BF16) { set_error("unknown dtype %d", p->dtype); return MLSTM_ERR_UNSUPPORTED; }
+  if (p->D % 8 != 0 || p->ld % 8 != 0 || p->ld < p->D) {
+    set_error("gate projection needs D and the row stride to be multiples of 8 (D=%d, ld=%lld)", p->D, (long long)p->ld);
+    return MLSTM_ERR_UNSUPPORTED;
+  }
+  if ((size_t)OG * 3 * p->D * sizeof(float) > 200 * 1024) { set_error("D=%d too large for the weight tile", p->D); return MLSTM_ERR_UNSUPPORTED; }
+  if (p->T == 0) return MLSTM_OK;
+  if (!p->q || !p->k || !p->v || !p->w_i || !p->w_f) { set_error("q, k, v, w_i, w_f must be non-NULL"); return MLSTM_ERR_INVALID_ARG; }
+  const uintptr_t al = (uintptr_t)p->q | (uintptr_t)p->k | (uintptr_t)p->v | (bwd ? ((uintptr_t)p->dq | (uintptr_t)p->dk | (uintptr_t)p->dv) : 0);
+  if (al % 16) { set_error("q, k, v (dq, dk, dv) must be 16-byte aligned"); return MLSTM_ERR_INVALID_ARG; }
+  if (!bwd && (!p->i || !p->f)) { set_error("i, f outputs must be non-NULL"); return MLSTM_ERR_INVALID_ARG; }
+  if (bwd) {
+    if (!p->di || !p->df || !p->dq || !p->dk || !p->dv || !p->dw_i || !p->dw_f) {
+      set_error("backward needs di, df, dq, dk, dv, dw_i, dw_f");
+      return MLSTM_ERR_INVALID_ARG;
+    }
+    const size_t need = mlstm_b200_gates_workspace_bytes(p);
+    if (!p->workspace || p->workspace_bytes < need) {
+      set_error("workspace too small: need %zu bytes, got %zu", need, p->workspace_bytes);
+      return MLSTM_ERR_WORKSPACE;
+    }
+  }
+  return MLSTM_OK;
+}
+
+int finish(const char* what) {
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("%s launch failed: %s", what, cudaGetErrorString(e)); return MLSTM_ERR_CUDA; }
+  return MLSTM_OK;
+}
+
+}  // namespace
+}  // namespace mlstm
+
+using namespace mlstm;
+
+extern "C" {
+
+size_t mlstm_b200_gates_workspace_bytes(const mlstm_gate_proj_params* p) {
+  if (!p || p->T <= 0) return 0;
+  const size_t NO = 2 * (size_t)p->NH, C3 = 3 * (size_t)p->D;
+  return sizeof(float) * (size_t)bwd_ranges(*p) * (NO * C3 + NO);
+}
+
+int mlstm_b200_gates_fwd(const mlstm_gate_proj_params* p, void* cuda_stream) {
+  clear_error();
+  int rc = validate(p, false);
+  if (rc || p->T == 0) return rc;
+  if ((rc = bind_device(p->q))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const size_t smem = (size_t)OG * 3 * p->D * sizeof(float);
+  const int tiles = (p->T + TT - 1) / TT, warps = FW_NT / 32;
+  int grid = (tiles + warps - 1) / warps;
+  const int cap = 2 * sm_count();
+  if (grid > cap) grid = cap;
+  cudaError_t e;
+  if (p->dtype == MLSTM_BF16) {
+    e = cudaFuncSetAttribute(gates_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) gates_fwd_kernel<__nv_bfloat16><<<grid, FW_NT, smem, st>>>(*p);
+  } else {
+    e = cudaFuncSetAttribute(gates_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) gates_fwd_kernel<float><<<grid, FW_NT, smem, st>>>(*p);
+  }
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e)); return MLSTM_ERR_CUDA; }
+  return finish("gates_fwd");
+}
+
+int mlstm_b200_gates_bwd(const mlstm_gate_proj_params* p, void* cuda_stream) {
+  clear_error();
+  int rc = validate(p, true);
+  if (rc || p->T == 0) return rc;
+  if ((rc = bind_device(p->q))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const int NO = 2 * p->NH, C3 = 3 * p->D;
+  const int ranges = bwd_ranges(*p), slabs = (C3 + BW_SLAB - 1) / BW_SLAB;
+  float* ws_w = reinterpret_cast<float*>(p->workspace);
+  float* ws_b = ws_w + (size_t)ranges * NO * C3;
+  for (int g0 = 0; g0 < NO; g0 += OG) {
+    if (p->dtype == MLSTM_BF16) gates_bwd_kernel<__nv_bfloat16><<<dim3(ranges, slabs), BW_NT, 0, st>>>(*p, ws_w, ws_b, g0);
+    else gates_bwd_kernel<float><<<dim3(ranges, slabs), BW_NT, 0, st>>>(*p, ws_w, ws_b, g0);
+    if ((rc = finish("gates_bwd"))) return rc;
+  }
+  const int n = NO * C3;
+  gates_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(*p, ws_w, ws_b, ranges);
+  return finish("gates_reduce");
+}
+
+}  // extern "C"

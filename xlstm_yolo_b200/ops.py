@@ -18,7 +18,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import Act, Gate, Params
+from ._lib import Act, Gate, GateProjParams, Params
 
 _DT = {torch.float32: _lib.MLSTM_F32, torch.bfloat16: _lib.MLSTM_BF16}
 
@@ -231,6 +231,126 @@ def mlstm(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, i: torch.Tensor, f:
         h, C, n, m = out
         return h.to(in_dtype), (C, n, m)
     return out.to(in_dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+# Fused cell: gate projection + mLSTM as one autograd node (vision_lstm2.py:895-948)
+# ---------------------------------------------------------------------------------------------
+def _gate_params(q3, k3, v3, w_i, b_i, w_f, b_f, NH) -> GateProjParams:
+    B, S, D = q3.shape
+    g = GateProjParams()
+    g.abi_version = _lib.ABI_VERSION
+    g.T, g.D, g.NH = B * S, D, NH
+    g.dtype = _DT[q3.dtype]
+    g.ld = q3.stride(1)
+    g.q, g.k, g.v = q3.data_ptr(), k3.data_ptr(), v3.data_ptr()
+    g.w_i, g.w_f = w_i.data_ptr(), w_f.data_ptr()
+    g.b_i, g.b_f = _ptr(b_i), _ptr(b_f)
+    return g
+
+
+def _rows_ok(t: torch.Tensor) -> bool:
+    """(B,S,D) tensor whose B*S rows are evenly strided (what the gate kernels stream over)."""
+    B, S, D = t.shape
+    return (t.stride(2) == 1 and t.stride(0) == S * t.stride(1) and t.stride(1) % 8 == 0 and D % 8 == 0
+            and t.data_ptr() % 16 == 0)
+
+
+def gate_proj_fwd_raw(q3, k3, v3, w_i, b_i, w_f, b_f, NH):
+    """i, f pre-activations (B,S,NH) fp32 from q,k,v (B,S,D) without the cat copy."""
+    lib = _lib.load()
+    B, S, D = q3.shape
+    i = torch.empty((B, S, NH), dtype=torch.float32, device=q3.device)
+    f = torch.empty((B, S, NH), dtype=torch.float32, device=q3.device)
+    g = _gate_params(q3, k3, v3, w_i, b_i, w_f, b_f, NH)
+    g.i, g.f = i.data_ptr(), f.data_ptr()
+    with torch.cuda.device(q3.device):
+        rc = lib.mlstm_b200_gates_fwd(C.byref(g), _stream())
+    if rc:
+        _fail(rc, "gate projection forward")
+    return i, f
+
+
+def gate_proj_bwd_raw(q3, k3, v3, w_i, w_f, NH, di, df, dq3, dk3, dv3, need_bias=True):
+    """In place: dq3,dk3,dv3 += di W_i + df W_f ; returns (dw_i, db_i, dw_f, db_f)."""
+    lib = _lib.load()
+    dev = q3.device
+    g = _gate_params(q3, k3, v3, w_i, None, w_f, None, NH)
+    dw_i, dw_f = torch.empty_like(w_i), torch.empty_like(w_f)
+    db_i = torch.empty(NH, dtype=torch.float32, device=dev) if need_bias else None
+    db_f = torch.empty(NH, dtype=torch.float32, device=dev) if need_bias else None
+    g.di, g.df = di.data_ptr(), df.data_ptr()
+    g.dq, g.dk, g.dv = dq3.data_ptr(), dk3.data_ptr(), dv3.data_ptr()
+    g.dw_i, g.dw_f, g.db_i, g.db_f = dw_i.data_ptr(), dw_f.data_ptr(), _ptr(db_i), _ptr(db_f)
+    need = lib.mlstm_b200_gates_workspace_bytes(C.byref(g))
+    ws = torch.empty(max(1, (need + 3) // 4), dtype=torch.float32, device=dev)
+    g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    with torch.cuda.device(dev):
+        rc = lib.mlstm_b200_gates_bwd(C.byref(g), _stream())
+    if rc:
+        _fail(rc, "gate projection backward")
+    return dw_i, db_i, dw_f, db_f
+
+
+class _FusedCellFn(torch.autograd.Function):
+    """q,k,v (B,S,D) + gate weights -> h (B,NH,S,DH view of (B,S,NH,DH) storage).  The backward runs
+    the cell's kernels, then one streaming pass that adds the gate path into dq,dk,dv in place and
+    reduces dW, db — nothing of size (B,S,3D) is ever materialised."""
+
+    @staticmethod
+    def forward(ctx, q3, k3, v3, w_i, b_i, w_f, b_f, NH, eps, chunk_size, reverse):
+        B, S, D = q3.shape
+        i3, f3 = gate_proj_fwd_raw(q3, k3, v3, w_i, b_i, w_f, b_f, NH)
+        heads = lambda t: t.view(B, S, NH, D // NH).transpose(1, 2)
+        q, k, v = heads(q3), heads(k3), heads(v3)
+        i, f = i3.transpose(1, 2), f3.transpose(1, 2)
+        need_grad = any(t is not None and t.requires_grad for t in (q3, k3, v3, w_i, b_i, w_f, b_f))
+        h, n_row, m_row, _, states = mlstm_fwd_raw(q, k, v, i, f, eps=eps, chunk_size=chunk_size, reverse=reverse,
+                                                   save_rows=need_grad)
+        if need_grad:
+            ctx.save_for_backward(q3, k3, v3, w_i, w_f, i3, f3, h, n_row, m_row, states)
+        ctx.cfg = (NH, eps, chunk_size, reverse, b_i is not None)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        q3, k3, v3, w_i, w_f, i3, f3, h, n_row, m_row, states = ctx.saved_tensors
+        NH, eps, chunk_size, reverse, has_bias = ctx.cfg
+        B, S, D = q3.shape
+        heads = lambda t: t.view(B, S, NH, D // NH).transpose(1, 2)
+        if dh.dtype != q3.dtype:
+            dh = dh.to(q3.dtype)
+        dh = _prep_act(dh)
+        dq, dk, dv, di, df = mlstm_bwd_raw(heads(q3), heads(k3), heads(v3), i3.transpose(1, 2), f3.transpose(1, 2), h,
+                                           n_row, m_row, dh, eps=eps, chunk_size=chunk_size, reverse=reverse,
+                                           states=states)
+        # dq,dk,dv are (B,NH,S,DH) views of fresh (B,S,NH,DH) storage; di,df views of (B,S,NH) storage
+        dq3, dk3, dv3 = (t.transpose(1, 2).reshape(B, S, D) for t in (dq, dk, dv))
+        dw_i, db_i, dw_f, db_f = gate_proj_bwd_raw(q3, k3, v3, w_i, w_f, NH, di.transpose(1, 2), df.transpose(1, 2),
+                                                   dq3, dk3, dv3, need_bias=has_bias)
+        return dq3, dk3, dv3, dw_i, db_i, dw_f, db_f, None, None, None, None
+
+
+def fused_cell(q3: torch.Tensor, k3: torch.Tensor, v3: torch.Tensor, w_i: torch.Tensor, b_i: Optional[torch.Tensor],
+               w_f: torch.Tensor, b_f: Optional[torch.Tensor], num_heads: int, *, eps: float = 1e-6,
+               chunk_size: int = 64, reverse: bool = False, kernel_dtype: Optional[torch.dtype] = None):
+    """``MatrixLSTMCell`` arithmetic up to (not including) the out-norm, on CUDA tensors:
+    q,k,v (B,S,D) -> h (B,NH,S,DH).  Gate weights are used in fp32 whatever the autocast state."""
+    if not q3.is_cuda:
+        raise RuntimeError("xlstm_yolo_b200.ops.fused_cell needs CUDA tensors (no CPU fallback)")
+    in_dtype = q3.dtype
+    if kernel_dtype is None:
+        kernel_dtype = torch.float32 if in_dtype == torch.float32 else torch.bfloat16
+    if kernel_dtype not in _DT:
+        raise ValueError(f"kernel_dtype must be float32 or bfloat16, got {kernel_dtype}")
+    q3, k3, v3 = (t.to(kernel_dtype) for t in (q3, k3, v3))
+    q3, k3, v3 = (t if _rows_ok(t) else t.contiguous() for t in (q3, k3, v3))
+    if q3.stride(1) != k3.stride(1) or q3.stride(1) != v3.stride(1):
+        q3, k3, v3 = q3.contiguous(), k3.contiguous(), v3.contiguous()
+    f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()
+    h = _FusedCellFn.apply(q3, k3, v3, f32(w_i), f32(b_i), f32(w_f), f32(b_f), int(num_heads), float(eps),
+                           int(chunk_size), bool(reverse))
+    return h.to(in_dtype)
 
 
 class MLSTMPlan:
