@@ -19,10 +19,11 @@ namespace {
 constexpr int OG = 8;            // gate outputs per pass (i_0..i_{NH-1}, f_0..f_{NH-1} in groups of 8)
 constexpr int FW_NT = 256;       // forward: 8 warps, each warp a tile of TT tokens
 constexpr int TT = 4;
-constexpr int BW_NT = 256;       // backward: each thread owns column pairs 2*(tid + BW_NT*j), j < BW_J
-constexpr int BW_J = 3;
-constexpr int BW_SLAB = 2 * BW_NT * BW_J;   // 1536 columns of the 3*D concatenated row per CTA column slab
+constexpr int BW_NT = 128;       // backward: each thread owns BW_CP adjacent columns of [q | k | v]
+constexpr int BW_CP = 4;
+constexpr int BW_SLAB = BW_CP * BW_NT;      // 512 columns per CTA column slab
 constexpr int BW_TU = 4;         // tokens in flight per thread
+constexpr int BW_TILE = 64;      // tokens per staged gate-gradient tile
 
 // weight row / bias of gate output o (o < NH: input gate head o; else forget gate head o-NH)
 __device__ __forceinline__ const float* w_row(const mlstm_gate_proj_params& p, int o) {
@@ -33,37 +34,48 @@ __device__ __forceinline__ float bias_of(const mlstm_gate_proj_params& p, int o)
   return b ? b[o < p.NH ? o : o - p.NH] : 0.f;
 }
 
-template <typename T> struct Vec8;
+template <typename T> struct Vec8;   // 8 adjacent elements: raw load now, unpack to fp32 later
 template <> struct Vec8<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const void* ptr, float* x) {
-    const uint4 w = *reinterpret_cast<const uint4*>(ptr);
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* ptr) { return *reinterpret_cast<const uint4*>(ptr); }
+  static __device__ __forceinline__ void unpack(const Raw& w, float* x) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
 #pragma unroll
     for (int e = 0; e < 4; ++e) { const float2 f2 = __bfloat1622float2(h[e]); x[2 * e] = f2.x; x[2 * e + 1] = f2.y; }
   }
 };
 template <> struct Vec8<float> {
-  static __device__ __forceinline__ void load(const void* ptr, float* x) {
-    const float4 a = reinterpret_cast<const float4*>(ptr)[0], b = reinterpret_cast<const float4*>(ptr)[1];
-    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  struct Raw { float4 a, b; };
+  static __device__ __forceinline__ Raw load_raw(const float* ptr) {
+    return Raw{reinterpret_cast<const float4*>(ptr)[0], reinterpret_cast<const float4*>(ptr)[1]};
+  }
+  static __device__ __forceinline__ void unpack(const Raw& r, float* x) {
+    x[0] = r.a.x; x[1] = r.a.y; x[2] = r.a.z; x[3] = r.a.w; x[4] = r.b.x; x[5] = r.b.y; x[6] = r.b.z; x[7] = r.b.w;
   }
 };
 
-template <typename T> struct Pair;
-template <> struct Pair<__nv_bfloat16> {
-  static __device__ __forceinline__ float2 load(const void* base, size_t idx) {
-    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
+template <typename T> struct Cols;   // BW_CP = 4 adjacent columns
+template <> struct Cols<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* ptr, float* x, bool valid) {
+    uint2 w = make_uint2(0u, 0u);
+    if (valid) w = *reinterpret_cast<const uint2*>(ptr);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
   }
-  static __device__ __forceinline__ void store(void* base, size_t idx, float2 v) {
-    *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = __floats2bfloat162_rn(v.x, v.y);
+  static __device__ __forceinline__ void store(__nv_bfloat16* ptr, const float* x) {
+    __nv_bfloat162 h[2] = {__floats2bfloat162_rn(x[0], x[1]), __floats2bfloat162_rn(x[2], x[3])};
+    *reinterpret_cast<uint2*>(ptr) = *reinterpret_cast<const uint2*>(h);
   }
 };
-template <> struct Pair<float> {
-  static __device__ __forceinline__ float2 load(const void* base, size_t idx) {
-    return *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(base) + idx);
+template <> struct Cols<float> {
+  static __device__ __forceinline__ void load(const float* ptr, float* x, bool valid) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) a = *reinterpret_cast<const float4*>(ptr);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
   }
-  static __device__ __forceinline__ void store(void* base, size_t idx, float2 v) {
-    *reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + idx) = v;
+  static __device__ __forceinline__ void store(float* ptr, const float* x) {
+    *reinterpret_cast<float4*>(ptr) = make_float4(x[0], x[1], x[2], x[3]);
   }
 };
 
@@ -73,12 +85,11 @@ template <> struct Pair<float> {
 // its lanes stride the 3D columns in 8-element (16/32-byte) chunks, then a butterfly reduction.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(FW_NT) gates_fwd_kernel(const mlstm_gate_proj_params p) {
+__global__ void __launch_bounds__(FW_NT, 2) gates_fwd_kernel(const mlstm_gate_proj_params p) {
   extern __shared__ float wsm[];   // [OG][3D]
   const int D = p.D, C3 = 3 * D, NO = 2 * p.NH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warps = FW_NT / 32;
-  const void* src[3] = {p.q, p.k, p.v};
   for (int g0 = 0; g0 < NO; g0 += OG) {
     __syncthreads();
     for (int e = tid; e < OG * C3; e += FW_NT) {
@@ -93,14 +104,24 @@ __global__ void __launch_bounds__(FW_NT) gates_fwd_kernel(const mlstm_gate_proj_
       for (int tt = 0; tt < TT; ++tt)
 #pragma unroll
         for (int o = 0; o < OG; ++o) acc[tt][o] = 0.f;
-      for (int c = lane * 8; c < C3; c += 256) {
-        const int s = c / D, col = c - s * D;   // D % 8 == 0: a chunk never straddles two sources
+      // chunks of 8 columns at c = lane*8 + 256*ci over the concatenated [q | k | v] row; the raw loads
+      // of chunk ci+1 are issued before the FMAs of chunk ci (D % 8 == 0: a chunk never straddles sources)
+      const int nchunk = (C3 - lane * 8 + 255) / 256;
+      typename Vec8<T>::Raw raw[TT], nxt[TT];
+      auto fetch = [&](int ci, typename Vec8<T>::Raw* dst) {
+        const int c = lane * 8 + 256 * ci;
+        const int s = c / D, col = c - s * D;
+        const T* base = reinterpret_cast<const T*>(s == 0 ? p.q : (s == 1 ? p.k : p.v)) + col;
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) dst[tt] = Vec8<T>::load_raw(base + (size_t)min(t0 + tt, p.T - 1) * p.ld);
+      };
+      if (nchunk > 0) fetch(0, raw);
+      for (int ci = 0; ci < nchunk; ++ci) {
+        if (ci + 1 < nchunk) fetch(ci + 1, nxt);
+        const int c = lane * 8 + 256 * ci;
         float x[TT][8];
 #pragma unroll
-        for (int tt = 0; tt < TT; ++tt) {
-          const int t = min(t0 + tt, p.T - 1);
-          Vec8<T>::load(reinterpret_cast<const T*>(src[s]) + (size_t)t * p.ld + col, x[tt]);
-        }
+        for (int tt = 0; tt < TT; ++tt) Vec8<T>::unpack(raw[tt], x[tt]);
 #pragma unroll
         for (int o = 0; o < OG; ++o) {
           const float4 wa = *reinterpret_cast<const float4*>(&wsm[o * C3 + c]);
@@ -111,6 +132,8 @@ __global__ void __launch_bounds__(FW_NT) gates_fwd_kernel(const mlstm_gate_proj_
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[tt][o] = fmaf(x[tt][e], w[e], acc[tt][o]);
         }
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) raw[tt] = nxt[tt];
       }
 #pragma unroll
       for (int tt = 0; tt < TT; ++tt)
@@ -135,95 +158,81 @@ __global__ void __launch_bounds__(FW_NT) gates_fwd_kernel(const mlstm_gate_proj_
 // ---------------------------------------------------------------------------------------------
 // Backward: dx[t, c] += sum_o dg[t, o] W[o, c]   (in place on dq | dk | dv)
 //           dW[o, c]  = sum_t dg[t, o] x[t, c] ,  db[o] = sum_t dg[t, o]
-// grid = (token ranges, column slabs, output groups); a thread owns BW_J column pairs with their
-// weights and dW accumulators in registers and streams over the tokens of its range.
+// grid = (token ranges, column slabs), one launch per output group; a thread owns BW_CP adjacent
+// columns with their weights and dW accumulators in registers and streams over the tokens of its
+// range (gate gradients staged through shared memory a tile at a time).
 // Partials: ws_w[range][NO][3D], ws_b[range][NO].
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(BW_NT) gates_bwd_kernel(const mlstm_gate_proj_params p, float* __restrict__ ws_w,
                                                           float* __restrict__ ws_b, const int g0) {
+  __shared__ __align__(16) float dgs[BW_TILE][OG];   // gate gradients of the current token tile
   const int D = p.D, C3 = 3 * D, NO = 2 * p.NH;
   const int tid = threadIdx.x;
-  const int c_base = blockIdx.y * BW_SLAB;
   const int per = (p.T + gridDim.x - 1) / gridDim.x;
   const int t_begin = blockIdx.x * per, t_end = min(p.T, t_begin + per);
-  const void* src[3] = {p.q, p.k, p.v};
-  void* dst[3] = {p.dq, p.dk, p.dv};
+  // this thread's BW_CP adjacent columns of the concatenated [q | k | v] row
+  const int c = blockIdx.y * BW_SLAB + BW_CP * tid;
+  const bool ok = c < C3;
+  const int cc = ok ? c : 0;
+  const int sidx = cc / D, col = cc - sidx * D;   // D % 8 == 0 and BW_CP | 8: never straddles two sources
+  const T* xs = reinterpret_cast<const T*>(sidx == 0 ? p.q : (sidx == 1 ? p.k : p.v)) + col;
+  T* ds = reinterpret_cast<T*>(sidx == 0 ? p.dq : (sidx == 1 ? p.dk : p.dv)) + col;
 
-  int col[BW_J], sidx[BW_J];
-  bool ok[BW_J];
-  float2 w[BW_J][OG], dw[BW_J][OG];
+  float w[OG][BW_CP], dw[OG][BW_CP], dbs[OG];
 #pragma unroll
-  for (int j = 0; j < BW_J; ++j) {
-    const int c = c_base + 2 * (tid + BW_NT * j);
-    ok[j] = c < C3;
-    const int cc = ok[j] ? c : 0;
-    sidx[j] = cc / D;
-    col[j] = cc - sidx[j] * D;
+  for (int o = 0; o < OG; ++o) {
+    const bool oo = ok && (g0 + o < NO);
+    dbs[o] = 0.f;
 #pragma unroll
-    for (int o = 0; o < OG; ++o) {
-      const bool oo = ok[j] && (g0 + o < NO);
-      w[j][o] = oo ? *reinterpret_cast<const float2*>(w_row(p, g0 + o) + cc) : make_float2(0.f, 0.f);
-      dw[j][o] = make_float2(0.f, 0.f);
+    for (int e = 0; e < BW_CP; ++e) {
+      w[o][e] = oo ? w_row(p, g0 + o)[cc + e] : 0.f;
+      dw[o][e] = 0.f;
     }
   }
-  float dbs[OG];
-#pragma unroll
-  for (int o = 0; o < OG; ++o) dbs[o] = 0.f;
 
-  for (int t0 = t_begin; t0 < t_end; t0 += BW_TU) {
-    float dg[BW_TU][OG];
-    float2 x[BW_TU][BW_J], d[BW_TU][BW_J];
-#pragma unroll
-    for (int u = 0; u < BW_TU; ++u) {
-      const int t = t0 + u;
-      const bool tv = t < t_end;
-#pragma unroll
-      for (int o = 0; o < OG; ++o) {
-        const int oo = g0 + o;
-        dg[u][o] = (tv && oo < NO) ? (oo < p.NH ? p.di[(size_t)t * p.NH + oo] : p.df[(size_t)t * p.NH + (oo - p.NH)]) : 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < BW_J; ++j) {
-        const bool v = tv && ok[j];
-        // the three sources are selected with a short branch-free chain (pointer arrays indexed by a
-        // runtime value would be spilled to local memory)
-        const void* sp = sidx[j] == 0 ? src[0] : (sidx[j] == 1 ? src[1] : src[2]);
-        const void* dp = sidx[j] == 0 ? dst[0] : (sidx[j] == 1 ? dst[1] : dst[2]);
-        const size_t idx = (size_t)(tv ? t : t_begin) * p.ld + col[j];
-        x[u][j] = v ? Pair<T>::load(sp, idx) : make_float2(0.f, 0.f);
-        d[u][j] = v ? Pair<T>::load(dp, idx) : make_float2(0.f, 0.f);
-      }
+  for (int tile = t_begin; tile < t_end; tile += BW_TILE) {
+    __syncthreads();
+    for (int e = tid; e < BW_TILE * OG; e += BW_NT) {
+      const int t = tile + e / OG, oo = g0 + e % OG;
+      dgs[e / OG][e % OG] = (t < t_end && oo < NO) ? (oo < p.NH ? p.di[(size_t)t * p.NH + oo] : p.df[(size_t)t * p.NH + (oo - p.NH)]) : 0.f;
     }
+    __syncthreads();
+    const int nt = min(BW_TILE, t_end - tile);
+    for (int u0 = 0; u0 < nt; u0 += BW_TU) {
+      float x[BW_TU][BW_CP], d[BW_TU][BW_CP];
 #pragma unroll
-    for (int u = 0; u < BW_TU; ++u) {
+      for (int u = 0; u < BW_TU; ++u) {
+        const bool v = ok && (u0 + u < nt);
+        const size_t row = (size_t)(tile + (v ? u0 + u : 0)) * p.ld;
+        Cols<T>::load(xs + row, x[u], v);
+        Cols<T>::load(ds + row, d[u], v);
+      }
 #pragma unroll
-      for (int o = 0; o < OG; ++o) dbs[o] += dg[u][o];
-#pragma unroll
-      for (int j = 0; j < BW_J; ++j) {
+      for (int u = 0; u < BW_TU; ++u) {
+        const float4 ga = *reinterpret_cast<const float4*>(&dgs[u0 + u][0]);
+        const float4 gb = *reinterpret_cast<const float4*>(&dgs[u0 + u][4]);
+        const float dg[OG] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
 #pragma unroll
         for (int o = 0; o < OG; ++o) {
-          dw[j][o].x = fmaf(dg[u][o], x[u][j].x, dw[j][o].x);
-          dw[j][o].y = fmaf(dg[u][o], x[u][j].y, dw[j][o].y);
-          d[u][j].x = fmaf(dg[u][o], w[j][o].x, d[u][j].x);
-          d[u][j].y = fmaf(dg[u][o], w[j][o].y, d[u][j].y);
+          dbs[o] += dg[o];
+#pragma unroll
+          for (int e = 0; e < BW_CP; ++e) {
+            dw[o][e] = fmaf(dg[o], x[u][e], dw[o][e]);
+            d[u][e] = fmaf(dg[o], w[o][e], d[u][e]);
+          }
         }
-        const int t = t0 + u;
-        if (t < t_end && ok[j]) {
-          void* dp = sidx[j] == 0 ? dst[0] : (sidx[j] == 1 ? dst[1] : dst[2]);
-          Pair<T>::store(dp, (size_t)t * p.ld + col[j], d[u][j]);
-        }
+        if (ok && (u0 + u < nt)) Cols<T>::store(ds + (size_t)(tile + u0 + u) * p.ld, d[u]);
       }
     }
   }
-  float* out_w = ws_w + (size_t)blockIdx.x * NO * C3;
-#pragma unroll
-  for (int j = 0; j < BW_J; ++j) {
-    if (!ok[j]) continue;
-    const int c = c_base + 2 * (tid + BW_NT * j);
+  if (ok) {
+    float* out_w = ws_w + (size_t)blockIdx.x * NO * C3 + c;
 #pragma unroll
     for (int o = 0; o < OG; ++o)
-      if (g0 + o < NO) *reinterpret_cast<float2*>(out_w + (size_t)(g0 + o) * C3 + c) = dw[j][o];
+      if (g0 + o < NO)
+#pragma unroll
+        for (int e = 0; e < BW_CP; ++e) out_w[(size_t)(g0 + o) * C3 + e] = dw[o][e];
   }
   if (blockIdx.y == 0 && tid == 0) {
 #pragma unroll
