@@ -8,7 +8,7 @@ _lib.LIB_PATH = _lib.LIB_PATH.replace("libmlstm_b200.so", "libmlstm_b200_tl.so")
 from xlstm_yolo_b200 import ops
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from test_gpu_parity import make
-B, NH, S, DH = 32, 4, 1600, 128
+B, NH, S, DH = (int(x) for x in (sys.argv[1:5] if len(sys.argv) >= 5 else (32, 4, 1600, 128)))
 q, k, v, i, f, dh = (x.cuda() for x in make(B, NH, S, DH, torch.bfloat16, "rand"))
 pl = ops.MLSTMPlan(q, k, v, i, f, dh)
 for _ in range(2):

@@ -17,6 +17,8 @@
 // CPU emulation in tests/emu_kernel_dataflow.py.)  The parallel kernels share one skeleton:
 // MMA1 (128x128 tile product) -> SIMT gating into a bf16 tile -> MMA2, with 16 compute warps,
 // one control warp issuing all TMA / tcgen05.mma, one gate warp preparing the next item.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace mlstm {
@@ -75,6 +77,15 @@ __device__ __forceinline__ void tile_row32(const uint8_t* tile, int row, int cb,
 //   tiles:  A : t0 = dH, t1 = V, t2 = K, st = Cs     thread row = query t
 //           B1: t0 = K,  t1 = Q, t2 = dH, st = dCs   thread row = key j
 //           B2: t0 = V,  t1 = dH, t2 = Q, st = dCs   thread row = key j
+//
+// TMEM (512 columns): tS[2] (128 each)  MMA1 output S = t0 t1^T, double-buffered: the MMA1 of the next
+//                                       item is issued right behind the MMA2 of the current one and runs
+//                                       under its epilogue (A: MMA2 writes dQ over the consumed S)
+//                     tO (128)          A: G = dH Cs^T          B: intra accumulator  X t2
+//                     tX (128)          A: gated tile dS as packed bf16 (64 columns) = A operand of MMA2,
+//                                          read by the tensor core straight from TMEM
+//                                       B: inter accumulator  t0 dCs(^T)  (row scale kw applied in the
+//                                          epilogue, so K / V are never modified in shared memory)
 // =============================================================================================
 template <int DH>
 struct SmemB {
@@ -84,7 +95,7 @@ struct SmemB {
   alignas(1024) uint8_t t1[KT * TILE];
   alignas(1024) uint8_t t2[KT * TILE];
   alignas(1024) uint8_t st[KT * TILE_C];
-  alignas(1024) uint8_t x[2 * TILE];               // h tile (A) -> gated bf16 tile (K-major) -> output staging
+  alignas(1024) uint8_t x[2 * TILE];               // A: h tile | B: gated bf16 tile (K-major) -> output staging
   alignas(1024) uint8_t t3[KT * TILE];             // q (A) / k (B2): rows for R = q.dq / K = k.dk
   GateBuf g[3];                                    // ring: the gate warp runs two items ahead
   alignas(16) float vecf[3][DH];                   // ns (A) / dns (B2) of the item
@@ -93,9 +104,11 @@ struct SmemB {
   uint32_t tmem_base;
 };
 
+// cta / ncta: this CTA's index and the number of CTAs sharing the item list (B1 and B2 run side by side
+// in one launch, each on its own slice of the grid — see tc_bwd_b12_kernel)
 template <int DH, int MODE>
-__global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant__ BwdMaps maps, const mlstm_params p,
-                                                           const float scale, const int n_items) {
+__device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params& p, const float scale, const int n_items,
+                                         const int order, const int cta, const int ncta) {
   constexpr int KT = DH / 64;
   constexpr int TILE_C = SmemB<DH>::TILE_C;
   constexpr int NB = DH / 32;
@@ -127,17 +140,16 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
     mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_i, 1); mbar_init(&sm.bar_m2, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(&sm.tmem_base, 256);
+  if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tm = sm.tmem_base, tS = tm, tO = tm + 128;   // tO: G (A) or the dv / dk accumulator (B)
+  const uint32_t tm = sm.tmem_base, tO = tm + 256, tX = tm + 384;
   const uint32_t lane_sel = (uint32_t)(rg * 32) << 16;
 
   const uint64_t d0k = make_sdesc(smem_u32(sm.t0), 16, 1024), d1k = make_sdesc(smem_u32(sm.t1), 16, 1024);
   const uint64_t d2mn = make_sdesc(smem_u32(sm.t2), TILE, 1024), dXk = make_sdesc(smem_u32(sm.x), 16, 1024);
   const uint64_t dStk = make_sdesc(smem_u32(sm.st), 16, 1024), dStmn = make_sdesc(smem_u32(sm.st), TILE_C, 1024);
-
   auto coords = [&](int item, int& b, int& h, int& tok0) {
     const int bh = item / NC, sc = item % NC;
     b = bh / p.NH; h = bh % p.NH; tok0 = mem_chunk(sc, NC, rev) * L;
@@ -151,31 +163,47 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
     mbar_arrive_expect_tx(&sm.bar_st, KT * TILE_C);
     for (int kt = 0; kt < KT; ++kt) tma_load_2d(sm.st + kt * TILE_C, &maps.st, &sm.bar_st, kt * 64, item * DH);
   };
-  auto issue_mma1 = [&]() {   // tS = t0 t1^T  (+ A: tO = G = dH Cs^T, Cs read as a K-major operand)
+  auto issue_mma1 = [&](uint32_t tS) {   // tS = t0 t1^T
     constexpr uint32_t id1 = make_idesc_bf16(128, 128, 0, 0);
 #pragma unroll
     for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tS, d0k + kstep(ks), d1k + kstep(ks), id1, ks > 0);
-    if (IS_A) {
+    umma_commit(&sm.bar_m1);
+  };
+  auto issue_state_mma = [&]() {   // the product with the chunk state; its result is needed in the epilogue only
+    if (IS_A) {                    // G = dH Cs^T : Cs read as a K-major operand
       constexpr uint32_t idG = make_idesc_bf16(128, DH, 0, 0);
 #pragma unroll
       for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tO, d0k + kstep(ks), dStk + kstep(ks, TILE_C), idG, ks > 0);
+    } else if (MODE == MODE_B1) {  // K dCs : dCs as MN-major B operand [dk][dv]
+      constexpr uint32_t idI = make_idesc_bf16(128, DH, 0, 1);
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tX, d0k + kstep(ks), dStmn + mnstep(ks), idI, ks > 0);
+    } else {                       // V dCs^T : dCs as K-major B operand (rows dk)
+      constexpr uint32_t idI = make_idesc_bf16(128, DH, 0, 0);
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tX, d0k + kstep(ks), dStk + kstep(ks, TILE_C), idI, ks > 0);
     }
-    umma_commit(&sm.bar_m1);
+    umma_commit(&sm.bar_i);
   };
   auto prep_item = [&](int item, int slot) {   // gate warp
     int b, h, tok0; coords(item, b, h, tok0);
     const int bh = item / NC, sc = item % NC;
     GateBuf& G = sm.g[slot];
     gates_warp_bwd(G, p, b, h, bh, mem_chunk(sc, NC, rev), lane, MODE == MODE_B2 ? ws_dn : nullptr);
-    if (MODE == MODE_B2) {   // row scale of the V tile: kw / s  (s is applied in the epilogue)
-      for (int r = lane; r < L; r += 32) G.w[r] = G.kw[r] / scale;
-    }
     for (int d = lane; d < DH; d += 32)
       sm.vecf[slot][d] = IS_A ? ns_all[(size_t)item * DH + d] : (MODE == MODE_B2 ? dns_all[(size_t)item * DH + d] : 0.f);
     __syncwarp();
   };
 
-  const int item0 = blockIdx.x;   // the grid is never larger than n_items
+  // Work order.  Items are (batch*head, chunk) pairs with linear id bh*NC + sc.  order 0 walks them
+  // head-major; 1 / 2 walk them chunk-major, ascending / descending chunk index.
+  const int n_bh = p.B * p.NH;
+  auto lin_of = [&](int i) {
+    if (order == 0 || i >= n_items) return i;
+    const int c = i / n_bh, bh_ = i - c * n_bh;
+    return bh_ * NC + (order == 1 ? c : NC - 1 - c);
+  };
+  const int item0 = lin_of(cta);   // ncta is never larger than n_items
   if (issuer) {
     load_act(sm.t0, &maps.t0, &sm.bar_t0, item0); load_act(sm.t1, &maps.t1, &sm.bar_t1, item0);
     load_st(item0); load_act(sm.t2, &maps.t2, &sm.bar_t2, item0);
@@ -184,27 +212,31 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
   }
   if (gatew) {
     prep_item(item0, 0);
-    if (item0 + (int)gridDim.x < n_items) prep_item(item0 + gridDim.x, 1);
+    if (cta + ncta < n_items) prep_item(lin_of(cta + ncta), 1);
   }
   __syncthreads();
   if (issuer) {
     mbar_wait(&sm.bar_t0, 0); mbar_wait(&sm.bar_t1, 0);
-    if (IS_A) mbar_wait(&sm.bar_st, 0);
     tc_fence_after();
-    issue_mma1();
+    issue_mma1(tm);
+    mbar_wait(&sm.bar_st, 0);
+    tc_fence_after();
+    issue_state_mma();
   }
 
 #ifdef MLSTM_TIMELINE
   long long* tlb = reinterpret_cast<long long*>(ws_kpart);
 #endif
   int n = 0;
-  for (int item = item0; item < n_items; item += gridDim.x, ++n) {
+  for (int it = cta; it < n_items; it += ncta, ++n) {
+    const int item = lin_of(it);
     TLB(0);
     const uint32_t ph = n & 1;
-    const int next = item + gridDim.x;
-    const bool has_next = next < n_items;
+    const uint32_t tS = tm + ph * 128;
+    const bool has_next = it + ncta < n_items;
+    const int next = lin_of(it + ncta);
     if (gatew) {
-      if (next + (int)gridDim.x < n_items) prep_item(next + gridDim.x, (n + 2) % 3);
+      if (it + 2 * ncta < n_items) prep_item(lin_of(it + 2 * ncta), (n + 2) % 3);
       __syncthreads();
       continue;
     }
@@ -216,10 +248,11 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
     const bool row_ok = compute && tok < S;
     const size_t grow = (size_t)bh * S + tok;          // index into the per-row workspace arrays
 
-    // ---- A: dn_t = dnf_t (dh_t . h_t): block partials from the h tile (parked in x) and the dH tile
+    // ---- A: dn_t = dnf_t (dh_t . h_t): block partials from the h tile (x) and the dH tile --------
     float dn_row = 0.f;
     if (IS_A) {
       mbar_wait(&sm.bar_h, ph);
+      mbar_wait(&sm.bar_t0, ph);
       float part = 0.f;
       if (cq < NB) {
 #pragma unroll
@@ -248,37 +281,19 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
     mbar_wait(&sm.bar_m1, ph);
     tc_fence_after();
     TLB(2);
-    if (issuer && has_next) {   // tiles MMA1 (and A's G) read are dead
-      load_act(sm.t1, &maps.t1, &sm.bar_t1, next);
-      if (IS_A) { load_act(sm.t0, &maps.t0, &sm.bar_t0, next); load_st(next); }
-    }
-
-    // ---- B: scale the rows of t0 in place (Kbar = kw K | Vbar = kw/s V), then the inter-chunk MMA
-    if (!IS_A) {
-      if (compute) scale_rows<DH>(sm.t0, MODE == MODE_B1 ? G.kw : G.w, tid);
-      fence_proxy_async_smem();
-      if (issuer) tma_store_wait_read<0>();   // previous item's staged output (in x) has been read
-      tc_fence_before();
-      named_sync(2, GT0);
-      if (issuer) {
-        mbar_wait(&sm.bar_st, ph);
-        tc_fence_after();
-        if (MODE == MODE_B1) {   // dV = Kbar dCs : dCs as MN-major B operand [dk][dv]
-          constexpr uint32_t idI = make_idesc_bf16(128, DH, 0, 1);
-#pragma unroll
-          for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tO, d0k + kstep(ks), dStmn + mnstep(ks), idI, ks > 0);
-        } else {                 // dK = Vbar dCs^T : dCs as K-major B operand (rows dk)
-          constexpr uint32_t idI = make_idesc_bf16(128, DH, 0, 0);
-#pragma unroll
-          for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tO, d0k + kstep(ks), dStk + kstep(ks, TILE_C), idI, ks > 0);
-        }
-        umma_commit(&sm.bar_i);
+    if (issuer) {
+      // MMA1 and the state product of this item are complete: t0, t1, st can take the next item's tiles
+      mbar_wait(&sm.bar_i, ph);
+      if (has_next) {
+        load_act(sm.t1, &maps.t1, &sm.bar_t1, next);
+        load_act(sm.t0, &maps.t0, &sm.bar_t0, next);
+        load_st(next);
       }
+      if (!IS_A) tma_store_wait_read<0>();   // the previous item's staged output (in x) has left
     }
-
-    // x is rewritten next: in A every warp must be done with the h tile parked there (B: the issuer
-    // waited for the previous output store before the barrier above)
-    if (IS_A) named_sync(2, GT0);
+    // B rewrites x next (gated tile): everybody must know the store above has read it.  In A the pass
+    // over the h tile (x) and dH (t0) ended at named barrier 3, before any thread could get here.
+    if (!IS_A) named_sync(2, GT0);
     TLB(3);
     // ---- gated bf16 tile: one 32x32 block per warp ----------------------------------------------
     if (compute) {
@@ -323,53 +338,60 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
 #pragma unroll
         for (int x = 0; x < 16; ++x) packed[x] = 0u;
       }
+      if (IS_A) {   // stays on the tensor-core side: packed bf16x2 into TMEM, the A operand of MMA2
+        tmem_st16(tX + lane_sel + cq * 16, packed);
+        tmem_st_wait();
+      } else {
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        const int col = cq * 32 + x * 8;
-        *reinterpret_cast<uint4*>(sm.x + (col >> 6) * TILE + swz128(row, col & 63)) =
-            make_uint4(packed[4 * x], packed[4 * x + 1], packed[4 * x + 2], packed[4 * x + 3]);
+        for (int x = 0; x < 4; ++x) {
+          const int col = cq * 32 + x * 8;
+          *reinterpret_cast<uint4*>(sm.x + (col >> 6) * TILE + swz128(row, col & 63)) =
+              make_uint4(packed[4 * x], packed[4 * x + 1], packed[4 * x + 2], packed[4 * x + 3]);
+        }
       }
     }
     TLB(4);
-    fence_proxy_async_smem();
+    if (!IS_A) fence_proxy_async_smem();
     tc_fence_before();
     named_sync(2, GT0);
     TLB(5);
 
-    // ---- MMA2: A: dQ = dS K (into tS) | B: tO += X t2 -------------------------------------------
+    // ---- MMA2, then the next item's MMA1 right behind it ------------------------------------------
     if (issuer) {
       mbar_wait(&sm.bar_t2, ph);
       tc_fence_after();
       constexpr uint32_t id2 = make_idesc_bf16(128, DH, 0, 1);
+      if (IS_A) {   // dQ = dS K over the consumed S; dS read from TMEM
 #pragma unroll
-      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(IS_A ? tS : tO, dXk + kstep(ks), d2mn + mnstep(ks), id2, IS_A ? (ks > 0) : 1u);
+        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ts(tS, tX + ks * 8, d2mn + mnstep(ks), id2, ks > 0);
+      } else {      // intra accumulator = X t2
+#pragma unroll
+        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tO, dXk + kstep(ks), d2mn + mnstep(ks), id2, ks > 0);
+      }
       umma_commit(&sm.bar_m2);
-      if (!IS_A) {   // the inter-chunk MMA is complete by now: its operands can be refilled
-        mbar_wait(&sm.bar_i, ph);
-        if (has_next) { load_act(sm.t0, &maps.t0, &sm.bar_t0, next); load_st(next); }
+      if (has_next) {
+        if (IS_A) load_act(sm.x, &maps.h, &sm.bar_h, next);   // every warp is past its h-tile reads
+        mbar_wait(&sm.bar_t0, ph ^ 1); mbar_wait(&sm.bar_t1, ph ^ 1);
+        tc_fence_after();
+        issue_mma1(tm + (ph ^ 1) * 128);
       }
     }
     TLB(6);
     mbar_wait(&sm.bar_m2, ph);
     tc_fence_after();
     TLB(7);
-    // A stages its output in the (now dead) t2 tile so that x is free for the next h tile at once;
-    // B stages in x and refills t2 now
-    if (issuer && has_next) {
-      if (IS_A) load_act(sm.x, &maps.h, &sm.bar_h, next);
-      else load_act(sm.t2, &maps.t2, &sm.bar_t2, next);
-    }
+    // A stages its output in the (now dead) t2 tile; B stages in x and refills t2 now
+    if (issuer && has_next && !IS_A) load_act(sm.t2, &maps.t2, &sm.bar_t2, next);
 
     // ---- epilogue: outputs packed in registers --------------------------------------------------
     uint32_t opk[16];
     float psum = 0.f;
     if (cq < NB) {
-      float acc[32];
+      float acc[32], gg[32];
       tmem_ld32((IS_A ? tS : tO) + lane_sel + cq * 32, acc);
+      tmem_ld32((IS_A ? tO : tX) + lane_sel + cq * 32, gg);    // state product (bar_i was awaited by MMA order)
+      tmem_ld_wait();
       if (IS_A) {
-        float gg[32];
-        tmem_ld32(tO + lane_sel + cq * 32, gg);
-        tmem_ld_wait();
         const float wt = G.w[row], invN = G.invN[row];
         float qr[32];
         mbar_wait(&sm.bar_t3, ph);
@@ -381,20 +403,19 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
           if (row_ok) psum = fmaf(qr[x], o0, fmaf(qr[x + 1], o1, psum));
           opk[x / 2] = pack_bf16x2(o0, o1);
         }
-      } else if (MODE == MODE_B1) {
-        tmem_ld_wait();
+      } else if (MODE == MODE_B1) {   // dv = E^T dH + kw (K dC)
+        const float kwj = G.kw[row];
 #pragma unroll
-        for (int x = 0; x < 32; x += 2) opk[x / 2] = pack_bf16x2(acc[x], acc[x + 1]);
-      } else {
-        tmem_ld_wait();
+        for (int x = 0; x < 32; x += 2) opk[x / 2] = pack_bf16x2(fmaf(kwj, gg[x], acc[x]), fmaf(kwj, gg[x + 1], acc[x + 1]));
+      } else {                        // dk = s dS^T Q + kw (V dC^T + dn_state)
         const float kwj = G.kw[row];
         float kr[32];
         mbar_wait(&sm.bar_t3, ph);
         tile_row32<DH>(sm.t3, row, cq, kr);
 #pragma unroll
         for (int x = 0; x < 32; x += 2) {
-          const float o0 = fmaf(kwj, vecf[cq * 32 + x], scale * acc[x]);
-          const float o1 = fmaf(kwj, vecf[cq * 32 + x + 1], scale * acc[x + 1]);
+          const float o0 = fmaf(kwj, gg[x] + vecf[cq * 32 + x], scale * acc[x]);
+          const float o1 = fmaf(kwj, gg[x + 1] + vecf[cq * 32 + x + 1], scale * acc[x + 1]);
           if (row_ok) psum = fmaf(kr[x], o0, fmaf(kr[x + 1], o1, psum));
           opk[x / 2] = pack_bf16x2(o0, o1);
         }
@@ -417,17 +438,16 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
     TLB(8);
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();   // end of item: TMEM free, next gates published (the gate warp joins here)
+    __syncthreads();   // end of item: tO / tX consumed, next gates published (the gate warp joins here)
     TLB(9);
     if (issuer) {
       for (int kt = 0; kt < KT; ++kt) tma_store_4d(&maps.out, stage + kt * TILE, kt * 64, tok0, h, b);
       tma_store_commit();
       if (has_next) {
         if (MODE != MODE_B1) load_act(sm.t3, &maps.t3, &sm.bar_t3, next);   // t3 rows were consumed in the epilogue
-        mbar_wait(&sm.bar_t0, ph ^ 1); mbar_wait(&sm.bar_t1, ph ^ 1);
-        if (IS_A) mbar_wait(&sm.bar_st, ph ^ 1);
+        mbar_wait(&sm.bar_st, ph ^ 1);
         tc_fence_after();
-        issue_mma1();
+        issue_state_mma();   // t0 of the next item landed before its MMA1 was issued
         if (IS_A) {   // refill t2 once the store above has read the staged rows
           tma_store_wait_read<0>();
           load_act(sm.t2, &maps.t2, &sm.bar_t2, next);
@@ -439,7 +459,25 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant
   if (issuer) tma_store_wait_all<0>();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, 256);
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+template <int DH, int MODE>
+__global__ void __launch_bounds__(NT, 1) tc_bwd_par_kernel(const __grid_constant__ BwdMaps maps, const mlstm_params p,
+                                                           const float scale, const int n_items, const int order) {
+  par_body<DH, MODE>(maps, p, scale, n_items, order, blockIdx.x, gridDim.x);
+}
+
+// B1 (dv) and B2 (dk) side by side in one launch: CTAs [0, n_b2) run B2, the rest run B1, both walking
+// the same item list in the same order.  Four of the five input tiles of an item (q, dh, dCs, and k)
+// are common to both; whichever CTA comes second finds them in the 126 MB L2, so DRAM sees them once —
+// the traffic of a fused dk/dv kernel without its shared-memory and TMEM bill.
+template <int DH>
+__global__ void __launch_bounds__(NT, 1) tc_bwd_b12_kernel(const __grid_constant__ BwdMaps maps1, const __grid_constant__ BwdMaps maps2,
+                                                           const mlstm_params p, const float scale, const int n_items,
+                                                           const int order, const int n_b2) {
+  if ((int)blockIdx.x < n_b2) par_body<DH, MODE_B2>(maps2, p, scale, n_items, order, blockIdx.x, n_b2);
+  else par_body<DH, MODE_B1>(maps1, p, scale, n_items, order, blockIdx.x - n_b2, gridDim.x - n_b2);
 }
 
 // =============================================================================================
@@ -714,6 +752,14 @@ int launched(const char* name) {
   return MLSTM_OK;
 }
 
+// item order of kernels A, B1, B2 (see lin_of); MLSTM_BWD_ORDER="abc" (digits 0-2) overrides for experiments
+int order_of(int k) {
+  static const char* env = getenv("MLSTM_BWD_ORDER");
+  static const int dflt[3] = {0, 0, 0};   // measured on B200: no order beats head-major (the kernels are not DRAM-bound)
+  if (env && env[0] && env[1] && env[2] && env[k] >= '0' && env[k] <= '2') return env[k] - '0';
+  return dflt[k];
+}
+
 template <int DH>
 int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
   const StateLayout slay(p.B, p.NH, p.S, DH);
@@ -749,7 +795,7 @@ int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
   if (part != 1) {
     BwdMaps m{mdh, mv, mk, mcs, mq, mh, mdq};
     if ((rc = prep(tc_bwd_par_kernel<DH, MODE_A>, smB, "tc_bwd_dq"))) return rc;
-    tc_bwd_par_kernel<DH, MODE_A><<<dim3(grid), dim3(NT), smB, st>>>(m, p, scale, n_items);
+    tc_bwd_par_kernel<DH, MODE_A><<<dim3(grid), dim3(NT), smB, st>>>(m, p, scale, n_items, order_of(0));
     if ((rc = launched("tc_bwd_dq"))) return rc;
   }
   if (part != 0) {
@@ -758,13 +804,22 @@ int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
     tc_state_bwd_kernel<DH><<<dim3(p.B * p.NH), dim3(NT), smSB, st>>>(ms, p, scale);
     if ((rc = launched("tc_state_bwd"))) return rc;
     BwdMaps m1{mk, mq, mdh, mdcs, mq, mh, mdv};
-    if ((rc = prep(tc_bwd_par_kernel<DH, MODE_B1>, smB, "tc_bwd_dv"))) return rc;
-    tc_bwd_par_kernel<DH, MODE_B1><<<dim3(grid), dim3(NT), smB, st>>>(m1, p, scale, n_items);
-    if ((rc = launched("tc_bwd_dv"))) return rc;
     BwdMaps m2{mv, mdh, mq, mdcs, mk, mh, mdk};
-    if ((rc = prep(tc_bwd_par_kernel<DH, MODE_B2>, smB, "tc_bwd_dk"))) return rc;
-    tc_bwd_par_kernel<DH, MODE_B2><<<dim3(grid), dim3(NT), smB, st>>>(m2, p, scale, n_items);
-    if ((rc = launched("tc_bwd_dk"))) return rc;
+    if (n_items < 4 * sms) {
+      // few items per CTA: two full-width launches balance better than two half-width groups
+      if ((rc = prep(tc_bwd_par_kernel<DH, MODE_B1>, smB, "tc_bwd_dv"))) return rc;
+      tc_bwd_par_kernel<DH, MODE_B1><<<dim3(grid), dim3(NT), smB, st>>>(m1, p, scale, n_items, order_of(1));
+      if ((rc = launched("tc_bwd_dv"))) return rc;
+      if ((rc = prep(tc_bwd_par_kernel<DH, MODE_B2>, smB, "tc_bwd_dk"))) return rc;
+      tc_bwd_par_kernel<DH, MODE_B2><<<dim3(grid), dim3(NT), smB, st>>>(m2, p, scale, n_items, order_of(2));
+      if ((rc = launched("tc_bwd_dk"))) return rc;
+    } else {
+      // B2 costs ~1.2x B1 per item: it gets the larger share of the CTAs
+      const int n_b2 = (sms * 6 + 5) / 11;
+      if ((rc = prep(tc_bwd_b12_kernel<DH>, smB, "tc_bwd_dkdv"))) return rc;
+      tc_bwd_b12_kernel<DH><<<dim3(sms), dim3(NT), smB, st>>>(m1, m2, p, scale, n_items, order_of(1), n_b2);
+      if ((rc = launched("tc_bwd_dkdv"))) return rc;
+    }
     tc_dfscan_kernel<<<dim3(n_items), dim3(L), 0, st>>>(p, DH);
     if ((rc = launched("tc_dfscan"))) return rc;
   }

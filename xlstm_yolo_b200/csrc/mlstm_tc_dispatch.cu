@@ -4,6 +4,8 @@
 // Single-pass kernels run one CTA per (batch, head) with the state on chip: best when there are
 // enough heads to fill the GPU and the per-head chunk chain is short.  The two-phase kernels
 // spill per-chunk states to HBM and are chunk-parallel: best for long sequences / small batches.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 namespace mlstm {
 
@@ -18,10 +20,21 @@ static int sm_count() {
   return sms;
 }
 
+// MLSTM_FORCE_VARIANT="<f><b>" (developer switch for A/B measurements): f = 1 single-pass / 2 two-phase
+// forward, b = 1 single-pass / 2 chunk-parallel backward, anything else = automatic.
+static int forced(int which) {
+  static const char* env = getenv("MLSTM_FORCE_VARIANT");
+  if (!env || !env[0] || !env[1]) return 0;
+  const char c = env[which];
+  return c == '1' ? 1 : (c == '2' ? 2 : 0);
+}
+
 bool tc_use_two_phase(const mlstm_params& p) {          // forward
+  if (forced(0)) return forced(0) == 2;
   return p.B * p.NH * 2 <= sm_count() && tc::num_chunks(p.S) >= 4;
 }
 bool tc_use_single_pass_bwd(const mlstm_params& p) {    // backward
+  if (forced(1)) return forced(1) == 1;
   return tc::num_chunks(p.S) <= 4 && p.B * p.NH * 2 > sm_count();
 }
 
