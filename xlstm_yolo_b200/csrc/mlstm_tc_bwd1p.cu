@@ -222,14 +222,14 @@ __device__ __forceinline__ void state_pass(SM& sm, uint32_t tC, uint32_t tN, boo
 }
 
 template <class SM>
-__device__ __forceinline__ void setup(SM& sm, int nbar_in) {
+__device__ __forceinline__ void setup(SM& sm, int nbar_in, uint32_t tmem_cols = 512) {
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
     for (int i = 0; i < nbar_in; ++i) mbar_init(&sm.bar_in[i], 1);
     mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_s, 1); mbar_init(&sm.bar_m2, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
+  if (warp == 0) tmem_alloc(&sm.tmem_base, tmem_cols);
 }
 
 // ======================================================================================
@@ -486,12 +486,16 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_dq_kernel(const __grid_constant_
 //   MODE 1 (dv): tiles in[0]=q in[1]=k  in[2]=dh ; out0 = dv
 //   MODE 2 (dk): tiles in[0]=q in[1]=v  in[2]=dh ; out0 = dk ; also di, df, carries dn_state
 // ======================================================================================
+// TMEM: S/Z 128 + O DH + dC DH columns.  At DH = 64 that is 256, so a dv CTA and a dk CTA share an SM
+// (two 96 KB CTAs) and the two reverse walks run side by side in one launch (tc_bwd_dkv12_kernel).
+// The dn_state recurrence of the dk walk is a [DH] vector: it lives in registers (SIMT column sums of
+// the Q tile) rather than in a fourth TMEM accumulator.
 template <int DH, int MODE>
-__global__ void __launch_bounds__(NT, 1) tc_bwd_dkv_kernel(const __grid_constant__ BwdMaps maps, const mlstm_params p,
-                                                           const float scale, const float* __restrict__ ws_dn,
-                                                           const float* __restrict__ ws_R) {
+__device__ __forceinline__ void dkv_body(const BwdMaps& maps, const mlstm_params& p, const float scale,
+                                         const float* __restrict__ ws_dn, const float* __restrict__ ws_R, const int bh) {
   constexpr int KT = DH / 64;
   constexpr int TILE_C = DH * 128;
+  constexpr uint32_t TCOLS = (DH == 64) ? 256 : 512;
   constexpr uint32_t A_LBO_STATE = (DH == 128) ? TILE : 0;
   using SM = SmemB<DH, 3>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -501,15 +505,18 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_dkv_kernel(const __grid_constant
   __shared__ __align__(16) float colv[3][L];     // per-query-row vectors: [0] exponent offset, [1] 1/N, [2] dn
   __shared__ __align__(16) float rowscale[L];    // (w s / N)_t for the dC update operand
   __shared__ __align__(16) float kwos[L];        // kw_j / s
+  __shared__ __align__(16) float ncoef[L];       // (w s dn)_t : weights of the dn_state update (dk walk)
+  __shared__ float npart[2][DH];
   __shared__ float df_carry;
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int bh = blockIdx.x, b = bh / p.NH, h = bh % p.NH;
+  const int b = bh / p.NH, h = bh % p.NH;
+  float nstate = 0.f;                            // thread dk < DH: decayed dn_state entering this step
   const int S = p.S, NC = (S + L - 1) / L;
   const bool rev = p.reverse != 0;
   const CUtensorMap* map_kv = (MODE == 1) ? &maps.k : &maps.v;
 
-  setup(sm, 3);
+  setup(sm, 3, TCOLS);
   if (tid == 0) { tma_prefetch_desc(&maps.q); tma_prefetch_desc(map_kv); tma_prefetch_desc(&maps.dh); tma_prefetch_desc(&maps.out0); df_carry = 0.f; }
   for (int e = tid; e < KT * TILE_C / 16; e += NT) reinterpret_cast<uint4*>(sm.cb)[e] = make_uint4(0, 0, 0, 0);
   for (int e = tid; e < DH; e += NT) sm.nvec[e] = 0.f;
@@ -517,7 +524,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_dkv_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = sm.tmem_base;
-  const uint32_t tS = tm, tO = tm + 128, tC = tm + 128 + DH, tN = tm + 128 + 2 * DH;
+  const uint32_t tS = tm, tO = tm + 128, tC = tm + 128 + DH;
   const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
 
   // processing step c (0 = scan-last chunk) -> memory chunk
@@ -559,11 +566,22 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_dkv_kernel(const __grid_constant
       colv[2][tid] = G.dn[tid];
       rowscale[tid] = G.w[tid] * scale * inv;
       kwos[tid] = G.kw[tid] / scale;
+      ncoef[tid] = G.w[tid] * scale * G.dn[tid];
     }
     mbar_wait(&sm.bar_in[MODE == 1 ? 2 : 0], ph);   // third tile (needed by the state MMAs)
     mbar_wait(&sm.bar_m1, ph);
     tc_fence_after();
     __syncthreads();   // colv / rowscale visible
+    if (MODE == 2) {   // dn_state += Q^T (w s dn): column dk of the (un-scaled) Q tile, half of the rows per thread
+      const int dk = tid % DH, part = tid / DH;
+      constexpr int PARTS = NT / DH, ROWS = L / PARTS;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int t = part * ROWS; t < (part + 1) * ROWS; ++t)
+        acc = fmaf(ncoef[t], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sq + (dk >> 6) * TILE + swz128(t, dk & 63))), acc);
+      if (PARTS == 2) npart[part][dk] = acc;
+      else npart[0][dk] = acc;
+    }
 
     // ---- in-place operand scaling ---------------------------------------------------------
     if (MODE == 1) scale_rows<DH>(skv, G.kw);                   // Kbar = kw_j k_j
@@ -571,7 +589,6 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_dkv_kernel(const __grid_constant
     if (MODE == 1) scale_rows<DH>(sq, rowscale);                // Qtilde = (w s / N)_t q_t
     else {
       scale_rows<DH>(sdh, rowscale);                            // dHtilde = (w s / N)_t dh_t
-      write_vec_tile(sm.vec, G.w[tid] * scale * G.dn[tid]);     // (w s dn)_t for dn_state += Q^T (.)
     }
     fence_proxy_async_smem();
     if (tid == 0) tma_store_wait_read<0>();
@@ -596,7 +613,6 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_dkv_kernel(const __grid_constant
       for (int ks = 0; ks < L / 16; ++ks) {
         const uint64_t a = dMN(smem_u32(sq), ks, A_LBO_STATE);
         umma_bf16_ss(tC, a, dMN(smem_u32(sdh), ks, TILE), idC, (ks > 0) ? 1u : acc0);
-        if (MODE == 2) umma_bf16_ss(tN, a, dK(smem_u32(sm.vec), ks, 2048), idN, (ks > 0) ? 1u : acc0);
       }
       umma_commit(&sm.bar_s);
     }
@@ -725,7 +741,12 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_dkv_kernel(const __grid_constant
       __syncthreads();   // nvec readers / uniform barrier count
     }
     const bool last = (c + 1 == NC);
-    state_pass<DH>(sm, tC, tN, MODE == 2, last ? 1.f : Gn.decay, last, lane_sel);
+    state_pass<DH>(sm, tC, 0u, false, last ? 1.f : Gn.decay, last, lane_sel);
+    if (MODE == 2 && tid < DH) {   // the epilogue above read the previous dn_state: publish this step's
+      const float nv = nstate + npart[0][tid] + ((NT / DH == 2) ? npart[1][tid] : 0.f);
+      sm.nvec[tid] = nv;
+      nstate = last ? 0.f : nv * Gn.decay;
+    }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -737,7 +758,23 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_dkv_kernel(const __grid_constant
   if (tid == 0) tma_store_wait_all<0>();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, 512);
+  if (warp == 0) tmem_dealloc(tm, TCOLS);
+}
+
+template <int DH, int MODE>
+__global__ void __launch_bounds__(NT, 2) tc_bwd_dkv_kernel(const __grid_constant__ BwdMaps maps, const mlstm_params p,
+                                                           const float scale, const float* __restrict__ ws_dn,
+                                                           const float* __restrict__ ws_R) {
+  dkv_body<DH, MODE>(maps, p, scale, ws_dn, ws_R, blockIdx.x);
+}
+
+// dv and dk walks of the same (batch, head) as neighbouring CTAs of one launch (DH = 64: both fit one SM)
+template <int DH>
+__global__ void __launch_bounds__(NT, 2) tc_bwd_dkv12_kernel(const __grid_constant__ BwdMaps maps_v, const __grid_constant__ BwdMaps maps_k,
+                                                             const mlstm_params p, const float scale,
+                                                             const float* __restrict__ ws_dn, const float* __restrict__ ws_R) {
+  if (blockIdx.x & 1) dkv_body<DH, 2>(maps_k, p, scale, ws_dn, ws_R, blockIdx.x >> 1);
+  else dkv_body<DH, 1>(maps_v, p, scale, ws_dn, ws_R, blockIdx.x >> 1);
 }
 
 template <class K>
@@ -788,12 +825,18 @@ int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
     r |= make_act_tmap(&mv.out0, p.dv.ptr, p.B, p.NH, p.S, DH, p.dv.stride_b, p.dv.stride_h, p.dv.stride_s, L);
     r |= make_act_tmap(&mk.out0, p.dk.ptr, p.B, p.NH, p.S, DH, p.dk.stride_b, p.dk.stride_h, p.dk.stride_s, L);
     if (r) { set_error("cuTensorMapEncodeTiled failed (%d)", r); return r == -1 ? MLSTM_ERR_NO_DEVICE : MLSTM_ERR_INVALID_ARG; }
-    if ((rc = prep_kernel(tc_bwd_dkv_kernel<DH, 1>, smB, "tc_bwd_dv"))) return rc;
-    if ((rc = prep_kernel(tc_bwd_dkv_kernel<DH, 2>, smB, "tc_bwd_dk"))) return rc;
-    tc_bwd_dkv_kernel<DH, 1><<<grid, block, smB, st>>>(mv, p, scale, ws_dn, ws_R);
-    if ((rc = launched("tc_bwd_dv"))) return rc;
-    tc_bwd_dkv_kernel<DH, 2><<<grid, block, smB, st>>>(mk, p, scale, ws_dn, ws_R);
-    if ((rc = launched("tc_bwd_dk"))) return rc;
+    if (DH == 64) {   // the two reverse walks side by side: 2 CTAs (96 KB, 256 TMEM columns each) per SM
+      if ((rc = prep_kernel(tc_bwd_dkv12_kernel<DH>, smB, "tc_bwd_dkdv"))) return rc;
+      tc_bwd_dkv12_kernel<DH><<<dim3(2 * p.B * p.NH), block, smB, st>>>(mv, mk, p, scale, ws_dn, ws_R);
+      if ((rc = launched("tc_bwd_dkdv"))) return rc;
+    } else {
+      if ((rc = prep_kernel(tc_bwd_dkv_kernel<DH, 1>, smB, "tc_bwd_dv"))) return rc;
+      if ((rc = prep_kernel(tc_bwd_dkv_kernel<DH, 2>, smB, "tc_bwd_dk"))) return rc;
+      tc_bwd_dkv_kernel<DH, 1><<<grid, block, smB, st>>>(mv, p, scale, ws_dn, ws_R);
+      if ((rc = launched("tc_bwd_dv"))) return rc;
+      tc_bwd_dkv_kernel<DH, 2><<<grid, block, smB, st>>>(mk, p, scale, ws_dn, ws_R);
+      if ((rc = launched("tc_bwd_dk"))) return rc;
+    }
   }
   return MLSTM_OK;
 }
