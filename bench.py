@@ -54,9 +54,9 @@ def algorithmic(B, NH, S, DH):
 # part, from the round-1 `ncu --set full` captures (profiles/r01_ncu_full_*_summary.csv).  Writes that
 # stay in the 126 MB L2 until after the kernel are not counted by ncu.
 NCU_TRAFFIC_BYTES = {
-    "cfg2_B32_NH4_S400_DH64": {"fwd": 20.14e6, "bwd_dq": 33.65e6, "bwd_dkv": 20.53e6 + 27.50e6},
-    "cfg3_B32_NH4_S1600_DH128": {"fwd": 159.13e6 + 70.44e6, "bwd_dq": 321.57e6 + 42.79e6,
-                                 "bwd_dkv": (160.54e6 + 34.42e6) + (215.18e6 + 34.46e6) + (269.97e6 + 40.74e6) + 7.39e6},
+    "cfg2_B32_NH4_S400_DH64": {"fwd": 20.14e6, "bwd_dq": 33.64e6, "bwd_dkv": 27.54e6},
+    "cfg3_B32_NH4_S1600_DH128": {"fwd": 159.12e6 + 70.82e6, "bwd_dq": 321.29e6 + 42.63e6,
+                                 "bwd_dkv": (160.53e6 + 32.77e6) + (282.38e6 + 85.76e6) + 7.39e6},
 }
 
 
