@@ -145,6 +145,39 @@ size_t mlstm_b200_gates_workspace_bytes(const mlstm_gate_proj_params* p);
 int mlstm_b200_gates_fwd(const mlstm_gate_proj_params* p, void* cuda_stream);
 int mlstm_b200_gates_bwd(const mlstm_gate_proj_params* p, void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused tail of a ViL layer (reference: vision_lstm2.py:950 out-norm -- MultiHeadLayerNorm :1309-1325,
+ * weight applied as 1 + w -- then :498 `+ learnable_skip * conv_act` and :499 `* silu(z)`):
+ *     y = (LN_head(h) * (1 + w) + b + skip * c) * silu(z)
+ * in one pass, and its backward (dh, dc, dz and the parameter gradients) in one pass.  Rows are
+ * tokens; h is the cell output with heads merged, (T, D) over the (B,S,NH,DH) storage the cell
+ * kernels write; every operand has its own row stride in elements (z is a column slice of proj_up's
+ * output).  D % 256 == 0, D <= 2048, DH = D / NH divides 256; all pointers 16-byte aligned. */
+typedef struct mlstm_glue_params {
+  int32_t abi_version;                  /* MLSTM_B200_ABI_VERSION */
+  int32_t T, D, NH;
+  int32_t dtype;                        /* mlstm_dtype of h, c, z, y and their gradients */
+  float eps;                            /* out-norm epsilon (1e-3 at vision_lstm2.py:812) */
+  const void* h;  int64_t ld_h;
+  const void* c;  int64_t ld_c;         /* conv_act */
+  const void* z;  int64_t ld_z;
+  const float* w;                       /* out-norm weight (D), applied as 1 + w; NULL = 0 */
+  const float* b;                       /* out-norm bias (D) or NULL */
+  const float* skip;                    /* learnable_skip (D); NULL = 1 */
+  void* y;        int64_t ld_y;         /* forward output */
+  const void* dy; int64_t ld_dy;        /* backward input */
+  void* dh;       int64_t ld_dh;        /* backward outputs */
+  void* dc;       int64_t ld_dc;
+  void* dz;       int64_t ld_dz;
+  float *dw, *db, *dskip;               /* (D) fp32, overwritten; each may be NULL */
+  void* workspace;                      /* >= mlstm_b200_glue_workspace_bytes() (backward only) */
+  size_t workspace_bytes;
+} mlstm_glue_params;
+
+size_t mlstm_b200_glue_workspace_bytes(const mlstm_glue_params* p);
+int mlstm_b200_glue_fwd(const mlstm_glue_params* p, void* cuda_stream);
+int mlstm_b200_glue_bwd(const mlstm_glue_params* p, void* cuda_stream);
+
 /* Library / ABI identification. */
 int mlstm_b200_abi_version(void);
 

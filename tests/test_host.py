@@ -33,7 +33,8 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.mlstm_b200_abi_version() == _lib.ABI_VERSION
 
 
-@pytest.mark.parametrize("cname,ctype", [("mlstm_params", _lib.Params), ("mlstm_gate_proj_params", _lib.GateProjParams)])
+@pytest.mark.parametrize("cname,ctype", [("mlstm_params", _lib.Params), ("mlstm_gate_proj_params", _lib.GateProjParams),
+                                         ("mlstm_glue_params", _lib.GlueParams)])
 def test_ctypes_struct_matches_c_layout(tmp_path, cname, ctype):
     fields = [n for n, _ in ctype._fields_]
     src = tmp_path / "layout.c"
@@ -111,6 +112,20 @@ def test_kernel_family_and_workspace(lib):
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) is None
     assert lib.mlstm_b200_kernel_variant(C.byref(p), 1) is None
     assert lib.mlstm_b200_kernel_variant(C.byref(_params()), 0) in (b"single_pass", b"two_phase")
+
+
+def test_layer_tail_validation_needs_no_gpu(lib):
+    g = _lib.GlueParams()
+    assert lib.mlstm_b200_glue_fwd(None, None) == -1
+    g.abi_version, g.T, g.D, g.NH, g.dtype, g.eps = _lib.ABI_VERSION, 64, 192, 4, _lib.MLSTM_BF16, 1e-3
+    assert lib.mlstm_b200_glue_fwd(C.byref(g), None) == -2 and b"multiple of 256" in lib.mlstm_b200_last_error()
+    g.D = 512
+    g.ld_h = g.ld_c = g.ld_y = 512
+    g.ld_z = 1024
+    assert lib.mlstm_b200_glue_fwd(C.byref(g), None) == -1          # null pointers
+    assert lib.mlstm_b200_glue_workspace_bytes(C.byref(g)) == 4 * 3 * 512 * 4   # 128 (token, segment) units / 32 per CTA
+    g.T = 0
+    assert lib.mlstm_b200_glue_fwd(C.byref(g), None) == 0
 
 
 def test_cuda_op_refuses_cpu_tensors():

@@ -29,6 +29,9 @@ EXPORTS = (
     "mlstm_b200_gates_workspace_bytes",
     "mlstm_b200_gates_fwd",
     "mlstm_b200_gates_bwd",
+    "mlstm_b200_glue_workspace_bytes",
+    "mlstm_b200_glue_fwd",
+    "mlstm_b200_glue_bwd",
     "mlstm_b200_launch_count",
     "mlstm_b200_last_error",
 )
@@ -78,6 +81,20 @@ class GateProjParams(C.Structure):
     ]
 
 
+class GlueParams(C.Structure):
+    """ctypes mirror of ``mlstm_glue_params`` (include/mlstm_b200.h)."""
+    _fields_ = [
+        ("abi_version", C.c_int32), ("T", C.c_int32), ("D", C.c_int32), ("NH", C.c_int32), ("dtype", C.c_int32),
+        ("eps", C.c_float),
+        ("h", C.c_void_p), ("ld_h", C.c_int64), ("c", C.c_void_p), ("ld_c", C.c_int64), ("z", C.c_void_p), ("ld_z", C.c_int64),
+        ("w", C.c_void_p), ("b", C.c_void_p), ("skip", C.c_void_p),
+        ("y", C.c_void_p), ("ld_y", C.c_int64), ("dy", C.c_void_p), ("ld_dy", C.c_int64),
+        ("dh", C.c_void_p), ("ld_dh", C.c_int64), ("dc", C.c_void_p), ("ld_dc", C.c_int64), ("dz", C.c_void_p), ("ld_dz", C.c_int64),
+        ("dw", C.c_void_p), ("db", C.c_void_p), ("dskip", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -123,6 +140,12 @@ def load() -> C.CDLL:
         lib.mlstm_b200_gates_fwd.argtypes = [C.POINTER(GateProjParams), C.c_void_p]
         lib.mlstm_b200_gates_bwd.restype = C.c_int
         lib.mlstm_b200_gates_bwd.argtypes = [C.POINTER(GateProjParams), C.c_void_p]
+        lib.mlstm_b200_glue_workspace_bytes.restype = C.c_size_t
+        lib.mlstm_b200_glue_workspace_bytes.argtypes = [C.POINTER(GlueParams)]
+        lib.mlstm_b200_glue_fwd.restype = C.c_int
+        lib.mlstm_b200_glue_fwd.argtypes = [C.POINTER(GlueParams), C.c_void_p]
+        lib.mlstm_b200_glue_bwd.restype = C.c_int
+        lib.mlstm_b200_glue_bwd.argtypes = [C.POINTER(GlueParams), C.c_void_p]
         lib.mlstm_b200_launch_count.restype = C.c_uint64
         lib.mlstm_b200_last_error.restype = C.c_char_p
         if lib.mlstm_b200_abi_version() != ABI_VERSION:

@@ -18,7 +18,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import Act, Gate, GateProjParams, Params
+from ._lib import Act, Gate, GateProjParams, GlueParams, Params
 
 _DT = {torch.float32: _lib.MLSTM_F32, torch.bfloat16: _lib.MLSTM_BF16}
 
@@ -351,6 +351,93 @@ def fused_cell(q3: torch.Tensor, k3: torch.Tensor, v3: torch.Tensor, w_i: torch.
     h = _FusedCellFn.apply(q3, k3, v3, f32(w_i), f32(b_i), f32(w_f), f32(b_f), int(num_heads), float(eps),
                            int(chunk_size), bool(reverse))
     return h.to(in_dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+# Fused layer tail: out-norm + learnable skip + SiLU(z) gate (vision_lstm2.py:950, :498-499)
+# ---------------------------------------------------------------------------------------------
+def glue_supported(h: torch.Tensor, c: torch.Tensor, z: torch.Tensor) -> bool:
+    """h (B,NH,S,DH) head-strided view of (B,S,NH,DH) storage; c, z (B,S,D) with evenly strided rows."""
+    if not h.is_cuda or h.dtype not in _DT or h.dim() != 4:
+        return False
+    B, NH, S, DH = h.shape
+    D = NH * DH
+    if D % 256 or D > 2048 or 256 % DH or DH % 8:
+        return False
+    if h.stride() != (S * D, DH, D, 1) or h.data_ptr() % 16:
+        return False
+    return all(t.dtype == h.dtype and t.shape == (B, S, D) and _rows_ok(t) for t in (c, z))
+
+
+def _glue_params(h, c, z, w, b, skip, eps) -> GlueParams:
+    B, NH, S, DH = h.shape
+    g = GlueParams()
+    g.abi_version = _lib.ABI_VERSION
+    g.T, g.D, g.NH = B * S, NH * DH, NH
+    g.dtype = _DT[h.dtype]
+    g.eps = float(eps)
+    g.h, g.ld_h = h.data_ptr(), NH * DH
+    g.c, g.ld_c = c.data_ptr(), c.stride(1)
+    g.z, g.ld_z = z.data_ptr(), z.stride(1)
+    g.w, g.b, g.skip = _ptr(w), _ptr(b), _ptr(skip)
+    return g
+
+
+class _GlueFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, c, z, w, b, skip, eps):
+        lib = _lib.load()
+        B, NH, S, DH = h.shape
+        y = torch.empty((B, S, NH * DH), dtype=h.dtype, device=h.device)
+        g = _glue_params(h, c, z, w, b, skip, eps)
+        g.y, g.ld_y = y.data_ptr(), NH * DH
+        with torch.cuda.device(h.device):
+            rc = lib.mlstm_b200_glue_fwd(C.byref(g), _stream())
+        if rc:
+            _fail(rc, "layer tail forward")
+        ctx.save_for_backward(h, c, z, w, b, skip)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        h, c, z, w, b, skip = ctx.saved_tensors
+        B, NH, S, DH = h.shape
+        D = NH * DH
+        dev = h.device
+        if dy.dtype != h.dtype:
+            dy = dy.to(h.dtype)
+        if not _rows_ok(dy):
+            dy = dy.contiguous()
+        dh = _empty_act(B, NH, S, DH, h.dtype, dev)
+        dc = torch.empty((B, S, D), dtype=h.dtype, device=dev)
+        dz = torch.empty((B, S, D), dtype=h.dtype, device=dev)
+        dw = torch.empty(D, dtype=torch.float32, device=dev) if w is not None else None
+        db = torch.empty(D, dtype=torch.float32, device=dev) if b is not None else None
+        dskip = torch.empty(D, dtype=torch.float32, device=dev) if skip is not None else None
+        g = _glue_params(h, c, z, w, b, skip, ctx.eps)
+        g.dy, g.ld_dy = dy.data_ptr(), dy.stride(1)
+        g.dh, g.ld_dh = dh.data_ptr(), D
+        g.dc, g.ld_dc = dc.data_ptr(), D
+        g.dz, g.ld_dz = dz.data_ptr(), D
+        g.dw, g.db, g.dskip = _ptr(dw), _ptr(db), _ptr(dskip)
+        need = lib.mlstm_b200_glue_workspace_bytes(C.byref(g))
+        ws = torch.empty(max(1, (need + 3) // 4), dtype=torch.float32, device=dev)
+        g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+        with torch.cuda.device(dev):
+            rc = lib.mlstm_b200_glue_bwd(C.byref(g), _stream())
+        if rc:
+            _fail(rc, "layer tail backward")
+        return dh, dc, dz, dw, db, dskip, None
+
+
+def layer_tail(h: torch.Tensor, conv_act: torch.Tensor, z: torch.Tensor, norm_weight: Optional[torch.Tensor],
+               norm_bias: Optional[torch.Tensor], skip: Optional[torch.Tensor], eps: float = 1e-3) -> torch.Tensor:
+    """``(LN_head(h) * (1 + w) + b + skip * conv_act) * silu(z)`` -> (B,S,D).  ``h`` is the raw cell output
+    (B,NH,S,DH); check ``glue_supported`` first."""
+    f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()
+    return _GlueFn.apply(h, conv_act, z, f32(norm_weight), f32(norm_bias), f32(skip), float(eps))
 
 
 class MLSTMPlan:

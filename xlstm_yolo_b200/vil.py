@@ -155,6 +155,7 @@ class ViLLayer(nn.Module):
         self.weight_mode = weight_mode
         self.num_blocks = num_blocks
         self.flip_free = flip_free
+        self.fused_tail = True    # CUDA: csrc/mlstm_glue.cu for out-norm + skip + SiLU(z)
 
         inner_dim = expansion * dim
         num_heads = inner_dim // qkv_block_size
@@ -187,9 +188,33 @@ class ViLLayer(nn.Module):
             y = y.flip(dims=[1])
         x_mlstm, z = self.proj_up(y).chunk(2, dim=-1)
         conv_act = F.silu(self.conv(x_mlstm, rotate=anti))
-        self.mlstm_cell.reverse = anti
-        h = self.mlstm_cell(q=self.q_proj(conv_act), k=self.k_proj(conv_act), v=self.v_proj(x_mlstm))
-        y = self.proj_down((h + self.learnable_skip * conv_act) * F.silu(z))
+        cell = self.mlstm_cell
+        cell.reverse = anti
+        q, k, v = self.q_proj(conv_act), self.k_proj(conv_act), self.v_proj(x_mlstm)
+        y = None
+        if x.is_cuda and getattr(self, "fused_tail", True) and not cell.raw_output:
+            # out-norm + skip + SiLU(z) gate as one streaming kernel over the raw cell output
+            # (vision_lstm2.py:950, :498-499 are four separate (B,S,inner) round trips)
+            from . import ops
+            cell.raw_output = True
+            try:
+                h_raw = cell(q=q, k=k, v=v)                 # (B,NH,S,DH)
+            finally:
+                cell.raw_output = False
+            if conv_act.dtype != h_raw.dtype:
+                conv_act_k, z_k = conv_act.to(h_raw.dtype), z.to(h_raw.dtype)
+            else:
+                conv_act_k, z_k = conv_act, z
+            if ops.glue_supported(h_raw, conv_act_k, z_k):
+                y = ops.layer_tail(h_raw, conv_act_k, z_k, cell.outnorm.weight, cell.outnorm.bias, self.learnable_skip,
+                                   eps=cell.outnorm.eps)
+            else:
+                y = (cell.outnorm(h_raw).transpose(1, 2).reshape(x.shape[0], x.shape[1], -1)
+                     + self.learnable_skip * conv_act) * F.silu(z)
+        if y is None:
+            h = cell(q=q, k=k, v=v)
+            y = (h + self.learnable_skip * conv_act) * F.silu(z)
+        y = self.proj_down(y)
         if literal_flip:
             y = y.flip(dims=[1])
         return x + y
