@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MLSTM_B200_ABI_VERSION 2
+#define MLSTM_B200_ABI_VERSION 3
 
 typedef enum mlstm_status {
   MLSTM_OK = 0,
@@ -52,6 +52,8 @@ typedef enum mlstm_status {
   MLSTM_ERR_CUDA = -4,          /* a CUDA runtime / driver call failed (see last_error)      */
   MLSTM_ERR_NO_DEVICE = -5      /* no sm_100 device / driver entry points unavailable        */
 } mlstm_status;
+
+typedef enum mlstm_igate { MLSTM_IGATE_EXP = 0, MLSTM_IGATE_SIGMOID = 1 } mlstm_igate;
 
 typedef enum mlstm_dtype {
   MLSTM_F32 = 0,   /* fp32 I/O, fp32 SIMT arithmetic ("fp32 mode", tolerance 1e-4)          */
@@ -111,6 +113,14 @@ typedef struct mlstm_params {
    * 0 bytes (NULL allowed) for the SIMT kernel family. */
   void* states;
   size_t states_bytes;
+
+  /* Input gate: MLSTM_IGATE_EXP (0) = exponential input gate with max-stabiliser m, the arithmetic of
+   * chunkwise_simple (backends.py:149-263) and of upstream's "chunkwise--native_autograd";
+   * MLSTM_IGATE_SIGMOID (1) = sigmoid input gate ("...xl_chunk_siging", the kernel string HEAD asks for
+   * on CUDA, vision_lstm2.py:835,866): log-gate logsigmoid(i), no stabiliser (m == 0, m_initial ignored,
+   * m_row / m_last written as 0), normaliser max(|n|, 1) + eps. */
+  int32_t gate_mode;
+  int32_t reserved_;
 } mlstm_params;
 
 /* ---------------------------------------------------------------------------------------------

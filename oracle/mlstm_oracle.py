@@ -226,10 +226,68 @@ def cell_forward(
     return h.transpose(1, 2).reshape(B, S, H)
 
 
-def mlstm_fwbw(q, k, v, i, f, dh, chunk_size=64, eps=1e-6, reverse=False, **kw):
+# ---------------------------------------------------------------------------------------------
+# Sigmoid-input-gate variant ("siging").  PARITY UNPINNED: HEAD asks for it on CUDA through the kernel
+# string "chunkwise--triton_xl_chunk_siging" (vision_lstm2.py:835,866), but the arithmetic lives in the
+# external, un-vendored, un-versioned ``mlstm_kernels`` package and nothing in the
+# reference tree restates or tests it.  What follows is its published algorithm (the package's native
+# parallel form): log input gate logsigmoid(i), log forget gate logsigmoid(f), no max-stabiliser
+# (every log-weight is <= 0), normaliser max(|n_t|, 1) + eps:
+#     D_tj = exp(logsig(i_j) + sum_{j<s<=t} logsig(f_s))   (j <= t)
+#     h_t  = sum_j D_tj (q_t.k_j / sqrt(DH)) v_j / (max(|sum_j D_tj q_t.k_j / sqrt(DH)|, 1) + eps)
+# The recurrent form below is the same thing step by step and carries (C, n) states (m == 0).
+# ---------------------------------------------------------------------------------------------
+def mlstm_siging_parallel(q: Tensor, k: Tensor, v: Tensor, i: Tensor, f: Tensor, eps: float = 1e-6,
+                          reverse: bool = False) -> Tensor:
+    if reverse:
+        q, k, v, i, f = _flip_seq(q, k, v, i, f)
+    S, DH = q.shape[2], q.shape[3]
+    b = F.logsigmoid(f).cumsum(-1)
+    logD = b[..., :, None] - b[..., None, :] + F.logsigmoid(i)[..., None, :]
+    causal = torch.ones(S, S, dtype=torch.bool, device=q.device).tril()
+    D = torch.exp(logD.masked_fill(~causal, -float("inf")))
+    E = (q @ k.transpose(-1, -2)) * (DH ** -0.5) * D
+    n = torch.maximum(E.sum(-1, keepdim=True).abs(), torch.ones((), dtype=q.dtype, device=q.device))
+    h = (E / (n + eps)) @ v
+    return h.flip(dims=[2]) if reverse else h
+
+
+def mlstm_siging_recurrent(q: Tensor, k: Tensor, v: Tensor, i: Tensor, f: Tensor, c_initial: Optional[Tensor] = None,
+                           n_initial: Optional[Tensor] = None, eps: float = 1e-6, return_last_states: bool = False,
+                           reverse: bool = False):
+    if reverse:
+        q, k, v, i, f = _flip_seq(q, k, v, i, f)
+    B, NH, S, DK = q.shape
+    DV = v.shape[-1]
+    C = q.new_zeros(B, NH, DK, DV) if c_initial is None else c_initial.to(q.dtype)
+    n = q.new_zeros(B, NH, DK) if n_initial is None else n_initial.to(q.dtype)
+    fg, ig = torch.sigmoid(f), torch.sigmoid(i)
+    outs = []
+    for t in range(S):
+        kt, vt, qt = k[:, :, t], v[:, :, t], q[:, :, t] * (DK ** -0.5)
+        C = fg[:, :, t, None, None] * C + ig[:, :, t, None, None] * kt[..., :, None] * vt[..., None, :]
+        n = fg[:, :, t, None] * n + ig[:, :, t, None] * kt
+        den = torch.maximum((qt * n).sum(-1).abs(), torch.ones((), dtype=q.dtype, device=q.device)) + eps
+        outs.append((qt[..., None, :] @ C).squeeze(-2) / den[..., None])
+    h = torch.stack(outs, dim=2)
+    if reverse:
+        h = h.flip(dims=[2])
+    if return_last_states:
+        return h, (C, n, q.new_zeros(B, NH, 1))
+    return h
+
+
+def mlstm_fwbw(q, k, v, i, f, dh, chunk_size=64, eps=1e-6, reverse=False, input_gate="exp", **kw):
     """Forward + autograd backward through the chunkwise oracle.  Returns
     (h, dq, dk, dv, di, df).  Used as the gradient oracle and as the CPU baseline step."""
     leaves = [t.detach().clone().requires_grad_(True) for t in (q, k, v, i, f)]
-    h = mlstm_chunkwise(*leaves, chunk_size=chunk_size, eps=eps, reverse=reverse, **kw)
+    if input_gate == "sigmoid":
+        if kw.get("c_initial") is not None or kw.get("n_initial") is not None:
+            h = mlstm_siging_recurrent(*leaves, c_initial=kw.get("c_initial"), n_initial=kw.get("n_initial"), eps=eps,
+                                       reverse=reverse)
+        else:
+            h = mlstm_siging_parallel(*leaves, eps=eps, reverse=reverse)
+    else:
+        h = mlstm_chunkwise(*leaves, chunk_size=chunk_size, eps=eps, reverse=reverse, **kw)
     h.backward(dh)
     return (h.detach(),) + tuple(t.grad for t in leaves)

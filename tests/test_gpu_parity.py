@@ -124,6 +124,58 @@ def test_cuda_matches_oracle(B, NH, S, DH, dtype, regime, reverse, eps):
     check(got, ref, dtype, f"B{B} NH{NH} S{S} DH{DH} {regime} rev={reverse}", tie)
 
 
+def siging_tie_rows(inputs, reverse=False, width=2e-2):
+    """Rows where |n_t| is within `width` of the sigmoid-gate normaliser's floor 1 (same discontinuity)."""
+    q, k, v, i, f = (x.double() for x in inputs[:5])
+    if reverse:
+        q, k, v, i, f = (x.flip(dims=[2]) for x in (q, k, v, i, f))
+    S, DH = q.shape[2], q.shape[3]
+    b = torch.nn.functional.logsigmoid(f).cumsum(-1)
+    logD = b[..., :, None] - b[..., None, :] + torch.nn.functional.logsigmoid(i)[..., None, :]
+    D = torch.exp(logD.masked_fill(~torch.ones(S, S, dtype=torch.bool).tril(), -float("inf")))
+    n = ((q @ k.transpose(-1, -2)) * DH ** -0.5 * D).sum(-1)
+    tie = (n.abs() - 1).abs() < width
+    return tie.flip(dims=[2]) if reverse else tie
+
+
+SIG_CASES = [
+    # B, NH, S, DH, dtype, regime, reverse   (PARITY UNPINNED: restated algorithm, see oracle/mlstm_oracle.py)
+    (2, 4, 400, 64, torch.bfloat16, "rand", False),
+    (2, 4, 400, 128, torch.bfloat16, "rand", True),
+    (1, 4, 1600, 128, torch.bfloat16, "rand", False),
+    (1, 2, 700, 64, torch.bfloat16, "forget", True),
+    (3, 2, 129, 64, torch.bfloat16, "refinit", False),
+    (2, 2, 100, 16, torch.float32, "rand", True),
+    (1, 2, 300, 128, torch.float32, "rand", False),
+    (1, 2, 200, 256, torch.bfloat16, "rand", False),
+]
+
+
+@pytest.mark.parametrize("B,NH,S,DH,dtype,regime,reverse", SIG_CASES)
+def test_sigmoid_input_gate_matches_oracle(B, NH, S, DH, dtype, regime, reverse):
+    inputs = make(B, NH, S, DH, dtype, regime)
+    ref = O.mlstm_fwbw(*(x.double() for x in inputs), eps=1e-6, reverse=reverse, input_gate="sigmoid")
+    got = run_cuda(inputs, reverse=reverse, input_gate="sigmoid")
+    tie = siging_tie_rows(inputs, reverse) if dtype == torch.bfloat16 else None
+    check(got, ref, dtype, f"siging B{B} NH{NH} S{S} DH{DH} {regime} rev={reverse}", tie)
+
+
+@pytest.mark.parametrize("dtype,DH", [(torch.float32, 32), (torch.bfloat16, 64), (torch.bfloat16, 128)])
+def test_sigmoid_input_gate_states(dtype, DH):
+    from xlstm_yolo_b200 import ops
+    B, NH, S = 2, 2, 300
+    inputs = make(B, NH, S, DH, dtype, "rand")
+    g = torch.Generator().manual_seed(7)
+    C0, n0 = torch.randn(B, NH, DH, DH, generator=g), torch.randn(B, NH, DH, generator=g)
+    q, k, v, i, f, _ = (x.cuda() for x in inputs)
+    h, (C, n, m) = ops.mlstm(q, k, v, i, f, C0.cuda(), n0.cuda(), torch.randn(B, NH, 1).cuda(), return_last_states=True,
+                             input_gate="sigmoid")   # m_initial is ignored by the sigmoid gate
+    hr, (Cr, nr, _) = O.mlstm_siging_recurrent(*(x.double() for x in inputs[:5]), C0.double(), n0.double(),
+                                               return_last_states=True)
+    th = TOL[dtype][0]
+    assert rel(h, hr) < th and rel(C, Cr) < th and rel(n, nr) < th and float(m.abs().max()) == 0.0
+
+
 def test_kernel_family_dispatch():
     from xlstm_yolo_b200 import ops
     bf = lambda d: torch.empty(1, 1, 8, d, dtype=torch.bfloat16, device="cuda")

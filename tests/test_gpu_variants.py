@@ -15,6 +15,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_parity_sweep_with_pinned_variant(variant):
     env = dict(os.environ, MLSTM_FORCE_VARIANT=variant)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q",
-                        "-x", "-k", "test_cuda_matches_oracle or test_initial_and_last_states", "-p", "no:cacheprovider"],
+                        "-x", "-k", "test_cuda_matches_oracle or test_initial_and_last_states or sigmoid_input_gate", "-p", "no:cacheprovider"],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -189,12 +189,24 @@ def test_cell_cpu_forward_matches_oracle(reverse):
 
 
 def test_backend_seam_cpu():
-    be = mLSTMBackend(mLSTMBackendConfig(chunkwise_kernel="chunkwise--triton_xl_chunk_siging", sequence_kernel="native_sequence__triton",
-                                         step_kernel="triton", chunk_size=16, autocast_kernel_dtype="bfloat16",
-                                         return_last_states=False, mode="train", eps=5e-5))
     g = torch.Generator().manual_seed(1)
     q, k, v = (torch.randn(2, 3, 40, 8, generator=g) for _ in range(3))
     i, f = torch.randn(2, 3, 40, generator=g), 3 + torch.randn(2, 3, 40, generator=g)
+    # the kernel string HEAD configures on CUDA names the sigmoid-input-gate arithmetic (vision_lstm2.py:835)
+    sig = mLSTMBackend(mLSTMBackendConfig(chunkwise_kernel="chunkwise--triton_xl_chunk_siging", sequence_kernel="native_sequence__triton",
+                                          step_kernel="triton", chunk_size=16, autocast_kernel_dtype="bfloat16",
+                                          return_last_states=False, mode="train", eps=5e-5))
+    assert sig.input_gate == "sigmoid"
+    assert (sig(q=q, k=k, v=v, i=i, f=f) - O.mlstm_siging_parallel(q, k, v, i, f, eps=5e-5)).abs().max() < 1e-5
+    C0s, n0s = torch.randn(2, 3, 8, 8, generator=g), torch.randn(2, 3, 8, generator=g)
+    hs, (Cs, ns, ms) = sig(q, k, v, i, f, c_initial=C0s, n_initial=n0s, return_last_states=True)
+    ws_, (Cws, nws, _) = O.mlstm_siging_recurrent(q, k, v, i, f, C0s, n0s, eps=5e-5, return_last_states=True)
+    assert (hs - ws_).abs().max() < 1e-5 and (Cs - Cws).abs().max() < 1e-4 and (ns - nws).abs().max() < 1e-4 and ms.abs().max() == 0
+    # the kernel string of the reference's CPU path: exponential input gate
+    be = mLSTMBackend(mLSTMBackendConfig(chunkwise_kernel="chunkwise--native_autograd", sequence_kernel="native_sequence__native",
+                                         step_kernel="native", chunk_size=16, autocast_kernel_dtype="bfloat16",
+                                         return_last_states=False, mode="train", eps=5e-5))
+    assert be.input_gate == "exp"
     h = be(q=q, k=k, v=v, i=i, f=f)
     want = O.mlstm_chunkwise(q, k, v, i, f, chunk_size=16, eps=5e-5)
     assert (h - want).abs().max() < 1e-5

@@ -12,7 +12,7 @@ import threading
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libmlstm_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MLSTM_F32, MLSTM_BF16 = 0, 1
 
 STATUS = {0: "OK", -1: "INVALID_ARG", -2: "UNSUPPORTED", -3: "WORKSPACE", -4: "CUDA", -5: "NO_DEVICE"}
@@ -63,6 +63,7 @@ class Params(C.Structure):
         ("di", Gate), ("df", Gate),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("states", C.c_void_p), ("states_bytes", C.c_size_t),
+        ("gate_mode", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

@@ -84,13 +84,13 @@ class mLSTMBackend(nn.Module):
             from . import ops
             return ops.mlstm(q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states,
                              eps=cfg.eps, chunk_size=cfg.chunk_size, reverse=reverse,
-                             kernel_dtype=_TORCH_DTYPE[cfg.autocast_kernel_dtype])
+                             kernel_dtype=_TORCH_DTYPE[cfg.autocast_kernel_dtype], input_gate=self.input_gate)
         from .native_cpu import mlstm_chunkwise_cpu
         in_dtype = q.dtype
         cdt = torch.float32 if in_dtype in (torch.float16, torch.bfloat16) else in_dtype
         out = mlstm_chunkwise_cpu(q.to(cdt), k.to(cdt), v.to(cdt), i.to(cdt), f.to(cdt), c_initial, n_initial,
                                   m_initial, return_last_states, eps=cfg.eps, chunk_size=cfg.chunk_size,
-                                  reverse=reverse)
+                                  reverse=reverse, input_gate=self.input_gate)
         if return_last_states:
             return out[0].to(in_dtype), out[1]
         return out.to(in_dtype)
@@ -103,7 +103,13 @@ class mLSTMBackend(nn.Module):
         from . import ops
         return ops.fused_cell(q, k, v, igate.weight, igate.bias, fgate.weight, fgate.bias, num_heads, eps=cfg.eps,
                               chunk_size=cfg.chunk_size, reverse=reverse,
-                              kernel_dtype=_TORCH_DTYPE[cfg.autocast_kernel_dtype])
+                              kernel_dtype=_TORCH_DTYPE[cfg.autocast_kernel_dtype], input_gate=self.input_gate)
+
+    @property
+    def input_gate(self) -> str:
+        """"sigmoid" when the configured kernel string names upstream's sigmoid-input-gate kernels
+        ("chunkwise--triton_xl_chunk_siging", vision_lstm2.py:835,866), else "exp"."""
+        return "sigmoid" if "siging" in str(self.config.chunkwise_kernel) else "exp"
 
     def extra_repr(self) -> str:
         return f"{self.config}"

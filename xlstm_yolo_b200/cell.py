@@ -13,6 +13,9 @@ Differences, all deliberate:
     adds the gate path into dq,dk,dv in place), on CPU through weight slices;
   * ``reverse=True`` scans from the last token, replacing the flip pair around the layer
     (:479-480,505-506);
+  * ``input_gate="sigmoid"`` selects the sigmoid-input-gate arithmetic that HEAD's CUDA kernel string
+    ("chunkwise--triton_xl_chunk_siging", :835,866) names; the default "exp" is the exponential gate
+    of the reference's in-tree PyTorch mLSTM (its CPU path, backends.py:149-263);
   * on CUDA the arithmetic is the sm_100a kernel library, not Triton.
 """
 from __future__ import annotations
@@ -70,7 +73,7 @@ class MultiHeadLayerNorm(nn.Module):
 
 class MatrixLSTMCell(nn.Module):
     def __init__(self, dim, num_heads, norm_bias=True, eps=1e-6, chunk_size=16, use_autocast=True,
-                 autocast_dtype=torch.bfloat16, reverse=False, raw_output=False):
+                 autocast_dtype=torch.bfloat16, reverse=False, raw_output=False, input_gate="exp"):
         super().__init__()
         self.dim = dim
         self.num_heads = num_heads
@@ -79,6 +82,11 @@ class MatrixLSTMCell(nn.Module):
         self.reverse = reverse
         self.raw_output = raw_output
         self.fused_gates = True   # CUDA: csrc/mlstm_gates.cu instead of three cuBLAS skinny GEMMs
+        if input_gate not in ("exp", "sigmoid"):
+            raise ValueError(f"input_gate must be 'exp' or 'sigmoid', got {input_gate!r}")
+        # "exp": the arithmetic of the reference's in-tree PyTorch mLSTM (its CPU path and our oracle);
+        # "sigmoid": what HEAD's CUDA kernel string "...xl_chunk_siging" names (vision_lstm2.py:835,866)
+        self.input_gate = input_gate
 
         self.igate = nn.Linear(3 * dim, num_heads)
         self.fgate = nn.Linear(3 * dim, num_heads)
@@ -91,7 +99,8 @@ class MatrixLSTMCell(nn.Module):
 
         def mk(mode):  # eps = 5e-5: what the reference passes (vision_lstm2.py:827)
             return mLSTMBackend(mLSTMBackendConfig(
-                chunkwise_kernel="chunkwise--b200_tcgen05", sequence_kernel="native_sequence__native",
+                chunkwise_kernel="chunkwise--b200_tcgen05" + ("_siging" if input_gate == "sigmoid" else ""),
+                sequence_kernel="native_sequence__native",
                 step_kernel="native", chunk_size=int(chunk_size), autocast_kernel_dtype=kdt,
                 return_last_states=False, mode=mode, eps=5e-5))
 

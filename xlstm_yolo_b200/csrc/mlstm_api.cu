@@ -47,6 +47,10 @@ int validate(const mlstm_params* p, int is_bwd) {
     set_error("unsupported dtype %d", p->dtype);
     return MLSTM_ERR_UNSUPPORTED;
   }
+  if (p->gate_mode != MLSTM_IGATE_EXP && p->gate_mode != MLSTM_IGATE_SIGMOID) {
+    set_error("unknown gate_mode %d", p->gate_mode);
+    return MLSTM_ERR_INVALID_ARG;
+  }
   if (p->B == 0 || p->S == 0) return MLSTM_OK;  // empty input: nothing to do
   int rc;
   if ((rc = check_act("q", p->q, true)) || (rc = check_act("k", p->k, true)) || (rc = check_act("v", p->v, true)) ||

@@ -45,6 +45,15 @@ __device__ __forceinline__ float log_sigmoid(float x) {
   return fminf(x, 0.f) - log1pf(__expf(-fabsf(x)));
 }
 
+// Input-gate pre-activation as it enters the log-space recurrence, and its derivative
+// (gate_mode 1: sigmoid input gate, log-gate = logsigmoid(i); d/di = sigmoid(-i)).
+__device__ __forceinline__ float igate_log(const mlstm_params& p, float i_raw) {
+  return p.gate_mode ? log_sigmoid(i_raw) : i_raw;
+}
+__device__ __forceinline__ float igate_dlog(const mlstm_params& p, float i_raw) {
+  return p.gate_mode ? 1.f / (1.f + __expf(i_raw)) : 1.f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

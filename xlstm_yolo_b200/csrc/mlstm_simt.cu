@@ -71,12 +71,13 @@ __device__ __forceinline__ void gates_forward(Gates& G, const mlstm_params& p, i
   if (valid) {
     int tok = tok_of(pos0 + lane, p.S, p.reverse);
     fi = *gate_ptr(p.f, b, h, tok);
-    ii = *gate_ptr(p.i, b, h, tok);
+    ii = igate_log(p, *gate_ptr(p.i, b, h, tok));
     logf = log_sigmoid(fi);
   }
+  if (p.gate_mode) m_prev = 0.f;   // sigmoid input gate: no stabiliser, m_t == 0
   float bsum = warp_scan_add(logf, lane);
   float u = ii - bsum;
-  float M = fmaxf(m_prev, warp_scan_max(u, lane));
+  float M = p.gate_mode ? -bsum : fmaxf(m_prev, warp_scan_max(u, lane));
   float ML = __shfl_sync(0xffffffffu, M, 31);
   float g = __shfl_sync(0xffffffffu, bsum, 31);
   G.u[lane] = u;
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(NT) simt_bwd_dkv_kernel(const mlstm_params p, 
       if (valid) {
         int tok = tok_of(pos0 + lane, S, p.reverse);
         fi = *gate_ptr(p.f, b, h, tok);
-        ii = *gate_ptr(p.i, b, h, tok);
+        ii = igate_log(p, *gate_ptr(p.i, b, h, tok));
         logf = log_sigmoid(fi);
         mrow = p.m_row[(int64_t)bh * S + tok];
         nr = p.n_row[(int64_t)bh * S + tok];
@@ -378,6 +379,7 @@ __global__ void __launch_bounds__(NT) simt_bwd_dkv_kernel(const mlstm_params p, 
       if (!valid) M = ML;
       float m_prev = (pos0 == 0) ? (p.m_initial ? p.m_initial[bh] : 0.f)
                                  : p.m_row[(int64_t)bh * S + tok_of(pos0 - 1, S, p.reverse)];
+      if (p.gate_mode) m_prev = 0.f;
       G.u[lane] = u;
       G.M[lane] = M;
       G.w[lane] = __expf(m_prev - M);
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(NT) simt_bwd_dkv_kernel(const mlstm_params p, 
         float* di = gate_ptr(p.di, b, h, tok);
         float* df = gate_ptr(p.df, b, h, tok);
         const float dfv = rc / (1.f + __expf(fi));  // sigmoid(-f)
-        *di = (sl.first ? 0.f : *di) + Kj;
+        *di = (sl.first ? 0.f : *di) + Kj * igate_dlog(p, *gate_ptr(p.i, b, h, tok));
         *df = (sl.first ? 0.f : *df) + dfv;
       }
       float c0 = __shfl_sync(0xffffffffu, rc, 0);

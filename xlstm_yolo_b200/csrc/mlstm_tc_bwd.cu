@@ -716,7 +716,8 @@ __global__ void __launch_bounds__(L) tc_dfscan_kernel(const mlstm_params p, cons
     const size_t g = (size_t)bh * S + tok;
     float R = 0.f, K = 0.f;
     for (int c = 0; c < nb; ++c) { R += rp[(size_t)c * rows_total + g]; K += kp[(size_t)c * rows_total + g]; }
-    p.di.ptr[(int64_t)b * p.di.stride_b + (int64_t)h * p.di.stride_h + (int64_t)tok * p.di.stride_s] = K;
+    const float i_raw = p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s];
+    p.di.ptr[(int64_t)b * p.di.stride_b + (int64_t)h * p.di.stride_h + (int64_t)tok * p.di.stride_s] = K * igate_dlog(p, i_raw);
     dB = R - K;
   }
   const float incl = warp_scan_add(dB, lane);

@@ -98,7 +98,7 @@ __device__ __forceinline__ void gates_from_rows(SM& sm, GateBufB& G, const mlstm
   if (valid) {
     const int tok = cg.tok0 + r;
     fi = p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s];
-    ii = p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s];
+    ii = igate_log(p, p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s]);
     logf = log_sigmoid(fi);
     mrow = p.m_row[(int64_t)bh * p.S + tok];
     nrow = p.n_row[(int64_t)bh * p.S + tok];
@@ -118,7 +118,8 @@ __device__ __forceinline__ void gates_from_rows(SM& sm, GateBufB& G, const mlstm
   float m_prev;
   {
     const int ptok = rev ? (cg.tok0 + cg.nvalid) : (cg.tok0 - 1);
-    m_prev = (ptok >= 0 && ptok < p.S) ? p.m_row[(int64_t)bh * p.S + ptok] : (p.m_initial ? p.m_initial[bh] : 0.f);
+    m_prev = p.gate_mode ? 0.f
+             : ((ptok >= 0 && ptok < p.S) ? p.m_row[(int64_t)bh * p.S + ptok] : (p.m_initial ? p.m_initial[bh] : 0.f));
   }
   __syncthreads();
   const float ML = sm.scan[4];
@@ -731,7 +732,8 @@ __device__ __forceinline__ void dkv_body(const BwdMaps& maps, const mlstm_params
       const float carry = df_carry;
       const float suf = rev ? pre : (tot - pre + dB);
       if (row_ok) {
-        p.di.ptr[(int64_t)b * p.di.stride_b + (int64_t)h * p.di.stride_h + (int64_t)tok * p.di.stride_s] = Kj;
+        const float i_raw = p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s];
+        p.di.ptr[(int64_t)b * p.di.stride_b + (int64_t)h * p.di.stride_h + (int64_t)tok * p.di.stride_s] = Kj * igate_dlog(p, i_raw);
         p.df.ptr[(int64_t)b * p.df.stride_b + (int64_t)h * p.df.stride_h + (int64_t)tok * p.df.stride_s] =
             (suf + carry) * G.sig[tid];
       }

@@ -95,6 +95,7 @@ __device__ __forceinline__ float log_sigmoid_fast(float x) {
 template <int DH>
 __device__ __forceinline__ void compute_gates(GateBuf& G, const mlstm_params& p, int b, int h, int c, int lane,
                                               float m_prev, float scale) {
+  if (p.gate_mode) m_prev = 0.f;   // sigmoid input gate: no stabiliser
   const int NCc = (p.S + L - 1) / L;
   const int mc = p.reverse ? (NCc - 1 - c) : c;
   const int tok0 = mc * L;
@@ -112,7 +113,7 @@ __device__ __forceinline__ void compute_gates(GateBuf& G, const mlstm_params& p,
     if (valid) {
       const int tok = tok0 + r[e];
       logf = log_sigmoid_fast(p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s]);
-      ii[e] = p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s];
+      ii[e] = igate_log(p, p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s]);
     }
     run += logf;
     bs[e] = run;
@@ -132,11 +133,11 @@ __device__ __forceinline__ void compute_gates(GateBuf& G, const mlstm_params& p,
   const float imax = warp_scan_max(lmax, lane);
   float emax = __shfl_up_sync(0xffffffffu, imax, 1);
   if (lane == 0) emax = -INFINITY;
-  const float ML = fmaxf(m_prev, __shfl_sync(0xffffffffu, imax, 31));
+  const float ML = p.gate_mode ? -g_tot : fmaxf(m_prev, __shfl_sync(0xffffffffu, imax, 31));
   const float l2s = log2f(scale);
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const float M = fmaxf(m_prev, fmaxf(emax, cm[e]));
+    const float M = p.gate_mode ? -bs[e] : fmaxf(m_prev, fmaxf(emax, cm[e]));   // sigmoid gate: m_t == 0
     G.u2[r[e]] = u[e] * LOG2E + l2s;
     G.M2[r[e]] = M * LOG2E;
     G.wq[r[e]] = __expf(m_prev - M) * scale;
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
     tc::store_row32(Cs_g + (size_t)row * DH + cq * 32, pk);
     if (cq == 0) ns_g[row] = has_init ? p.n_initial[(int64_t)bh * DH + row] : 0.f;
   }
-  if (save_states && issuer) ms_g[0] = p.m_initial ? p.m_initial[bh] : 0.f;
+  if (save_states && issuer) ms_g[0] = (p.m_initial && !p.gate_mode) ? p.m_initial[bh] : 0.f;
   if (issuer) {   // MMA1 of chunk 0 (later chunks: issued while the previous epilogue finishes)
     mbar_wait(&sm.bar_q, 0);
     mbar_wait(&sm.bar_k[0], 0);

@@ -79,6 +79,7 @@ struct alignas(16) GateBuf {
 
 // Forward-style gates: one warp, lane l owns scan-local indices 4l..4l+3; m_prev is known.
 __device__ __forceinline__ void gates_warp_fwd(GateBuf& G, const mlstm_params& p, int b, int h, int mc, int lane, float m_prev) {
+  if (p.gate_mode) m_prev = 0.f;   // sigmoid input gate: every log-weight is <= 0, no stabiliser
   const int tok0 = mc * L;
   const int nvalid = min(L, p.S - tok0);
   float ii[4], bs[4], fraw[4];
@@ -94,7 +95,7 @@ __device__ __forceinline__ void gates_warp_fwd(GateBuf& G, const mlstm_params& p
     if (valid) {
       const int tok = tok0 + r[e];
       fraw[e] = p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s];
-      ii[e] = p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s];
+      ii[e] = igate_log(p, p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s]);
     }
   }
   float run = 0.f;
@@ -118,10 +119,10 @@ __device__ __forceinline__ void gates_warp_fwd(GateBuf& G, const mlstm_params& p
   const float imax = warp_scan_max(lmax, lane);
   float emax = __shfl_up_sync(0xffffffffu, imax, 1);
   if (lane == 0) emax = -INFINITY;
-  const float ML = fmaxf(m_prev, __shfl_sync(0xffffffffu, imax, 31));
+  const float ML = p.gate_mode ? -g_tot : fmaxf(m_prev, __shfl_sync(0xffffffffu, imax, 31));
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const float M = fmaxf(m_prev, fmaxf(emax, cm[e]));
+    const float M = p.gate_mode ? -bs[e] : fmaxf(m_prev, fmaxf(emax, cm[e]));   // sigmoid gate: m_t = b_t + M_t == 0
     G.u2[r[e]] = u[e] * LOG2E;
     G.M2[r[e]] = M * LOG2E;
     G.w[r[e]] = __expf(m_prev - M);
@@ -146,7 +147,8 @@ __device__ __forceinline__ void gates_warp_bwd(GateBuf& G, const mlstm_params& p
   int r[4];
   // all global loads first (independent), then the dependent math
   const int ptok = rev ? (tok0 + nvalid) : (tok0 - 1);
-  const float m_prev = (ptok >= 0 && ptok < p.S) ? p.m_row[(int64_t)bh * p.S + ptok] : (p.m_initial ? p.m_initial[bh] : 0.f);
+  const float m_prev = p.gate_mode ? 0.f
+                       : ((ptok >= 0 && ptok < p.S) ? p.m_row[(int64_t)bh * p.S + ptok] : (p.m_initial ? p.m_initial[bh] : 0.f));
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int t = lane * 4 + e;
@@ -156,7 +158,7 @@ __device__ __forceinline__ void gates_warp_bwd(GateBuf& G, const mlstm_params& p
     if (valid) {
       const int tok = tok0 + r[e];
       fi[e] = p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s];
-      ii[e] = p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s];
+      ii[e] = igate_log(p, p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s]);
       mr[e] = p.m_row[(int64_t)bh * p.S + tok];
       nr[e] = p.n_row[(int64_t)bh * p.S + tok];
       if (ws_dn) dnv[e] = ws_dn[(int64_t)bh * p.S + tok];

@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 
 def mlstm_chunkwise_cpu(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None, return_last_states=False,
-                        eps=1e-6, chunk_size=64, reverse=False):
+                        eps=1e-6, chunk_size=64, reverse=False, input_gate="exp"):
     if q.is_cuda:
         raise RuntimeError("native_cpu.mlstm_chunkwise_cpu is for CPU tensors only")
     if reverse:
@@ -32,13 +32,17 @@ def mlstm_chunkwise_cpu(q, k, v, i, f, c_initial=None, n_initial=None, m_initial
     m = q.new_zeros(B, NH) if m_initial is None else m_initial.to(q.dtype).reshape(B, NH)
     logf = F.logsigmoid(f.to(q.dtype))
     i = i.to(q.dtype)
+    sig = input_gate == "sigmoid"   # log-gate logsigmoid(i), no stabiliser: m == 0, normaliser max(|n|, 1)
+    if sig:
+        i = F.logsigmoid(i)
+        m = torch.zeros_like(m)
     outs = []
     for a in range(0, S, L):
         e = min(S, a + L)
         qc, kc, vc = q[:, :, a:e] * scale, k[:, :, a:e], v[:, :, a:e]
         b = logf[:, :, a:e].cumsum(-1)
         u = i[:, :, a:e] - b
-        M = torch.maximum(m[..., None], u.cummax(-1).values)
+        M = -b if sig else torch.maximum(m[..., None], u.cummax(-1).values)
         causal = torch.ones(e - a, e - a, dtype=torch.bool, device=q.device).tril()
         D = torch.exp(u[..., None, :] - M[..., :, None]).masked_fill(~causal, 0.0)
         w = torch.exp(m[..., None] - M)

@@ -71,7 +71,7 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def _base_params(q, k, v, i, f, eps, chunk_size, reverse, qk_scale) -> Params:
+def _base_params(q, k, v, i, f, eps, chunk_size, reverse, qk_scale, gate_mode=0) -> Params:
     B, NH, S, DK = q.shape
     p = Params()
     p.abi_version = _lib.ABI_VERSION
@@ -81,9 +81,18 @@ def _base_params(q, k, v, i, f, eps, chunk_size, reverse, qk_scale) -> Params:
     p.chunk_size = int(chunk_size)
     p.eps = float(eps)
     p.qk_scale = float(qk_scale or 0.0)
+    p.gate_mode = int(gate_mode)
     p.q, p.k, p.v = _act(q), _act(k), _act(v)
     p.i, p.f = _gate(i), _gate(f)
     return p
+
+
+def gate_mode_of(input_gate) -> int:
+    if input_gate in (0, "exp", "exponential", None):
+        return 0
+    if input_gate in (1, "sigmoid", "siging"):
+        return 1
+    raise ValueError(f"input_gate must be 'exp' or 'sigmoid', got {input_gate!r}")
 
 
 def kernel_family(q: torch.Tensor, v: torch.Tensor) -> str:
@@ -107,7 +116,7 @@ def _alloc_states(lib, p, dev):
 
 
 def mlstm_fwd_raw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None, *, eps=1e-6, chunk_size=64,
-                  reverse=False, save_rows=True, return_last_states=False, qk_scale=None):
+                  reverse=False, save_rows=True, return_last_states=False, qk_scale=None, gate_mode=0):
     """One forward launch through the C ABI.  Inputs must already be CUDA, fp32 or bf16
     (q,k,v same dtype), gates fp32.  Returns (h, n_row, m_row, last_states_or_None, chunk_states)."""
     lib = _lib.load()
@@ -124,7 +133,7 @@ def mlstm_fwd_raw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None,
         last = (torch.empty((B, NH, DK, DV), dtype=torch.float32, device=dev),
                 torch.empty((B, NH, DK), dtype=torch.float32, device=dev),
                 torch.empty((B, NH, 1), dtype=torch.float32, device=dev))
-    p = _base_params(q, k, v, i, f, eps, chunk_size, reverse, qk_scale)
+    p = _base_params(q, k, v, i, f, eps, chunk_size, reverse, qk_scale, gate_mode)
     p.c_initial, p.n_initial, p.m_initial = _ptr(c_initial), _ptr(n_initial), _ptr(m_initial)
     p.h = _act(h)
     p.n_row, p.m_row = _ptr(n_row), _ptr(m_row)
@@ -139,7 +148,7 @@ def mlstm_fwd_raw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None,
 
 
 def mlstm_bwd_raw(q, k, v, i, f, h, n_row, m_row, dh, c_initial=None, n_initial=None, m_initial=None, *, eps=1e-6,
-                  chunk_size=64, reverse=False, qk_scale=None, states=None):
+                  chunk_size=64, reverse=False, qk_scale=None, states=None, gate_mode=0):
     """One backward call through the C ABI.  Returns (dq, dk, dv, di, df) — dq,dk,dv in the
     layout/dtype of q,k,v; di,df fp32 (B,NH,S)."""
     lib = _lib.load()
@@ -151,7 +160,7 @@ def mlstm_bwd_raw(q, k, v, i, f, h, n_row, m_row, dh, c_initial=None, n_initial=
     dv = _empty_act(B, NH, S, DV, q.dtype, dev)
     di = torch.empty((B, S, NH), dtype=torch.float32, device=dev).transpose(1, 2)
     df = torch.empty((B, S, NH), dtype=torch.float32, device=dev).transpose(1, 2)
-    p = _base_params(q, k, v, i, f, eps, chunk_size, reverse, qk_scale)
+    p = _base_params(q, k, v, i, f, eps, chunk_size, reverse, qk_scale, gate_mode)
     p.c_initial, p.n_initial, p.m_initial = _ptr(c_initial), _ptr(n_initial), _ptr(m_initial)
     p.h = _act(h)
     p.n_row, p.m_row = _ptr(n_row), _ptr(m_row)
@@ -177,14 +186,15 @@ class _MLSTMCellFn(torch.autograd.Function):
     recomputed per chunk in the backward kernels."""
 
     @staticmethod
-    def forward(ctx, q, k, v, i, f, c_initial, n_initial, m_initial, eps, chunk_size, reverse, return_last_states):
+    def forward(ctx, q, k, v, i, f, c_initial, n_initial, m_initial, eps, chunk_size, reverse, return_last_states,
+                gate_mode=0):
         need_grad = any(t.requires_grad for t in (q, k, v, i, f))
         h, n_row, m_row, last, states = mlstm_fwd_raw(
             q, k, v, i, f, c_initial, n_initial, m_initial, eps=eps, chunk_size=chunk_size, reverse=reverse,
-            save_rows=need_grad, return_last_states=return_last_states)
+            save_rows=need_grad, return_last_states=return_last_states, gate_mode=gate_mode)
         if need_grad:
             ctx.save_for_backward(q, k, v, i, f, h, n_row, m_row, c_initial, n_initial, m_initial, states)
-        ctx.cfg = (eps, chunk_size, reverse)
+        ctx.cfg = (eps, chunk_size, reverse, gate_mode)
         if return_last_states:
             ctx.mark_non_differentiable(*last)
             return (h,) + tuple(last)
@@ -193,25 +203,28 @@ class _MLSTMCellFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dh, *dstates):
         q, k, v, i, f, h, n_row, m_row, c0, n0, m0, states = ctx.saved_tensors
-        eps, chunk_size, reverse = ctx.cfg
+        eps, chunk_size, reverse, gate_mode = ctx.cfg
         if dh.dtype != q.dtype:
             dh = dh.to(q.dtype)  # e.g. loss-scaled fp16 -> bf16: no clamping, inf/NaN propagate
         dh = _prep_act(dh)
         dq, dk, dv, di, df = mlstm_bwd_raw(q, k, v, i, f, h, n_row, m_row, dh, c0, n0, m0, eps=eps,
-                                           chunk_size=chunk_size, reverse=reverse, states=states)
-        return dq, dk, dv, di, df, None, None, None, None, None, None, None
+                                           chunk_size=chunk_size, reverse=reverse, states=states, gate_mode=gate_mode)
+        return dq, dk, dv, di, df, None, None, None, None, None, None, None, None
 
 
 def mlstm(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, i: torch.Tensor, f: torch.Tensor,
           c_initial: Optional[torch.Tensor] = None, n_initial: Optional[torch.Tensor] = None,
           m_initial: Optional[torch.Tensor] = None, return_last_states: bool = False, *, eps: float = 1e-6,
-          chunk_size: int = 64, reverse: bool = False, kernel_dtype: Optional[torch.dtype] = None):
+          chunk_size: int = 64, reverse: bool = False, kernel_dtype: Optional[torch.dtype] = None,
+          input_gate: str = "exp"):
     """mLSTM cell on CUDA tensors.
 
     ``kernel_dtype``: torch.bfloat16 -> tcgen05 kernels (bf16 operands, fp32 accumulation);
     torch.float32 -> fp32 SIMT kernels.  Default: bf16 for bf16/fp16 inputs, fp32 for fp32
     inputs.  The result has the dtype of ``q``.  Initial/last states are fp32 and carry no
-    gradient (the reference never differentiates through them).
+    gradient (the reference never differentiates through them).  ``input_gate``: "exp" (exponential input
+    gate with max-stabiliser, backends.py:149-263) or "sigmoid" (the "siging" kernels HEAD names on CUDA,
+    vision_lstm2.py:835: log-gate logsigmoid(i), no stabiliser, normaliser max(|n|, 1)).
     """
     if not q.is_cuda:
         raise RuntimeError("xlstm_yolo_b200.ops.mlstm needs CUDA tensors (no CPU fallback)")
@@ -226,7 +239,7 @@ def mlstm(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, i: torch.Tensor, f:
     n0 = None if n_initial is None else n_initial.detach().to(torch.float32).contiguous()
     m0 = None if m_initial is None else m_initial.detach().to(torch.float32).reshape(q.shape[0], q.shape[1]).contiguous()
     out = _MLSTMCellFn.apply(q, k, v, i, f, c0, n0, m0, float(eps), int(chunk_size), bool(reverse),
-                             bool(return_last_states))
+                             bool(return_last_states), gate_mode_of(input_gate))
     if return_last_states:
         h, C, n, m = out
         return h.to(in_dtype), (C, n, m)
@@ -298,7 +311,7 @@ class _FusedCellFn(torch.autograd.Function):
     reduces dW, db — nothing of size (B,S,3D) is ever materialised."""
 
     @staticmethod
-    def forward(ctx, q3, k3, v3, w_i, b_i, w_f, b_f, NH, eps, chunk_size, reverse):
+    def forward(ctx, q3, k3, v3, w_i, b_i, w_f, b_f, NH, eps, chunk_size, reverse, gate_mode=0):
         B, S, D = q3.shape
         i3, f3 = gate_proj_fwd_raw(q3, k3, v3, w_i, b_i, w_f, b_f, NH)
         heads = lambda t: t.view(B, S, NH, D // NH).transpose(1, 2)
@@ -306,16 +319,16 @@ class _FusedCellFn(torch.autograd.Function):
         i, f = i3.transpose(1, 2), f3.transpose(1, 2)
         need_grad = any(t is not None and t.requires_grad for t in (q3, k3, v3, w_i, b_i, w_f, b_f))
         h, n_row, m_row, _, states = mlstm_fwd_raw(q, k, v, i, f, eps=eps, chunk_size=chunk_size, reverse=reverse,
-                                                   save_rows=need_grad)
+                                                   save_rows=need_grad, gate_mode=gate_mode)
         if need_grad:
             ctx.save_for_backward(q3, k3, v3, w_i, w_f, i3, f3, h, n_row, m_row, states)
-        ctx.cfg = (NH, eps, chunk_size, reverse, b_i is not None)
+        ctx.cfg = (NH, eps, chunk_size, reverse, b_i is not None, gate_mode)
         return h
 
     @staticmethod
     def backward(ctx, dh):
         q3, k3, v3, w_i, w_f, i3, f3, h, n_row, m_row, states = ctx.saved_tensors
-        NH, eps, chunk_size, reverse, has_bias = ctx.cfg
+        NH, eps, chunk_size, reverse, has_bias, gate_mode = ctx.cfg
         B, S, D = q3.shape
         heads = lambda t: t.view(B, S, NH, D // NH).transpose(1, 2)
         if dh.dtype != q3.dtype:
@@ -323,17 +336,18 @@ class _FusedCellFn(torch.autograd.Function):
         dh = _prep_act(dh)
         dq, dk, dv, di, df = mlstm_bwd_raw(heads(q3), heads(k3), heads(v3), i3.transpose(1, 2), f3.transpose(1, 2), h,
                                            n_row, m_row, dh, eps=eps, chunk_size=chunk_size, reverse=reverse,
-                                           states=states)
+                                           states=states, gate_mode=gate_mode)
         # dq,dk,dv are (B,NH,S,DH) views of fresh (B,S,NH,DH) storage; di,df views of (B,S,NH) storage
         dq3, dk3, dv3 = (t.transpose(1, 2).reshape(B, S, D) for t in (dq, dk, dv))
         dw_i, db_i, dw_f, db_f = gate_proj_bwd_raw(q3, k3, v3, w_i, w_f, NH, di.transpose(1, 2), df.transpose(1, 2),
                                                    dq3, dk3, dv3, need_bias=has_bias)
-        return dq3, dk3, dv3, dw_i, db_i, dw_f, db_f, None, None, None, None
+        return dq3, dk3, dv3, dw_i, db_i, dw_f, db_f, None, None, None, None, None
 
 
 def fused_cell(q3: torch.Tensor, k3: torch.Tensor, v3: torch.Tensor, w_i: torch.Tensor, b_i: Optional[torch.Tensor],
                w_f: torch.Tensor, b_f: Optional[torch.Tensor], num_heads: int, *, eps: float = 1e-6,
-               chunk_size: int = 64, reverse: bool = False, kernel_dtype: Optional[torch.dtype] = None):
+               chunk_size: int = 64, reverse: bool = False, kernel_dtype: Optional[torch.dtype] = None,
+               input_gate: str = "exp"):
     """``MatrixLSTMCell`` arithmetic up to (not including) the out-norm, on CUDA tensors:
     q,k,v (B,S,D) -> h (B,NH,S,DH).  Gate weights are used in fp32 whatever the autocast state."""
     if not q3.is_cuda:
@@ -349,7 +363,7 @@ def fused_cell(q3: torch.Tensor, k3: torch.Tensor, v3: torch.Tensor, w_i: torch.
         q3, k3, v3 = q3.contiguous(), k3.contiguous(), v3.contiguous()
     f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()
     h = _FusedCellFn.apply(q3, k3, v3, f32(w_i), f32(b_i), f32(w_f), f32(b_f), int(num_heads), float(eps),
-                           int(chunk_size), bool(reverse))
+                           int(chunk_size), bool(reverse), gate_mode_of(input_gate))
     return h.to(in_dtype)
 
 
@@ -447,7 +461,7 @@ class MLSTMPlan:
     single C-ABI call each (plus the host-side TMA descriptor encode inside the library).
     """
 
-    def __init__(self, q, k, v, i, f, dh, *, eps=1e-6, chunk_size=64, reverse=False):
+    def __init__(self, q, k, v, i, f, dh, *, eps=1e-6, chunk_size=64, reverse=False, input_gate="exp"):
         self.lib = _lib.load()
         B, NH, S, DK = q.shape
         DV = v.shape[-1]
@@ -461,7 +475,7 @@ class MLSTMPlan:
         self.dv = _empty_act(B, NH, S, DV, q.dtype, dev)
         self.di = torch.empty((B, S, NH), dtype=torch.float32, device=dev).transpose(1, 2)
         self.df = torch.empty((B, S, NH), dtype=torch.float32, device=dev).transpose(1, 2)
-        p = _base_params(q, k, v, i, f, eps, chunk_size, reverse, None)
+        p = _base_params(q, k, v, i, f, eps, chunk_size, reverse, None, gate_mode_of(input_gate))
         p.h = _act(self.h)
         p.n_row, p.m_row = _ptr(self.n_row), _ptr(self.m_row)
         p.dh = _act(dh)
