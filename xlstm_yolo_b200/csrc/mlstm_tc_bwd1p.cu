@@ -609,7 +609,6 @@ __device__ __forceinline__ void dkv_body(const BwdMaps& maps, const mlstm_params
           umma_bf16_ss(tO, dK(smem_u32(skv), ks, TILE), dK(smem_u32(sm.cb), ks, TILE_C), idI, ks > 0);
       }
       constexpr uint32_t idC = make_idesc_bf16(128, DH, 1, 1);
-      constexpr uint32_t idN = make_idesc_bf16(128, 16, 1, 0);
       const uint32_t acc0 = (c > 0) ? 1u : 0u;
       for (int ks = 0; ks < L / 16; ++ks) {
         const uint64_t a = dMN(smem_u32(sq), ks, A_LBO_STATE);
