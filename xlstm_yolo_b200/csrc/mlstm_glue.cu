@@ -94,24 +94,34 @@ __global__ void __launch_bounds__(GL_NT) glue_fwd_kernel(const mlstm_glue_params
   load_param8(p.skip, col, sk, 1.f);
 #pragma unroll
   for (int e = 0; e < 8; ++e) w1[e] += 1.f;
-  for (int t = gw / nseg; t < p.T; t += nw / nseg) {
-    float h[8], c[8], z[8], xhat[8], y[8], rstd;
-    Ld8<T>::load(p.h, (size_t)t * p.ld_h + col, h);
-    Ld8<T>::load(p.c, (size_t)t * p.ld_c + col, c);
-    Ld8<T>::load(p.z, (size_t)t * p.ld_z + col, z);
-    head_norm(h, lph, inv_dh, p.eps, xhat, rstd);
+  const int step = nw / nseg;
+  for (int t0 = gw / nseg; t0 < p.T; t0 += 2 * step) {   // two tokens in flight per warp
+    float h[2][8], c[2][8], z[2][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float pre = fmaf(xhat[e], w1[e], bb[e]) + sk[e] * c[e];
-      y[e] = pre * z[e] / (1.f + __expf(-z[e]));
+    for (int u = 0; u < 2; ++u) {
+      const int t = min(t0 + u * step, p.T - 1);
+      Ld8<T>::load(p.h, (size_t)t * p.ld_h + col, h[u]);
+      Ld8<T>::load(p.c, (size_t)t * p.ld_c + col, c[u]);
+      Ld8<T>::load(p.z, (size_t)t * p.ld_z + col, z[u]);
     }
-    Ld8<T>::store(p.y, (size_t)t * p.ld_y + col, y);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int t = t0 + u * step;
+      float xhat[8], y[8], rstd;
+      head_norm(h[u], lph, inv_dh, p.eps, xhat, rstd);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float pre = fmaf(xhat[e], w1[e], bb[e]) + sk[e] * c[u][e];
+        y[e] = pre * z[u][e] / (1.f + __expf(-z[u][e]));
+      }
+      if (t < p.T) Ld8<T>::store(p.y, (size_t)t * p.ld_y + col, y);
+    }
   }
 }
 
 // ws: [gridDim.x][3][D] per-CTA partials of (dw, db, dskip)
 template <typename T>
-__global__ void __launch_bounds__(GL_NT) glue_bwd_kernel(const mlstm_glue_params p, float* __restrict__ ws) {
+__global__ void __launch_bounds__(GL_NT, 2) glue_bwd_kernel(const mlstm_glue_params p, float* __restrict__ ws) {
   __shared__ float red[GL_NT / 32][3][GL_SEG];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gw = blockIdx.x * (GL_NT / 32) + warp, nw = gridDim.x * (GL_NT / 32);
@@ -124,37 +134,51 @@ __global__ void __launch_bounds__(GL_NT) glue_bwd_kernel(const mlstm_glue_params
   load_param8(p.skip, col, sk, 1.f);
 #pragma unroll
   for (int e = 0; e < 8; ++e) { w1[e] += 1.f; aw[e] = 0.f; ab[e] = 0.f; as[e] = 0.f; }
-  for (int t = gw / nseg; t < p.T; t += nw / nseg) {
-    float h[8], c[8], z[8], dy[8], xhat[8], rstd;
-    Ld8<T>::load(p.h, (size_t)t * p.ld_h + col, h);
-    Ld8<T>::load(p.c, (size_t)t * p.ld_c + col, c);
-    Ld8<T>::load(p.z, (size_t)t * p.ld_z + col, z);
-    Ld8<T>::load(p.dy, (size_t)t * p.ld_dy + col, dy);
-    head_norm(h, lph, inv_dh, p.eps, xhat, rstd);
-    float dz[8], dc[8], dx[8], m1 = 0.f, m2 = 0.f;
+  const int step = nw / nseg;
+  for (int t0 = gw / nseg; t0 < p.T; t0 += 2 * step) {   // two tokens in flight per warp
+    float hh[2][8], cc[2][8], zz[2][8], dd[2][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float sg = 1.f / (1.f + __expf(-z[e]));
-      const float silu = z[e] * sg;
-      const float pre = fmaf(xhat[e], w1[e], bb[e]) + sk[e] * c[e];
-      const float g = dy[e] * silu;                                  // d pre
-      dz[e] = dy[e] * pre * sg * (1.f + z[e] * (1.f - sg));
-      dc[e] = g * sk[e];
-      as[e] = fmaf(g, c[e], as[e]);
-      aw[e] = fmaf(g, xhat[e], aw[e]);
-      ab[e] += g;
-      dx[e] = g * w1[e];                                             // d xhat
-      m1 += dx[e];
-      m2 = fmaf(dx[e], xhat[e], m2);
+    for (int u = 0; u < 2; ++u) {
+      const int t = min(t0 + u * step, p.T - 1);
+      Ld8<T>::load(p.h, (size_t)t * p.ld_h + col, hh[u]);
+      Ld8<T>::load(p.c, (size_t)t * p.ld_c + col, cc[u]);
+      Ld8<T>::load(p.z, (size_t)t * p.ld_z + col, zz[u]);
+      Ld8<T>::load(p.dy, (size_t)t * p.ld_dy + col, dd[u]);
     }
-    m1 = head_sum(m1, lph) * inv_dh;
-    m2 = head_sum(m2, lph) * inv_dh;
-    float dh[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) dh[e] = rstd * (dx[e] - m1 - xhat[e] * m2);
-    Ld8<T>::store(p.dh, (size_t)t * p.ld_dh + col, dh);
-    Ld8<T>::store(p.dc, (size_t)t * p.ld_dc + col, dc);
-    Ld8<T>::store(p.dz, (size_t)t * p.ld_dz + col, dz);
+    for (int u = 0; u < 2; ++u) {
+      const int t = t0 + u * step;
+      const bool live = t < p.T;                 // warp-uniform
+      const float* h = hh[u]; const float* c = cc[u]; const float* z = zz[u]; const float* dy = dd[u];
+      float xhat[8], rstd;
+      head_norm(h, lph, inv_dh, p.eps, xhat, rstd);
+      float dz[8], dc[8], dx[8], m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float sg = 1.f / (1.f + __expf(-z[e]));
+        const float silu = z[e] * sg;
+        const float pre = fmaf(xhat[e], w1[e], bb[e]) + sk[e] * c[e];
+        const float g = live ? dy[e] * silu : 0.f;                     // d pre
+        dz[e] = dy[e] * pre * sg * (1.f + z[e] * (1.f - sg));
+        dc[e] = g * sk[e];
+        as[e] = fmaf(g, c[e], as[e]);
+        aw[e] = fmaf(g, xhat[e], aw[e]);
+        ab[e] += g;
+        dx[e] = g * w1[e];                                             // d xhat
+        m1 += dx[e];
+        m2 = fmaf(dx[e], xhat[e], m2);
+      }
+      m1 = head_sum(m1, lph) * inv_dh;
+      m2 = head_sum(m2, lph) * inv_dh;
+      float dh[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dh[e] = rstd * (dx[e] - m1 - xhat[e] * m2);
+      if (live) {
+        Ld8<T>::store(p.dh, (size_t)t * p.ld_dh + col, dh);
+        Ld8<T>::store(p.dc, (size_t)t * p.ld_dc + col, dc);
+        Ld8<T>::store(p.dz, (size_t)t * p.ld_dz + col, dz);
+      }
+    }
   }
   // CTA-level reduction over the warps that own the same segment, then one partial row per CTA
 #pragma unroll
