@@ -210,7 +210,7 @@ int glue_grid(const mlstm_glue_params& p) {
   const int nseg = p.D / GL_SEG;
   const long long units = (long long)p.T * nseg;                 // (token, segment) work units, one per warp step
   long long g = (units + (GL_NT / 32) * 4 - 1) / ((GL_NT / 32) * 4);   // >= 4 units per warp
-  if (g > 4 * 148) g = 4 * 148;                                  // fixed cap: workspace size independent of the device
+  if (g > 2 * 148) g = 2 * 148;                                  // fixed cap: workspace size independent of the device
   return g < 1 ? 1 : (int)g;
 }
 

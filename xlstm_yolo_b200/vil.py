@@ -74,10 +74,50 @@ class SequenceConv2d(nn.Conv2d):
         assert x.ndim == 3
         B, S, C = x.shape
         gh = _grid_height(S, self.seqlens)
-        img = x.transpose(1, 2).reshape(B, C, gh, S // gh)
+        # token-major (B, H*W, C) storage IS the channels-last image: a permuted view, no transpose copy; cuDNN's
+        # NHWC depthwise kernels write channels-last, so the way back to (B, S, C) is a view as well
+        img = x.reshape(B, gh, S // gh, C).permute(0, 3, 1, 2)
         w = self.weight.flip(-1, -2) if rotate else self.weight
         y = self._conv_forward(img, w, self.bias)
-        return y.flatten(2).transpose(1, 2)
+        return y.permute(0, 2, 3, 1).reshape(B, S, C)
+
+
+class _HeadwiseLinearFn(torch.autograd.Function):
+    """Block-diagonal linear on (T, NH*d) rows as NH strided GEMMs that read and write the head slices
+    of the token-major tensors in place (lda = ldc = NH*d): no (NH, T, d) transposed copies in either
+    direction, bias fused into the GEMM epilogue."""
+
+    @staticmethod
+    def forward(ctx, x2, weight, bias):
+        T, D = x2.shape
+        NH, d = weight.shape[0], weight.shape[1]
+        y = torch.empty((T, D), dtype=x2.dtype, device=x2.device)
+        for n in range(NH):
+            xs, ys = x2[:, n * d:(n + 1) * d], y[:, n * d:(n + 1) * d]
+            if bias is None:
+                torch.mm(xs, weight[n].t(), out=ys)
+            else:
+                torch.addmm(bias[n * d:(n + 1) * d], xs, weight[n].t(), out=ys)
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        NH, d = weight.shape[0], weight.shape[1]
+        if dy.stride(1) != 1:
+            dy = dy.contiguous()
+        dx = torch.empty_like(x2, memory_format=torch.contiguous_format) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(weight) if ctx.needs_input_grad[1] else None
+        for n in range(NH):
+            dys = dy[:, n * d:(n + 1) * d]
+            if dx is not None:
+                torch.mm(dys, weight[n], out=dx[:, n * d:(n + 1) * d])
+            if dw is not None:
+                torch.mm(dys.t(), x2[:, n * d:(n + 1) * d], out=dw[n])
+        db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db
 
 
 class LinearHeadwiseExpand(nn.Module):
@@ -100,10 +140,11 @@ class LinearHeadwiseExpand(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         lead = x.shape[:-1]
-        xh = x.reshape(-1, self.num_heads, self.dim // self.num_heads)          # (T, NH, d)
-        y = torch.bmm(xh.transpose(0, 1), self.weight.transpose(1, 2))          # (NH, T, d_out)
-        y = y.transpose(0, 1).reshape(*lead, self.dim)
-        return y if self.bias is None else y + self.bias
+        x2 = x.reshape(-1, self.dim)
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        bias = None if self.bias is None else self.bias.to(x2.dtype)
+        return _HeadwiseLinearFn.apply(x2, self.weight.to(x2.dtype), bias).view(*lead, self.dim)
 
     def extra_repr(self):
         return f"dim={self.dim}, num_heads={self.num_heads}, bias={self.bias is not None}, "
