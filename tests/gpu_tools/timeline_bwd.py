@@ -15,8 +15,11 @@ for _ in range(2):
     pl.forward(); pl.backward(0)
 torch.cuda.synchronize()
 rows = B * NH * S
-kpart_off = rows * 4 + 4 * rows * 4          # BwdLayout: dn | rpart(4) | kpart(4)
+mode_b2 = os.environ.get("TL_B2") == "1"     # library built with -DMLSTM_TL_MODE=2: stamps of kernel B2 in the R partials
+kpart_off = rows * 4 + (0 if mode_b2 else 4 * rows * 4)          # BwdLayout: dn | rpart(4) | kpart(4)
 pl.forward(); pl.backward(0)
+if mode_b2:
+    pl.backward(1)
 torch.cuda.synchronize()
 tl = pl.ws.view(torch.uint8)[kpart_off:kpart_off + 8 * 32 * 8].view(torch.int64).cpu().view(8, 32)
 names = ["top", "dn+sync3", "MMA1-wait", "xfree-sync", "tile", "sync", "MMA2iss", "MMA2-wait", "epilogue", "end-sync", "store+MMA1iss"]

@@ -31,7 +31,10 @@ enum { MODE_A = 0, MODE_B1 = 1, MODE_B2 = 2 };
 // Developer aid (-DMLSTM_TIMELINE): CTA 0 of kernel A dumps clock64() stamps per item into the
 // (otherwise unused by A) K-partials region of the workspace; see tests/gpu_tools/timeline_bwd.py.
 #ifdef MLSTM_TIMELINE
-#define TLB(k) do { if (IS_A && blockIdx.x == 0 && n < 8) { \
+#ifndef MLSTM_TL_MODE
+#define MLSTM_TL_MODE 0   // which kernel of the chunk-parallel family is stamped: 0 = A, 2 = B2 (stamps go to the R partials)
+#endif
+#define TLB(k) do { if (MODE == MLSTM_TL_MODE && blockIdx.x == 0 && n < 8) { \
     if (threadIdx.x == 0) tlb[n * 32 + (k)] = clock64(); \
     if (threadIdx.x == CT) tlb[n * 32 + 16 + (k)] = clock64(); } } while (0)
 #else
@@ -78,14 +81,15 @@ __device__ __forceinline__ void tile_row32(const uint8_t* tile, int row, int cb,
 //           B1: t0 = K,  t1 = Q, t2 = dH, st = dCs   thread row = key j
 //           B2: t0 = V,  t1 = dH, t2 = Q, st = dCs   thread row = key j
 //
-// TMEM (512 columns): tS[2] (128 each)  MMA1 output S = t0 t1^T, double-buffered: the MMA1 of the next
+// TMEM (512 columns): tS[2] (128 each)  MMA1 output S = t0 t1^T, double-buffered in A: the MMA1 of the next
 //                                       item is issued right behind the MMA2 of the current one and runs
 //                                       under its epilogue (A: MMA2 writes dQ over the consumed S)
 //                     tO (128)          A: G = dH Cs^T          B: intra accumulator  X t2
-//                     tX (128)          A: gated tile dS as packed bf16 (64 columns) = A operand of MMA2,
-//                                          read by the tensor core straight from TMEM
-//                                       B: inter accumulator  t0 dCs(^T)  (row scale kw applied in the
-//                                          epilogue, so K / V are never modified in shared memory)
+//                     tP (64)           the gated tile (dS | E^T | dS^T) as packed bf16: the A operand of MMA2,
+//                                       read by the tensor core straight from TMEM (no shared-memory round trip)
+//                     tI (128, B only)  inter accumulator  t0 dCs(^T)  (row scale kw applied in the epilogue,
+//                                       so K / V are never modified in shared memory).  B needs a single S
+//                                       buffer: MMA2 writes tO, so S is free as soon as the gated tile is built
 // =============================================================================================
 template <int DH>
 struct SmemB {
@@ -144,11 +148,12 @@ __device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tm = sm.tmem_base, tO = tm + 256, tX = tm + 384;
+  // A: tS[0] tS[1] tO=G tP(64)        B: tS tI tO tP(64)
+  const uint32_t tm = sm.tmem_base, tO = tm + 256, tP = tm + 384, tI = tm + 128;
   const uint32_t lane_sel = (uint32_t)(rg * 32) << 16;
 
   const uint64_t d0k = make_sdesc(smem_u32(sm.t0), 16, 1024), d1k = make_sdesc(smem_u32(sm.t1), 16, 1024);
-  const uint64_t d2mn = make_sdesc(smem_u32(sm.t2), TILE, 1024), dXk = make_sdesc(smem_u32(sm.x), 16, 1024);
+  const uint64_t d2mn = make_sdesc(smem_u32(sm.t2), TILE, 1024);
   const uint64_t dStk = make_sdesc(smem_u32(sm.st), 16, 1024), dStmn = make_sdesc(smem_u32(sm.st), TILE_C, 1024);
   auto coords = [&](int item, int& b, int& h, int& tok0) {
     const int bh = item / NC, sc = item % NC;
@@ -177,11 +182,11 @@ __device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params
     } else if (MODE == MODE_B1) {  // K dCs : dCs as MN-major B operand [dk][dv]
       constexpr uint32_t idI = make_idesc_bf16(128, DH, 0, 1);
 #pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tX, d0k + kstep(ks), dStmn + mnstep(ks), idI, ks > 0);
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tI, d0k + kstep(ks), dStmn + mnstep(ks), idI, ks > 0);
     } else {                       // V dCs^T : dCs as K-major B operand (rows dk)
       constexpr uint32_t idI = make_idesc_bf16(128, DH, 0, 0);
 #pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tX, d0k + kstep(ks), dStk + kstep(ks, TILE_C), idI, ks > 0);
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tI, d0k + kstep(ks), dStk + kstep(ks, TILE_C), idI, ks > 0);
     }
     umma_commit(&sm.bar_i);
   };
@@ -225,14 +230,14 @@ __device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params
   }
 
 #ifdef MLSTM_TIMELINE
-  long long* tlb = reinterpret_cast<long long*>(ws_kpart);
+  long long* tlb = reinterpret_cast<long long*>(MLSTM_TL_MODE == 0 ? ws_kpart : ws_rpart);
 #endif
   int n = 0;
   for (int it = cta; it < n_items; it += ncta, ++n) {
     const int item = lin_of(it);
     TLB(0);
     const uint32_t ph = n & 1;
-    const uint32_t tS = tm + ph * 128;
+    const uint32_t tS = IS_A ? tm + ph * 128 : tm;   // B: S is dead once the gated tile is built, one buffer suffices
     const bool has_next = it + ncta < n_items;
     const int next = lin_of(it + ncta);
     if (gatew) {
@@ -289,11 +294,12 @@ __device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params
         load_act(sm.t0, &maps.t0, &sm.bar_t0, next);
         load_st(next);
       }
-      if (!IS_A) tma_store_wait_read<0>();   // the previous item's staged output (in x) has left
+      // The previous item's output store must have read its staging tile (A: t3, B: x) before it is
+      // touched again.  A refills t3 (this item's q rows, needed in the epilogue) right behind the wait;
+      // B's epilogue writes x after the barrier that ends the gated-tile phase, which this warp joins.
+      tma_store_wait_read<0>();
+      if (IS_A && n > 0) load_act(sm.t3, &maps.t3, &sm.bar_t3, item);
     }
-    // B rewrites x next (gated tile): everybody must know the store above has read it.  In A the pass
-    // over the h tile (x) and dH (t0) ended at named barrier 3, before any thread could get here.
-    if (!IS_A) named_sync(2, GT0);
     TLB(3);
     // ---- gated bf16 tile: one 32x32 block per warp ----------------------------------------------
     if (compute) {
@@ -338,20 +344,11 @@ __device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params
 #pragma unroll
         for (int x = 0; x < 16; ++x) packed[x] = 0u;
       }
-      if (IS_A) {   // stays on the tensor-core side: packed bf16x2 into TMEM, the A operand of MMA2
-        tmem_st16(tX + lane_sel + cq * 16, packed);
-        tmem_st_wait();
-      } else {
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const int col = cq * 32 + x * 8;
-          *reinterpret_cast<uint4*>(sm.x + (col >> 6) * TILE + swz128(row, col & 63)) =
-              make_uint4(packed[4 * x], packed[4 * x + 1], packed[4 * x + 2], packed[4 * x + 3]);
-        }
-      }
+      // the gated tile stays on the tensor-core side: packed bf16x2 into TMEM, the A operand of MMA2
+      tmem_st16(tP + lane_sel + cq * 16, packed);
+      tmem_st_wait();
     }
     TLB(4);
-    if (!IS_A) fence_proxy_async_smem();
     tc_fence_before();
     named_sync(2, GT0);
     TLB(5);
@@ -361,27 +358,25 @@ __device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params
       mbar_wait(&sm.bar_t2, ph);
       tc_fence_after();
       constexpr uint32_t id2 = make_idesc_bf16(128, DH, 0, 1);
-      if (IS_A) {   // dQ = dS K over the consumed S; dS read from TMEM
+      // A: dQ = dS K over the consumed S | B: intra accumulator = X t2 ; X (dS | E^T | dS^T) read from TMEM
 #pragma unroll
-        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ts(tS, tX + ks * 8, d2mn + mnstep(ks), id2, ks > 0);
-      } else {      // intra accumulator = X t2
-#pragma unroll
-        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tO, dXk + kstep(ks), d2mn + mnstep(ks), id2, ks > 0);
-      }
+      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ts(IS_A ? tS : tO, tP + ks * 8, d2mn + mnstep(ks), id2, ks > 0);
       umma_commit(&sm.bar_m2);
       if (has_next) {
-        if (IS_A) load_act(sm.x, &maps.h, &sm.bar_h, next);   // every warp is past its h-tile reads
+        // A: every warp is past its h-tile reads (named barrier 3 precedes the barrier this thread just left).
+        // (Letting the control warp join barrier 3 to issue this earlier was measured slower: it is still
+        // draining the previous item's output store when the compute warps get there.)
+        if (IS_A) load_act(sm.x, &maps.h, &sm.bar_h, next);
         mbar_wait(&sm.bar_t0, ph ^ 1); mbar_wait(&sm.bar_t1, ph ^ 1);
         tc_fence_after();
-        issue_mma1(tm + (ph ^ 1) * 128);
+        issue_mma1(IS_A ? tm + (ph ^ 1) * 128 : tm);
       }
     }
     TLB(6);
     mbar_wait(&sm.bar_m2, ph);
     tc_fence_after();
     TLB(7);
-    // A stages its output in the (now dead) t2 tile; B stages in x and refills t2 now
-    if (issuer && has_next && !IS_A) load_act(sm.t2, &maps.t2, &sm.bar_t2, next);
+    if (issuer && has_next) load_act(sm.t2, &maps.t2, &sm.bar_t2, next);   // MMA2 was t2's last reader
 
     // ---- epilogue: outputs packed in registers --------------------------------------------------
     uint32_t opk[16];
@@ -389,7 +384,7 @@ __device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params
     if (cq < NB) {
       float acc[32], gg[32];
       tmem_ld32((IS_A ? tS : tO) + lane_sel + cq * 32, acc);
-      tmem_ld32((IS_A ? tO : tX) + lane_sel + cq * 32, gg);    // state product (bar_i was awaited by MMA order)
+      tmem_ld32((IS_A ? tO : tI) + lane_sel + cq * 32, gg);    // state product (complete by MMA issue order)
       tmem_ld_wait();
       if (IS_A) {
         const float wt = G.w[row], invN = G.invN[row];
@@ -421,8 +416,10 @@ __device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params
         }
       }
     }
-    // stage the output rows (A: in t2, B: in x — both dead after MMA2) for one coalesced TMA store
-    uint8_t* stage = IS_A ? sm.t2 : sm.x;
+    // stage the output rows for one coalesced TMA store.  A: in t3, over the q rows — each thread has just
+    // read exactly the (row, 32-column) block it now overwrites, and t3 is the tile needed latest in the
+    // next item, so its refill can wait for the store to drain without stalling anything.  B: in x.
+    uint8_t* stage = IS_A ? sm.t3 : sm.x;
     if (cq < NB) {
 #pragma unroll
       for (int x4 = 0; x4 < 4; ++x4) {
@@ -438,20 +435,16 @@ __device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params
     TLB(8);
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();   // end of item: tO / tX consumed, next gates published (the gate warp joins here)
+    __syncthreads();   // end of item: accumulators consumed, next gates published (the gate warp joins here)
     TLB(9);
     if (issuer) {
       for (int kt = 0; kt < KT; ++kt) tma_store_4d(&maps.out, stage + kt * TILE, kt * 64, tok0, h, b);
       tma_store_commit();
       if (has_next) {
-        if (MODE != MODE_B1) load_act(sm.t3, &maps.t3, &sm.bar_t3, next);   // t3 rows were consumed in the epilogue
+        if (MODE == MODE_B2) load_act(sm.t3, &maps.t3, &sm.bar_t3, next);   // k rows were consumed in the epilogue
         mbar_wait(&sm.bar_st, ph ^ 1);
         tc_fence_after();
         issue_state_mma();   // t0 of the next item landed before its MMA1 was issued
-        if (IS_A) {   // refill t2 once the store above has read the staged rows
-          tma_store_wait_read<0>();
-          load_act(sm.t2, &maps.t2, &sm.bar_t2, next);
-        }
       }
     }
     TLB(10);
