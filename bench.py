@@ -55,8 +55,8 @@ def algorithmic(B, NH, S, DH):
 # stay in the 126 MB L2 until after the kernel are not counted by ncu.
 NCU_TRAFFIC_BYTES = {
     "cfg2_B32_NH4_S400_DH64": {"fwd": 20.14e6, "bwd_dq": 33.64e6, "bwd_dkv": 27.54e6},
-    "cfg3_B32_NH4_S1600_DH128": {"fwd": 159.12e6 + 70.82e6, "bwd_dq": 321.29e6 + 42.63e6,
-                                 "bwd_dkv": (160.53e6 + 32.77e6) + (282.38e6 + 85.76e6) + 7.39e6},
+    "cfg3_B32_NH4_S1600_DH128": {"fwd": 159.12e6 + 70.35e6, "bwd_dq": 320.92e6 + 42.60e6,
+                                 "bwd_dkv": (160.54e6 + 33.21e6) + (271.65e6 + 88.60e6) + 7.39e6},
 }
 
 
