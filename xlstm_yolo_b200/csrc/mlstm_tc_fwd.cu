@@ -64,7 +64,6 @@ struct Smem {
   alignas(1024) uint8_t q[KT * TILE];
   alignas(1024) uint8_t k[2][KT * TILE];           // double buffered: K(c+1) streams in during chunk c
   alignas(1024) uint8_t v[KT * TILE];
-  alignas(1024) uint8_t p[2 * TILE];               // P (K-major, 2 tiles over j); h staging reuses it
   alignas(1024) uint8_t cb[KT * TILE_C];           // bf16 C, MN-major [dk][dv]
   alignas(1024) uint8_t ones[2048];                // bf16 1.0 (B operand of n += Kbar^T 1)
   GateBuf g[3];                                    // ring: chunk c uses g[c % 3]
@@ -198,6 +197,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
   tc_fence_after();
   const uint32_t tm = sm.tmem_base;
   const uint32_t tS = tm, tG = tm + 128, tC = tm + 128 + DH, tN = tm + 128 + 2 * DH;
+  const uint32_t tP = tm + 448;   // P as packed bf16 (64 columns): the A operand of MMA2, read from TMEM
   const uint32_t lane_sel = (uint32_t)(rg * 32) << 16;
 
   auto tok0_of = [&](int c) { return (rev ? (NC - 1 - c) : c) * L; };
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
   // adding a constant to the start-address field (issue cost: a couple of instructions per MMA).
   const uint64_t dQ = make_sdesc(smem_u32(sm.q), 16, 1024);
   const uint64_t dCbmn = make_sdesc(smem_u32(sm.cb), TILE_C, 1024), dVmn = make_sdesc(smem_u32(sm.v), TILE, 1024);
-  const uint64_t dP = make_sdesc(smem_u32(sm.p), 16, 1024), dOnes = make_sdesc(smem_u32(sm.ones), 1024, 1024);
+  const uint64_t dOnes = make_sdesc(smem_u32(sm.ones), 1024, 1024);
   const uint64_t dKk0 = make_sdesc(smem_u32(sm.k[0]), 16, 1024), dKmn0 = make_sdesc(smem_u32(sm.k[0]), A_LBO_STATE, 1024);
   constexpr uint64_t KBUF_STEP = (uint64_t)(KT * TILE) >> 4;     // descriptor distance between the two K buffers
   auto kstep = [](int ks) { return (uint64_t)((((ks >> 2) * TILE) + (ks & 3) * 32) >> 4); };   // K-major advance
@@ -364,15 +364,12 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
         for (int x = 0; x < 16; ++x) packed[x] = 0u;
       }
       sm.part_rs[cq][row] = rowsum;
-#pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        const int j = cq * 32 + x * 8;
-        *reinterpret_cast<uint4*>(sm.p + (j >> 6) * TILE + swz128(row, j & 63)) =
-            make_uint4(packed[4 * x], packed[4 * x + 1], packed[4 * x + 2], packed[4 * x + 3]);
-      }
+      // P stays on the tensor-core side: no shared-memory round trip, and MMA2 reads only V from smem
+      // (an SS-form MMA at this shape is shared-memory-read bound and starves the SIMT work in its shadow)
+      tmem_st16(tP + lane_sel + cq * 16, packed);
+      tmem_st_wait();
     }
     TL_STAMP(4);
-    fence_proxy_async_smem();
     tc_fence_before();
     named_sync(2, GT0);
     TL_STAMP(5);
@@ -384,7 +381,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
       tc_fence_after();
       constexpr uint32_t idH = make_idesc_bf16(128, DH, 0, 1);
 #pragma unroll
-      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tS, dP + kstep(ks), dVmn + mnstep(ks), idH, ks > 0);
+      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ts(tS, tP + ks * 8, dVmn + mnstep(ks), idH, ks > 0);
       umma_commit(&sm.bar_m2);
     }
     // ---- in the MMA2 shadow: normaliser, n-state partials, Kbar = kw * K in place ------------
