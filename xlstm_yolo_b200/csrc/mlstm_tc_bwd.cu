@@ -486,17 +486,21 @@ struct SmemSB {
   alignas(1024) uint8_t cst[KT * DH * 128];        // forward entry state Cs[sc] (bf16), for the boundary flow <dC, C>
   GateBuf g[3];
   float fpart[16];
-  uint64_t bar_q[2], bar_dh[2], bar_mma, bar_cs;
+  uint64_t bar_q[2], bar_dh[2], bar_mma[2], bar_cs;
   uint32_t tmem_base;
 };
 
+// The recurrence  dC_{sc-1} = decay_{sc-1} dC_sc + Qtilde_sc^T dH_sc  is split so that the tensor-core half does
+// not wait for the SIMT half: the per-chunk update U = Qtilde^T dH (and its n column) goes into one of two
+// alternating TMEM buffers with a fresh accumulation, the running state lives in a third TMEM region that only
+// the state pass touches.  U of step pc+1 is therefore computed while the state pass of step pc runs.
 template <int DH>
 __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_constant__ BwdMaps maps, const mlstm_params p,
                                                              const float scale) {
   constexpr int KT = DH / 64;
   constexpr int NB = DH / 32;
   constexpr uint32_t A_LBO = (DH == 128) ? TILE : 0;
-  constexpr uint32_t TCOLS = 256;
+  constexpr uint32_t TCOLS = 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   SmemSB<DH>& sm = *reinterpret_cast<SmemSB<DH>*>(smem_raw);
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -516,14 +520,15 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
   if (issuer) {
     tma_prefetch_desc(&maps.t0); tma_prefetch_desc(&maps.t1);
     mbar_init(&sm.bar_q[0], 1); mbar_init(&sm.bar_q[1], 1); mbar_init(&sm.bar_dh[0], 1); mbar_init(&sm.bar_dh[1], 1);
-    mbar_init(&sm.bar_mma, 1); mbar_init(&sm.bar_cs, 1);
+    mbar_init(&sm.bar_mma[0], 1); mbar_init(&sm.bar_mma[1], 1); mbar_init(&sm.bar_cs, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&sm.tmem_base, TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tm = sm.tmem_base, tC = tm, tN = tm + DH;
+  // tU[b] = tm + b*DH (update of a step), tC = running state, tUn[b] / tN: their n columns (16 wide)
+  const uint32_t tm = sm.tmem_base, tC = tm + 2 * DH, tUn0 = tm + 3 * DH, tN = tm + 3 * DH + 32;
   const uint32_t lane_sel = (uint32_t)(rg * 32) << 16;
   const StateLayout slay(p.B, p.NH, S, DH);
   const float* ns_f = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.states) + slay.ns_off) + (size_t)bh * NC * DH;
@@ -564,6 +569,17 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
   const uint64_t dVec0 = make_sdesc(smem_u32(sm.vec[0]), 16, 1024);
   constexpr uint64_t BUF_STEP = (uint64_t)(KT * TILE) >> 4, VEC_STEP = (uint64_t)(2 * 2048) >> 4;
 
+  auto issue_update = [&](int pc) {   // U(pc) = Qtilde^T dH and its n column, fresh accumulation into buffer pc & 1
+    const int buf = pc & 1;
+    const uint64_t dQ = dQ0 + buf * BUF_STEP, dH_ = dH0 + buf * BUF_STEP, dVec = dVec0 + buf * VEC_STEP;
+    constexpr uint32_t idC = make_idesc_bf16(128, DH, 1, 1), idN = make_idesc_bf16(128, 16, 1, 0);
+#pragma unroll
+    for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tm + buf * DH, dQ + mnstep(ks), dH_ + mnstep(ks), idC, ks > 0);
+#pragma unroll
+    for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tUn0 + buf * 16, dQ + mnstep(ks), dVec + kstep(ks, 2048), idN, ks > 0);
+    umma_commit(&sm.bar_mma[buf]);
+  };
+
   if (issuer) { load_qd(0); if (NC > 1) { load_qd(1); load_cs(NC - 1); } }
   if (gatew) { gates_of(0); if (NC > 1) gates_of(1); }
   // adjoint state leaving the last chunk is zero (the last states carry no gradient)
@@ -580,6 +596,11 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (issuer && NC > 1) {
+    mbar_wait(&sm.bar_dh[0], 0);
+    tc_fence_after();
+    issue_update(0);
+  }
 
   for (int pc = 0; pc < NC; ++pc) {
     const bool last = (pc + 1 == NC);
@@ -590,35 +611,41 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
       continue;
     }
     if (last) break;   // the state leaving chunk -1 is not needed (initial states carry no gradient)
-    if (issuer) {
-      mbar_wait(&sm.bar_dh[buf], (pc >> 1) & 1);
-      tc_fence_after();
-      const uint64_t dQ = dQ0 + buf * BUF_STEP, dH_ = dH0 + buf * BUF_STEP, dVec = dVec0 + buf * VEC_STEP;
-      constexpr uint32_t idC = make_idesc_bf16(128, DH, 1, 1), idN = make_idesc_bf16(128, 16, 1, 0);
-      const uint32_t acc0 = (pc > 0) ? 1u : 0u;
-#pragma unroll
-      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tC, dQ + mnstep(ks), dH_ + mnstep(ks), idC, (ks > 0) ? 1u : acc0);
-#pragma unroll
-      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tN, dQ + mnstep(ks), dVec + kstep(ks, 2048), idN, (ks > 0) ? 1u : acc0);
-      umma_commit(&sm.bar_mma);
-    }
-    if (pc + 1 < NC) {   // operands of the next step, in the MMA shadow
+    const bool more = pc + 2 < NC;   // step pc+1 still produces a state
+    // ---- operands and update of the next step, under this step's MMA / state pass --------------
+    if (more) {
       mbar_wait(&sm.bar_q[buf ^ 1], ((pc + 1) >> 1) & 1);
       if (compute) prep_operands(pc + 1);
       fence_proxy_async_smem();
     }
-    mbar_wait(&sm.bar_mma, pc & 1);
+    if (issuer) tma_store_wait_read<0>();   // the previous step's staged dC tile has left shared memory
+    tc_fence_before();
+    named_sync(2, GT0);
+    if (issuer && more) {
+      mbar_wait(&sm.bar_dh[buf ^ 1], ((pc + 1) >> 1) & 1);
+      tc_fence_after();
+      issue_update(pc + 1);
+    }
+    mbar_wait(&sm.bar_mma[buf], (pc >> 1) & 1);
     tc_fence_after();
-    if (issuer && pc + 2 < NC) load_qd(pc + 2);
+    if (issuer && more) load_qd(pc + 2);   // q / dh of this step are free: U(pc) is complete
 
-    // state pass: dC_{sc-1} -> workspace (bf16), then TMEM <- decay_{sc-1} dC_{sc-1}
+    // ---- state pass: dC_{sc-1} = (decayed running state) + U -> workspace (bf16), running state <- decay dC_{sc-1}
     const float dnext = sm.g[(pc + 1) % 3].decay;
     float fl = 0.f;   // partial of the boundary flow <dC_{sc-1}, Cs[sc]> + <dn_{sc-1}, ns[sc]>
     mbar_wait(&sm.bar_cs, pc & 1);
     if (row < DH && cq < NB) {
       float r[32];
-      tmem_ld32(tC + lane_sel + cq * 32, r);
-      tmem_ld_wait();
+      tmem_ld32(tm + buf * DH + lane_sel + cq * 32, r);
+      if (pc > 0) {
+        float acc[32];
+        tmem_ld32(tC + lane_sel + cq * 32, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int x = 0; x < 32; ++x) r[x] += acc[x];
+      } else {
+        tmem_ld_wait();
+      }
 #pragma unroll
       for (int x = 0; x < 32; x += 8) {
         const int dv = cq * 32 + x;
@@ -637,20 +664,30 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
             make_uint4(pack_bf16x2(r[x], r[x + 1]), pack_bf16x2(r[x + 2], r[x + 3]), pack_bf16x2(r[x + 4], r[x + 5]),
                        pack_bf16x2(r[x + 6], r[x + 7]));
       }
+      if (more) {
 #pragma unroll
-      for (int x = 0; x < 32; ++x) r[x] *= dnext;
-      tmem_st32(tC + lane_sel + cq * 32, r);
+        for (int x = 0; x < 32; ++x) r[x] *= dnext;
+        tmem_st32(tC + lane_sel + cq * 32, r);
+      }
       if (cq == 0) {
-        float rn[16];
-        tmem_ld16(tN + lane_sel, rn);
-        tmem_ld_wait();
+        float rn[16], an[16];
+        tmem_ld16(tUn0 + buf * 16 + lane_sel, rn);
+        if (pc > 0) {
+          tmem_ld16(tN + lane_sel, an);
+          tmem_ld_wait();
+          rn[0] += an[0];
+        } else {
+          tmem_ld_wait();
+        }
         dns[(size_t)(sc - 1) * DH + row] = rn[0];
         fl = fmaf(rn[0], ns_f[(size_t)sc * DH + row], fl);
+        if (more) {
 #pragma unroll
-        for (int x = 0; x < 32; ++x) r[x] = rn[0] * dnext;
-        tmem_st32(tN + lane_sel, r);
+          for (int x = 0; x < 32; ++x) r[x] = rn[0] * dnext;
+          tmem_st32(tN + lane_sel, r);   // 16 columns used; the next 16 are scratch
+        }
       }
-      tmem_st_wait();
+      if (more) tmem_st_wait();
     }
     if (compute) {
       fl = warp_sum(fl);
@@ -666,11 +703,10 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
       flow[sc] = f_;
     }
     if (issuer && sc - 1 > 0) load_cs(sc - 1);   // (the boundary before chunk 0 is the initial state: not needed)
-    if (issuer) {   // dC_{sc-1} tile -> workspace; the staging tile is rewritten one step later
+    if (issuer) {   // dC_{sc-1} tile -> workspace; its shared-memory copy is rewritten one step later
       for (int kt = 0; kt < KT; ++kt)
         tma_store_2d(&maps.st, sm.stage + kt * (DH * 128), kt * 64, (bh * NC + (sc - 1)) * DH);
       tma_store_commit();
-      tma_store_wait_read<0>();
     }
   }
   if (issuer) tma_store_wait_all<0>();
