@@ -178,6 +178,20 @@ def test_sigmoid_input_gate_states(dtype, DH):
     assert rel(h, hr) < th and rel(C, Cr) < th and rel(n, nr) < th and float(m.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("DH", [64, 128])
+def test_long_sequence_inference_forward(DH):
+    """BASELINE configs[4] regime: 1280x1280 input -> 160x160 P3 map = 25600 tokens, forward only (no saved rows)."""
+    from xlstm_yolo_b200 import ops
+    B, NH, S = 1, 2, 25600
+    q, k, v, i, f, _ = make(B, NH, S, DH, torch.bfloat16, "rand")
+    with torch.no_grad():
+        h = ops.mlstm(q.cuda(), k.cuda(), v.cuda(), i.cuda(), f.cuda(), eps=1e-6)
+        hr = ops.mlstm(q.cuda(), k.cuda(), v.cuda(), i.cuda(), f.cuda(), eps=1e-6, reverse=True)
+    ref = O.mlstm_chunkwise(*(x.double() for x in (q, k, v, i, f)), chunk_size=64, eps=1e-6)
+    refr = O.mlstm_chunkwise(*(x.double() for x in (q, k, v, i, f)), chunk_size=64, eps=1e-6, reverse=True)
+    assert torch.isfinite(h).all() and rel(h, ref) < 1e-2 and rel(hr, refr) < 1e-2
+
+
 def test_kernel_family_dispatch():
     from xlstm_yolo_b200 import ops
     bf = lambda d: torch.empty(1, 1, 8, d, dtype=torch.bfloat16, device="cuda")

@@ -35,16 +35,22 @@ struct SmemS {
   static constexpr int KT = DH / 64;
   alignas(1024) uint8_t k[2][KT * TILE];
   alignas(1024) uint8_t v[2][KT * TILE];
+  alignas(1024) uint8_t stage[2][KT * DH * 128];   // bf16 entry-state tiles staged for TMA stores (double buffered)
   alignas(1024) uint8_t ones[2048];                // bf16 1.0 (B operand of n += Kbar^T 1)
   GateBuf g[3];                                    // ring: chunk sc uses g[sc % 3]
   uint64_t bar_k[2], bar_v[2], bar_mma;
   uint32_t tmem_base;
 };
 
+// gridDim.y value slices: the state C [dk][dv] splits by dv columns into independent recurrences (same K, same
+// gates), so a small batch can still put a CTA on most SMs: a sequential kernel is bound by what ONE SM can pull
+// from HBM per step (K + V + Cs tiles), and a slice pulls less.  Slice 0 also carries n and m.
 template <int DH>
 __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_constant__ FwdMaps maps, const mlstm_params p) {
   constexpr int KT = DH / 64;
-  constexpr int NB = DH / 32;
+  const int nsl = gridDim.y, sl = blockIdx.y;
+  const int DVs = DH / nsl, col0 = sl * DVs;   // this CTA's value columns [col0, col0 + DVs)
+  const int NB = DVs / 32, KTV = DVs / 64;     // active 32-column blocks / 64-column tiles of V and of the state
   constexpr uint32_t A_LBO = (DH == 128) ? TILE : 0;   // DH=64: the 2nd 64-row M block aliases the 1st
   constexpr uint32_t TCOLS = 256;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -80,8 +86,8 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
     const int buf = sc & 1, tok0 = mem_chunk(sc, NC, rev) * L;
     mbar_arrive_expect_tx(&sm.bar_k[buf], KT * TILE);
     for (int kt = 0; kt < KT; ++kt) tma_load_4d(sm.k[buf] + kt * TILE, &maps.k, &sm.bar_k[buf], kt * 64, tok0, h, b);
-    mbar_arrive_expect_tx(&sm.bar_v[buf], KT * TILE);
-    for (int kt = 0; kt < KT; ++kt) tma_load_4d(sm.v[buf] + kt * TILE, &maps.v, &sm.bar_v[buf], kt * 64, tok0, h, b);
+    mbar_arrive_expect_tx(&sm.bar_v[buf], KTV * TILE);
+    for (int kt = 0; kt < KTV; ++kt) tma_load_4d(sm.v[buf] + kt * TILE, &maps.v, &sm.bar_v[buf], col0 + kt * 64, tok0, h, b);
   };
   const uint64_t dK0 = make_sdesc(smem_u32(sm.k[0]), A_LBO, 1024), dV0 = make_sdesc(smem_u32(sm.v[0]), TILE, 1024);
   const uint64_t dOnes = make_sdesc(smem_u32(sm.ones), 1024, 1024);
@@ -97,20 +103,20 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
   // entry state of chunk 0 -> workspace; TMEM C <- decay_0 * C_0 when an initial state is given
   if (row < DH && cq < NB) {
     float r[32];
-    const float* crow = has_init ? p.c_initial + ((int64_t)bh * DH + row) * DH + cq * 32 : nullptr;
+    const float* crow = has_init ? p.c_initial + ((int64_t)bh * DH + row) * DH + col0 + cq * 32 : nullptr;
 #pragma unroll
     for (int x = 0; x < 32; ++x) r[x] = has_init ? crow[x] : 0.f;
     uint32_t pk[16];
 #pragma unroll
     for (int x = 0; x < 32; x += 2) pk[x / 2] = pack_bf16x2(r[x], r[x + 1]);
-    store_row32(Cs + (size_t)row * DH + cq * 32, pk);
+    store_row32(Cs + (size_t)row * DH + col0 + cq * 32, pk);
     if (has_init) {
       const float d0 = sm.g[0].decay;
 #pragma unroll
       for (int x = 0; x < 32; ++x) r[x] *= d0;
       tmem_st32(tC + lane_sel + cq * 32, r);
     }
-    if (cq == 0) {
+    if (cq == 0 && sl == 0) {
       const float n0 = has_init ? p.n_initial[(int64_t)bh * DH + row] : 0.f;
       ns[row] = n0;
       if (has_init) {
@@ -121,7 +127,7 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
     }
     if (has_init) tmem_st_wait();
   }
-  if (issuer) ms[0] = sm.g[0].m_prev;
+  if (issuer && sl == 0) ms[0] = sm.g[0].m_prev;
   // Kbar(0) = kw * K(0), in place
   if (!gatew) mbar_wait(&sm.bar_k[0], 0);
   if (compute) scale_rows<DH>(sm.k[0], sm.g[0].kw, tid);
@@ -142,12 +148,15 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
       mbar_wait(&sm.bar_v[buf], (sc >> 1) & 1);
       tc_fence_after();
       const uint64_t dK = dK0 + buf * BUF_STEP, dV = dV0 + buf * BUF_STEP;
-      constexpr uint32_t idC = make_idesc_bf16(128, DH, 1, 1), idN = make_idesc_bf16(128, 16, 1, 1);
+      const uint32_t idC = make_idesc_bf16(128, DVs, 1, 1);
+      constexpr uint32_t idN = make_idesc_bf16(128, 16, 1, 1);
       const uint32_t acc0 = (sc > 0 || has_init) ? 1u : 0u;
 #pragma unroll
       for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tC, dK + mnstep(ks), dV + mnstep(ks), idC, (ks > 0) ? 1u : acc0);
+      if (sl == 0) {
 #pragma unroll
-      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tN, dK + mnstep(ks), dOnes, idN, (ks > 0) ? 1u : acc0);
+        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tN, dK + mnstep(ks), dOnes, idN, (ks > 0) ? 1u : acc0);
+      }
       umma_commit(&sm.bar_mma);
     }
     if (!last) {
@@ -166,19 +175,24 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
       tmem_ld32(tC + lane_sel + cq * 32, r);
       tmem_ld_wait();
       if (!last) {
-        uint32_t pk[16];
+        // entry state of chunk sc+1: bf16 into a swizzled staging tile, one TMA tile store after the barrier
+        // (per-thread 64-byte row stores to global were the slowest part of this step)
 #pragma unroll
-        for (int x = 0; x < 32; x += 2) pk[x / 2] = pack_bf16x2(r[x], r[x + 1]);
-        store_row32(Cs + ((size_t)(sc + 1) * DH + row) * DH + cq * 32, pk);
+        for (int x = 0; x < 32; x += 8) {
+          const int dv = cq * 32 + x;
+          *reinterpret_cast<uint4*>(sm.stage[buf] + (dv >> 6) * (DH * 128) + swz128(row, dv & 63)) =
+              make_uint4(pack_bf16x2(r[x], r[x + 1]), pack_bf16x2(r[x + 2], r[x + 3]), pack_bf16x2(r[x + 4], r[x + 5]),
+                         pack_bf16x2(r[x + 6], r[x + 7]));
+        }
 #pragma unroll
         for (int x = 0; x < 32; ++x) r[x] *= dnext;
         tmem_st32(tC + lane_sel + cq * 32, r);
       } else if (p.c_last) {
-        float* dst = p.c_last + ((int64_t)bh * DH + row) * DH + cq * 32;
+        float* dst = p.c_last + ((int64_t)bh * DH + row) * DH + col0 + cq * 32;
 #pragma unroll
         for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4*>(dst + x) = make_float4(r[x], r[x + 1], r[x + 2], r[x + 3]);
       }
-      if (cq == 0) {
+      if (cq == 0 && sl == 0) {
         float rn[16];
         tmem_ld16(tN + lane_sel, rn);
         tmem_ld_wait();
@@ -193,13 +207,21 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
       }
       if (!last) tmem_st_wait();
     }
-    if (issuer) {
+    if (issuer && sl == 0) {
       if (!last) ms[sc + 1] = sm.g[sc % 3].m_next;
       else if (p.m_last) p.m_last[bh] = sm.g[sc % 3].m_next;
     }
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (issuer && !last) {
+      for (int kt = 0; kt < KTV; ++kt)
+        tma_store_2d(&maps.cs, sm.stage[buf] + kt * (DH * 128), col0 + kt * 64, (bh * NC + sc + 1) * DH);
+      tma_store_commit();
+      tma_store_wait_read<1>();   // the other staging buffer (written again in the next step) has been read
+    }
   }
+  if (issuer) tma_store_wait_all<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tm, TCOLS);
@@ -481,7 +503,11 @@ int launch_fwd(const mlstm_params& p, cudaStream_t st) {
   const size_t smS = sizeof(SmemS<DH>), smP = sizeof(SmemP<DH>);
   if ((rc = prep(tc_state_fwd_kernel<DH>, smS, "tc_state_fwd"))) return rc;
   if ((rc = prep(tc_fwd_par_kernel<DH>, smP, "tc_fwd_par"))) return rc;
-  tc_state_fwd_kernel<DH><<<dim3(p.B * p.NH), dim3(NT), smS, st>>>(maps, p);
+  int dev_s = 0, sms_s = 148;
+  cudaGetDevice(&dev_s);
+  cudaDeviceGetAttribute(&sms_s, cudaDevAttrMultiProcessorCount, dev_s);
+  const int nsl = (DH == 128 && 2 * p.B * p.NH <= sms_s) ? 2 : 1;   // 64-column value slices while they fit the SMs
+  tc_state_fwd_kernel<DH><<<dim3(p.B * p.NH, nsl), dim3(NT), smS, st>>>(maps, p);
   if ((rc = launched("tc_state_fwd"))) return rc;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
