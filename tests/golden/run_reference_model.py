@@ -24,35 +24,7 @@ from ultralytics.nn.tasks import DetectionModel  # noqa: E402
 
 import xlstm_yolo_b200 as X  # noqa: E402
 
-YAML = """
-nc: 80
-scales: {n: [0.50, 0.25, 1024], s: [0.50, 0.50, 1024], m: [0.50, 1.00, 512]}
-backbone:
-  - [-1, 1, Conv, [64, 3, 2]]
-  - [-1, 1, Conv, [128, 3, 2]]
-  - [-1, 2, C3k2, [256, False, 0.25]]
-  - [-1, 1, Conv, [256, 3, 2]]
-  - [-1, 2, C3k2, [512, False, 0.25]]
-  - [-1, 1, Conv, [512, 3, 2]]
-  - [-1, 1, ViLFusionBlock, [128, 128, {seqlens: [40, 40], mlp_ratio: 4.0, chunk_size: 16, qkv_block_size: 64}]]
-  - [-1, 1, Conv, [1024, 3, 2]]
-  - [-1, 1, ViLFusionBlock, [256, 256, {seqlens: [20, 20], mlp_ratio: 4.0, chunk_size: 16, qkv_block_size: 128}]]
-  - [-1, 1, SPPF, [1024, 5]]
-head:
-  - [-1, 1, nn.Upsample, [None, 2, "nearest"]]
-  - [[-1, 6], 1, Concat, [1]]
-  - [-1, 2, C3k2, [512, False]]
-  - [-1, 1, nn.Upsample, [None, 2, "nearest"]]
-  - [[-1, 4], 1, Concat, [1]]
-  - [-1, 2, C3k2, [256, False]]
-  - [-1, 1, Conv, [256, 3, 2]]
-  - [[-1, 12], 1, Concat, [1]]
-  - [-1, 2, C3k2, [512, False]]
-  - [-1, 1, Conv, [512, 3, 2]]
-  - [[-1, 9], 1, Concat, [1]]
-  - [-1, 2, C3k2, [1024, True]]
-  - [[15, 18, 21], 1, Detect, [nc]]
-"""
+YAML = open(os.path.join(os.path.dirname(os.path.dirname(HERE)), "xlstm_yolo_b200", "compat", "yamls", "xlstm-yolo.yaml")).read()
 
 
 def run(model, x):
