@@ -150,7 +150,7 @@ const char* mlstm_b200_kernel_variant(const mlstm_params* p, int is_backward) {
   if (!p) return nullptr;
   switch (pick(*p)) {
     case FAM_TC:
-      if (is_backward) return tc_use_single_pass_bwd(*p) ? "single_pass" : "chunk_parallel";
+      if (is_backward) return tc_use_fused_bwd(*p) ? "fused_walk" : (tc_use_single_pass_bwd(*p) ? "single_pass" : "chunk_parallel");
       return tc_use_two_phase(*p) ? "two_phase" : "single_pass";
     case FAM_SIMT: return "simt";
     default: return nullptr;

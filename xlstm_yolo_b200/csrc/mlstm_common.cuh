@@ -26,6 +26,7 @@ size_t tc_bwd_workspace(const mlstm_params& p);
 size_t tc_state_bytes(const mlstm_params& p);
 bool tc_use_two_phase(const mlstm_params& p);
 bool tc_use_single_pass_bwd(const mlstm_params& p);
+bool tc_use_fused_bwd(const mlstm_params& p);
 bool tc_supported(const mlstm_params& p);
 
 __host__ __device__ inline float resolve_scale(const mlstm_params& p) {

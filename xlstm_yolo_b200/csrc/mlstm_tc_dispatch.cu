@@ -26,16 +26,26 @@ static int forced(int which) {
   static const char* env = getenv("MLSTM_FORCE_VARIANT");
   if (!env || !env[0] || !env[1]) return 0;
   const char c = env[which];
-  return c == '1' ? 1 : (c == '2' ? 2 : 0);
+  return c == '1' ? 1 : (c == '2' ? 2 : (c == '3' ? 3 : 0));
 }
 
 bool tc_use_two_phase(const mlstm_params& p) {          // forward
   if (forced(0)) return forced(0) == 2;
   return p.B * p.NH * 2 <= sm_count() && tc::num_chunks(p.S) >= 4;
 }
-bool tc_use_single_pass_bwd(const mlstm_params& p) {    // backward
+static bool short_and_wide(const mlstm_params& p) { return tc::num_chunks(p.S) <= 4 && p.B * p.NH * 2 > sm_count(); }
+
+// DH = 64, short sequences: one reverse walk producing dq, dk, dv together from the forward's chunk states
+// (mlstm_tc_bwd_fused.cu).  MLSTM_FORCE_VARIANT backward digit 3 pins it (DH = 64 only).
+bool tc_use_fused_bwd(const mlstm_params& p) {
+  if (p.DHQK != 64) return false;
+  if (forced(1)) return forced(1) == 3;
+  return short_and_wide(p);
+}
+bool tc_use_single_pass_bwd(const mlstm_params& p) {    // backward, two-walk single-pass kernels
+  if (tc_use_fused_bwd(p)) return false;
   if (forced(1)) return forced(1) == 1;
-  return tc::num_chunks(p.S) <= 4 && p.B * p.NH * 2 > sm_count();
+  return short_and_wide(p);
 }
 
 // The chunk-state buffer is needed by the two-phase forward itself and by the chunk-parallel
