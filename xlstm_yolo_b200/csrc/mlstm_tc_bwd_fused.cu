@@ -45,11 +45,10 @@ __device__ __forceinline__ void tile_row32_64(const uint8_t* tile, int row, int 
 struct SmemF {
   alignas(1024) uint8_t q[2][TILE];
   alignas(1024) uint8_t dh[2][TILE];
-  alignas(1024) uint8_t k[TILE];
+  alignas(1024) uint8_t k[2][TILE];
   alignas(1024) uint8_t v[TILE];
-  alignas(1024) uint8_t h[TILE];
-  alignas(1024) uint8_t xs[2 * TILE];        // dS [t][j] (two 64-column tiles); then staging of dq | dk
-  alignas(1024) uint8_t xe[2 * TILE];        // E  [t][j];                      then staging of dv
+  alignas(1024) uint8_t xs[2 * TILE];        // dS  [t][j] (two 64-column tiles); then staging of dq | dk
+  alignas(1024) uint8_t xe[2 * TILE];        // E^T [j][t]; then tile 0 = staging of dv, tile 1 = the next chunk's h tile
   alignas(1024) uint8_t cs[DH * 128];        // forward entry state of the chunk, bf16 [dk][dv]
   alignas(1024) uint8_t dcb[DH * 128];       // bf16 copy of the adjoint state leaving the chunk, [dk][dv]
   GateBuf g[3];
@@ -62,7 +61,7 @@ struct SmemF {
   float partR[2][L], partK[2][L];
   float scan[8];
   float df_carry;
-  uint64_t bar_q[2], bar_dh[2], bar_k, bar_v, bar_h, bar_cs, bar_m1, bar_m2, bar_m3;
+  uint64_t bar_q[2], bar_dh[2], bar_k[2], bar_v, bar_h, bar_cs, bar_m1, bar_m2, bar_m3;
   uint32_t tmem_base;
 };
 
@@ -86,7 +85,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.v); tma_prefetch_desc(&maps.dh);
     tma_prefetch_desc(&maps.h); tma_prefetch_desc(&maps.cs);
     mbar_init(&sm.bar_q[0], 1); mbar_init(&sm.bar_q[1], 1); mbar_init(&sm.bar_dh[0], 1); mbar_init(&sm.bar_dh[1], 1);
-    mbar_init(&sm.bar_k, 1); mbar_init(&sm.bar_v, 1); mbar_init(&sm.bar_h, 1); mbar_init(&sm.bar_cs, 1);
+    mbar_init(&sm.bar_k[0], 1); mbar_init(&sm.bar_k[1], 1); mbar_init(&sm.bar_v, 1); mbar_init(&sm.bar_h, 1); mbar_init(&sm.bar_cs, 1);
     mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_m2, 1); mbar_init(&sm.bar_m3, 1);
     fence_mbar_init();
     sm.df_carry = 0.f;
@@ -125,19 +124,21 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
   const uint64_t dQmnA[2] = {make_sdesc(smem_u32(sm.q[0]), 0, 1024), make_sdesc(smem_u32(sm.q[1]), 0, 1024)};   // M = dk = 64: 2nd M block aliases the 1st
   const uint64_t dHk[2] = {make_sdesc(smem_u32(sm.dh[0]), 16, 1024), make_sdesc(smem_u32(sm.dh[1]), 16, 1024)};
   const uint64_t dHmn[2] = {make_sdesc(smem_u32(sm.dh[0]), TILE, 1024), make_sdesc(smem_u32(sm.dh[1]), TILE, 1024)};
-  const uint64_t dKk = make_sdesc(smem_u32(sm.k), 16, 1024), dKmn = make_sdesc(smem_u32(sm.k), TILE, 1024);
+  const uint64_t dKk[2] = {make_sdesc(smem_u32(sm.k[0]), 16, 1024), make_sdesc(smem_u32(sm.k[1]), 16, 1024)};
+  const uint64_t dKmn[2] = {make_sdesc(smem_u32(sm.k[0]), TILE, 1024), make_sdesc(smem_u32(sm.k[1]), TILE, 1024)};
   const uint64_t dVk = make_sdesc(smem_u32(sm.v), 16, 1024);
   const uint64_t dXSk = make_sdesc(smem_u32(sm.xs), 16, 1024), dXSmn = make_sdesc(smem_u32(sm.xs), TILE, 1024);
-  const uint64_t dXEmn = make_sdesc(smem_u32(sm.xe), TILE, 1024);
+  const uint64_t dXEk = make_sdesc(smem_u32(sm.xe), 16, 1024);
+  uint8_t* const sh = sm.xe + TILE;   // h tile of the chunk: parked in the second E^T tile between MMA group 2 and the next P2
   const uint64_t dCsk = make_sdesc(smem_u32(sm.cs), 16, 1024);
   const uint64_t dCbk = make_sdesc(smem_u32(sm.dcb), 16, 1024), dCbmn = make_sdesc(smem_u32(sm.dcb), DH * 128, 1024);
 
-  auto issue_g1 = [&](int buf) {   // Z = dH V^T, S = Q K^T, G = dH Cs^T
+  auto issue_g1 = [&](int buf) {   // Z = dH V^T (rows t), S^T = K Q^T (rows j), G = dH Cs^T
     constexpr uint32_t id128 = make_idesc_bf16(128, 128, 0, 0), id64 = make_idesc_bf16(128, DH, 0, 0);
 #pragma unroll
     for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tZ, dHk[buf] + kstep(ks), dVk + kstep(ks), id128, ks > 0);
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tS, dQk[buf] + kstep(ks), dKk + kstep(ks), id128, ks > 0);
+    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tS, dKk[buf] + kstep(ks), dQk[buf] + kstep(ks), id128, ks > 0);
 #pragma unroll
     for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tG, dHk[buf] + kstep(ks), dCsk + kstep(ks), id64, ks > 0);
     umma_commit(&sm.bar_m1);
@@ -145,14 +146,14 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
 
   if (issuer) {
     load1(sm.dh[0], &maps.dh, &sm.bar_dh[0], 0); load1(sm.v, &maps.v, &sm.bar_v, 0);
-    load1(sm.q[0], &maps.q, &sm.bar_q[0], 0); load1(sm.k, &maps.k, &sm.bar_k, 0);
-    load_cs(0); load1(sm.h, &maps.h, &sm.bar_h, 0);
-    if (NC > 1) { load1(sm.dh[1], &maps.dh, &sm.bar_dh[1], 1); load1(sm.q[1], &maps.q, &sm.bar_q[1], 1); }
+    load1(sm.q[0], &maps.q, &sm.bar_q[0], 0); load1(sm.k[0], &maps.k, &sm.bar_k[0], 0);
+    load_cs(0); load1(sh, &maps.h, &sm.bar_h, 0);
+    if (NC > 1) { load1(sm.dh[1], &maps.dh, &sm.bar_dh[1], 1); load1(sm.q[1], &maps.q, &sm.bar_q[1], 1); load1(sm.k[1], &maps.k, &sm.bar_k[1], 1); }
   }
   if (gatew) { gates_of(0); if (NC > 1) gates_of(1); }
   __syncthreads();
   if (issuer) {
-    mbar_wait(&sm.bar_dh[0], 0); mbar_wait(&sm.bar_v, 0); mbar_wait(&sm.bar_q[0], 0); mbar_wait(&sm.bar_k, 0);
+    mbar_wait(&sm.bar_dh[0], 0); mbar_wait(&sm.bar_v, 0); mbar_wait(&sm.bar_q[0], 0); mbar_wait(&sm.bar_k[0], 0);
     mbar_wait(&sm.bar_cs, 0);
     tc_fence_after();
     issue_g1(0);
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
 #pragma unroll
       for (int x8 = 0; x8 < 32; x8 += 8) {
         const uint32_t off = swz128(row, cq * 32 + x8);
-        const uint4 wh = *reinterpret_cast<const uint4*>(sm.h + off);
+        const uint4 wh = *reinterpret_cast<const uint4*>(sh + off);
         const uint4 wd = *reinterpret_cast<const uint4*>(sm.dh[buf] + off);
         const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&wh);
         const __nv_bfloat162* dd = reinterpret_cast<const __nv_bfloat162*>(&wd);
@@ -210,44 +211,65 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     // the previous step's output stores read xs / xe: the control warp drained them before joining this barrier
     named_sync(2, GT0);
 
-    // ---- P2: gated tiles dS -> xs, E -> xe (rows t, columns j; one 32x32 block per warp) --------
+    // ---- P2: gated tiles.  dS -> xs with rows = queries t (causal work grows with the row group), E^T -> xe with
+    //      rows = keys j (causal work shrinks with the row group): together every scheduler gets five 32x32 blocks
     if (compute) {
-      const bool full = rev ? (cq > rg) : (cq < rg);
+      const bool fullA = rev ? (cq > rg) : (cq < rg), fullB = rev ? (cq < rg) : (cq > rg);
       const bool diag = (cq == rg);
-      uint32_t pks[16], pke[16];
-      if (full || diag) {
-        float z[32], s_[32];
+      uint32_t pk[16];
+      if (fullA || diag) {   // dS[t][j] = (Z invN_t + dn_t) 2^(u2_j - M2_t), keep j <= t (reverse: j >= t)
+        float z[32];
         tmem_ld32(tZ + lane_sel + cq * 32, z);
-        tmem_ld32(tS + lane_sel + cq * 32, s_);
         tmem_ld_wait();
-        const float M2t = G.M2[row], invN = G.invN[row], c2t = G.c2[row];
+        const float M2t = G.M2[row], invN = G.invN[row];
 #pragma unroll
         for (int x = 0; x < 32; x += 4) {
           const float4 u4 = *reinterpret_cast<const float4*>(&G.u2[cq * 32 + x]);
           const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
-          float ds[4], ev[4];
+          float ds[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int col = cq * 32 + x + e;
-            const bool keep = full || (rev ? (col >= row) : (col <= row));
-            const float dsv = fmaf(z[x + e], invN, dn_row) * ex2(uu[e] - M2t);
-            const float evv = s_[x + e] * ex2(uu[e] + l2s - c2t);
-            ds[e] = keep ? dsv : 0.f;
-            ev[e] = keep ? evv : 0.f;
+            const bool keep = fullA || (rev ? (col >= row) : (col <= row));
+            ds[e] = keep ? fmaf(z[x + e], invN, dn_row) * ex2(uu[e] - M2t) : 0.f;
           }
-          pks[x / 2] = pack_bf16x2(ds[0], ds[1]); pks[x / 2 + 1] = pack_bf16x2(ds[2], ds[3]);
-          pke[x / 2] = pack_bf16x2(ev[0], ev[1]); pke[x / 2 + 1] = pack_bf16x2(ev[2], ev[3]);
+          pk[x / 2] = pack_bf16x2(ds[0], ds[1]); pk[x / 2 + 1] = pack_bf16x2(ds[2], ds[3]);
         }
       } else {
 #pragma unroll
-        for (int x = 0; x < 16; ++x) { pks[x] = 0u; pke[x] = 0u; }
+        for (int x = 0; x < 16; ++x) pk[x] = 0u;
       }
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
         const int col = cq * 32 + x * 8;
-        const uint32_t off = (col >> 6) * TILE + swz128(row, col & 63);
-        *reinterpret_cast<uint4*>(sm.xs + off) = make_uint4(pks[4 * x], pks[4 * x + 1], pks[4 * x + 2], pks[4 * x + 3]);
-        *reinterpret_cast<uint4*>(sm.xe + off) = make_uint4(pke[4 * x], pke[4 * x + 1], pke[4 * x + 2], pke[4 * x + 3]);
+        *reinterpret_cast<uint4*>(sm.xs + (col >> 6) * TILE + swz128(row, col & 63)) = make_uint4(pk[4 * x], pk[4 * x + 1], pk[4 * x + 2], pk[4 * x + 3]);
+      }
+      if (fullB || diag) {   // E^T[j][t] = S^T 2^(u2_j + log2 s - c2_t), keep t >= j (reverse: t <= j)
+        float s_[32];
+        tmem_ld32(tS + lane_sel + cq * 32, s_);
+        tmem_ld_wait();
+        const float u2j = G.u2[row] + l2s;
+#pragma unroll
+        for (int x = 0; x < 32; x += 4) {
+          const float4 c4 = *reinterpret_cast<const float4*>(&G.c2[cq * 32 + x]);
+          const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+          float ev[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = cq * 32 + x + e;
+            const bool keep = fullB || (rev ? (col <= row) : (col >= row));
+            ev[e] = keep ? s_[x + e] * ex2(u2j - cc[e]) : 0.f;
+          }
+          pk[x / 2] = pack_bf16x2(ev[0], ev[1]); pk[x / 2 + 1] = pack_bf16x2(ev[2], ev[3]);
+        }
+      } else {
+#pragma unroll
+        for (int x = 0; x < 16; ++x) pk[x] = 0u;
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int col = cq * 32 + x * 8;
+        *reinterpret_cast<uint4*>(sm.xe + (col >> 6) * TILE + swz128(row, col & 63)) = make_uint4(pk[4 * x], pk[4 * x + 1], pk[4 * x + 2], pk[4 * x + 3]);
       }
       // dn_state contribution: column sums of the (un-scaled) Q tile, 16 rows per thread
       {
@@ -270,21 +292,23 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
       constexpr uint32_t idMM = make_idesc_bf16(128, DH, 1, 1);    // A MN-major, B MN-major
       constexpr uint32_t idKK = make_idesc_bf16(128, DH, 0, 0);
 #pragma unroll
-      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tZ, dXSk + kstep(ks), dKmn + mnstep(ks), idKmn, ks > 0);              // dQ = dS K
+      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tZ, dXSk + kstep(ks), dKmn[buf] + mnstep(ks), idKmn, ks > 0);         // dQ = dS K
 #pragma unroll
       for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tS, dXSmn + mnstep(ks), dQmnB[buf] + mnstep(ks), idMM, ks > 0);     // dK = dS^T Q
 #pragma unroll
-      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tS + 64, dXEmn + mnstep(ks), dHmn[buf] + mnstep(ks), idMM, ks > 0); // dV = E^T dH
+      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tS + 64, dXEk + kstep(ks), dHmn[buf] + mnstep(ks), idKmn, ks > 0);   // dV = E^T dH
 #pragma unroll
       for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tIk, dVk + kstep(ks), dCbk + kstep(ks), idKK, ks > 0);              // V dCb^T
 #pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tIv, dKk + kstep(ks), dCbmn + mnstep(ks), idKmn, ks > 0);           // K dCb
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tIv, dKk[buf] + kstep(ks), dCbmn + mnstep(ks), idKmn, ks > 0);      // K dCb
       umma_commit(&sm.bar_m2);
-      if (!last) load1(sm.h, &maps.h, &sm.bar_h, c + 1);   // every warp is past its h reads
     }
     mbar_wait(&sm.bar_m2, ph);
     tc_fence_after();
-    if (issuer && !last) load1(sm.v, &maps.v, &sm.bar_v, c + 1);
+    if (issuer && !last) {
+      load1(sm.v, &maps.v, &sm.bar_v, c + 1);
+      load1(sh, &maps.h, &sm.bar_h, c + 1);   // second E^T tile is dead (dv is staged in the first): park the next h there
+    }
 
     // ---- P3: epilogues.  cq 0,1: dq blocks ; cq 2,3: dk then dv blocks -------------------------------
     if (compute) {
@@ -312,7 +336,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
         tmem_ld32(tS + lane_sel + cb * 32, acc);
         tmem_ld32(tIk + lane_sel + cb * 32, gi);
         tmem_ld_wait();
-        tile_row32_64(sm.k, row, cb, kr);
+        tile_row32_64(sm.k[buf], row, cb, kr);
 #pragma unroll
         for (int x = 0; x < 32; x += 2) {
           const float o0 = fmaf(kwj, gi[x] + sm.nvec[cb * 32 + x], scale * acc[x]);
@@ -381,7 +405,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
 #pragma unroll
       for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tdC, dQmnA[buf] + mnstep(ks), dHmn[buf] + mnstep(ks), idMM, (ks > 0 || c > 0) ? 1u : 0u);
       umma_commit(&sm.bar_m3);
-      if (!last) load1(sm.k, &maps.k, &sm.bar_k, c + 1);   // k rows were consumed in the epilogue
+      if (c + 2 < NC) load1(sm.k[buf], &maps.k, &sm.bar_k[buf], c + 2);   // k rows were consumed in the epilogue
     }
     mbar_wait(&sm.bar_m3, ph);
     tc_fence_after();
@@ -421,7 +445,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
       if (!last) {
         const int nb = buf ^ 1;
         mbar_wait(&sm.bar_dh[nb], ((c + 1) >> 1) & 1); mbar_wait(&sm.bar_v, ph ^ 1);
-        mbar_wait(&sm.bar_q[nb], ((c + 1) >> 1) & 1); mbar_wait(&sm.bar_k, ph ^ 1);
+        mbar_wait(&sm.bar_q[nb], ((c + 1) >> 1) & 1); mbar_wait(&sm.bar_k[nb], ((c + 1) >> 1) & 1);
         mbar_wait(&sm.bar_cs, ph ^ 1);
         tc_fence_after();
         issue_g1(nb);
