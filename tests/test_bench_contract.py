@@ -42,7 +42,7 @@ def test_b200_arm_line():
     assert BASE_KEYS | {"clocks", "gpu_launches", "roofline", "cpu_baseline"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] >= 3 and d["dtype"] == "bf16" and d["data"] == "synthetic"
     assert d["config"]["workload"] == "cfg2_B32_NH4_S400_DH64" and d["config"]["kernel_family"] == "tcgen05"
-    assert d["gpu_launches"] >= 3 * d["steps"]
+    assert d["gpu_launches"] >= 2 * d["steps"]   # forward + the fused backward walk (3+ with the multi-kernel backward)
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and 0 < rf["frac"] < 1 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] < d["value"]

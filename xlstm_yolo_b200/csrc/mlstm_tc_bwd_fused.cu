@@ -25,6 +25,15 @@ using namespace tc;
 constexpr int DH = 64;
 constexpr int NB = DH / 32;   // 32-column blocks of a DH-wide accumulator
 
+// Developer aid (-DMLSTM_TIMELINE): CTA 0 stamps clock64() per phase into the workspace (tests/gpu_tools/timeline_fused.py)
+#ifdef MLSTM_TIMELINE
+#define TLF(k) do { if (blockIdx.x == 0 && c < 8) { \
+    if (threadIdx.x == 0) tlf[c * 32 + (k)] = clock64(); \
+    if (threadIdx.x == CT) tlf[c * 32 + 16 + (k)] = clock64(); } } while (0)
+#else
+#define TLF(k) do { } while (0)
+#endif
+
 struct FMaps { CUtensorMap q, k, v, dh, h, cs, dq, dk, dv; };
 
 // 32 columns [32 cb, 32 cb + 32) of row `row` of one swizzled [128][64] bf16 tile -> fp32
@@ -61,7 +70,7 @@ struct SmemF {
   float partR[2][L], partK[2][L];
   float scan[8];
   float df_carry;
-  uint64_t bar_q[2], bar_dh[2], bar_k[2], bar_v, bar_h, bar_cs, bar_m1, bar_m2, bar_m3;
+  uint64_t bar_q[2], bar_dh[2], bar_k[2], bar_v, bar_h, bar_cs, bar_m1, bar_i, bar_m2, bar_m3;
   uint32_t tmem_base;
 };
 
@@ -86,7 +95,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     tma_prefetch_desc(&maps.h); tma_prefetch_desc(&maps.cs);
     mbar_init(&sm.bar_q[0], 1); mbar_init(&sm.bar_q[1], 1); mbar_init(&sm.bar_dh[0], 1); mbar_init(&sm.bar_dh[1], 1);
     mbar_init(&sm.bar_k[0], 1); mbar_init(&sm.bar_k[1], 1); mbar_init(&sm.bar_v, 1); mbar_init(&sm.bar_h, 1); mbar_init(&sm.bar_cs, 1);
-    mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_m2, 1); mbar_init(&sm.bar_m3, 1);
+    mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_i, 1); mbar_init(&sm.bar_m2, 1); mbar_init(&sm.bar_m3, 1);
     fence_mbar_init();
     sm.df_carry = 0.f;
   }
@@ -144,6 +153,17 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     umma_commit(&sm.bar_m1);
   };
 
+  // products with the adjoint state leaving the chunk: needed by the epilogues only, issued as soon as the state
+  // pass of the previous step has refreshed dCb — V is then dead early and the next V tile has a whole step to land
+  auto issue_g1b = [&](int buf) {
+    constexpr uint32_t idKK = make_idesc_bf16(128, DH, 0, 0), idKmn_ = make_idesc_bf16(128, DH, 0, 1);
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tIk, dVk + kstep(ks), dCbk + kstep(ks), idKK, ks > 0);                // V dCb^T
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tIv, dKk[buf] + kstep(ks), dCbmn + mnstep(ks), idKmn_, ks > 0);      // K dCb
+    umma_commit(&sm.bar_i);
+  };
+
   if (issuer) {
     load1(sm.dh[0], &maps.dh, &sm.bar_dh[0], 0); load1(sm.v, &maps.v, &sm.bar_v, 0);
     load1(sm.q[0], &maps.q, &sm.bar_q[0], 0); load1(sm.k[0], &maps.k, &sm.bar_k[0], 0);
@@ -157,9 +177,13 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     mbar_wait(&sm.bar_cs, 0);
     tc_fence_after();
     issue_g1(0);
+    issue_g1b(0);   // dCb = 0: zero products
   }
 
   float nstate = 0.f;   // thread dk < DH: decayed dn_state entering the step
+#ifdef MLSTM_TIMELINE
+  long long* tlf = reinterpret_cast<long long*>(p.workspace);
+#endif
   for (int c = 0; c < NC; ++c) {
     const uint32_t ph = c & 1;
     const int buf = c & 1;
@@ -177,6 +201,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     const bool row_ok = compute && tok < S;
 
     // ---- P1: dn_t = dnf_t (dh_t . h_t) ---------------------------------------------------------
+    TLF(0);
     mbar_wait(&sm.bar_h, ph);
     mbar_wait(&sm.bar_dh[buf], (c >> 1) & 1);
     if (cq < NB) {
@@ -205,18 +230,22 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
         sm.rowscale[row] = G.w[row] * scale * G.invN[row];
       }
     }
+    TLF(1);
     mbar_wait(&sm.bar_m1, ph);
     tc_fence_after();
-    if (issuer && !last) load_cs(c + 1);   // G was the last reader of the Cs tile
-    // the previous step's output stores read xs / xe: the control warp drained them before joining this barrier
-    named_sync(2, GT0);
+    TLF(2);
+    if (issuer) {
+      mbar_wait(&sm.bar_i, ph);             // V dCb^T, K dCb complete: with group 1 done, V and Cs are dead
+      if (!last) { load1(sm.v, &maps.v, &sm.bar_v, c + 1); load_cs(c + 1); }
+    }
+    TLF(3);
 
     // ---- P2: gated tiles.  dS -> xs with rows = queries t (causal work grows with the row group), E^T -> xe with
     //      rows = keys j (causal work shrinks with the row group): together every scheduler gets five 32x32 blocks
     if (compute) {
       const bool fullA = rev ? (cq > rg) : (cq < rg), fullB = rev ? (cq < rg) : (cq > rg);
       const bool diag = (cq == rg);
-      uint32_t pk[16];
+      uint32_t pk[16], pe[16];
       if (fullA || diag) {   // dS[t][j] = (Z invN_t + dn_t) 2^(u2_j - M2_t), keep j <= t (reverse: j >= t)
         float z[32];
         tmem_ld32(tZ + lane_sel + cq * 32, z);
@@ -239,11 +268,6 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
 #pragma unroll
         for (int x = 0; x < 16; ++x) pk[x] = 0u;
       }
-#pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        const int col = cq * 32 + x * 8;
-        *reinterpret_cast<uint4*>(sm.xs + (col >> 6) * TILE + swz128(row, col & 63)) = make_uint4(pk[4 * x], pk[4 * x + 1], pk[4 * x + 2], pk[4 * x + 3]);
-      }
       if (fullB || diag) {   // E^T[j][t] = S^T 2^(u2_j + log2 s - c2_t), keep t >= j (reverse: t <= j)
         float s_[32];
         tmem_ld32(tS + lane_sel + cq * 32, s_);
@@ -260,16 +284,21 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
             const bool keep = fullB || (rev ? (col <= row) : (col >= row));
             ev[e] = keep ? s_[x + e] * ex2(u2j - cc[e]) : 0.f;
           }
-          pk[x / 2] = pack_bf16x2(ev[0], ev[1]); pk[x / 2 + 1] = pack_bf16x2(ev[2], ev[3]);
+          pe[x / 2] = pack_bf16x2(ev[0], ev[1]); pe[x / 2 + 1] = pack_bf16x2(ev[2], ev[3]);
         }
       } else {
 #pragma unroll
-        for (int x = 0; x < 16; ++x) pk[x] = 0u;
+        for (int x = 0; x < 16; ++x) pe[x] = 0u;
       }
+      // xs / xe still feed the previous step's output stores: the control warp drains them before it joins this
+      // barrier, and that wait hides behind the tile math above (the packed tiles sit in registers meanwhile)
+      named_sync(5, GT0);
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
         const int col = cq * 32 + x * 8;
-        *reinterpret_cast<uint4*>(sm.xe + (col >> 6) * TILE + swz128(row, col & 63)) = make_uint4(pk[4 * x], pk[4 * x + 1], pk[4 * x + 2], pk[4 * x + 3]);
+        const uint32_t off = (col >> 6) * TILE + swz128(row, col & 63);
+        *reinterpret_cast<uint4*>(sm.xs + off) = make_uint4(pk[4 * x], pk[4 * x + 1], pk[4 * x + 2], pk[4 * x + 3]);
+        *reinterpret_cast<uint4*>(sm.xe + off) = make_uint4(pe[4 * x], pe[4 * x + 1], pe[4 * x + 2], pe[4 * x + 3]);
       }
       // dn_state contribution: column sums of the (un-scaled) Q tile, 16 rows per thread
       {
@@ -281,34 +310,31 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
         sm.npart[pt][dk] = acc;
       }
     }
+    if (!compute) named_sync(5, GT0);   // control warp: its store drain (end of the previous step) is complete
+    TLF(4);
     fence_proxy_async_smem();
     tc_fence_before();
     named_sync(2, GT0);
+    TLF(5);
 
     // ---- MMA group 2 ------------------------------------------------------------------------------
     if (issuer) {
       tc_fence_after();
       constexpr uint32_t idKmn = make_idesc_bf16(128, DH, 0, 1);   // A K-major, B MN-major
       constexpr uint32_t idMM = make_idesc_bf16(128, DH, 1, 1);    // A MN-major, B MN-major
-      constexpr uint32_t idKK = make_idesc_bf16(128, DH, 0, 0);
 #pragma unroll
       for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tZ, dXSk + kstep(ks), dKmn[buf] + mnstep(ks), idKmn, ks > 0);         // dQ = dS K
 #pragma unroll
       for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tS, dXSmn + mnstep(ks), dQmnB[buf] + mnstep(ks), idMM, ks > 0);     // dK = dS^T Q
 #pragma unroll
       for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tS + 64, dXEk + kstep(ks), dHmn[buf] + mnstep(ks), idKmn, ks > 0);   // dV = E^T dH
-#pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tIk, dVk + kstep(ks), dCbk + kstep(ks), idKK, ks > 0);              // V dCb^T
-#pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tIv, dKk[buf] + kstep(ks), dCbmn + mnstep(ks), idKmn, ks > 0);      // K dCb
       umma_commit(&sm.bar_m2);
     }
+    TLF(6);
     mbar_wait(&sm.bar_m2, ph);
     tc_fence_after();
-    if (issuer && !last) {
-      load1(sm.v, &maps.v, &sm.bar_v, c + 1);
-      load1(sh, &maps.h, &sm.bar_h, c + 1);   // second E^T tile is dead (dv is staged in the first): park the next h there
-    }
+    TLF(7);
+    if (issuer && !last) load1(sh, &maps.h, &sm.bar_h, c + 1);   // second E^T tile is dead (dv is staged in the first): park the next h there
 
     // ---- P3: epilogues.  cq 0,1: dq blocks ; cq 2,3: dk then dv blocks -------------------------------
     if (compute) {
@@ -396,19 +422,30 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
       named_sync(3, CT);
       scale_rows<DH>(sm.q[buf], sm.rowscale, tid);
     }
+    TLF(8);
     fence_proxy_async_smem();
     tc_fence_before();
     named_sync(2, GT0);
+    TLF(9);
     if (issuer) {
       tc_fence_after();
       constexpr uint32_t idMM = make_idesc_bf16(128, DH, 1, 1);
 #pragma unroll
       for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tdC, dQmnA[buf] + mnstep(ks), dHmn[buf] + mnstep(ks), idMM, (ks > 0 || c > 0) ? 1u : 0u);
       umma_commit(&sm.bar_m3);
+      if (!last) {   // group 1 of the next chunk right behind: Z, S^T, G were consumed by the epilogues above
+        const int nb = buf ^ 1;
+        mbar_wait(&sm.bar_dh[nb], ((c + 1) >> 1) & 1); mbar_wait(&sm.bar_v, ph ^ 1);
+        mbar_wait(&sm.bar_q[nb], ((c + 1) >> 1) & 1); mbar_wait(&sm.bar_k[nb], ((c + 1) >> 1) & 1);
+        mbar_wait(&sm.bar_cs, ph ^ 1);
+        tc_fence_after();
+        issue_g1(nb);
+      }
       if (c + 2 < NC) load1(sm.k[buf], &maps.k, &sm.bar_k[buf], c + 2);   // k rows were consumed in the epilogue
     }
     mbar_wait(&sm.bar_m3, ph);
     tc_fence_after();
+    TLF(10);
     if (issuer && c + 2 < NC) { load1(sm.dh[buf], &maps.dh, &sm.bar_dh[buf], c + 2); load1(sm.q[buf], &maps.q, &sm.bar_q[buf], c + 2); }
 
     // ---- P5: state pass: dCb <- bf16(dC), dC <- decay_next dC ; dn_state likewise ----------------------
@@ -434,24 +471,23 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
       sm.nvec[tid] = nv;
       nstate = nv * dnext;
     }
+    TLF(11);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();   // end of step (the gate warp joins)
+    TLF(12);
     if (issuer) {
       tma_store_4d(&maps.dq, sm.xs, 0, tok0, h, b);
       tma_store_4d(&maps.dk, sm.xs + TILE, 0, tok0, h, b);
       tma_store_4d(&maps.dv, sm.xe, 0, tok0, h, b);
       tma_store_commit();
       if (!last) {
-        const int nb = buf ^ 1;
-        mbar_wait(&sm.bar_dh[nb], ((c + 1) >> 1) & 1); mbar_wait(&sm.bar_v, ph ^ 1);
-        mbar_wait(&sm.bar_q[nb], ((c + 1) >> 1) & 1); mbar_wait(&sm.bar_k[nb], ((c + 1) >> 1) & 1);
-        mbar_wait(&sm.bar_cs, ph ^ 1);
         tc_fence_after();
-        issue_g1(nb);
+        issue_g1b(buf ^ 1);       // its operands (V, K of the next chunk) landed before group 1 of that chunk was issued
       }
-      tma_store_wait_read<0>();   // before this warp joins the next step's first barrier (xs / xe are rewritten after it)
+      tma_store_wait_read<0>();   // before this warp joins barrier 5 of the next step (xs / xe are rewritten after it)
     }
+    TLF(13);
   }
   if (issuer) tma_store_wait_all<0>();
   tc_fence_before();
@@ -463,7 +499,11 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
 
 bool tc_use_fused_bwd(const mlstm_params& p);
 
+#ifdef MLSTM_TIMELINE
+size_t tc_bwd_fused_workspace(const mlstm_params&) { return 16384; }
+#else
 size_t tc_bwd_fused_workspace(const mlstm_params&) { return 0; }
+#endif
 
 int tc_bwd_fused(const mlstm_params& p, cudaStream_t st, int part) {
   if (part == 0) return MLSTM_OK;   // one kernel: everything runs as "part 1"
