@@ -15,12 +15,19 @@ print("variants", pl.variant_fwd, pl.variant_bwd)
 for _ in range(3):
     pl.forward(); pl.backward(1)
 torch.cuda.synchronize()
-tl = pl.ws.view(torch.uint8)[: 8 * 32 * 8].view(torch.int64).cpu().view(8, 32)
-names = ["top", "P1 dn", "G1 wait", "sync0", "P2 tiles", "sync", "G2 issue", "G2 wait", "P3+P4 epi", "sync", "G3 wait", "P5 state", "end sync", "tail"]
-t0 = tl[0, 0].item()
-for who, off in (("compute thread 0", 0), ("issuer", 16)):
-    print(who)
+raw = pl.ws.view(torch.uint8)[: 600 * 8].view(torch.int64).cpu()
+tl = raw[:512].view(8, 4, 16)
+hd = raw[512:512 + 32].view(4, 8)
+names = ["top", "P1 dn", "G1 wait", "Vload", "P2 all", "sync", "G2 issue", "G2 wait", "P3+P4 epi", "sync", "G3 wait", "P5 state", "end sync", "tail"]
+t0 = hd[0, 0].item()
+whos = ["thread 0 (rg0,cq0 diag)", "thread 96 (rg3,cq0)", "thread 480 (rg3,cq3 diag)", "issuer"]
+for w, who in enumerate(whos):
+    h_ = (hd[w] - t0).tolist()
+    print(f"{who}: entry {h_[0]} prologue-sync {h_[1]} gates+loads-sync {h_[2]} loop-start {h_[3]} loop-end {h_[4]} drained {h_[5]} exit {h_[6]}")
     for c in range(4):
-        row = tl[c, off:off + 14] - t0
+        row = tl[c, w] - t0
         d = [(row[j] - row[j - 1]).item() for j in range(1, 14)]
-        print(f"step {c} start {row[0].item():7d}  " + " ".join(f"{n_[:8]}:{x:5d}" for n_, x in zip(names[1:], d)))
+        extra = ""
+        if w < 3:
+            extra = f"  [P2: tiles {(row[14] - row[3]).item()} sync5+st {(row[15] - row[14]).item()} colsum {(row[4] - row[15]).item()}]"
+        print(f" step {c} start {row[0].item():7d}  " + " ".join(f"{n_[:8]}:{x:5d}" for n_, x in zip(names[1:], d)) + extra)

@@ -311,6 +311,7 @@ __device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params
       if (full || diag) {
         float a[32];
         tmem_ld32(tS + lane_sel + cq * 32, a);
+        const uint32_t cbits = causal_bits(full, IS_A ? !rev : rev, lane);
         tmem_ld_wait();
         const float r0 = IS_A ? G.M2[row] : (MODE == MODE_B1 ? G.u2[row] + l2s : G.u2[row]);
         const float r1 = IS_A ? G.invN[row] : 0.f;
@@ -329,8 +330,7 @@ __device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params
           float pv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int col = c0 + e;
-            const bool keep = full || (IS_A ? (rev ? (col >= row) : (col <= row)) : (rev ? (col <= row) : (col >= row)));
+            const bool keep = (cbits >> (x + e)) & 1u;
             float val;
             if (IS_A) val = fmaf(a[x + e], r1, dn_row) * ex2(ee[e] - r0);
             else if (MODE == MODE_B1) val = a[x + e] * ex2(r0 - ee[e]);

@@ -395,6 +395,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_dq_kernel(const __grid_constant_
       if (full || diag) {
         float z[32];
         tmem_ld32(tZ + lane_sel + cbk * 32, z);
+        const uint32_t cbits = causal_bits(full, !rev, tid & 31);
         tmem_ld_wait();
 #pragma unroll
         for (int x = 0; x < 32; x += 4) {
@@ -403,8 +404,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_dq_kernel(const __grid_constant_
           float pv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int j = cbk * 32 + x + e;
-            const bool keep = full || (rev ? (j >= tid) : (j <= tid));
+            const bool keep = (cbits >> (x + e)) & 1u;
             pv[e] = keep ? fmaf(z[x + e], invN, dn) * ex2(uu[e] - M2t) : 0.f;
           }
           packed[x / 2] = pack_bf16x2(pv[0], pv[1]);
@@ -630,6 +630,7 @@ __device__ __forceinline__ void dkv_body(const BwdMaps& maps, const mlstm_params
       if (full || diag) {
         float s_[32];
         tmem_ld32(tS + lane_sel + cbk * 32, s_);
+        const uint32_t cbits = causal_bits(full, rev, tid & 31);
         tmem_ld_wait();
 #pragma unroll
         for (int x = 0; x < 32; x += 4) {
@@ -645,8 +646,7 @@ __device__ __forceinline__ void dkv_body(const BwdMaps& maps, const mlstm_params
           float pv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int t = cbk * 32 + x + e;
-            const bool keep = full || (rev ? (t <= tid) : (t >= tid));
+            const bool keep = (cbits >> (x + e)) & 1u;
             const float dd = ex2(u2j - cc[e]);
             const float val = (MODE == 1) ? s_[x + e] * dd : fmaf(s_[x + e], in4[e], dn4[e]) * dd;
             pv[e] = keep ? val : 0.f;

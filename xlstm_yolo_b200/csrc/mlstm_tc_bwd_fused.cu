@@ -28,8 +28,8 @@ constexpr int NB = DH / 32;   // 32-column blocks of a DH-wide accumulator
 // Developer aid (-DMLSTM_TIMELINE): CTA 0 stamps clock64() per phase into the workspace (tests/gpu_tools/timeline_fused.py)
 #ifdef MLSTM_TIMELINE
 #define TLF(k) do { if (blockIdx.x == 0 && c < 8) { \
-    if (threadIdx.x == 0) tlf[c * 32 + (k)] = clock64(); \
-    if (threadIdx.x == CT) tlf[c * 32 + 16 + (k)] = clock64(); } } while (0)
+    const int who_ = threadIdx.x == 0 ? 0 : threadIdx.x == 96 ? 1 : threadIdx.x == 480 ? 2 : threadIdx.x == CT ? 3 : -1; \
+    if (who_ >= 0) tlf[c * 64 + who_ * 16 + (k)] = clock64(); } } while (0)
 #else
 #define TLF(k) do { } while (0)
 #endif
@@ -79,6 +79,14 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+#ifdef MLSTM_TIMELINE
+  long long* tlf = reinterpret_cast<long long*>(p.workspace);
+  const int who_h = threadIdx.x == 0 ? 0 : threadIdx.x == 96 ? 1 : threadIdx.x == 480 ? 2 : threadIdx.x == 512 ? 3 : -1;
+#define TLH(k) do { if (blockIdx.x == 0 && who_h >= 0) tlf[512 + who_h * 8 + (k)] = clock64(); } while (0)
+#else
+#define TLH(k) do { } while (0)
+#endif
+  TLH(0);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool compute = tid < CT, issuer = tid == CT, gatew = tid >= GT0;
@@ -95,7 +103,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     tma_prefetch_desc(&maps.h); tma_prefetch_desc(&maps.cs);
     mbar_init(&sm.bar_q[0], 1); mbar_init(&sm.bar_q[1], 1); mbar_init(&sm.bar_dh[0], 1); mbar_init(&sm.bar_dh[1], 1);
     mbar_init(&sm.bar_k[0], 1); mbar_init(&sm.bar_k[1], 1); mbar_init(&sm.bar_v, 1); mbar_init(&sm.bar_h, 1); mbar_init(&sm.bar_cs, 1);
-    mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_i, 1); mbar_init(&sm.bar_m2, 1); mbar_init(&sm.bar_m3, 1);
+    mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_i, 1); mbar_init(&sm.bar_m2, 3); mbar_init(&sm.bar_m3, 1);
     fence_mbar_init();
     sm.df_carry = 0.f;
   }
@@ -105,6 +113,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  TLH(1);
   const uint32_t tm = sm.tmem_base;
   const uint32_t tZ = tm, tS = tm + 128, tG = tm + 256, tIk = tm + 320, tIv = tm + 384, tdC = tm + 448;
   const uint32_t lane_sel = (uint32_t)(rg * 32) << 16;
@@ -128,13 +137,13 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
   };
 
   // operand descriptors (all tiles are [rows][64 bf16], 128-byte swizzled)
-  const uint64_t dQk[2] = {make_sdesc(smem_u32(sm.q[0]), 16, 1024), make_sdesc(smem_u32(sm.q[1]), 16, 1024)};
-  const uint64_t dQmnB[2] = {make_sdesc(smem_u32(sm.q[0]), TILE, 1024), make_sdesc(smem_u32(sm.q[1]), TILE, 1024)};
-  const uint64_t dQmnA[2] = {make_sdesc(smem_u32(sm.q[0]), 0, 1024), make_sdesc(smem_u32(sm.q[1]), 0, 1024)};   // M = dk = 64: 2nd M block aliases the 1st
-  const uint64_t dHk[2] = {make_sdesc(smem_u32(sm.dh[0]), 16, 1024), make_sdesc(smem_u32(sm.dh[1]), 16, 1024)};
-  const uint64_t dHmn[2] = {make_sdesc(smem_u32(sm.dh[0]), TILE, 1024), make_sdesc(smem_u32(sm.dh[1]), TILE, 1024)};
-  const uint64_t dKk[2] = {make_sdesc(smem_u32(sm.k[0]), 16, 1024), make_sdesc(smem_u32(sm.k[1]), 16, 1024)};
-  const uint64_t dKmn[2] = {make_sdesc(smem_u32(sm.k[0]), TILE, 1024), make_sdesc(smem_u32(sm.k[1]), TILE, 1024)};
+  // double-buffered tiles: descriptor of buffer 0 plus a constant per buffer (a descriptor array indexed by `buf` would live in
+  // local memory and cost four register-to-uniform moves in front of every MMA)
+  constexpr uint64_t BUF_STEP = (uint64_t)TILE >> 4;
+  const uint64_t dQk0 = make_sdesc(smem_u32(sm.q[0]), 16, 1024), dQmnB0 = make_sdesc(smem_u32(sm.q[0]), TILE, 1024);
+  const uint64_t dQmnA0 = make_sdesc(smem_u32(sm.q[0]), 0, 1024);   // M = dk = 64: 2nd M block aliases the 1st
+  const uint64_t dHk0 = make_sdesc(smem_u32(sm.dh[0]), 16, 1024), dHmn0 = make_sdesc(smem_u32(sm.dh[0]), TILE, 1024);
+  const uint64_t dKk0 = make_sdesc(smem_u32(sm.k[0]), 16, 1024), dKmn0 = make_sdesc(smem_u32(sm.k[0]), TILE, 1024);
   const uint64_t dVk = make_sdesc(smem_u32(sm.v), 16, 1024);
   const uint64_t dXSk = make_sdesc(smem_u32(sm.xs), 16, 1024), dXSmn = make_sdesc(smem_u32(sm.xs), TILE, 1024);
   const uint64_t dXEk = make_sdesc(smem_u32(sm.xe), 16, 1024);
@@ -145,11 +154,11 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
   auto issue_g1 = [&](int buf) {   // Z = dH V^T (rows t), S^T = K Q^T (rows j), G = dH Cs^T
     constexpr uint32_t id128 = make_idesc_bf16(128, 128, 0, 0), id64 = make_idesc_bf16(128, DH, 0, 0);
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tZ, dHk[buf] + kstep(ks), dVk + kstep(ks), id128, ks > 0);
+    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tZ, (dHk0 + buf * BUF_STEP) + kstep(ks), dVk + kstep(ks), id128, ks > 0);
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tS, dKk[buf] + kstep(ks), dQk[buf] + kstep(ks), id128, ks > 0);
+    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tS, (dKk0 + buf * BUF_STEP) + kstep(ks), (dQk0 + buf * BUF_STEP) + kstep(ks), id128, ks > 0);
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tG, dHk[buf] + kstep(ks), dCsk + kstep(ks), id64, ks > 0);
+    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tG, (dHk0 + buf * BUF_STEP) + kstep(ks), dCsk + kstep(ks), id64, ks > 0);
     umma_commit(&sm.bar_m1);
   };
 
@@ -158,9 +167,9 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
   auto issue_g1b = [&](int buf) {
     constexpr uint32_t idKK = make_idesc_bf16(128, DH, 0, 0), idKmn_ = make_idesc_bf16(128, DH, 0, 1);
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tIk, dVk + kstep(ks), dCbk + kstep(ks), idKK, ks > 0);                // V dCb^T
+    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tIk, dVk + kstep(ks), dCbk + kstep(ks), idKK, ks > 0);                // V dCb^T
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tIv, dKk[buf] + kstep(ks), dCbmn + mnstep(ks), idKmn_, ks > 0);      // K dCb
+    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tIv, (dKk0 + buf * BUF_STEP) + kstep(ks), dCbmn + mnstep(ks), idKmn_, ks > 0);      // K dCb
     umma_commit(&sm.bar_i);
   };
 
@@ -170,8 +179,10 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     load_cs(0); load1(sh, &maps.h, &sm.bar_h, 0);
     if (NC > 1) { load1(sm.dh[1], &maps.dh, &sm.bar_dh[1], 1); load1(sm.q[1], &maps.q, &sm.bar_q[1], 1); load1(sm.k[1], &maps.k, &sm.bar_k[1], 1); }
   }
-  if (gatew) { gates_of(0); if (NC > 1) gates_of(1); }
+  if (gatew) gates_of(0);
+  if (warp == 1 && NC > 1) gates_of(1);   // the compute warps are idle here: the first two chunks' gates side by side
   __syncthreads();
+  TLH(2);
   if (issuer) {
     mbar_wait(&sm.bar_dh[0], 0); mbar_wait(&sm.bar_v, 0); mbar_wait(&sm.bar_q[0], 0); mbar_wait(&sm.bar_k[0], 0);
     mbar_wait(&sm.bar_cs, 0);
@@ -181,16 +192,14 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
   }
 
   float nstate = 0.f;   // thread dk < DH: decayed dn_state entering the step
-#ifdef MLSTM_TIMELINE
-  long long* tlf = reinterpret_cast<long long*>(p.workspace);
-#endif
+  TLH(3);
   for (int c = 0; c < NC; ++c) {
     const uint32_t ph = c & 1;
     const int buf = c & 1;
     const bool last = (c + 1 == NC);
     if (gatew) {
       if (c + 2 < NC) gates_of(c + 2);
-      __syncthreads();
+      named_sync(7, GT0);   // with the compute warps: gates two steps ahead are complete
       continue;
     }
     const GateBuf& G = sm.g[c % 3];
@@ -245,6 +254,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     if (compute) {
       const bool fullA = rev ? (cq > rg) : (cq < rg), fullB = rev ? (cq < rg) : (cq > rg);
       const bool diag = (cq == rg);
+      const uint32_t bitsA = causal_bits(fullA, !rev, lane), bitsB = causal_bits(fullB, rev, lane);
       uint32_t pk[16], pe[16];
       if (fullA || diag) {   // dS[t][j] = (Z invN_t + dn_t) 2^(u2_j - M2_t), keep j <= t (reverse: j >= t)
         float z[32];
@@ -258,8 +268,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
           float ds[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int col = cq * 32 + x + e;
-            const bool keep = fullA || (rev ? (col >= row) : (col <= row));
+            const bool keep = (bitsA >> (x + e)) & 1u;
             ds[e] = keep ? fmaf(z[x + e], invN, dn_row) * ex2(uu[e] - M2t) : 0.f;
           }
           pk[x / 2] = pack_bf16x2(ds[0], ds[1]); pk[x / 2 + 1] = pack_bf16x2(ds[2], ds[3]);
@@ -280,8 +289,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
           float ev[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int col = cq * 32 + x + e;
-            const bool keep = fullB || (rev ? (col <= row) : (col >= row));
+            const bool keep = (bitsB >> (x + e)) & 1u;
             ev[e] = keep ? s_[x + e] * ex2(u2j - cc[e]) : 0.f;
           }
           pe[x / 2] = pack_bf16x2(ev[0], ev[1]); pe[x / 2 + 1] = pack_bf16x2(ev[2], ev[3]);
@@ -290,6 +298,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
 #pragma unroll
         for (int x = 0; x < 16; ++x) pe[x] = 0u;
       }
+      TLF(14);
       // xs / xe still feed the previous step's output stores: the control warp drains them before it joins this
       // barrier, and that wait hides behind the tile math above (the packed tiles sit in registers meanwhile)
       named_sync(5, GT0);
@@ -300,6 +309,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
         *reinterpret_cast<uint4*>(sm.xs + off) = make_uint4(pk[4 * x], pk[4 * x + 1], pk[4 * x + 2], pk[4 * x + 3]);
         *reinterpret_cast<uint4*>(sm.xe + off) = make_uint4(pe[4 * x], pe[4 * x + 1], pe[4 * x + 2], pe[4 * x + 3]);
       }
+      TLF(15);
       // dn_state contribution: column sums of the (un-scaled) Q tile, 16 rows per thread
       {
         const int dk = tid & 63, pt = tid >> 6;
@@ -317,18 +327,25 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     named_sync(2, GT0);
     TLF(5);
 
-    // ---- MMA group 2 ------------------------------------------------------------------------------
-    if (issuer) {
+    // ---- MMA group 2: three independent products, one issuing lane each.  ptxas wraps every tcgen05.mma whose descriptors
+    //      depend on the step in a register-to-uniform waterfall (~100 cycles per MMA from one lane; the tensor pipe needs
+    //      ~51), and every compute warp is idle here: lanes 0 of compute warps 1 and 2 issue dK and dV next to the control lane
+    const int g2 = issuer ? 0 : (tid == 32 ? 1 : (tid == 64 ? 2 : -1));
+    if (g2 >= 0) {
       tc_fence_after();
       constexpr uint32_t idKmn = make_idesc_bf16(128, DH, 0, 1);   // A K-major, B MN-major
       constexpr uint32_t idMM = make_idesc_bf16(128, DH, 1, 1);    // A MN-major, B MN-major
+      if (g2 == 0) {
 #pragma unroll
-      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tZ, dXSk + kstep(ks), dKmn[buf] + mnstep(ks), idKmn, ks > 0);         // dQ = dS K
+        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss_lo(tZ, dXSk + kstep(ks), (dKmn0 + buf * BUF_STEP) + mnstep(ks), idKmn, ks > 0);         // dQ = dS K
+      } else if (g2 == 1) {
 #pragma unroll
-      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tS, dXSmn + mnstep(ks), dQmnB[buf] + mnstep(ks), idMM, ks > 0);     // dK = dS^T Q
+        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss_lo(tS, dXSmn + mnstep(ks), (dQmnB0 + buf * BUF_STEP) + mnstep(ks), idMM, ks > 0);     // dK = dS^T Q
+      } else {
 #pragma unroll
-      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tS + 64, dXEk + kstep(ks), dHmn[buf] + mnstep(ks), idKmn, ks > 0);   // dV = E^T dH
-      umma_commit(&sm.bar_m2);
+        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss_lo(tS + 64, dXEk + kstep(ks), (dHmn0 + buf * BUF_STEP) + mnstep(ks), idKmn, ks > 0);   // dV = E^T dH
+      }
+      umma_commit(&sm.bar_m2);   // three arrivals complete the phase
     }
     TLF(6);
     mbar_wait(&sm.bar_m2, ph);
@@ -431,7 +448,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
       tc_fence_after();
       constexpr uint32_t idMM = make_idesc_bf16(128, DH, 1, 1);
 #pragma unroll
-      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tdC, dQmnA[buf] + mnstep(ks), dHmn[buf] + mnstep(ks), idMM, (ks > 0 || c > 0) ? 1u : 0u);
+      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss_lo(tdC, (dQmnA0 + buf * BUF_STEP) + mnstep(ks), (dHmn0 + buf * BUF_STEP) + mnstep(ks), idMM, (ks > 0 || c > 0) ? 1u : 0u);
       umma_commit(&sm.bar_m3);
       if (!last) {   // group 1 of the next chunk right behind: Z, S^T, G were consumed by the epilogues above
         const int nb = buf ^ 1;
@@ -474,7 +491,11 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     TLF(11);
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();   // end of step (the gate warp joins)
+    // end of step.  The control warp needs every compute warp's staged outputs and dCb (barrier 6) but produces nothing
+    // they wait for here, so the compute warps only arrive on it and run ahead into the next step's dn pass while the
+    // issuer lane is still blocked issuing MMAs; they meet the gate warp on barrier 7.
+    if (compute) { named_arrive(6, GT0); named_sync(7, GT0); }
+    else named_sync(6, GT0);
     TLF(12);
     if (issuer) {
       tma_store_4d(&maps.dq, sm.xs, 0, tok0, h, b);
@@ -489,10 +510,13 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     }
     TLF(13);
   }
-  if (issuer) tma_store_wait_all<0>();
+  TLH(4);
+  if (issuer) tma_store_wait_read<0>();   // the staged tiles have been read; the global writes complete on their own
   tc_fence_before();
   __syncthreads();
+  TLH(5);
   if (warp == 0) tmem_dealloc(tm, 512);
+  TLH(6);
 }
 
 }  // namespace

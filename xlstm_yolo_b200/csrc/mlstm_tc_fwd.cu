@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
       if (full || diag) {
         float s[32];
         tmem_ld32(tS + lane_sel + cq * 32, s);
+        const uint32_t cbits = causal_bits(full, !rev, lane);
         tmem_ld_wait();
 #pragma unroll
         for (int x = 0; x < 32; x += 4) {
@@ -351,8 +352,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
           float pv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int j = cq * 32 + x + e;
-            const bool keep = full || (rev ? (j >= row) : (j <= row));
+            const bool keep = (cbits >> (x + e)) & 1u;
             pv[e] = keep ? s[x + e] * ex2(uu[e] - M2t) : 0.f;
             rowsum += pv[e];
           }

@@ -22,13 +22,16 @@ __global__ void __launch_bounds__(128) rate_kernel(long long* out) {
     int slot = 0;
     for (int amn = 0; amn < 2; ++amn) for (int bmn = 0; bmn < 2; ++bmn) for (int n : {128, 64, 16}) {
       const uint32_t idesc = make_idesc_bf16(128, n, amn, bmn);
+      uint64_t a[8], b[8];   // descriptors pre-built, as in the kernels: the loop below times issue + execution only
+      for (int ks = 0; ks < 8; ++ks) {
+        a[ks] = amn ? make_sdesc(a0 + ks * 2048, TILE, 1024) : make_sdesc(a0 + (ks >> 2) * TILE + (ks & 3) * 32, 16, 1024);
+        b[ks] = bmn ? make_sdesc(b0 + ks * 2048, TILE, 1024) : make_sdesc(b0 + (ks >> 2) * TILE + (ks & 3) * 32, 16, 1024);
+      }
       long long t0 = clock64();
+#pragma unroll
       for (int rep = 0; rep < 4; ++rep)
-        for (int ks = 0; ks < 8; ++ks) {
-          uint64_t a = amn ? make_sdesc(a0 + ks * 2048, TILE, 1024) : make_sdesc(a0 + (ks >> 2) * TILE + (ks & 3) * 32, 16, 1024);
-          uint64_t b = bmn ? make_sdesc(b0 + ks * 2048, TILE, 1024) : make_sdesc(b0 + (ks >> 2) * TILE + (ks & 3) * 32, 16, 1024);
-          umma_bf16_ss(tm, a, b, idesc, (rep | ks) > 0);
-        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) umma_bf16_ss(tm, a[ks], b[ks], idesc, (rep | ks) > 0);
       long long t1 = clock64();
       umma_commit(&bar);
       mbar_wait(&bar, phase); phase ^= 1;
