@@ -15,9 +15,9 @@ print("variants", pl.variant_fwd, pl.variant_bwd)
 for _ in range(3):
     pl.forward(); pl.backward(1)
 torch.cuda.synchronize()
-raw = pl.ws.view(torch.uint8)[: 600 * 8].view(torch.int64).cpu()
-tl = raw[:512].view(8, 4, 16)
-hd = raw[512:512 + 32].view(4, 8)
+raw = pl.ws.view(torch.uint8)[: 840 * 8].view(torch.int64).cpu()
+tl = raw[:768].view(8, 4, 24)
+hd = raw[800:800 + 32].view(4, 8)
 names = ["top", "P1 dn", "G1 wait", "Vload", "P2 all", "sync", "G2 issue", "G2 wait", "P3+P4 epi", "sync", "G3 wait", "P5 state", "end sync", "tail"]
 t0 = hd[0, 0].item()
 whos = ["thread 0 (rg0,cq0 diag)", "thread 96 (rg3,cq0)", "thread 480 (rg3,cq3 diag)", "issuer"]
@@ -29,5 +29,6 @@ for w, who in enumerate(whos):
         d = [(row[j] - row[j - 1]).item() for j in range(1, 14)]
         extra = ""
         if w < 3:
-            extra = f"  [P2: tiles {(row[14] - row[3]).item()} sync5+st {(row[15] - row[14]).item()} colsum {(row[4] - row[15]).item()}]"
+            extra = (f"  [P2: ldZ {(row[16] - row[3]).item()} dS {(row[17] - row[16]).item()} ldS {(row[18] - row[17]).item()} E {(row[14] - row[18]).item()} "
+                     f"sync5+st {(row[15] - row[14]).item()} colsum {(row[4] - row[15]).item()}]")
         print(f" step {c} start {row[0].item():7d}  " + " ".join(f"{n_[:8]}:{x:5d}" for n_, x in zip(names[1:], d)) + extra)

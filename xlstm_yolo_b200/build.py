@@ -56,6 +56,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         out, _ = pr.communicate()
         log.append(f"== {os.path.basename(src)}\n{out}")
         if pr.returncode != 0:
+            if os.path.exists(LIB):
+                os.remove(LIB)   # never leave a stale library behind a failed build: tests would silently run the old kernels
             raise RuntimeError(f"nvcc failed for {src}:\n{out}")
     cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

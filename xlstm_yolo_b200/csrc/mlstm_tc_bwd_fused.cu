@@ -29,7 +29,7 @@ constexpr int NB = DH / 32;   // 32-column blocks of a DH-wide accumulator
 #ifdef MLSTM_TIMELINE
 #define TLF(k) do { if (blockIdx.x == 0 && c < 8) { \
     const int who_ = threadIdx.x == 0 ? 0 : threadIdx.x == 96 ? 1 : threadIdx.x == 480 ? 2 : threadIdx.x == CT ? 3 : -1; \
-    if (who_ >= 0) tlf[c * 64 + who_ * 16 + (k)] = clock64(); } } while (0)
+    if (who_ >= 0) tlf[c * 96 + who_ * 24 + (k)] = clock64(); } } while (0)
 #else
 #define TLF(k) do { } while (0)
 #endif
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
 #ifdef MLSTM_TIMELINE
   long long* tlf = reinterpret_cast<long long*>(p.workspace);
   const int who_h = threadIdx.x == 0 ? 0 : threadIdx.x == 96 ? 1 : threadIdx.x == 480 ? 2 : threadIdx.x == 512 ? 3 : -1;
-#define TLH(k) do { if (blockIdx.x == 0 && who_h >= 0) tlf[512 + who_h * 8 + (k)] = clock64(); } while (0)
+#define TLH(k) do { if (blockIdx.x == 0 && who_h >= 0) tlf[800 + who_h * 8 + (k)] = clock64(); } while (0)
 #else
 #define TLH(k) do { } while (0)
 #endif
@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
         float z[32];
         tmem_ld32(tZ + lane_sel + cq * 32, z);
         tmem_ld_wait();
+        TLF(16);
         const float M2t = G.M2[row], invN = G.invN[row];
 #pragma unroll
         for (int x = 0; x < 32; x += 4) {
@@ -277,10 +278,12 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
 #pragma unroll
         for (int x = 0; x < 16; ++x) pk[x] = 0u;
       }
+      TLF(17);
       if (fullB || diag) {   // E^T[j][t] = S^T 2^(u2_j + log2 s - c2_t), keep t >= j (reverse: t <= j)
         float s_[32];
         tmem_ld32(tS + lane_sel + cq * 32, s_);
         tmem_ld_wait();
+        TLF(18);
         const float u2j = G.u2[row] + l2s;
 #pragma unroll
         for (int x = 0; x < 32; x += 4) {

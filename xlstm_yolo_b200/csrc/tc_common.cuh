@@ -26,12 +26,6 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// Causal mask of one 32x32 block of a gated tile as a bit set over the block's columns: bit e <=> column e of the block is kept
-// for this thread's row (lane = row within the block).  Full blocks keep everything, the diagonal block keeps col <= row
-// (lower) or col >= row.  One shift per block and a bit test per element instead of a compare chain per element.
-__device__ __forceinline__ uint32_t causal_bits(bool full, bool lower, int lane) {
-  return full ? 0xffffffffu : (lower ? (0xffffffffu >> (31 - lane)) : (0xffffffffu << lane));
-}
 __device__ __forceinline__ void named_arrive(int id, int nthreads) {   // arrive without waiting (producer side)
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

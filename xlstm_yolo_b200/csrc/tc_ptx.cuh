@@ -112,6 +112,12 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Causal mask of one 32x32 block of a gated tile as a bit set over the block's columns: bit e <=> column e of the block is kept
+// for this thread's row (lane = row within the block).  Full blocks keep everything, the diagonal block keeps col <= row
+// (lower) or col >= row.  One shift per block and a bit test per element instead of a compare chain per element.
+__device__ __forceinline__ uint32_t causal_bits(bool full, bool lower, int lane) {
+  return full ? 0xffffffffu : (lower ? (0xffffffffu >> (31 - lane)) : (0xffffffffu << lane));
+}
 // Same product with the descriptors given by their low words.  Every tile of these kernels has SBO = 1024 bytes, descriptor
 // version 1 and the 128-byte swizzle, so the high word is one constant: passing it as an immediate halves the
 // register-to-uniform moves ptxas puts in front of each MMA (two instead of four).
