@@ -30,5 +30,5 @@ for w, who in enumerate(whos):
         extra = ""
         if w < 3:
             extra = (f"  [P2: ldZ {(row[16] - row[3]).item()} dS {(row[17] - row[16]).item()} ldS {(row[18] - row[17]).item()} E {(row[14] - row[18]).item()} "
-                     f"sync5+st {(row[15] - row[14]).item()} colsum {(row[4] - row[15]).item()}]")
+                     f"sync5+st {(row[4] - row[14]).item()} | colsum in G2 shadow {(row[15] - row[6]).item()}]")
         print(f" step {c} start {row[0].item():7d}  " + " ".join(f"{n_[:8]}:{x:5d}" for n_, x in zip(names[1:], d)) + extra)

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     tma_prefetch_desc(&maps.h); tma_prefetch_desc(&maps.cs);
     mbar_init(&sm.bar_q[0], 1); mbar_init(&sm.bar_q[1], 1); mbar_init(&sm.bar_dh[0], 1); mbar_init(&sm.bar_dh[1], 1);
     mbar_init(&sm.bar_k[0], 1); mbar_init(&sm.bar_k[1], 1); mbar_init(&sm.bar_v, 1); mbar_init(&sm.bar_h, 1); mbar_init(&sm.bar_cs, 1);
-    mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_i, 1); mbar_init(&sm.bar_m2, 3); mbar_init(&sm.bar_m3, 1);
+    mbar_init(&sm.bar_m1, 3); mbar_init(&sm.bar_i, 2); mbar_init(&sm.bar_m2, 3); mbar_init(&sm.bar_m3, 1);
     fence_mbar_init();
     sm.df_carry = 0.f;
   }
@@ -151,25 +151,36 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
   const uint64_t dCsk = make_sdesc(smem_u32(sm.cs), 16, 1024);
   const uint64_t dCbk = make_sdesc(smem_u32(sm.dcb), 16, 1024), dCbmn = make_sdesc(smem_u32(sm.dcb), DH * 128, 1024);
 
-  auto issue_g1 = [&](int buf) {   // Z = dH V^T (rows t), S^T = K Q^T (rows j), G = dH Cs^T
+  // MMA group 1 of a chunk, one product per call (each arrives once on bar_m1): 0: Z = dH V^T (rows t), 1: S^T = K Q^T (rows j),
+  // 2: G = dH Cs^T.  ptxas wraps every tcgen05.mma whose descriptors depend on the step in a register-to-uniform waterfall
+  // (~100 cycles per MMA from one lane, the tensor pipe needs ~51), so independent products are issued by different lanes.
+  auto issue_g1 = [&](int which, int buf) {
     constexpr uint32_t id128 = make_idesc_bf16(128, 128, 0, 0), id64 = make_idesc_bf16(128, DH, 0, 0);
+    if (which == 0) {
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tZ, (dHk0 + buf * BUF_STEP) + kstep(ks), dVk + kstep(ks), id128, ks > 0);
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tZ, (dHk0 + buf * BUF_STEP) + kstep(ks), dVk + kstep(ks), id128, ks > 0);
+    } else if (which == 1) {
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tS, (dKk0 + buf * BUF_STEP) + kstep(ks), (dQk0 + buf * BUF_STEP) + kstep(ks), id128, ks > 0);
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tS, (dKk0 + buf * BUF_STEP) + kstep(ks), (dQk0 + buf * BUF_STEP) + kstep(ks), id128, ks > 0);
+    } else {
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tG, (dHk0 + buf * BUF_STEP) + kstep(ks), dCsk + kstep(ks), id64, ks > 0);
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tG, (dHk0 + buf * BUF_STEP) + kstep(ks), dCsk + kstep(ks), id64, ks > 0);
+    }
     umma_commit(&sm.bar_m1);
   };
 
-  // products with the adjoint state leaving the chunk: needed by the epilogues only, issued as soon as the state
-  // pass of the previous step has refreshed dCb — V is then dead early and the next V tile has a whole step to land
-  auto issue_g1b = [&](int buf) {
+  // products with the adjoint state leaving the chunk (0: Ik = V dCb^T, 1: Iv = K dCb; each arrives once on bar_i): needed by
+  // the epilogues only, issued as soon as the state pass of the previous step has refreshed dCb — V is then dead early and
+  // the next V tile has a whole step to land
+  auto issue_g1b = [&](int which, int buf) {
     constexpr uint32_t idKK = make_idesc_bf16(128, DH, 0, 0), idKmn_ = make_idesc_bf16(128, DH, 0, 1);
+    if (which == 0) {
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tIk, dVk + kstep(ks), dCbk + kstep(ks), idKK, ks > 0);                // V dCb^T
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tIk, dVk + kstep(ks), dCbk + kstep(ks), idKK, ks > 0);
+    } else {
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tIv, (dKk0 + buf * BUF_STEP) + kstep(ks), dCbmn + mnstep(ks), idKmn_, ks > 0);      // K dCb
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tIv, (dKk0 + buf * BUF_STEP) + kstep(ks), dCbmn + mnstep(ks), idKmn_, ks > 0);
+    }
     umma_commit(&sm.bar_i);
   };
 
@@ -187,10 +198,43 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     mbar_wait(&sm.bar_dh[0], 0); mbar_wait(&sm.bar_v, 0); mbar_wait(&sm.bar_q[0], 0); mbar_wait(&sm.bar_k[0], 0);
     mbar_wait(&sm.bar_cs, 0);
     tc_fence_after();
-    issue_g1(0);
-    issue_g1b(0);   // dCb = 0: zero products
+    issue_g1(0, 0); issue_g1(1, 0); issue_g1(2, 0);
+    issue_g1b(0, 0); issue_g1b(1, 0);   // dCb = 0: zero products
   }
 
+  // dn pass of processing step c (compute warps): dn_t = dnf_t (dh_t . h_t), plus the row coefficients the state update and the
+  // dn_state sums use.  Runs one step ahead: step 0 here, step c + 1 in the shadow of step c's state MMA.
+  auto dn_pass = [&](int c) -> float {
+    const int bf = c & 1;
+    const GateBuf& Gc = sm.g[c % 3];
+    mbar_wait(&sm.bar_h, c & 1);
+    mbar_wait(&sm.bar_dh[bf], (c >> 1) & 1);
+    if (cq < NB) {
+      float part = 0.f;
+#pragma unroll
+      for (int x8 = 0; x8 < 32; x8 += 8) {
+        const uint32_t off = swz128(row, cq * 32 + x8);
+        const uint4 wh = *reinterpret_cast<const uint4*>(sh + off);
+        const uint4 wd = *reinterpret_cast<const uint4*>(sm.dh[bf] + off);
+        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&wh);
+        const __nv_bfloat162* dd = reinterpret_cast<const __nv_bfloat162*>(&wd);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __bfloat1622float2(hh[e]), c2 = __bfloat1622float2(dd[e]);
+          part = fmaf(a.x, c2.x, fmaf(a.y, c2.y, part));
+        }
+      }
+      sm.part[cq][row] = part;
+    }
+    named_sync(3, CT);
+    const float dn = Gc.dnf[row] * (sm.part[0][row] + sm.part[1][row]);
+    if (cq == 0) {
+      sm.ncoef[row] = Gc.w[row] * scale * dn;
+      sm.rowscale[row] = Gc.w[row] * scale * Gc.invN[row];
+    }
+    return dn;
+  };
+  float dn_next = compute ? dn_pass(0) : 0.f;
   float nstate = 0.f;   // thread dk < DH: decayed dn_state entering the step
   TLH(3);
   for (int c = 0; c < NC; ++c) {
@@ -209,36 +253,9 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     const int tok = tok0 + row;
     const bool row_ok = compute && tok < S;
 
-    // ---- P1: dn_t = dnf_t (dh_t . h_t) ---------------------------------------------------------
+    // ---- P1 ran one step ahead (in the shadow of the previous step's state MMA, or in the prologue)
     TLF(0);
-    mbar_wait(&sm.bar_h, ph);
-    mbar_wait(&sm.bar_dh[buf], (c >> 1) & 1);
-    if (cq < NB) {
-      float part = 0.f;
-#pragma unroll
-      for (int x8 = 0; x8 < 32; x8 += 8) {
-        const uint32_t off = swz128(row, cq * 32 + x8);
-        const uint4 wh = *reinterpret_cast<const uint4*>(sh + off);
-        const uint4 wd = *reinterpret_cast<const uint4*>(sm.dh[buf] + off);
-        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&wh);
-        const __nv_bfloat162* dd = reinterpret_cast<const __nv_bfloat162*>(&wd);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 a = __bfloat1622float2(hh[e]), c2 = __bfloat1622float2(dd[e]);
-          part = fmaf(a.x, c2.x, fmaf(a.y, c2.y, part));
-        }
-      }
-      sm.part[cq][row] = part;
-    }
-    if (compute) named_sync(3, CT);
-    float dn_row = 0.f;
-    if (compute) {
-      dn_row = G.dnf[row] * (sm.part[0][row] + sm.part[1][row]);
-      if (cq == 0) {
-        sm.ncoef[row] = G.w[row] * scale * dn_row;
-        sm.rowscale[row] = G.w[row] * scale * G.invN[row];
-      }
-    }
+    const float dn_row = dn_next;
     TLF(1);
     mbar_wait(&sm.bar_m1, ph);
     tc_fence_after();
@@ -312,16 +329,6 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
         *reinterpret_cast<uint4*>(sm.xs + off) = make_uint4(pk[4 * x], pk[4 * x + 1], pk[4 * x + 2], pk[4 * x + 3]);
         *reinterpret_cast<uint4*>(sm.xe + off) = make_uint4(pe[4 * x], pe[4 * x + 1], pe[4 * x + 2], pe[4 * x + 3]);
       }
-      TLF(15);
-      // dn_state contribution: column sums of the (un-scaled) Q tile, 16 rows per thread
-      {
-        const int dk = tid & 63, pt = tid >> 6;
-        float acc = 0.f;
-#pragma unroll 4
-        for (int t = pt * 16; t < pt * 16 + 16; ++t)
-          acc = fmaf(sm.ncoef[t], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm.q[buf] + swz128(t, dk))), acc);
-        sm.npart[pt][dk] = acc;
-      }
     }
     if (!compute) named_sync(5, GT0);   // control warp: its store drain (end of the previous step) is complete
     TLF(4);
@@ -351,6 +358,18 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
       umma_commit(&sm.bar_m2);   // three arrivals complete the phase
     }
     TLF(6);
+    // in the shadow of group 2: dn_state contribution = column sums of the (un-scaled) Q tile, 16 rows per thread
+    if (compute) {
+      {
+        const int dk = tid & 63, pt = tid >> 6;
+        float acc = 0.f;
+#pragma unroll 4
+        for (int t = pt * 16; t < pt * 16 + 16; ++t)
+          acc = fmaf(sm.ncoef[t], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm.q[buf] + swz128(t, dk))), acc);
+        sm.npart[pt][dk] = acc;
+      }
+    }
+    TLF(15);
     mbar_wait(&sm.bar_m2, ph);
     tc_fence_after();
     TLF(7);
@@ -453,15 +472,25 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
 #pragma unroll
       for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss_lo(tdC, (dQmnA0 + buf * BUF_STEP) + mnstep(ks), (dHmn0 + buf * BUF_STEP) + mnstep(ks), idMM, (ks > 0 || c > 0) ? 1u : 0u);
       umma_commit(&sm.bar_m3);
-      if (!last) {   // group 1 of the next chunk right behind: Z, S^T, G were consumed by the epilogues above
-        const int nb = buf ^ 1;
-        mbar_wait(&sm.bar_dh[nb], ((c + 1) >> 1) & 1); mbar_wait(&sm.bar_v, ph ^ 1);
-        mbar_wait(&sm.bar_q[nb], ((c + 1) >> 1) & 1); mbar_wait(&sm.bar_k[nb], ((c + 1) >> 1) & 1);
-        mbar_wait(&sm.bar_cs, ph ^ 1);
-        tc_fence_after();
-        issue_g1(nb);
-      }
+      // the staged outputs are final: store them now, so the drain is over long before the next gated tiles overwrite xs / xe
+      tma_store_4d(&maps.dq, sm.xs, 0, tok0, h, b);
+      tma_store_4d(&maps.dk, sm.xs + TILE, 0, tok0, h, b);
+      tma_store_4d(&maps.dv, sm.xe, 0, tok0, h, b);
+      tma_store_commit();
       if (c + 2 < NC) load1(sm.k[buf], &maps.k, &sm.bar_k[buf], c + 2);   // k rows were consumed in the epilogue
+    }
+    if (compute && !last) dn_next = dn_pass(c + 1);   // in the shadow of the state MMA
+    // group 1 of the next chunk (Z, S^T, G were consumed by the epilogues above), one product per lane: lanes 0 of compute warps
+    // 2, 3 and 6, which have no rows in the state pass below — their issue time hides behind it
+    const int g1w = (warp == 2) ? 0 : (warp == 3) ? 1 : (warp == 6) ? 2 : -1;
+    if (!last && lane == 0 && g1w >= 0) {
+      const int nb = buf ^ 1;
+      const uint32_t pn = ((c + 1) >> 1) & 1;
+      if (g1w == 0) { mbar_wait(&sm.bar_dh[nb], pn); mbar_wait(&sm.bar_v, ph ^ 1); }
+      else if (g1w == 1) { mbar_wait(&sm.bar_k[nb], pn); mbar_wait(&sm.bar_q[nb], pn); }
+      else { mbar_wait(&sm.bar_dh[nb], pn); mbar_wait(&sm.bar_cs, ph ^ 1); }
+      tc_fence_after();
+      issue_g1(g1w, nb);
     }
     mbar_wait(&sm.bar_m3, ph);
     tc_fence_after();
@@ -494,23 +523,16 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     TLF(11);
     fence_proxy_async_smem();
     tc_fence_before();
-    // end of step.  The control warp needs every compute warp's staged outputs and dCb (barrier 6) but produces nothing
-    // they wait for here, so the compute warps only arrive on it and run ahead into the next step's dn pass while the
-    // issuer lane is still blocked issuing MMAs; they meet the gate warp on barrier 7.
-    if (compute) { named_arrive(6, GT0); named_sync(7, GT0); }
-    else named_sync(6, GT0);
+    // end of step: the compute warps meet the gate warp (gates two steps ahead are complete).  The control warp takes no part:
+    // it stored the outputs behind the state MMA and the products with dCb are issued by compute lanes, so it runs ahead to
+    // the next step's loads and meets the compute warps again at barrier 5.
+    if (compute) named_sync(7, GT0);
     TLF(12);
-    if (issuer) {
-      tma_store_4d(&maps.dq, sm.xs, 0, tok0, h, b);
-      tma_store_4d(&maps.dk, sm.xs + TILE, 0, tok0, h, b);
-      tma_store_4d(&maps.dv, sm.xe, 0, tok0, h, b);
-      tma_store_commit();
-      if (!last) {
-        tc_fence_after();
-        issue_g1b(buf ^ 1);       // its operands (V, K of the next chunk) landed before group 1 of that chunk was issued
-      }
-      tma_store_wait_read<0>();   // before this warp joins barrier 5 of the next step (xs / xe are rewritten after it)
+    if (!last && (tid == 32 || tid == 64)) {   // V, K of the next chunk landed before group 1 of that chunk was issued
+      tc_fence_after();
+      issue_g1b(tid == 32 ? 0 : 1, buf ^ 1);
     }
+    if (issuer) tma_store_wait_read<0>();   // before this warp joins barrier 5 of the next step (xs / xe are rewritten after it)
     TLF(13);
   }
   TLH(4);
