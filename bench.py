@@ -29,6 +29,9 @@ WORKLOADS = {
     "cfg3_B32_NH4_S1600_DH128": (32, 4, 1600, 128),
     "cfg3_B32_NH4_S6400_DH128": (32, 4, 6400, 128),
     "ddp_B8_NH4_S1600_DH128": (8, 4, 1600, 128),
+    # developer shapes (dispatch thresholds of the DH = 64 backward variants; not BASELINE configs)
+    "dev_B32_NH4_S800_DH64": (32, 4, 800, 64),
+    "dev_B32_NH4_S1600_DH64": (32, 4, 1600, 64),
 }
 DEFAULT_WORKLOAD = "cfg2_B32_NH4_S400_DH64"
 CHUNK = 64          # the config's chunk size (algorithmic FLOP formula; kernels tile on their own)
@@ -54,7 +57,7 @@ def algorithmic(B, NH, S, DH):
 # part, from the round-1 `ncu --set full` captures (profiles/r01_ncu_full_*_summary.csv).  Writes that
 # stay in the 126 MB L2 until after the kernel are not counted by ncu.
 NCU_TRAFFIC_BYTES = {
-    "cfg2_B32_NH4_S400_DH64": {"fwd": 20.14e6, "bwd_dq": 33.64e6, "bwd_dkv": 27.54e6},
+    "cfg2_B32_NH4_S400_DH64": {"fwd": 20.14e6, "bwd_dq": None, "bwd_dkv": 38.03e6 + 0.25e6},   # fused backward: one kernel
     "cfg3_B32_NH4_S1600_DH128": {"fwd": 159.12e6 + 70.35e6, "bwd_dq": 320.92e6 + 42.60e6,
                                  "bwd_dkv": (160.54e6 + 33.21e6) + (271.65e6 + 88.60e6) + 7.39e6},
 }
@@ -352,10 +355,12 @@ def main():
         print("debug run(20) host/dev ms", timed(lambda j: e2e_run(20), 1), file=sys.stderr)
 
     # ---- roofline of the dominant kernel --------------------------------------------------
+    pl0 = plans[0]
     parts = {"fwd": (fwd_ms, alg["bytes_fwd"]), "bwd_dq": (dq_ms, alg["bytes_bwd_dq"]), "bwd_dkv": (dkv_ms, alg["bytes_bwd_dkv"])}
+    if pl0.variant_bwd == "fused_walk":   # one kernel does the whole backward (part 0 launches nothing): SURVEY.md §8(d)'s 14 DH + 24 B
+        parts["bwd_dkv"] = (dkv_ms, alg["bytes_bwd"])
     dom = max(parts, key=lambda n: parts[n][0])
     dom_ms, dom_bytes = parts[dom]
-    pl0 = plans[0]
     launches_of = {   # kernels behind each timed part, per variant (csrc/mlstm_tc_*.cu)
         "fwd": {"single_pass": ["tc_fwd_kernel"], "two_phase": ["tc_state_fwd_kernel", "tc_fwd_par_kernel"],
                 "simt": ["simt_fwd_kernel"]}[pl0.variant_fwd],

@@ -106,6 +106,7 @@ CASES = [
     (1, 4, 1600, 128, torch.bfloat16, "refinit", True, 5e-5),
     (1, 2, 6400, 128, torch.bfloat16, "rand", True, 1e-6),      # 80x80 map: df stays anchored over 50 chunks
     (1, 2, 3200, 64, torch.bfloat16, "forget", False, 1e-6),
+    (1, 2, 6400, 64, torch.bfloat16, "rand", False, 1e-6),      # 50 chunks at DH 64 (fused-walk pin: df carried over the whole walk)
     (3, 2, 129, 64, torch.bfloat16, "rand", False, 1e-6),
     (3, 2, 127, 128, torch.bfloat16, "rand", True, 1e-6),
     (2, 2, 1, 64, torch.bfloat16, "rand", False, 1e-6),

@@ -1,6 +1,8 @@
 """Every kernel variant against the oracle: the parity sweep of test_gpu_parity.py re-run in a child
 process with the dispatch pinned (MLSTM_FORCE_VARIANT is read once per process): single-pass forward
-+ single-pass backward, and two-phase forward + chunk-parallel backward, whatever the shape would pick."""
++ single-pass backward, two-phase forward + chunk-parallel backward, and the fused single-walk backward (pin 3, DH = 64;
+other head dims fall through to the chunk-parallel kernels), whatever the shape would pick — the oracle cases are small
+batches, which the automatic dispatch would never send to the wide-batch kernels the bench runs."""
 import os
 import subprocess
 import sys
@@ -11,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["11", "22", "12", "21"])
+@pytest.mark.parametrize("variant", ["11", "22", "12", "21", "13", "23"])
 def test_parity_sweep_with_pinned_variant(variant):
     env = dict(os.environ, MLSTM_FORCE_VARIANT=variant)
     select = "(test_cuda_matches_oracle or test_initial_and_last_states or sigmoid_input_gate)"

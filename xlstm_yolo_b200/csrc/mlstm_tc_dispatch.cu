@@ -1,6 +1,7 @@
 // Shape/dtype gate and kernel-variant selection of the tcgen05 family.
 //   forward : single pass (mlstm_tc_fwd.cu)   | two-phase (mlstm_tc_fwd2p.cu)
-//   backward: single pass (mlstm_tc_bwd1p.cu) | chunk-parallel two-phase (mlstm_tc_bwd.cu)
+//   backward: single pass (mlstm_tc_bwd1p.cu) | chunk-parallel two-phase (mlstm_tc_bwd.cu) | fused single walk, DH = 64
+//             (mlstm_tc_bwd_fused.cu)
 // Single-pass kernels run one CTA per (batch, head) with the state on chip: best when there are
 // enough heads to fill the GPU and the per-head chunk chain is short.  The two-phase kernels
 // spill per-chunk states to HBM and are chunk-parallel: best for long sequences / small batches.
@@ -35,12 +36,14 @@ bool tc_use_two_phase(const mlstm_params& p) {          // forward
 }
 static bool short_and_wide(const mlstm_params& p) { return tc::num_chunks(p.S) <= 4 && p.B * p.NH * 2 > sm_count(); }
 
-// DH = 64, short sequences: one reverse walk producing dq, dk, dv together from the forward's chunk states
-// (mlstm_tc_bwd_fused.cu).  MLSTM_FORCE_VARIANT backward digit 3 pins it (DH = 64 only).
+// DH = 64 with enough (batch, head) pairs to fill the GPU: one reverse walk producing dq, dk, dv together from the forward's
+// chunk states (mlstm_tc_bwd_fused.cu), at any sequence length — it reads every tile once, so it also beats the chunk-parallel
+// kernels on long sequences (B32 NH4 DH64: 244 vs 135 M tok/s at S=800, 309 vs 180 at S=1600).  MLSTM_FORCE_VARIANT backward
+// digit 3 pins it (DH = 64 only).
 bool tc_use_fused_bwd(const mlstm_params& p) {
   if (p.DHQK != 64) return false;
   if (forced(1)) return forced(1) == 3;
-  return short_and_wide(p);
+  return p.B * p.NH * 2 > sm_count();
 }
 bool tc_use_single_pass_bwd(const mlstm_params& p) {    // backward, two-walk single-pass kernels
   if (tc_use_fused_bwd(p)) return false;
