@@ -42,8 +42,11 @@ struct FwdMaps { CUtensorMap q, k, v, h, cs; };   // cs: the per-chunk state buf
 #ifdef MLSTM_TIMELINE
 #define TL_STAMP(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) tl_buf[(c) * 32 + (k)] = clock64(); \
                           if (blockIdx.x == 0 && threadIdx.x == CT) tl_buf[(c) * 32 + 16 + (k)] = clock64(); } while (0)
+#define TL_HEAD(k) do { if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == CT)) \
+    reinterpret_cast<long long*>(p.workspace)[1024 + (threadIdx.x == 0 ? 0 : 8) + (k)] = clock64(); } while (0)
 #else
 #define TL_STAMP(k) do { } while (0)
+#define TL_HEAD(k) do { } while (0)
 #endif
 
 struct alignas(16) GateBuf {       // indexed by tile row
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled tiles need 1024-byte alignment
   Smem<DH>& sm = *reinterpret_cast<Smem<DH>*>(smem_raw);       // no pointer arithmetic: keeps the shared address space (LDS/STS)
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  TL_HEAD(0);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool compute = tid < CT;
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
   if (issuer) {
     tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.v); tma_prefetch_desc(&maps.h);
     mbar_init(&sm.bar_q, 1); mbar_init(&sm.bar_k[0], 1); mbar_init(&sm.bar_k[1], 1); mbar_init(&sm.bar_v, 1);
-    mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_kv, 1); mbar_init(&sm.bar_m2, 1);
+    mbar_init(&sm.bar_m1, 2); mbar_init(&sm.bar_kv, 2); mbar_init(&sm.bar_m2, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
@@ -214,18 +218,25 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
   constexpr uint64_t KBUF_STEP = (uint64_t)(KT * TILE) >> 4;     // descriptor distance between the two K buffers
   auto kstep = [](int ks) { return (uint64_t)((((ks >> 2) * TILE) + (ks & 3) * 32) >> 4); };   // K-major advance
   auto mnstep = [](int ks) { return (uint64_t)((ks * 2048) >> 4); };                             // MN-major advance
-  auto issue_mma1 = [&](int c) {   // S = Q K^T, G = Q Cb   (chunk c)
-    const uint64_t dKk = dKk0 + (c & 1) * KBUF_STEP;
-    constexpr uint32_t idS = make_idesc_bf16(128, 128, 0, 0);
+  // MMA1 of chunk c, one product per call (each arrives once on bar_m1): part 0: S = Q K^T, part 1: G = Q Cb.  A single lane
+  // issues at ~100 cycles per MMA (register-to-uniform waterfall in front of each tcgen05.mma) while the tensor pipe needs
+  // 50-70, so the two independent products go out from two lanes (control lane; lane 0 of compute warp 1).
+  auto issue_mma1 = [&](int c, int part) {
+    if (part == 0) {
+      const uint64_t dKk = dKk0 + (c & 1) * KBUF_STEP;
+      constexpr uint32_t idS = make_idesc_bf16(128, 128, 0, 0);
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tS, dQ + kstep(ks), dKk + kstep(ks), idS, ks > 0);
-    constexpr uint32_t idG = make_idesc_bf16(128, DH, 0, 1);
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tS, dQ + kstep(ks), dKk + kstep(ks), idS, ks > 0);
+    } else {
+      constexpr uint32_t idG = make_idesc_bf16(128, DH, 0, 1);
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tG, dQ + kstep(ks), dCbmn + mnstep(ks), idG, ks > 0);
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tG, dQ + kstep(ks), dCbmn + mnstep(ks), idG, ks > 0);
+    }
     umma_commit(&sm.bar_m1);
   };
 
   // ---- prologue: first loads, gates of chunks 0 and 1, initial state -----------------------
+  TL_HEAD(1);
   if (issuer) {
     issue_loads(sm.q, &maps.q, &sm.bar_q, 0);
     issue_loads(sm.k[0], &maps.k, &sm.bar_k[0], 0);
@@ -233,9 +244,11 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
   }
   if (gatew) {
     compute_gates<DH>(sm.g[0], p, b, h, 0, lane, p.m_initial ? p.m_initial[bh] : 0.f, scale);
-    if (NC > 1) compute_gates<DH>(sm.g[1], p, b, h, 1, lane, sm.g[0].m_next, scale);
+    // chunk 1's gates need chunk 0's m_next (serial) but nobody reads them before the state pass of chunk 0:
+    // they are computed during chunk 0 (barrier 6 below) instead of lengthening the prologue
   }
   __syncthreads();
+  TL_HEAD(2);
 
   if (has_init) {  // TMEM C <- decay_0 * C_0 ; Cb <- bf16(C_0) ; n likewise  (thread: state row `row`, block cq)
     const float d0 = sm.g[0].decay;
@@ -281,18 +294,24 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
     mbar_wait(&sm.bar_q, 0);
     mbar_wait(&sm.bar_k[0], 0);
     tc_fence_after();
-    issue_mma1(0);
+    issue_mma1(0, 0);
+    issue_mma1(0, 1);
   }
 
 #ifdef MLSTM_TIMELINE
   long long* tl_buf = reinterpret_cast<long long*>(p.workspace);
 #endif
+  TL_HEAD(3);
   for (int c = 0; c < NC; ++c) {
     TL_STAMP(0);
     const uint32_t ph = c & 1;
     const bool last = (c + 1 == NC);
     if (gatew) {
       // two chunks ahead, into the ring slot chunk c-1 just released
+      if (c == 0 && NC > 1) {
+        compute_gates<DH>(sm.g[1], p, b, h, 1, lane, sm.g[0].m_next, scale);
+        named_sync(6, GT0);   // with the compute warps, ahead of chunk 0's state pass (first reader: decay of chunk 1)
+      }
       if (c + 2 < NC) compute_gates<DH>(sm.g[(c + 2) % 3], p, b, h, c + 2, lane, sm.g[(c + 1) % 3].m_next, scale);
       __syncthreads();   // the end-of-chunk barrier is the only one the gate warp takes part in
       continue;
@@ -421,10 +440,16 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
       tc_fence_after();
       const uint64_t dKmn = dKmn0 + (c & 1) * KBUF_STEP;
       constexpr uint32_t idC = make_idesc_bf16(128, DH, 1, 1);
-      constexpr uint32_t idN = make_idesc_bf16(128, 16, 1, 1);
       const uint32_t acc0 = (c > 0 || has_init) ? 1u : 0u;
 #pragma unroll
       for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tC, dKmn + mnstep(ks), dVmn + mnstep(ks), idC, (ks > 0) ? 1u : acc0);
+      umma_commit(&sm.bar_kv);
+    }
+    if (tid == 32) {   // n += Kbar^T 1 from a second lane (lane 0 of compute warp 1); two arrivals complete bar_kv
+      tc_fence_after();
+      const uint64_t dKmn = dKmn0 + (c & 1) * KBUF_STEP;
+      constexpr uint32_t idN = make_idesc_bf16(128, 16, 1, 1);
+      const uint32_t acc0 = (c > 0 || has_init) ? 1u : 0u;
 #pragma unroll
       for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tN, dKmn + mnstep(ks), dOnes, idN, (ks > 0) ? 1u : acc0);
       umma_commit(&sm.bar_kv);
@@ -451,6 +476,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
     if (issuer && !last) issue_loads(sm.v, &maps.v, &sm.bar_v, c + 1);
 
     // ---- state pass: Cb <- bf16(C); C <- decay_next C (state row `row`, block cq); n in smem ----
+    if (c == 0 && NC > 1 && compute) named_sync(6, GT0);   // chunk 1's gates (gate warp, computed during this chunk) are complete
     const float dnext = last ? 1.f : sm.g[(c + 1) % 3].decay;
     if (cq < NB) {
       if (row < DH) {
@@ -513,18 +539,25 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
       if (save_states && !last)   // entry state of chunk c+1 = the bf16 C tile just written (read again by the next state pass only)
         for (int kt = 0; kt < KT; ++kt) tma_store_2d(&maps.cs, sm.cb + kt * TILE_C, kt * 64, (bh * NC + c + 1) * DH);
       tma_store_commit();
-      if (!last) {   // MMA1 of the next chunk: nobody waits for this issue loop
+      if (!last) {   // MMA1 of the next chunk, S part
         mbar_wait(&sm.bar_q, ph ^ 1);
         mbar_wait(&sm.bar_k[(c + 1) & 1], ((c + 1) >> 1) & 1);
         tc_fence_after();
-        issue_mma1(c + 1);
+        issue_mma1(c + 1, 0);
       }
+    }
+    if (tid == 32 && !last) {   // G part (Cb was refreshed by the state pass above)
+      mbar_wait(&sm.bar_q, ph ^ 1);
+      tc_fence_after();
+      issue_mma1(c + 1, 1);
     }
   }
 
+  TL_HEAD(4);
   if (issuer) tma_store_wait_all<0>();
   tc_fence_before();
   __syncthreads();
+  TL_HEAD(5);
   if (warp == 0) tmem_dealloc(tm, 512);
 }
 
