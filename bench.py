@@ -237,24 +237,65 @@ def main():
     for w in range(W):
         step(plans[w % nsets])
     torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    step(plans[W % nsets])
+    launches_per_step = _lib.launch_count() - l0
+    torch.cuda.synchronize()
+
+    # The timed region replays a CUDA graph of one round over the input sets (nsets steps, so the L2 rotation is kept): the
+    # kernels are the same launches with the same arguments, without the ~20 us of Python / ctypes / tensor-map encoding per
+    # step that otherwise competes with a 70 us step (and with the other ranks' host threads at N > 1).  BENCH_NO_GRAPH=1
+    # times eager launches instead.
+    graph = None
+    if not os.environ.get("BENCH_NO_GRAPH"):
+        try:
+            cap = torch.cuda.Stream(device=dev)
+            cap.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(cap):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=cap):
+                    for s_ in range(nsets):
+                        step(plans[s_])
+            torch.cuda.current_stream(dev).wait_stream(cap)
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as exc:   # capture unsupported: fall back to eager launches, say so
+            print(f"bench: CUDA graph capture failed ({exc}); timing eager launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_steps(n, first):
+        if graph is not None:
+            for _ in range(n // nsets):
+                graph.replay()
+            for s_ in range(n - n % nsets, n):
+                step(plans[s_ % nsets])
+        else:
+            for s_ in range(n):
+                step(plans[(first + s_) % nsets])
+
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
-    launches0 = _lib.launch_count()
     torch.cuda.synchronize()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
-    for s_ in range(K):
-        step(plans[(W + s_) % nsets], evs[s_])
+    run_steps(K, W)
     t_end.record()
     torch.cuda.synchronize()
-    launches = _lib.launch_count() - launches0
+    launches = launches_per_step * K
     if world > 1:
         dist.barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
+    # Second pass, same K steps, eager, with an event pair around every launch: the per-kernel durations the roofline uses.
+    # Kept out of the headline region because the events themselves cost ~2.7 us per pair (the fused backward's empty
+    # part 0 measures exactly that) and serialise consecutive launches.
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    for s_ in range(K):
+        step(plans[(W + s_) % nsets], evs[s_])
+    torch.cuda.synchronize()
     # keep the sampler alive long enough for at least a few samples of a very short region
     t_hold = time.time()
     while len(sampler.samples) < 3 and time.time() - t_hold < 0.2:
@@ -389,7 +430,9 @@ def main():
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "B_per_gpu": B, "NH": NH, "S": S, "DH": DH, "chunk_size": CHUNK,
                    "reverse": int(args.reverse), "kernel_family": family,
-                   "l2": f"inputs rotate over {nsets} sets x {set_bytes / 1e6:.0f} MB > 126 MB L2", "parallelism": f"dp{world}"},
+                   "l2": f"inputs rotate over {nsets} sets x {set_bytes / 1e6:.0f} MB > 126 MB L2", "parallelism": f"dp{world}",
+                   "launch": (f"CUDA graph of {nsets} steps (one per input set) replayed" if graph is not None else "eager ctypes launches"),
+                   "per_kernel_ms": "second pass of the same K steps with an event pair around every launch"},
         "clocks": sampler.result(),
         "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "api": "xlstm_yolo_b200.mLSTMBackend + autograd", "pipeline": "H2D of step s+1 on a copy stream overlaps step s"},

@@ -94,8 +94,15 @@ int bind_device(const void* dev_ptr) {
     set_error("q does not point to device memory (%s)", e == cudaSuccess ? "host/unregistered pointer" : cudaGetErrorString(e));
     return MLSTM_ERR_INVALID_ARG;
   }
+  // Once per thread and device: later calls only check that the device is still current.  (cudaFree is not allowed while a
+  // stream of the process is being captured into a CUDA graph; with the binding cached, forward and backward are plain kernel
+  // launches and can be captured.)
+  thread_local int bound = -1;
+  int cur = -1;
+  if (bound == attr.device && cudaGetDevice(&cur) == cudaSuccess && cur == attr.device) return MLSTM_OK;
   e = cudaSetDevice(attr.device);
   if (e == cudaSuccess) e = cudaFree(nullptr);   // forces the primary context current on this thread
+  if (e == cudaSuccess) bound = attr.device;
   if (e != cudaSuccess) {
     set_error("cudaSetDevice(%d): %s", attr.device, cudaGetErrorString(e));
     return MLSTM_ERR_CUDA;
