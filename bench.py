@@ -172,8 +172,20 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    emit(out)
     return 0
+
+
+_OUT_FD = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _OUT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_OUT_FD, line)
 
 
 def main():
@@ -187,6 +199,12 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner under NCCL_DEBUG=VERSION,
+    # for one) is sent to stderr by pointing fd 1 at fd 2; emit() writes to the saved descriptor
+    global _OUT_FD
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -253,7 +271,8 @@ def main():
             cap.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(cap):
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=cap):
+                # thread_local: other threads of the process (NCCL's watchdog at N > 1) may keep calling the CUDA runtime
+                with torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):
                     for s_ in range(nsets):
                         step(plans[s_])
             torch.cuda.current_stream(dev).wait_stream(cap)
@@ -456,7 +475,7 @@ def main():
         out["cpu_baseline"] = {"value": Bs * S / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
                                "sample": f"batch slice {Bs}/{B} of {args.workload}, {n} steps, fp32 torch CPU ops"}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
