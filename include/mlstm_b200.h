@@ -22,7 +22,9 @@
  *   - The caller (PyTorch) owns every buffer, including the workspace; the library borrows
  *     pointers for the duration of the launch, allocates nothing persistent on the device
  *     and keeps no mutable global state except a launch counter and a thread-local error
- *     string.  All work is enqueued on the CUDA stream passed in; no host synchronisation.
+ *     string.  All work is enqueued on the CUDA stream passed in; no host synchronisation;
+ *     after one warm-up call on the thread (which binds the device) the calls can be captured
+ *     into a CUDA graph.
  *   - Every function returns 0 on success or a negative mlstm_status; no C++ exception
  *     crosses the ABI.  mlstm_b200_last_error() describes the last failure on this thread.
  *   - Re-entrant: forward is called from the main thread, backward from autograd's worker
