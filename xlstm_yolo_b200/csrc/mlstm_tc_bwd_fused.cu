@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
       }
       // ---- P4: Qtilde = (w s / N) Q in place (q rows were consumed above) -------------------------------
       named_sync(3, CT);
-      scale_rows<DH>(sm.q[buf], sm.rowscale, tid);
+      if (!last) scale_rows<DH>(sm.q[buf], sm.rowscale, tid);   // the adjoint state leaving the first chunk is not an output
     }
     TLF(8);
     fence_proxy_async_smem();
@@ -468,10 +468,12 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     TLF(9);
     if (issuer) {
       tc_fence_after();
-      constexpr uint32_t idMM = make_idesc_bf16(128, DH, 1, 1);
+      if (!last) {
+        constexpr uint32_t idMM = make_idesc_bf16(128, DH, 1, 1);
 #pragma unroll
-      for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss_lo(tdC, (dQmnA0 + buf * BUF_STEP) + mnstep(ks), (dHmn0 + buf * BUF_STEP) + mnstep(ks), idMM, (ks > 0 || c > 0) ? 1u : 0u);
-      umma_commit(&sm.bar_m3);
+        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss_lo(tdC, (dQmnA0 + buf * BUF_STEP) + mnstep(ks), (dHmn0 + buf * BUF_STEP) + mnstep(ks), idMM, (ks > 0 || c > 0) ? 1u : 0u);
+        umma_commit(&sm.bar_m3);
+      }
       // the staged outputs are final: store them now, so the drain is over long before the next gated tiles overwrite xs / xe
       tma_store_4d(&maps.dq, sm.xs, 0, tok0, h, b);
       tma_store_4d(&maps.dk, sm.xs + TILE, 0, tok0, h, b);
@@ -492,8 +494,10 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
       tc_fence_after();
       issue_g1(g1w, nb);
     }
-    mbar_wait(&sm.bar_m3, ph);
-    tc_fence_after();
+    if (!last) {
+      mbar_wait(&sm.bar_m3, ph);
+      tc_fence_after();
+    }
     TLF(10);
     if (issuer && c + 2 < NC) { load1(sm.dh[buf], &maps.dh, &sm.bar_dh[buf], c + 2); load1(sm.q[buf], &maps.q, &sm.bar_q[buf], c + 2); }
 

@@ -319,6 +319,9 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
     GateBuf& G = sm.g[c % 3];
     const int tok0 = tok0_of(c);
     uint8_t* sk = sm.k[c & 1];
+    // the state leaving the last chunk is only needed when the caller asked for it: otherwise the last step skips the K
+    // rescale, the state MMA and the state pass
+    const bool do_state = !last || p.c_last != nullptr;
 
     // ---- top: K(c+1) streams into the other buffer (once the h(c-1) staged there has been read)
     if (issuer && !last) {
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
       }
     }
 #pragma unroll
-    for (int it = 0; it < (compute ? KT * TILE / 16 / CT : 0); ++it) {
+    for (int it = 0; it < ((compute && do_state) ? KT * TILE / 16 / CT : 0); ++it) {
       const uint32_t o = (uint32_t)(tid + it * CT) * 16u;
       const int krow = (o >> 7) & (L - 1);
       const float s = G.kw[krow];
@@ -436,7 +439,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
     TL_STAMP(7);
 
     // ---- state MMA: C += Kbar^T V ------------------------------------------------------------
-    if (issuer) {
+    if (issuer && do_state) {
       tc_fence_after();
       const uint64_t dKmn = dKmn0 + (c & 1) * KBUF_STEP;
       constexpr uint32_t idC = make_idesc_bf16(128, DH, 1, 1);
@@ -445,7 +448,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
       for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tC, dKmn + mnstep(ks), dVmn + mnstep(ks), idC, (ks > 0) ? 1u : acc0);
       umma_commit(&sm.bar_kv);
     }
-    if (tid == 32) {   // n += Kbar^T 1 from a second lane (lane 0 of compute warp 1); two arrivals complete bar_kv
+    if (tid == 32 && do_state) {   // n += Kbar^T 1 from a second lane (lane 0 of compute warp 1); two arrivals complete bar_kv
       tc_fence_after();
       const uint64_t dKmn = dKmn0 + (c & 1) * KBUF_STEP;
       constexpr uint32_t idN = make_idesc_bf16(128, 16, 1, 1);
@@ -470,8 +473,10 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
         hpk[x / 2] = pack_bf16x2((hi[x] + wq * gg[x]) * inv, (hi[x + 1] + wq * gg[x + 1]) * inv);
     }
     TL_STAMP(9);
-    mbar_wait(&sm.bar_kv, ph);   // state update complete: C final, Kbar and V dead
-    tc_fence_after();
+    if (do_state) {
+      mbar_wait(&sm.bar_kv, ph);   // state update complete: C final, Kbar and V dead
+      tc_fence_after();
+    }
     TL_STAMP(10);
     if (issuer && !last) issue_loads(sm.v, &maps.v, &sm.bar_v, c + 1);
 
@@ -479,7 +484,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_kernel(const __grid_constant__ F
     if (c == 0 && NC > 1 && compute) named_sync(6, GT0);   // chunk 1's gates (gate warp, computed during this chunk) are complete
     const float dnext = last ? 1.f : sm.g[(c + 1) % 3].decay;
     if (cq < NB) {
-      if (row < DH) {
+      if (row < DH && do_state) {
         float r[32];
         tmem_ld32(tC + lane_sel + cq * 32, r);
         tmem_ld_wait();
