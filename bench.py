@@ -433,7 +433,7 @@ def main():
     }
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": f"{family}:{dom}", "launches": launches_of[dom],
+        "bound": "hbm", "kernel": f"{family}:{'bwd_fused' if (dom == 'bwd_dkv' and pl0.variant_bwd == 'fused_walk') else dom}", "launches": launches_of[dom],
         "variants": {"fwd": pl0.variant_fwd, "bwd": pl0.variant_bwd}, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
         "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_BYTES.get(args.workload, {}).get(dom),
         "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_full_*_summary.csv)",
