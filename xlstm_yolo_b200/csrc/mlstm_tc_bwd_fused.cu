@@ -158,13 +158,13 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     constexpr uint32_t id128 = make_idesc_bf16(128, 128, 0, 0), id64 = make_idesc_bf16(128, DH, 0, 0);
     if (which == 0) {
 #pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tZ, (dHk0 + buf * BUF_STEP) + kstep(ks), dVk + kstep(ks), id128, ks > 0);
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tZ, (dHk0 + buf * BUF_STEP) + kstep(ks), dVk + kstep(ks), id128, ks > 0);
     } else if (which == 1) {
 #pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tS, (dKk0 + buf * BUF_STEP) + kstep(ks), (dQk0 + buf * BUF_STEP) + kstep(ks), id128, ks > 0);
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tS, (dKk0 + buf * BUF_STEP) + kstep(ks), (dQk0 + buf * BUF_STEP) + kstep(ks), id128, ks > 0);
     } else {
 #pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tG, (dHk0 + buf * BUF_STEP) + kstep(ks), dCsk + kstep(ks), id64, ks > 0);
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tG, (dHk0 + buf * BUF_STEP) + kstep(ks), dCsk + kstep(ks), id64, ks > 0);
     }
     umma_commit(&sm.bar_m1);
   };
@@ -176,10 +176,10 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
     constexpr uint32_t idKK = make_idesc_bf16(128, DH, 0, 0), idKmn_ = make_idesc_bf16(128, DH, 0, 1);
     if (which == 0) {
 #pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tIk, dVk + kstep(ks), dCbk + kstep(ks), idKK, ks > 0);
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tIk, dVk + kstep(ks), dCbk + kstep(ks), idKK, ks > 0);
     } else {
 #pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss_lo(tIv, (dKk0 + buf * BUF_STEP) + kstep(ks), dCbmn + mnstep(ks), idKmn_, ks > 0);
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16_ss(tIv, (dKk0 + buf * BUF_STEP) + kstep(ks), dCbmn + mnstep(ks), idKmn_, ks > 0);
     }
     umma_commit(&sm.bar_i);
   };
@@ -347,13 +347,13 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
       constexpr uint32_t idMM = make_idesc_bf16(128, DH, 1, 1);    // A MN-major, B MN-major
       if (g2 == 0) {
 #pragma unroll
-        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss_lo(tZ, dXSk + kstep(ks), (dKmn0 + buf * BUF_STEP) + mnstep(ks), idKmn, ks > 0);         // dQ = dS K
+        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tZ, dXSk + kstep(ks), (dKmn0 + buf * BUF_STEP) + mnstep(ks), idKmn, ks > 0);         // dQ = dS K
       } else if (g2 == 1) {
 #pragma unroll
-        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss_lo(tS, dXSmn + mnstep(ks), (dQmnB0 + buf * BUF_STEP) + mnstep(ks), idMM, ks > 0);     // dK = dS^T Q
+        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tS, dXSmn + mnstep(ks), (dQmnB0 + buf * BUF_STEP) + mnstep(ks), idMM, ks > 0);     // dK = dS^T Q
       } else {
 #pragma unroll
-        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss_lo(tS + 64, dXEk + kstep(ks), (dHmn0 + buf * BUF_STEP) + mnstep(ks), idKmn, ks > 0);   // dV = E^T dH
+        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tS + 64, dXEk + kstep(ks), (dHmn0 + buf * BUF_STEP) + mnstep(ks), idKmn, ks > 0);   // dV = E^T dH
       }
       umma_commit(&sm.bar_m2);   // three arrivals complete the phase
     }
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused_kernel(const __grid_consta
       if (!last) {
         constexpr uint32_t idMM = make_idesc_bf16(128, DH, 1, 1);
 #pragma unroll
-        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss_lo(tdC, (dQmnA0 + buf * BUF_STEP) + mnstep(ks), (dHmn0 + buf * BUF_STEP) + mnstep(ks), idMM, (ks > 0 || c > 0) ? 1u : 0u);
+        for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tdC, (dQmnA0 + buf * BUF_STEP) + mnstep(ks), (dHmn0 + buf * BUF_STEP) + mnstep(ks), idMM, (ks > 0 || c > 0) ? 1u : 0u);
         umma_commit(&sm.bar_m3);
       }
       // the staged outputs are final: store them now, so the drain is over long before the next gated tiles overwrite xs / xe

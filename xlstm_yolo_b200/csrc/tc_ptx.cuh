@@ -118,22 +118,6 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
 __device__ __forceinline__ uint32_t causal_bits(bool full, bool lower, int lane) {
   return full ? 0xffffffffu : (lower ? (0xffffffffu >> (31 - lane)) : (0xffffffffu << lane));
 }
-// Same product with the descriptors given by their low words.  Every tile of these kernels has SBO = 1024 bytes, descriptor
-// version 1 and the 128-byte swizzle, so the high word is one constant: passing it as an immediate halves the
-// register-to-uniform moves ptxas puts in front of each MMA (two instead of four).
-constexpr uint32_t SDESC_HI = 0x40004040u;
-__device__ __forceinline__ void umma_bf16_ss_lo(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "mov.b64 da, {%1, %5};\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
-      :
-      : "r"(d_tmem), "r"((uint32_t)a_desc), "r"((uint32_t)b_desc), "r"(idesc), "r"(accumulate), "n"(SDESC_HI)
-      : "memory");
-}
 // D[tmem] (+)= A[tmem] * B[smem]: A is a K-major [128 lanes][K] bf16 operand held in TMEM, two elements
 // per 32-bit column (what tcgen05.st of packed bf16x2 registers produces); 8 columns per K=16 step.
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
