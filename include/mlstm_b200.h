@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define MLSTM_B200_ABI_VERSION 3
+#define MLSTM_B200_ABI_VERSION 4
 
 typedef enum mlstm_status {
   MLSTM_OK = 0,
@@ -140,19 +140,24 @@ typedef struct mlstm_gate_proj_params {
   int32_t D;                            /* cell dim = NH * DH */
   int32_t NH;
   int32_t dtype;                        /* mlstm_dtype of q,k,v,dq,dk,dv */
-  int64_t ld;                           /* row stride of q,k,v,dq,dk,dv (elements) */
+  int64_t ld;                           /* row stride of q,k,v (elements) */
   const void *q, *k, *v;
   const float *w_i, *w_f;               /* (NH, 3*D) */
   const float *b_i, *b_f;               /* (NH) or NULL */
   float *i, *f;                         /* forward outputs (T, NH) */
   const float *di, *df;                 /* backward inputs (T, NH) */
   void *dq, *dk, *dv;                   /* backward in/out (T, D): dx += di W_i[:, x] + df W_f[:, x] */
+  int64_t ld_d;                         /* row stride of dq,dk,dv (elements; ABI 4: independent of `ld`, the
+                                           cell's gradients are dense even when q,k,v are column slices) */
   float *dw_i, *dw_f;                   /* backward outputs (NH, 3*D), overwritten */
   float *db_i, *db_f;                   /* backward outputs (NH), overwritten; NULL allowed */
   void* workspace;                      /* >= mlstm_b200_gates_workspace_bytes() (backward only) */
   size_t workspace_bytes;
 } mlstm_gate_proj_params;
 
+/* 1 when the gate kernels take a (T, D) operand with row stride ld: D % 8 == 0, ld % 8 == 0, ld >= D and
+ * the 8 x 3D fp32 weight tile fits in shared memory (D <= 2133). */
+int mlstm_b200_gates_supported(int D, int64_t ld);
 size_t mlstm_b200_gates_workspace_bytes(const mlstm_gate_proj_params* p);
 int mlstm_b200_gates_fwd(const mlstm_gate_proj_params* p, void* cuda_stream);
 int mlstm_b200_gates_bwd(const mlstm_gate_proj_params* p, void* cuda_stream);
@@ -186,6 +191,9 @@ typedef struct mlstm_glue_params {
   size_t workspace_bytes;
 } mlstm_glue_params;
 
+/* 1 when the fused tail handles (D, NH): D % 256 == 0 with D / 256 in {1, 2, 4, 8}, DH = D / NH a multiple of 8
+ * dividing 256. */
+int mlstm_b200_glue_supported(int D, int NH);
 size_t mlstm_b200_glue_workspace_bytes(const mlstm_glue_params* p);
 int mlstm_b200_glue_fwd(const mlstm_glue_params* p, void* cuda_stream);
 int mlstm_b200_glue_bwd(const mlstm_glue_params* p, void* cuda_stream);

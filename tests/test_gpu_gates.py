@@ -53,7 +53,9 @@ def test_gate_projection_forward(B, S, D, NH, dtype):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_gate_projection_backward_in_place(B, S, D, NH, dtype):
     from xlstm_yolo_b200 import ops
-    q, k, v, w_i, b_i, w_f, b_f = make(B, S, D, NH, dtype, seed=1)
+    # q,k,v as column slices of a wider buffer (row stride D + 8) while the gradients are dense (row stride D):
+    # the two strides travel separately through the ABI (ld / ld_d)
+    q, k, v, w_i, b_i, w_f, b_f = make(B, S, D, NH, dtype, seed=1, padded=(D in (256, 1024)))
     g = torch.Generator().manual_seed(5)
     di, df = (torch.randn(B, S, NH, generator=g).cuda() for _ in range(2))
     dq0, dk0, dv0 = (torch.randn(B, S, D, generator=g).to(dtype).cuda() for _ in range(3))
@@ -134,3 +136,62 @@ def test_fused_cell_under_fp16_autocast_scaler():
     assert y.dtype in (torch.float16, torch.float32)
     for p in cell.parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all()
+
+
+@pytest.mark.parametrize("mode", ["chunk3", "padded"])
+def test_fused_cell_backward_with_strided_qkv(mode):
+    """q,k,v handed over as row-strided views (bf16 ``qkv.chunk(3, -1)`` or a padded ``[..., :D]`` slice) stay strided in
+    the fused node; the backward must write the dense dq,dk,dv with their own row stride (single `ld`)."""
+    from xlstm_yolo_b200 import MatrixLSTMCell
+    torch.manual_seed(0)
+    dim, NH, B, S = 256, 4, 2, 200
+    cell = MatrixLSTMCell(dim=dim, num_heads=NH, chunk_size=64)
+    with torch.no_grad():
+        cell.igate.weight.normal_(0, 0.05); cell.fgate.weight.normal_(0, 0.05); cell.igate.bias.normal_(0, 1.0)
+    cell = cell.cuda().to(torch.bfloat16)
+    width = 3 * dim if mode == "chunk3" else dim + 8
+    base = [(torch.randn(B, S, width, device="cuda") * 0.2).bfloat16().requires_grad_(True) for _ in range(1 if mode == "chunk3" else 3)]
+    if mode == "chunk3":
+        q, k, v = base[0].chunk(3, dim=-1)
+    else:
+        q, k, v = (t[..., :dim] for t in base)
+    assert q.stride(1) != dim
+    dy = torch.randn(B, S, dim, device="cuda").bfloat16()
+    y = cell(q, k, v)
+    y.backward(dy)
+    got = [t.grad.clone() for t in base]
+    dw = cell.igate.weight.grad.clone()
+    for t in base:
+        t.grad = None
+    cell.zero_grad()
+    # same inputs, contiguous
+    qc, kc, vc = (t.detach().contiguous().requires_grad_(True) for t in (q, k, v))
+    y2 = cell(qc, kc, vc)
+    y2.backward(dy)
+    assert torch.equal(y, y2)
+    if mode == "chunk3":
+        want = [torch.cat([qc.grad, kc.grad, vc.grad], dim=-1)]
+    else:
+        want = [torch.nn.functional.pad(t.grad, (0, 8)) for t in (qc, kc, vc)]
+    for a, b in zip(got, want):
+        assert torch.isfinite(a).all() and torch.equal(a, b)
+    assert torch.equal(dw, cell.igate.weight.grad)
+
+
+def test_unsupported_dims_fall_back_instead_of_raising():
+    """inner dim 768 (D / 256 = 3: no fused tail) and 2560 (gate weight tile > shared memory) run through the
+    PyTorch tail / cuBLAS gates instead of raising UNSUPPORTED."""
+    from xlstm_yolo_b200 import ops
+    from xlstm_yolo_b200.vil import ViLLayer, SequenceTraversal
+    assert not ops.gates_supported(2560) and ops.gates_supported(2048) and ops.gates_supported(768)
+    torch.manual_seed(0)
+    layer = ViLLayer(dim=384, direction=SequenceTraversal.ROWWISE_FROM_TOP_LEFT, qkv_block_size=64, chunk_size=64).cuda()
+    x = torch.randn(1, 64, 384, device="cuda", requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = layer(x)
+    y.float().square().mean().backward()
+    assert y.shape == x.shape and torch.isfinite(y).all() and torch.isfinite(x.grad).all()
+    from xlstm_yolo_b200 import MatrixLSTMCell
+    cell = MatrixLSTMCell(dim=2560, num_heads=20, chunk_size=64).cuda().to(torch.bfloat16)
+    q = torch.randn(1, 64, 2560, device="cuda").bfloat16()
+    assert torch.isfinite(cell(q, q, q)).all()

@@ -99,6 +99,8 @@ def test_kernel_family_and_workspace(lib):
     rows, items = 2 * 2 * 64, 2 * 2 * 1
     assert lib.mlstm_b200_workspace_bytes(C.byref(p), 1) >= 9 * 4 * rows + items * (64 * 64 * 2 + 64 * 4)   # dn, R/K partials, dCs, dns
     assert lib.mlstm_b200_workspace_bytes(C.byref(p), 0) == 0
+    assert lib.mlstm_b200_state_bytes(C.byref(p)) == 0   # forward-only call (no saved rows): the single-pass forward keeps its states on chip
+    p.n_row = p.m_row = 0x1000                             # a backward will follow
     assert lib.mlstm_b200_state_bytes(C.byref(p)) >= 2 * 2 * 1 * (64 * 64 * 2 + 64 * 4 + 4)   # per-chunk entry states
     p = _params(DHQK=16, DHV=16)
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
@@ -145,7 +147,10 @@ def test_cell_constructor_signature_matches_reference():
     d = {k: v.default for k, v in sig.parameters.items()}
     assert d["norm_bias"] is True and d["eps"] == 1e-6 and d["chunk_size"] == 16 and d["use_autocast"] is True
     assert d["autocast_dtype"] == torch.bfloat16
-    assert list(inspect.signature(MatrixLSTMCell.forward).parameters) == ["self", "q", "k", "v"]
+    fwd = inspect.signature(MatrixLSTMCell.forward).parameters
+    assert list(fwd)[:4] == ["self", "q", "k", "v"]                 # the reference's positional signature (vision_lstm2.py:882)
+    # anything beyond it is keyword-only with a default: per-call overrides instead of mutated module state
+    assert all(p.kind is inspect.Parameter.KEYWORD_ONLY and p.default is None for p in list(fwd.values())[4:])
 
 
 def test_cell_state_dict_and_init():

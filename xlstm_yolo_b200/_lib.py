@@ -12,7 +12,7 @@ import threading
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libmlstm_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MLSTM_F32, MLSTM_BF16 = 0, 1
 
 STATUS = {0: "OK", -1: "INVALID_ARG", -2: "UNSUPPORTED", -3: "WORKSPACE", -4: "CUDA", -5: "NO_DEVICE"}
@@ -26,9 +26,11 @@ EXPORTS = (
     "mlstm_b200_bwd_part",
     "mlstm_b200_kernel_name",
     "mlstm_b200_kernel_variant",
+    "mlstm_b200_gates_supported",
     "mlstm_b200_gates_workspace_bytes",
     "mlstm_b200_gates_fwd",
     "mlstm_b200_gates_bwd",
+    "mlstm_b200_glue_supported",
     "mlstm_b200_glue_workspace_bytes",
     "mlstm_b200_glue_fwd",
     "mlstm_b200_glue_bwd",
@@ -76,7 +78,7 @@ class GateProjParams(C.Structure):
         ("w_i", C.c_void_p), ("w_f", C.c_void_p), ("b_i", C.c_void_p), ("b_f", C.c_void_p),
         ("i", C.c_void_p), ("f", C.c_void_p),
         ("di", C.c_void_p), ("df", C.c_void_p),
-        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("ld_d", C.c_int64),
         ("dw_i", C.c_void_p), ("dw_f", C.c_void_p), ("db_i", C.c_void_p), ("db_f", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
@@ -135,6 +137,10 @@ def load() -> C.CDLL:
         lib.mlstm_b200_kernel_variant.restype = C.c_char_p
         lib.mlstm_b200_kernel_variant.argtypes = [C.POINTER(Params), C.c_int]
         lib.mlstm_b200_kernel_name.argtypes = [C.POINTER(Params), C.c_int]
+        lib.mlstm_b200_gates_supported.restype = C.c_int
+        lib.mlstm_b200_gates_supported.argtypes = [C.c_int, C.c_int64]
+        lib.mlstm_b200_glue_supported.restype = C.c_int
+        lib.mlstm_b200_glue_supported.argtypes = [C.c_int, C.c_int]
         lib.mlstm_b200_gates_workspace_bytes.restype = C.c_size_t
         lib.mlstm_b200_gates_workspace_bytes.argtypes = [C.POINTER(GateProjParams)]
         lib.mlstm_b200_gates_fwd.restype = C.c_int

@@ -48,13 +48,14 @@ class mLSTMBackendConfig:
             raise ValueError(f"unknown mode {self.mode!r}")
         if self.autocast_kernel_dtype not in _TORCH_DTYPE:
             raise ValueError(f"unknown autocast_kernel_dtype {self.autocast_kernel_dtype!r}")
-        if "siging" in self.chunkwise_kernel:
-            # The reference's CUDA config string names upstream's sigmoid-input-gate variant
-            # (vision_lstm2.py:835,866) while its CPU path and BASELINE.json's north star are
-            # the exponential-input-gate cell.  This build implements the exponential gate.
-            self.input_gate = "exp"
-        else:
-            self.input_gate = "exp"
+
+    @property
+    def input_gate(self) -> str:
+        """Gate arithmetic the kernel string selects, on every device: "sigmoid" for upstream's sigmoid-input-gate
+        kernels ("...xl_chunk_siging", what HEAD configures for CUDA tensors, vision_lstm2.py:835,866), else "exp"
+        (the exponential gate with max-stabiliser of the in-tree PyTorch mLSTM, backends.py:149-263, which is what
+        HEAD's CPU strings "chunkwise--native_autograd" name, vision_lstm2.py:819-828,850-859)."""
+        return "sigmoid" if "siging" in str(self.chunkwise_kernel) else "exp"
 
 
 class mLSTMBackend(nn.Module):
@@ -107,9 +108,7 @@ class mLSTMBackend(nn.Module):
 
     @property
     def input_gate(self) -> str:
-        """"sigmoid" when the configured kernel string names upstream's sigmoid-input-gate kernels
-        ("chunkwise--triton_xl_chunk_siging", vision_lstm2.py:835,866), else "exp"."""
-        return "sigmoid" if "siging" in str(self.config.chunkwise_kernel) else "exp"
+        return self.config.input_gate
 
     def extra_repr(self) -> str:
         return f"{self.config}"

@@ -71,6 +71,11 @@ class MultiHeadLayerNorm(nn.Module):
             nn.init.zeros_(self.bias)
 
 
+def _fused_gates_ok(dim: int) -> bool:
+    from . import ops
+    return ops.gates_supported(dim)
+
+
 class MatrixLSTMCell(nn.Module):
     def __init__(self, dim, num_heads, norm_bias=True, eps=1e-6, chunk_size=16, use_autocast=True,
                  autocast_dtype=torch.bfloat16, reverse=False, raw_output=False, input_gate="exp"):
@@ -119,22 +124,27 @@ class MatrixLSTMCell(nn.Module):
         i, f = g.split(self.num_heads, dim=-1)              # (B,S,NH) each
         return i.transpose(-1, -2), f.transpose(-1, -2)     # (B,NH,S) views
 
-    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, reverse=None, raw_output=None) -> torch.Tensor:
+        """``forward(q, k, v)`` is the reference signature (vision_lstm2.py:882).  The keyword-only ``reverse`` /
+        ``raw_output`` override the module attributes of the same name for this call only, so a caller (``ViLLayer``)
+        never has to mutate the module: the forward stays re-entrant and traceable."""
+        reverse = self.reverse if reverse is None else bool(reverse)
+        raw_output = self.raw_output if raw_output is None else bool(raw_output)
         B, S, H = q.shape
         if not (q.device == k.device == v.device):
             raise ValueError("All input tensors (q, k, v) must be on the same device.")
         backend = self.gpu_backend if self.training else self.gpu_backend_infer
         with torch.autograd.profiler.record_function("ViLLayer::mlstm_cell"):
-            if q.is_cuda and getattr(self, "fused_gates", True) and H % 8 == 0:
+            if q.is_cuda and getattr(self, "fused_gates", True) and _fused_gates_ok(H):
                 # hand-written gate projection fused with the cell into one autograd node
-                h = backend.fused_cell(q, k, v, self.igate, self.fgate, self.num_heads, reverse=self.reverse)
+                h = backend.fused_cell(q, k, v, self.igate, self.fgate, self.num_heads, reverse=reverse)
             else:
                 i, f = self._gates(q, k, v)
                 qh = q.view(B, S, self.num_heads, -1).transpose(1, 2)
                 kh = k.view(B, S, self.num_heads, -1).transpose(1, 2)
                 vh = v.view(B, S, self.num_heads, -1).transpose(1, 2)
-                h = backend(q=qh, k=kh, v=vh, i=i, f=f, reverse=self.reverse)  # (B,NH,S,DH)
-            if self.raw_output:
+                h = backend(q=qh, k=kh, v=vh, i=i, f=f, reverse=reverse)  # (B,NH,S,DH)
+            if raw_output:
                 return h
             h = self.outnorm(h)
             return h.transpose(1, 2).reshape(B, S, -1)

@@ -25,10 +25,28 @@ namespace {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-int check_act(const char* name, const mlstm_act& a, bool required) {
+// Null check for every family; for the tcgen05 family (bf16, TMA tensor maps over the caller's strided storage) also
+// the layout the tensor maps need, so a bad view is reported by name here and not as a cuTensorMapEncodeTiled code later.
+int check_act(const char* name, const mlstm_act& a, bool required, bool tma, const mlstm_params& p, int dh) {
   if (!a.ptr) {
     if (required) { set_error("%s: null pointer", name); return MLSTM_ERR_INVALID_ARG; }
     return MLSTM_OK;
+  }
+  if (!tma) return MLSTM_OK;
+  if (!aligned16(a.ptr)) {
+    set_error("%s: base pointer %p is not 16-byte aligned (TMA needs it; pass an aligned view or a copy)", name, a.ptr);
+    return MLSTM_ERR_INVALID_ARG;
+  }
+  const int64_t st[3] = {a.stride_b, a.stride_h, a.stride_s};
+  const int32_t ext[3] = {p.B, p.NH, p.S};
+  const char* which[3] = {"batch", "head", "token"};
+  for (int d = 0; d < 3; ++d) {
+    if (ext[d] <= 1) continue;   // the stride of a size-1 dimension is never used
+    if (st[d] % 8 != 0 || st[d] < dh) {
+      set_error("%s: %s stride %lld elements must be a multiple of 8 and >= the head dim %d (bf16 TMA rows are 16-byte units)",
+                name, which[d], (long long)st[d], dh);
+      return MLSTM_ERR_INVALID_ARG;
+    }
   }
   return MLSTM_OK;
 }
@@ -53,8 +71,9 @@ int validate(const mlstm_params* p, int is_bwd) {
   }
   if (p->B == 0 || p->S == 0) return MLSTM_OK;  // empty input: nothing to do
   int rc;
-  if ((rc = check_act("q", p->q, true)) || (rc = check_act("k", p->k, true)) || (rc = check_act("v", p->v, true)) ||
-      (rc = check_act("h", p->h, true)))
+  const bool tma = p->dtype == MLSTM_BF16 && tc_supported(*p);
+  if ((rc = check_act("q", p->q, true, tma, *p, p->DHQK)) || (rc = check_act("k", p->k, true, tma, *p, p->DHQK)) ||
+      (rc = check_act("v", p->v, true, tma, *p, p->DHV)) || (rc = check_act("h", p->h, true, tma, *p, p->DHV)))
     return rc;
   if (!p->i.ptr || !p->f.ptr) { set_error("gate pre-activations i/f: null pointer"); return MLSTM_ERR_INVALID_ARG; }
   if ((p->c_last != nullptr) != (p->n_last != nullptr) || (p->c_last != nullptr) != (p->m_last != nullptr)) {
@@ -66,8 +85,8 @@ int validate(const mlstm_params* p, int is_bwd) {
     return MLSTM_ERR_INVALID_ARG;
   }
   if (is_bwd) {
-    if ((rc = check_act("dh", p->dh, true)) || (rc = check_act("dq", p->dq, true)) ||
-        (rc = check_act("dk", p->dk, true)) || (rc = check_act("dv", p->dv, true)))
+    if ((rc = check_act("dh", p->dh, true, tma, *p, p->DHV)) || (rc = check_act("dq", p->dq, true, tma, *p, p->DHQK)) ||
+        (rc = check_act("dk", p->dk, true, tma, *p, p->DHQK)) || (rc = check_act("dv", p->dv, true, tma, *p, p->DHV)))
       return rc;
     if (!p->di.ptr || !p->df.ptr) { set_error("di/df: null pointer"); return MLSTM_ERR_INVALID_ARG; }
     if (!p->n_row || !p->m_row) { set_error("backward needs n_row and m_row from the forward"); return MLSTM_ERR_INVALID_ARG; }

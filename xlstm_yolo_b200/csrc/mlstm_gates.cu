@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(BW_NT) gates_bwd_kernel(const mlstm_gate_proj_
         const bool v = ok && (u0 + u < nt);
         const size_t row = (size_t)(tile + (v ? u0 + u : 0)) * p.ld;
         Cols<T>::load(xs + row, x[u], v);
-        Cols<T>::load(ds + row, d[u], v);
+        Cols<T>::load(ds + (size_t)(tile + (v ? u0 + u : 0)) * p.ld_d, d[u], v);
       }
 #pragma unroll
       for (int u = 0; u < BW_TU; ++u) {
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(BW_NT) gates_bwd_kernel(const mlstm_gate_proj_
             d[u][e] = fmaf(dg[o], w[o][e], d[u][e]);
           }
         }
-        if (ok && (u0 + u < nt)) Cols<T>::store(ds + (size_t)(tile + u0 + u) * p.ld, d[u]);
+        if (ok && (u0 + u < nt)) Cols<T>::store(ds + (size_t)(tile + u0 + u) * p.ld_d, d[u]);
       }
     }
   }
@@ -288,6 +288,10 @@ int validate(const mlstm_gate_proj_params* p, bool bwd) {
     return MLSTM_ERR_UNSUPPORTED;
   }
   if ((size_t)OG * 3 * p->D * sizeof(float) > 200 * 1024) { set_error("D=%d too large for the weight tile", p->D); return MLSTM_ERR_UNSUPPORTED; }
+  if (bwd && (p->ld_d % 8 != 0 || p->ld_d < p->D)) {
+    set_error("gate projection backward needs the row stride of dq, dk, dv to be a multiple of 8 and >= D (D=%d, ld_d=%lld)", p->D, (long long)p->ld_d);
+    return MLSTM_ERR_UNSUPPORTED;
+  }
   if (p->T == 0) return MLSTM_OK;
   if (!p->q || !p->k || !p->v || !p->w_i || !p->w_f) { set_error("q, k, v, w_i, w_f must be non-NULL"); return MLSTM_ERR_INVALID_ARG; }
   const uintptr_t al = (uintptr_t)p->q | (uintptr_t)p->k | (uintptr_t)p->v | (bwd ? ((uintptr_t)p->dq | (uintptr_t)p->dk | (uintptr_t)p->dv) : 0);
@@ -320,6 +324,10 @@ int finish(const char* what) {
 using namespace mlstm;
 
 extern "C" {
+
+int mlstm_b200_gates_supported(int D, int64_t ld) {
+  return D >= 8 && D % 8 == 0 && ld % 8 == 0 && ld >= D && (size_t)OG * 3 * (size_t)D * sizeof(float) <= 200 * 1024;
+}
 
 size_t mlstm_b200_gates_workspace_bytes(const mlstm_gate_proj_params* p) {
   if (!p || p->T <= 0) return 0;

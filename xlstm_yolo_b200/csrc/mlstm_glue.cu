@@ -264,6 +264,12 @@ using namespace mlstm;
 
 extern "C" {
 
+int mlstm_b200_glue_supported(int D, int NH) {
+  if (D < 1 || NH < 1 || D % NH) return 0;
+  const int DH = D / NH;
+  return !(D % GL_SEG || DH % GL_EPL || GL_SEG % DH || (GL_NT / 32) % (D / GL_SEG));
+}
+
 size_t mlstm_b200_glue_workspace_bytes(const mlstm_glue_params* p) {
   if (!p || p->T <= 0 || p->D < GL_SEG) return 0;
   return sizeof(float) * 3 * (size_t)p->D * glue_grid(*p);

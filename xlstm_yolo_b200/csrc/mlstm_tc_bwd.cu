@@ -765,7 +765,7 @@ __global__ void __launch_bounds__(L) tc_dfscan_kernel(const mlstm_params p, cons
 
 template <class K>
 int prep(K kernel, size_t smem, const char* name) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(kernel), smem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(%s, %zu B): %s", name, smem, cudaGetErrorString(e));
     return MLSTM_ERR_CUDA;
@@ -815,9 +815,7 @@ int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
     set_error("cuTensorMapEncodeTiled failed (%d)", r);
     return r == -1 ? MLSTM_ERR_NO_DEVICE : MLSTM_ERR_INVALID_ARG;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count_of(p.q.ptr);
   const int grid = n_items < sms ? n_items : sms;
   const float scale = resolve_scale(p);
   const size_t smB = sizeof(SmemB<DH>), smSB = sizeof(SmemSB<DH>);

@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(NT, 2) tc_bwd_dkv12_kernel(const __grid_consta
 
 template <class K>
 int prep_kernel(K kernel, size_t smem, const char* name) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(kernel), smem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(%s, %zu B): %s", name, smem, cudaGetErrorString(e));
     return MLSTM_ERR_CUDA;

@@ -582,7 +582,7 @@ int tc_bwd_fused(const mlstm_params& p, cudaStream_t st, int part) {
     return r == -1 ? MLSTM_ERR_NO_DEVICE : MLSTM_ERR_INVALID_ARG;
   }
   const size_t smem = sizeof(SmemF);
-  cudaError_t e = cudaFuncSetAttribute(tc_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(tc_bwd_fused_kernel), smem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(tc_bwd_fused, %zu B): %s", smem, cudaGetErrorString(e));
     return MLSTM_ERR_CUDA;

@@ -14,12 +14,8 @@ bool tc_supported(const mlstm_params& p) {
   return p.dtype == MLSTM_BF16 && p.DHQK == p.DHV && (p.DHQK == 64 || p.DHQK == 128);
 }
 
-static int sm_count() {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sms;
-}
+// of the device that owns the tensors, not of whichever device is current when a size query is made
+static int sm_count(const mlstm_params& p) { return sm_count_of(p.q.ptr); }
 
 // MLSTM_FORCE_VARIANT="<f><b>" (developer switch for A/B measurements): f = 1 single-pass / 2 two-phase
 // forward, b = 1 single-pass / 2 chunk-parallel backward, anything else = automatic.
@@ -32,9 +28,9 @@ static int forced(int which) {
 
 bool tc_use_two_phase(const mlstm_params& p) {          // forward
   if (forced(0)) return forced(0) == 2;
-  return p.B * p.NH * 2 <= sm_count() && tc::num_chunks(p.S) >= 4;
+  return p.B * p.NH * 2 <= sm_count(p) && tc::num_chunks(p.S) >= 4;
 }
-static bool short_and_wide(const mlstm_params& p) { return tc::num_chunks(p.S) <= 4 && p.B * p.NH * 2 > sm_count(); }
+static bool short_and_wide(const mlstm_params& p) { return tc::num_chunks(p.S) <= 4 && p.B * p.NH * 2 > sm_count(p); }
 
 // DH = 64 with enough (batch, head) pairs to fill the GPU: one reverse walk producing dq, dk, dv together from the forward's
 // chunk states (mlstm_tc_bwd_fused.cu), at any sequence length — it reads every tile once, so it also beats the chunk-parallel
@@ -43,7 +39,7 @@ static bool short_and_wide(const mlstm_params& p) { return tc::num_chunks(p.S) <
 bool tc_use_fused_bwd(const mlstm_params& p) {
   if (p.DHQK != 64) return false;
   if (forced(1)) return forced(1) == 3;
-  return p.B * p.NH * 2 > sm_count();
+  return p.B * p.NH * 2 > sm_count(p);
 }
 bool tc_use_single_pass_bwd(const mlstm_params& p) {    // backward, two-walk single-pass kernels
   if (tc_use_fused_bwd(p)) return false;
@@ -54,7 +50,8 @@ bool tc_use_single_pass_bwd(const mlstm_params& p) {    // backward, two-walk si
 // The chunk-state buffer is needed by the two-phase forward itself and by the chunk-parallel
 // backward whichever forward variant ran.
 size_t tc_state_bytes(const mlstm_params& p) {
-  if (!tc_use_two_phase(p) && tc_use_single_pass_bwd(p)) return 0;
+  // forward-only call (no saved rows => no backward will follow) through the single-pass forward: nothing reads the states
+  if (!tc_use_two_phase(p) && (p.n_row == nullptr || tc_use_single_pass_bwd(p))) return 0;
   return tc::StateLayout(p.B, p.NH, p.S, p.DHQK).total;
 }
 

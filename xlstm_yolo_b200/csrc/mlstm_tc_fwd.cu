@@ -589,7 +589,7 @@ int launch_fwd(const mlstm_params& p, cudaStream_t st) {
     return r == -1 ? MLSTM_ERR_NO_DEVICE : MLSTM_ERR_INVALID_ARG;
   }
   const size_t smem = sizeof(Smem<DH>) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(tc_fwd_kernel<DH>), smem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(tc_fwd, %zu B): %s", smem, cudaGetErrorString(e));
     return MLSTM_ERR_CUDA;

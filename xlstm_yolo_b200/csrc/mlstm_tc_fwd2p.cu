@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_par_kernel(const __grid_constant
 
 template <class K>
 int prep(K kernel, size_t smem, const char* name) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(kernel), smem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(%s, %zu B): %s", name, smem, cudaGetErrorString(e));
     return MLSTM_ERR_CUDA;
@@ -503,15 +503,11 @@ int launch_fwd(const mlstm_params& p, cudaStream_t st) {
   const size_t smS = sizeof(SmemS<DH>), smP = sizeof(SmemP<DH>);
   if ((rc = prep(tc_state_fwd_kernel<DH>, smS, "tc_state_fwd"))) return rc;
   if ((rc = prep(tc_fwd_par_kernel<DH>, smP, "tc_fwd_par"))) return rc;
-  int dev_s = 0, sms_s = 148;
-  cudaGetDevice(&dev_s);
-  cudaDeviceGetAttribute(&sms_s, cudaDevAttrMultiProcessorCount, dev_s);
+  const int sms_s = sm_count_of(p.q.ptr);
   const int nsl = (DH == 128 && 2 * p.B * p.NH <= sms_s) ? 2 : 1;   // 64-column value slices while they fit the SMs
   tc_state_fwd_kernel<DH><<<dim3(p.B * p.NH, nsl), dim3(NT), smS, st>>>(maps, p);
   if ((rc = launched("tc_state_fwd"))) return rc;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sms_s;
   const int grid = n_items < sms ? n_items : sms;
   tc_fwd_par_kernel<DH><<<dim3(grid), dim3(NT), smP, st>>>(maps, p, resolve_scale(p), n_items);
   return launched("tc_fwd_par");

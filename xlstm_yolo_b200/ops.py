@@ -107,7 +107,8 @@ def kernel_family(q: torch.Tensor, v: torch.Tensor) -> str:
 
 def _alloc_states(lib, p, dev):
     """Per-chunk entry-state buffer of the tcgen05 family (None for SIMT); attaches it to p."""
-    need = lib.mlstm_b200_state_bytes(C.byref(p))
+    with torch.cuda.device(dev):   # size and variant queries see the device the launch will see
+        need = lib.mlstm_b200_state_bytes(C.byref(p))
     if not need:
         return None
     states = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -169,12 +170,12 @@ def mlstm_bwd_raw(q, k, v, i, f, h, n_row, m_row, dh, c_initial=None, n_initial=
     p.di, p.df = _gate(di), _gate(df)
     if states is not None:
         p.states, p.states_bytes = states.data_ptr(), states.numel()
-    need = lib.mlstm_b200_workspace_bytes(C.byref(p), 1)
-    ws = None
-    if need:
-        ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=dev)
-        p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     with torch.cuda.device(dev):
+        need = lib.mlstm_b200_workspace_bytes(C.byref(p), 1)
+        ws = None
+        if need:
+            ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=dev)
+            p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel() * 4
         rc = lib.mlstm_b200_bwd(C.byref(p), _stream())
     if rc:
         _fail(rc, "backward")
@@ -269,6 +270,12 @@ def _rows_ok(t: torch.Tensor) -> bool:
             and t.data_ptr() % 16 == 0)
 
 
+def gates_supported(D: int, ld: Optional[int] = None) -> bool:
+    """Whether csrc/mlstm_gates.cu takes a cell of inner dim D (asks the library: the 8 x 3D fp32 weight tile
+    must fit in shared memory, i.e. D <= 2133)."""
+    return bool(_lib.load().mlstm_b200_gates_supported(int(D), int(D if ld is None else ld)))
+
+
 def gate_proj_fwd_raw(q3, k3, v3, w_i, b_i, w_f, b_f, NH):
     """i, f pre-activations (B,S,NH) fp32 from q,k,v (B,S,D) without the cat copy."""
     lib = _lib.load()
@@ -294,6 +301,9 @@ def gate_proj_bwd_raw(q3, k3, v3, w_i, w_f, NH, di, df, dq3, dk3, dv3, need_bias
     db_f = torch.empty(NH, dtype=torch.float32, device=dev) if need_bias else None
     g.di, g.df = di.data_ptr(), df.data_ptr()
     g.dq, g.dk, g.dv = dq3.data_ptr(), dk3.data_ptr(), dv3.data_ptr()
+    if not (dq3.stride() == dk3.stride() == dv3.stride()) or dq3.stride(2) != 1 or dq3.stride(0) != dq3.shape[1] * dq3.stride(1):
+        raise ValueError("dq3, dk3, dv3 must share one evenly strided (B,S,D) row layout")
+    g.ld_d = dq3.stride(1)   # the cell's gradients are dense even when q,k,v are column slices (ld != ld_d)
     g.dw_i, g.dw_f, g.db_i, g.db_f = dw_i.data_ptr(), dw_f.data_ptr(), _ptr(db_i), _ptr(db_f)
     need = lib.mlstm_b200_gates_workspace_bytes(C.byref(g))
     ws = torch.empty(max(1, (need + 3) // 4), dtype=torch.float32, device=dev)
@@ -376,7 +386,7 @@ def glue_supported(h: torch.Tensor, c: torch.Tensor, z: torch.Tensor) -> bool:
         return False
     B, NH, S, DH = h.shape
     D = NH * DH
-    if D % 256 or D > 2048 or 256 % DH or DH % 8:
+    if not _lib.load().mlstm_b200_glue_supported(D, NH):   # the C-side shape gate (D / 256 in {1, 2, 4, 8}, DH | 256)
         return False
     if h.stride() != (S * D, DH, D, 1) or h.data_ptr() % 16:
         return False

@@ -83,21 +83,22 @@ class SequenceConv2d(nn.Conv2d):
 
 
 class _HeadwiseLinearFn(torch.autograd.Function):
-    """Block-diagonal linear on (T, NH*d) rows as NH strided GEMMs that read and write the head slices
-    of the token-major tensors in place (lda = ldc = NH*d): no (NH, T, d) transposed copies in either
-    direction, bias fused into the GEMM epilogue."""
+    """Block-diagonal linear on (T, NH*d) rows as ONE strided batched GEMM over the (NH, T, d) view of the
+    token-major tensors (lda = ldc = NH*d): it reads and writes the head slices in place — no (NH, T, d)
+    transposed copies in either direction, one launch per projection whatever NH is (the reference default
+    qkv_block_size=16 gives NH = 32-64), bias fused into the GEMM epilogue."""
 
     @staticmethod
     def forward(ctx, x2, weight, bias):
         T, D = x2.shape
         NH, d = weight.shape[0], weight.shape[1]
         y = torch.empty((T, D), dtype=x2.dtype, device=x2.device)
-        for n in range(NH):
-            xs, ys = x2[:, n * d:(n + 1) * d], y[:, n * d:(n + 1) * d]
-            if bias is None:
-                torch.mm(xs, weight[n].t(), out=ys)
-            else:
-                torch.addmm(bias[n * d:(n + 1) * d], xs, weight[n].t(), out=ys)
+        xh, yh = x2.view(T, NH, d).transpose(0, 1), y.view(T, NH, d).transpose(0, 1)   # (NH, T, d) strided views
+        wt = weight.transpose(1, 2)                                                      # (NH, d_in, d_out) view
+        if bias is None:
+            torch.bmm(xh, wt, out=yh)
+        else:
+            torch.baddbmm(bias.view(NH, 1, d), xh, wt, out=yh)
         ctx.save_for_backward(x2, weight)
         ctx.has_bias = bias is not None
         return y
@@ -106,16 +107,16 @@ class _HeadwiseLinearFn(torch.autograd.Function):
     def backward(ctx, dy):
         x2, weight = ctx.saved_tensors
         NH, d = weight.shape[0], weight.shape[1]
-        if dy.stride(1) != 1:
+        T = x2.shape[0]
+        if dy.stride(1) != 1 or dy.stride(0) != NH * d:
             dy = dy.contiguous()
-        dx = torch.empty_like(x2, memory_format=torch.contiguous_format) if ctx.needs_input_grad[0] else None
-        dw = torch.empty_like(weight) if ctx.needs_input_grad[1] else None
-        for n in range(NH):
-            dys = dy[:, n * d:(n + 1) * d]
-            if dx is not None:
-                torch.mm(dys, weight[n], out=dx[:, n * d:(n + 1) * d])
-            if dw is not None:
-                torch.mm(dys.t(), x2[:, n * d:(n + 1) * d], out=dw[n])
+        dyh = dy.view(T, NH, d).transpose(0, 1)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((T, NH * d), dtype=x2.dtype, device=x2.device)
+            torch.bmm(dyh, weight, out=dx.view(T, NH, d).transpose(0, 1))
+        if ctx.needs_input_grad[1]:
+            dw = torch.bmm(dyh.transpose(1, 2), x2.view(T, NH, d).transpose(0, 1))
         db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return dx, dw, db
 
@@ -230,18 +231,14 @@ class ViLLayer(nn.Module):
         x_mlstm, z = self.proj_up(y).chunk(2, dim=-1)
         conv_act = F.silu(self.conv(x_mlstm, rotate=anti))
         cell = self.mlstm_cell
-        cell.reverse = anti
         q, k, v = self.q_proj(conv_act), self.k_proj(conv_act), self.v_proj(x_mlstm)
         y = None
         if x.is_cuda and getattr(self, "fused_tail", True) and not cell.raw_output:
             # out-norm + skip + SiLU(z) gate as one streaming kernel over the raw cell output
-            # (vision_lstm2.py:950, :498-499 are four separate (B,S,inner) round trips)
+            # (vision_lstm2.py:950, :498-499 are four separate (B,S,inner) round trips).  Direction and output
+            # form are call arguments: no module state is touched, so the forward is re-entrant.
             from . import ops
-            cell.raw_output = True
-            try:
-                h_raw = cell(q=q, k=k, v=v)                 # (B,NH,S,DH)
-            finally:
-                cell.raw_output = False
+            h_raw = cell(q, k, v, reverse=anti, raw_output=True)                 # (B,NH,S,DH)
             if conv_act.dtype != h_raw.dtype:
                 conv_act_k, z_k = conv_act.to(h_raw.dtype), z.to(h_raw.dtype)
             else:
@@ -253,7 +250,7 @@ class ViLLayer(nn.Module):
                 y = (cell.outnorm(h_raw).transpose(1, 2).reshape(x.shape[0], x.shape[1], -1)
                      + self.learnable_skip * conv_act) * F.silu(z)
         if y is None:
-            h = cell(q=q, k=k, v=v)
+            h = cell(q, k, v, reverse=anti)
             y = (h + self.learnable_skip * conv_act) * F.silu(z)
         y = self.proj_down(y)
         if literal_flip:
