@@ -116,8 +116,16 @@ def mlstm_chunkwise(
     c_initial: Optional[Tensor] = None, n_initial: Optional[Tensor] = None,
     m_initial: Optional[Tensor] = None, chunk_size: int = 64, eps: float = 1e-6,
     return_last_states: bool = False, reverse: bool = False,
+    kink_side: Optional[Tensor] = None, return_rows: bool = False,
 ):
     """Chunkwise-parallel form with inter-chunk (C, n, m) carry (backends.py:149-263).
+
+    ``return_rows`` also returns the per-token normaliser sum ``n_t`` and stabiliser ``m_t`` (B,NH,S, token order).
+    ``kink_side`` (bool (B,NH,S), token order; True = the ``|n_t|`` side) replaces the ``max(|n_t|, exp(-m_t))`` of
+    backends.py:249-252 by the named side of it.  With ``kink_side = (|n_t| >= exp(-m_t))`` nothing changes; the
+    tests use it to evaluate the one-sided derivative on the side a bf16 kernel landed on for the few rows that sit
+    within rounding distance of the kink, where ``max`` is not differentiable and the reference's gradient is
+    whichever side its own rounding picked.
 
     Differences from the reference function, none of which change its results where it
     is defined: any ``S`` is accepted (the last chunk is masked; the reference needs
@@ -173,14 +181,28 @@ def mlstm_chunkwise(
     w = torch.exp(m_prev[:, :, :-1, None] - M)                         # :235
     E = (qc @ kc.transpose(-1, -2)) * scale * D                        # :246-247
     n_row = E.sum(-1) + w * scale * (qc * ns[:, :, :-1, None, :]).sum(-1)        # :237-239,250
-    den = torch.maximum(n_row.abs(), torch.exp(-(b + M))) + eps        # :249-254
+    floor_ = torch.exp(-(b + M))
+    if kink_side is None:
+        den = torch.maximum(n_row.abs(), floor_) + eps                 # :249-254
+    else:
+        side = kink_side.flip(dims=[2]) if reverse else kink_side
+        side = F.pad(side, (0, pad), value=True).reshape(B, NH, NC, L)
+        den = torch.where(side, n_row.abs(), floor_) + eps
     num = E @ vc + (w * scale)[..., None] * (qc @ Cs[:, :, :-1])       # :234-236,257
     h = (num / den[..., None]).reshape(B, NH, NC * L, DV)[:, :, :S]
+    rows = None
+    if return_rows:
+        rows = (n_row.reshape(B, NH, NC * L)[:, :, :S].detach(), (b + M).reshape(B, NH, NC * L)[:, :, :S].detach())
+        if reverse:
+            rows = _flip_seq(*rows)
     if reverse:
         h = h.flip(dims=[2])
+    out = (h,)
     if return_last_states:
-        return h, (Cs[:, :, -1], ns[:, :, -1], m_prev[:, :, -1].reshape(B, NH, 1))
-    return h
+        out = out + ((Cs[:, :, -1], ns[:, :, -1], m_prev[:, :, -1].reshape(B, NH, 1)),)
+    if return_rows:
+        out = out + (rows,)
+    return out if len(out) > 1 else h
 
 
 def multihead_layernorm(h: Tensor, weight: Optional[Tensor], bias: Optional[Tensor],
@@ -238,7 +260,8 @@ def cell_forward(
 # The recurrent form below is the same thing step by step and carries (C, n) states (m == 0).
 # ---------------------------------------------------------------------------------------------
 def mlstm_siging_parallel(q: Tensor, k: Tensor, v: Tensor, i: Tensor, f: Tensor, eps: float = 1e-6,
-                          reverse: bool = False) -> Tensor:
+                          reverse: bool = False, kink_side: Optional[Tensor] = None, return_rows: bool = False):
+    """``kink_side`` / ``return_rows``: as in ``mlstm_chunkwise`` (the floor of this normaliser is 1, m == 0)."""
     if reverse:
         q, k, v, i, f = _flip_seq(q, k, v, i, f)
     S, DH = q.shape[2], q.shape[3]
@@ -247,9 +270,20 @@ def mlstm_siging_parallel(q: Tensor, k: Tensor, v: Tensor, i: Tensor, f: Tensor,
     causal = torch.ones(S, S, dtype=torch.bool, device=q.device).tril()
     D = torch.exp(logD.masked_fill(~causal, -float("inf")))
     E = (q @ k.transpose(-1, -2)) * (DH ** -0.5) * D
-    n = torch.maximum(E.sum(-1, keepdim=True).abs(), torch.ones((), dtype=q.dtype, device=q.device))
+    n_row = E.sum(-1, keepdim=True)
+    one = torch.ones((), dtype=q.dtype, device=q.device)
+    if kink_side is None:
+        n = torch.maximum(n_row.abs(), one)
+    else:
+        side = kink_side.flip(dims=[2]) if reverse else kink_side
+        n = torch.where(side[..., None], n_row.abs(), one)
     h = (E / (n + eps)) @ v
-    return h.flip(dims=[2]) if reverse else h
+    h = h.flip(dims=[2]) if reverse else h
+    if return_rows:
+        nr = n_row.squeeze(-1).detach()
+        nr = nr.flip(dims=[2]) if reverse else nr
+        return h, (nr, torch.zeros_like(nr))
+    return h
 
 
 def mlstm_siging_recurrent(q: Tensor, k: Tensor, v: Tensor, i: Tensor, f: Tensor, c_initial: Optional[Tensor] = None,
@@ -277,17 +311,32 @@ def mlstm_siging_recurrent(q: Tensor, k: Tensor, v: Tensor, i: Tensor, f: Tensor
     return h
 
 
-def mlstm_fwbw(q, k, v, i, f, dh, chunk_size=64, eps=1e-6, reverse=False, input_gate="exp", **kw):
+def mlstm_fwbw(q, k, v, i, f, dh, chunk_size=64, eps=1e-6, reverse=False, input_gate="exp", kink_side=None, **kw):
     """Forward + autograd backward through the chunkwise oracle.  Returns
-    (h, dq, dk, dv, di, df).  Used as the gradient oracle and as the CPU baseline step."""
+    (h, dq, dk, dv, di, df).  Used as the gradient oracle and as the CPU baseline step.
+    ``kink_side``: see ``mlstm_chunkwise`` (h is always the un-overridden forward)."""
     leaves = [t.detach().clone().requires_grad_(True) for t in (q, k, v, i, f)]
-    if input_gate == "sigmoid":
-        if kw.get("c_initial") is not None or kw.get("n_initial") is not None:
-            h = mlstm_siging_recurrent(*leaves, c_initial=kw.get("c_initial"), n_initial=kw.get("n_initial"), eps=eps,
-                                       reverse=reverse)
-        else:
-            h = mlstm_siging_parallel(*leaves, eps=eps, reverse=reverse)
-    else:
-        h = mlstm_chunkwise(*leaves, chunk_size=chunk_size, eps=eps, reverse=reverse, **kw)
+
+    def fwd(side):
+        if input_gate == "sigmoid":
+            if kw.get("c_initial") is not None or kw.get("n_initial") is not None:
+                assert side is None, "kink_side is not available in the recurrent sigmoid-gate form"
+                return mlstm_siging_recurrent(*leaves, c_initial=kw.get("c_initial"), n_initial=kw.get("n_initial"),
+                                              eps=eps, reverse=reverse)
+            return mlstm_siging_parallel(*leaves, eps=eps, reverse=reverse, kink_side=side)
+        return mlstm_chunkwise(*leaves, chunk_size=chunk_size, eps=eps, reverse=reverse, kink_side=side, **kw)
+
+    h = fwd(kink_side)
     h.backward(dh)
-    return (h.detach(),) + tuple(t.grad for t in leaves)
+    h_out = h.detach()
+    if kink_side is not None:
+        with torch.no_grad():
+            h_out = fwd(None)
+    return (h_out,) + tuple(t.grad for t in leaves)
+
+
+def kink_rows(n_row: Tensor, m_row: Tensor, width: float = 2e-2):
+    """(side, near): side = |n_t| >= exp(-m_t) (the branch max() takes), near = |n_t| within ``width`` (relative) of
+    the floor exp(-m_t), i.e. rows whose side a bf16-level perturbation of n_t can flip."""
+    floor_ = torch.exp(-m_row)
+    return n_row.abs() >= floor_, ((n_row.abs() - floor_).abs() / floor_) < width

@@ -53,34 +53,49 @@ def run_cuda(inputs, eps=1e-6, reverse=False, states=None, **kw):
     return [h.detach()] + [l.grad for l in leaves]
 
 
-def near_tie_rows(inputs, reverse=False, states=None, eps=1e-6, width=2e-2):
-    """Rows where |n_t| is within `width` of exp(-m_t).  The reference normaliser
-    max(|n|, exp(-m)) (backends.py:249-252) makes dh/dn discontinuous there: any bf16-level
-    perturbation of n flips the branch and changes that row's dq by O(1).  Such rows are a
-    property of the reference's math, not of an implementation, and are excluded from the dq
-    comparison (they are counted and must stay rare)."""
-    from emu_kernel_dataflow import emu_forward
-    a = [x.double() for x in inputs[:5]]
-    if reverse:
-        a = [x.flip(dims=[2]) for x in a]
-    st = {} if states is None else dict(c0=states["c_initial"].double(), n0=states["n_initial"].double(),
-                                        m0=states["m_initial"].double())
-    _, nr, mr, _, _ = emu_forward(*a, L=64, eps=eps, **st)
-    floor_ = torch.exp(-mr)
-    tie = ((nr.abs() - floor_).abs() / floor_) < width
-    return tie.flip(dims=[2]) if reverse else tie
+KINK_STATS = []   # (what, fraction of rows within 2 % of the kink, rows whose side the kernel flipped)
 
 
-def check(got, ref, dtype, what="", tie=None):
+def oracle_on_kernel_side(inputs, eps=1e-6, reverse=False, states=None, input_gate="exp", batch_rows=None, what=""):
+    """fp64 oracle (h, dq, dk, dv, di, df) for a bf16 kernel run.
+
+    The reference normaliser max(|n_t|, exp(-m_t)) (backends.py:249-252) has a kink at |n_t| = exp(-m_t): dh/dn jumps
+    there, so for a row within rounding distance of it the gradient is whichever side the implementation's own
+    rounding of n_t picks (the reference's fp32 rounding included), and a flipped row changes its dq by O(1) and leaks
+    into dk / di / df of every earlier key.  Instead of masking such rows and relaxing the tolerance for the rest
+    (round 1), the oracle evaluates the one-sided derivative on the side the kernel's saved n_t, m_t landed on — for
+    the rows within 2 % of the kink only; every other row uses the oracle's own side — and then EVERY row of every
+    gradient is held to the north-star tolerance.  The fraction of near-kink rows and the number of flipped rows are
+    recorded (printed by test_zz_kink_report)."""
+    from xlstm_yolo_b200 import ops
+    dbl = [x.double() for x in inputs]
+    kw = {} if states is None else {n: s.double() for n, s in states.items()}
+    q, k, v, i, f = (x.cuda() for x in inputs[:5])
+    st = [None, None, None] if states is None else [states["c_initial"].float().cuda().contiguous(),
+                                                     states["n_initial"].float().cuda().contiguous(),
+                                                     states["m_initial"].float().reshape(q.shape[0], q.shape[1]).cuda().contiguous()]
+    _, n_g, m_g, _, _ = ops.mlstm_fwd_raw(ops._prep_act(q), ops._prep_act(k), ops._prep_act(v), i.float(), f.float(), *st,
+                                          eps=eps, reverse=reverse, gate_mode=ops.gate_mode_of(input_gate))
+    n_g, m_g = n_g.double().cpu(), m_g.double().cpu()
+    if batch_rows is not None:
+        dbl = [x[batch_rows] for x in dbl]
+        kw = {n: s[batch_rows] for n, s in kw.items()}
+        n_g, m_g = n_g[batch_rows], m_g[batch_rows]
+    with torch.no_grad():
+        if input_gate == "sigmoid":
+            _, (n_o, m_o) = O.mlstm_siging_parallel(*dbl[:5], eps=eps, reverse=reverse, return_rows=True)
+        else:
+            _, (n_o, m_o) = O.mlstm_chunkwise(*dbl[:5], chunk_size=64, eps=eps, reverse=reverse, return_rows=True, **kw)
+    side_o, near = O.kink_rows(n_o, m_o)
+    side_g, _ = O.kink_rows(n_g, m_g)
+    side = torch.where(near, side_g, side_o)
+    KINK_STATS.append((what, near.float().mean().item(), int((side != side_o).sum())))
+    assert near.float().mean().item() < 0.02, "too many near-kink rows for a meaningful comparison"
+    return O.mlstm_fwbw(*dbl, chunk_size=64, eps=eps, reverse=reverse, input_gate=input_gate, kink_side=side, **kw)
+
+
+def check(got, ref, dtype, what=""):
     th, tg = TOL[dtype]
-    got, ref = list(got), list(ref)
-    if tie is not None and tie.any():
-        assert tie.float().mean().item() < 0.02, "too many near-tie rows for a meaningful comparison"
-        keep = (~tie)[..., None]
-        got[1], ref[1] = got[1].cpu() * keep, ref[1] * keep
-        # a flipped row also leaks into dk and, through the suffix sum, into df of every earlier
-        # position (the CPU emulation of the kernel dataflow shows the same 2.2e-2): relax those.
-        tg = 2.5 * tg
     for name, a, b in zip(["h", "dq", "dk", "dv", "di", "df"], got, ref):
         assert torch.isfinite(a).all(), f"{what} {name} not finite"
         tol = th if name == "h" else tg
@@ -121,24 +136,13 @@ CASES = [
 @pytest.mark.parametrize("B,NH,S,DH,dtype,regime,reverse,eps", CASES)
 def test_cuda_matches_oracle(B, NH, S, DH, dtype, regime, reverse, eps):
     inputs = make(B, NH, S, DH, dtype, regime)
-    ref = O.mlstm_fwbw(*(x.double() for x in inputs), chunk_size=64, eps=eps, reverse=reverse)
+    what = f"B{B} NH{NH} S{S} DH{DH} {regime} rev={reverse}"
+    if dtype == torch.bfloat16:
+        ref = oracle_on_kernel_side(inputs, eps=eps, reverse=reverse, what=what)
+    else:
+        ref = O.mlstm_fwbw(*(x.double() for x in inputs), chunk_size=64, eps=eps, reverse=reverse)
     got = run_cuda(inputs, eps=eps, reverse=reverse)
-    tie = near_tie_rows(inputs, reverse, eps=eps) if dtype == torch.bfloat16 else None
-    check(got, ref, dtype, f"B{B} NH{NH} S{S} DH{DH} {regime} rev={reverse}", tie)
-
-
-def siging_tie_rows(inputs, reverse=False, width=2e-2):
-    """Rows where |n_t| is within `width` of the sigmoid-gate normaliser's floor 1 (same discontinuity)."""
-    q, k, v, i, f = (x.double() for x in inputs[:5])
-    if reverse:
-        q, k, v, i, f = (x.flip(dims=[2]) for x in (q, k, v, i, f))
-    S, DH = q.shape[2], q.shape[3]
-    b = torch.nn.functional.logsigmoid(f).cumsum(-1)
-    logD = b[..., :, None] - b[..., None, :] + torch.nn.functional.logsigmoid(i)[..., None, :]
-    D = torch.exp(logD.masked_fill(~torch.ones(S, S, dtype=torch.bool).tril(), -float("inf")))
-    n = ((q @ k.transpose(-1, -2)) * DH ** -0.5 * D).sum(-1)
-    tie = (n.abs() - 1).abs() < width
-    return tie.flip(dims=[2]) if reverse else tie
+    check(got, ref, dtype, what)
 
 
 SIG_CASES = [
@@ -157,10 +161,13 @@ SIG_CASES = [
 @pytest.mark.parametrize("B,NH,S,DH,dtype,regime,reverse", SIG_CASES)
 def test_sigmoid_input_gate_matches_oracle(B, NH, S, DH, dtype, regime, reverse):
     inputs = make(B, NH, S, DH, dtype, regime)
-    ref = O.mlstm_fwbw(*(x.double() for x in inputs), eps=1e-6, reverse=reverse, input_gate="sigmoid")
+    what = f"siging B{B} NH{NH} S{S} DH{DH} {regime} rev={reverse}"
+    if dtype == torch.bfloat16:
+        ref = oracle_on_kernel_side(inputs, reverse=reverse, input_gate="sigmoid", what=what)
+    else:
+        ref = O.mlstm_fwbw(*(x.double() for x in inputs), eps=1e-6, reverse=reverse, input_gate="sigmoid")
     got = run_cuda(inputs, reverse=reverse, input_gate="sigmoid")
-    tie = siging_tie_rows(inputs, reverse) if dtype == torch.bfloat16 else None
-    check(got, ref, dtype, f"siging B{B} NH{NH} S{S} DH{DH} {regime} rev={reverse}", tie)
+    check(got, ref, dtype, what)
 
 
 @pytest.mark.parametrize("dtype,DH", [(torch.float32, 32), (torch.bfloat16, 64), (torch.bfloat16, 128)])
@@ -212,10 +219,13 @@ def test_initial_and_last_states(dtype, DH, reverse):
     g = torch.Generator().manual_seed(7)
     st = dict(c_initial=torch.randn(B, NH, DH, DH, generator=g), n_initial=torch.randn(B, NH, DH, generator=g),
               m_initial=torch.randn(B, NH, 1, generator=g))
-    ref = O.mlstm_fwbw(*(x.double() for x in inputs), chunk_size=64, eps=1e-6, reverse=reverse,
-                       **{n: s.double() for n, s in st.items()})
+    if dtype == torch.bfloat16:
+        ref = oracle_on_kernel_side(inputs, reverse=reverse, states=st, what=f"states DH{DH} rev={reverse}")
+    else:
+        ref = O.mlstm_fwbw(*(x.double() for x in inputs), chunk_size=64, eps=1e-6, reverse=reverse,
+                           **{n: s.double() for n, s in st.items()})
     got = run_cuda(inputs, reverse=reverse, states=st)
-    check(got, ref, dtype, "states", near_tie_rows(inputs, reverse, st) if dtype == torch.bfloat16 else None)
+    check(got, ref, dtype, "states")
     from xlstm_yolo_b200 import ops
     q, k, v, i, f, _ = (x.cuda() for x in inputs)
     h, (C, n, m) = ops.mlstm(q, k, v, i, f, *(s.cuda() for s in st.values()), return_last_states=True, reverse=reverse)
@@ -341,6 +351,52 @@ def test_full_size_gradient_identities(B, NH, S, DH):
         assert torch.isfinite(t).all()
 
 
+@pytest.mark.parametrize("B,NH,S,DH,reverse", [(32, 4, 400, 64, False), (32, 4, 400, 64, True), (32, 4, 1600, 128, False),
+                                                (32, 4, 1600, 128, True), (8, 4, 1600, 128, False)])
+def test_full_size_batch_rows_match_oracle(B, NH, S, DH, reverse):
+    """The BASELINE-size launches themselves (the wide-batch kernels bench.py times, and the per-GPU DDP shape) against
+    the fp64 oracle on batch rows 0, mid and last — h and all five gradients, north-star tolerances: a (batch, head)
+    indexing or stride bug that is self-consistent under the property tests above shows up here."""
+    inputs = make(B, NH, S, DH, torch.bfloat16, "rand", seed=21)
+    rows = sorted({0, (17 * B) // 32, B - 1})
+    got = [t[rows] for t in run_cuda(inputs, reverse=reverse)]
+    what = f"full B{B} NH{NH} S{S} DH{DH} rev={reverse} rows {rows}"
+    ref = oracle_on_kernel_side(inputs, reverse=reverse, batch_rows=rows, what=what)
+    check(got, ref, torch.bfloat16, what)
+
+
+REF_CONFIGS = {   # the four configs MatrixLSTMCell builds at HEAD, vision_lstm2.py:819-877 (train and infer differ in `mode` only)
+    "cpu": dict(chunkwise_kernel="chunkwise--native_autograd", sequence_kernel="native_sequence__native", step_kernel="native"),
+    "gpu": dict(chunkwise_kernel="chunkwise--triton_xl_chunk_siging", sequence_kernel="native_sequence__triton", step_kernel="triton"),
+}
+
+
+@pytest.mark.parametrize("which,mode", [("cpu", "train"), ("cpu", "inference"), ("gpu", "train"), ("gpu", "inference")])
+def test_backend_built_from_the_references_own_config_strings(which, mode):
+    """Through the import shim, with the literal keyword arguments of vision_lstm2.py:819-877.  Documents which gate
+    arithmetic each string selects here: "chunkwise--native_autograd" -> exponential input gate with max-stabiliser
+    (backends.py:149-263; the oracle, parity pinned), "chunkwise--triton_xl_chunk_siging" -> sigmoid input gate
+    (upstream's published form; parity UNPINNED, oracle/mlstm_oracle.py) — on CUDA and on CPU tensors alike."""
+    from xlstm_yolo_b200 import compat
+    compat.install()
+    from mlstm_kernels.torch.backend_module import mLSTMBackend, mLSTMBackendConfig
+    cfg = mLSTMBackendConfig(**REF_CONFIGS[which], chunk_size=64, autocast_kernel_dtype="bfloat16",
+                             return_last_states=False, mode=mode, eps=5e-5)
+    be = mLSTMBackend(config=cfg)
+    gate = {"cpu": "exp", "gpu": "sigmoid"}[which]
+    assert be.input_gate == gate and cfg.input_gate == gate
+    inputs = make(2, 4, 400, 64, torch.bfloat16, "rand", seed=4)
+    q, k, v, i, f, dh = inputs
+    ref = oracle_on_kernel_side(inputs, eps=5e-5, input_gate=gate, what=f"refcfg {which} {mode}")
+    leaves = [x.cuda().detach().requires_grad_(True) for x in (q, k, v, i, f)]
+    h = be(q=leaves[0], k=leaves[1], v=leaves[2], i=leaves[3], f=leaves[4])
+    h.backward(dh.cuda())
+    check([h.detach()] + [l.grad for l in leaves], ref, torch.bfloat16, f"refcfg {which} {mode}")
+    # the same backend object on CPU tensors (the constructor-time stride probe, nn/tasks.py:353-362) uses the same gate
+    hc = be(q=q.float(), k=k.float(), v=v.float(), i=i, f=f)
+    assert rel(hc, ref[0]) < 1e-4
+
+
 def test_empty_and_unaligned_inputs():
     from xlstm_yolo_b200 import ops
     z = torch.empty(0, 2, 16, 64, dtype=torch.bfloat16, device="cuda")
@@ -412,3 +468,14 @@ def test_full_size_backward_is_deterministic(reverse):
         torch.cuda.synchronize()
         for a, b in zip((pl.h, pl.dq, pl.dk, pl.dv, pl.di, pl.df), want):
             assert torch.equal(a, b)
+
+
+def test_zz_kink_report(capsys):
+    """Not a check: prints how often the near-kink rule of oracle_on_kernel_side was in play in this session."""
+    with capsys.disabled():
+        tot = len(KINK_STATS)
+        hit = [s for s in KINK_STATS if s[2] > 0]
+        print(f"\n[kink] {tot} bf16 oracle comparisons; {len(hit)} had rows whose side of max(|n|, e^-m) the kernel flipped")
+        for what, frac, flipped in KINK_STATS:
+            if frac > 0:
+                print(f"[kink]   {what}: {100 * frac:.3f} % of rows within 2 % of the kink, {flipped} flipped")
