@@ -428,7 +428,7 @@ def main():
                    "fused_walk": [], "simt": ["simt_bwd_dq_kernel"]}[pl0.variant_bwd],
         "bwd_dkv": {"single_pass": ["tc_bwd_dkv12_kernel (dv and dk walks co-resident)" if DH == 64 else "tc_bwd_dkv_kernel<1>, <2>"],
                     "chunk_parallel": ["tc_state_bwd_kernel", "tc_bwd_b12_kernel (B1 dv | B2 dk side by side)", "tc_dfscan_kernel"],
-                    "fused_walk": ["tc_bwd_fused_kernel (dq, dk, dv, di, df in one reverse walk)"],
+                    "fused_walk": [("tc_bwd_fused_kernel" if DH == 64 else "tc_bwd_fused128_kernel") + " (dq, dk, dv, di, df in one reverse walk)"],
                     "simt": ["simt_bwd_dkv_kernel"]}[pl0.variant_bwd],
     }
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9

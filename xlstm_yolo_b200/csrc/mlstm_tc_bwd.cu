@@ -865,14 +865,16 @@ bool tc_use_single_pass_bwd(const mlstm_params& p);
 
 size_t tc_bwd_fused_workspace(const mlstm_params& p);
 int tc_bwd_fused(const mlstm_params& p, cudaStream_t st, int part);
+size_t tc_bwd_fused128_workspace(const mlstm_params& p);
+int tc_bwd_fused128(const mlstm_params& p, cudaStream_t st, int part);
 
 size_t tc_bwd_workspace(const mlstm_params& p) {
-  if (tc_use_fused_bwd(p)) return tc_bwd_fused_workspace(p);
+  if (tc_use_fused_bwd(p)) return p.DHQK == 64 ? tc_bwd_fused_workspace(p) : tc_bwd_fused128_workspace(p);
   return tc_use_single_pass_bwd(p) ? tc_bwd1p_workspace(p) : BwdLayout(p.B, p.NH, p.S, p.DHQK).total;
 }
 
 int tc_bwd(const mlstm_params& p, cudaStream_t st, int part) {
-  if (tc_use_fused_bwd(p)) return tc_bwd_fused(p, st, part);
+  if (tc_use_fused_bwd(p)) return p.DHQK == 64 ? tc_bwd_fused(p, st, part) : tc_bwd_fused128(p, st, part);
   if (tc_use_single_pass_bwd(p)) return tc_bwd1p(p, st, part);
   if (p.DHQK == 64) return launch_bwd<64>(p, st, part);
   return launch_bwd<128>(p, st, part);

@@ -32,12 +32,11 @@ bool tc_use_two_phase(const mlstm_params& p) {          // forward
 }
 static bool short_and_wide(const mlstm_params& p) { return tc::num_chunks(p.S) <= 4 && p.B * p.NH * 2 > sm_count(p); }
 
-// DH = 64 with enough (batch, head) pairs to fill the GPU: one reverse walk producing dq, dk, dv together from the forward's
+// Enough (batch, head) pairs to fill the GPU (DH = 64: mlstm_tc_bwd_fused.cu, DH = 128: mlstm_tc_bwd_fused128.cu): one reverse walk producing dq, dk, dv together from the forward's
 // chunk states (mlstm_tc_bwd_fused.cu), at any sequence length — it reads every tile once, so it also beats the chunk-parallel
 // kernels on long sequences (B32 NH4 DH64: 244 vs 135 M tok/s at S=800, 309 vs 180 at S=1600).  MLSTM_FORCE_VARIANT backward
 // digit 3 pins it (DH = 64 only).
 bool tc_use_fused_bwd(const mlstm_params& p) {
-  if (p.DHQK != 64) return false;
   if (forced(1)) return forced(1) == 3;
   return p.B * p.NH * 2 > sm_count(p);
 }
