@@ -448,6 +448,28 @@ def test_forward_backward_capture_into_cuda_graph():
 
 
 @pytest.mark.parametrize("reverse", [False, True])
+def test_full_size_backward_is_deterministic_dh128(reverse):
+    """Same for the DH = 128 fused walk (mlstm_tc_bwd_fused128.cu: TMEM regions and the Cs tile change hands several times per
+    step between the compute warps, the control warp's MMAs and the TMA proxies) at the north-star shape."""
+    from xlstm_yolo_b200 import ops
+    q, k, v, i, f, dh = (x.cuda() for x in make(32, 4, 1600, 128, torch.bfloat16, "rand", seed=9))
+    pl = ops.MLSTMPlan(q, k, v, i, f, dh, reverse=reverse)
+    assert pl.variant_bwd == "fused_walk"
+    pl.forward(); pl.backward()
+    torch.cuda.synchronize()
+    want = [t.clone() for t in (pl.h, pl.dq, pl.dk, pl.dv, pl.di, pl.df)]
+    for t in want:
+        assert torch.isfinite(t).all()
+    for _ in range(10):
+        for t in (pl.h, pl.dq, pl.dk, pl.dv, pl.di, pl.df):
+            t.fill_(float("nan"))
+        pl.forward(); pl.backward()
+        torch.cuda.synchronize()
+        for a, b in zip((pl.h, pl.dq, pl.dk, pl.dv, pl.di, pl.df), want):
+            assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("reverse", [False, True])
 def test_full_size_backward_is_deterministic(reverse):
     """The wide-batch kernels (single-pass forward, fused single-walk backward: products issued from several lanes, warps
     running ahead of the control warp, barrier-free hand-offs through mbarriers) give bit-identical results on every run —

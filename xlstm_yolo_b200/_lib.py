@@ -10,7 +10,8 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libmlstm_b200.so")
+# MLSTM_B200_LIB: developer override for A/B builds (build.build_variant); the product path is the in-tree library
+LIB_PATH = os.environ.get("MLSTM_B200_LIB") or os.path.join(_PKG, "lib", "libmlstm_b200.so")
 
 ABI_VERSION = 4
 MLSTM_F32, MLSTM_BF16 = 0, 1

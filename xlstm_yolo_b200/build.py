@@ -70,5 +70,35 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(tag: str, defines=(), sources=("mlstm_tc_bwd_fused128.cu",)) -> str:
+    """Developer build: ``lib/libmlstm_b200_<tag>.so`` = the normal objects with the named sources recompiled under the
+    given -D defines (A/B experiments; select it with MLSTM_B200_LIB=<path>)."""
+    build()
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    for src in _sources():
+        base = os.path.basename(src)
+        if base.startswith("probe_"):
+            continue
+        obj = os.path.join(LIBDIR, base[:-3] + ".o")
+        if base in sources:
+            obj = os.path.join(LIBDIR, base[:-3] + f"_{tag}.o")
+            subprocess.run([nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", src, "-o", obj], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+        objs.append(obj)
+    out = os.path.join(LIBDIR, f"libmlstm_b200_{tag}.so")
+    subprocess.run([nvcc, "-shared", "-o", out, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"], check=True)
+    return out
+
+
+def build_timeline(sources=("mlstm_tc_bwd_fused128.cu",)) -> str:
+    """``lib/libmlstm_b200_tl.so``: the named sources under -DMLSTM_TIMELINE (CTA 0 stamps clock64() per phase into the
+    workspace; tests/gpu_tools/timeline_*.py read it)."""
+    return build_variant("tl", ("MLSTM_TIMELINE",), sources)
+
+
 if __name__ == "__main__":
+    if "--timeline" in sys.argv:
+        print(build_timeline())
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -24,14 +24,14 @@
 //
 // Per chunk (reverse scan order; chains Q, V, K):
 //   in(Q)   X0 = Z   = dH V^T            in(V)  X1 = S^T = K Q^T           (issued one step ahead)
-//   P0      dn_t = dnf_t (dh_t . h_t)
-//   P1      Ps = dHs, Pg = dS' = s (Z / N + dn) D         out(Q)  X0 = Ps Cs^T + Pg K
-//   P2      Ps = Ks,  Pg = E^T = s S^T D / N              out(V)  X1 = Ps dCb  + Pg dH
-//   P3      dq = X0 + s w dn n_prev  -> stage, R = q.dq   in(K)   X0 = Z^T = V dH^T
-//   P4      Ps = Vs,  Pg = dS'^T ; dh <- dHs in place     dC += Q^T dHs ;  out(K)  X0 = Ps dCb^T + Pg Q
-//   P5      dv = X1 -> stage ; dn_state column sums
-//   P6      dk = X0 + kw dn_state -> stage, K = k.dk ; di, df (suffix sum carried along the walk)
-//           state pass: dCb <- bf16(dC), dC <- decay dC
+//   S1      dn_t = dnf_t (dh_t . h_t) ; Ps = dHs, Pg = dS' = s (Z / N + dn) D            out(Q)  X0 = Ps Cs^T + Pg K
+//           Ks, E^T = s S^T D / N into registers (the two tiles balance the causal work across the schedulers)
+//   S2      dn_state column sums (under out(Q)) ; Ps = Ks, Pg = E^T                       out(V)  X1 = Ps dCb  + Pg dH
+//   S3      dq = X0 + s w dn n_prev  -> stage, R = q.dq                                   in(K)   X0 = Z^T = V dH^T
+//   S4      Ps = Vs,  Pg = dS'^T ; dh <- dHs in place                      dC += Q^T dHs ; out(K)  X0 = Ps dCb^T + Pg Q
+//   S5      dv = X1 -> stage
+//   S6      dk = X0 + kw dn_state -> stage, K = k.dk ; state pass: dCb <- bf16(dC), dC <- decay dC
+//   gate warp, one step behind: di = K, df = sigmoid(-f) (suffix sum of R - K carried along the walk)
 #include "tc_common.cuh"
 
 namespace mlstm {
@@ -43,6 +43,12 @@ constexpr int DH = 128;
 constexpr int KT = DH / 64;            // 64-wide sub-tiles per operand
 constexpr int TILE2 = KT * TILE;       // bytes of one [128][128] bf16 operand (two swizzled sub-tiles)
 constexpr int TILE_C = DH * 128;       // bytes of one [DH rows][64] sub-tile of a state matrix
+#ifndef MLSTM_F128_LB
+#define MLSTM_F128_LB 128
+#endif
+constexpr int LB = MLSTM_F128_LB;      // rows per TMA load box (a tile is fetched as L / LB boxes per 64-column half).  Measured
+                                       // at B32 NH4 S1600: 128 rows 191.5 us, 64: 192.0, 32: 196.0, 16: 205.9 — more, smaller
+                                       // boxes only cost issue slots; the ~4 us a tile load takes under load is not per-box work
 
 #ifdef MLSTM_TIMELINE
 #define TLG(k) do { if (blockIdx.x == 0 && c < 6 && (threadIdx.x == 0 || threadIdx.x == CT)) \
@@ -65,14 +71,14 @@ struct SmemF128 {
   alignas(16) float nvec[DH];                // dn_state leaving the chunk
   alignas(16) float ncoef[L];                // (w s dn)_t
   alignas(16) float rowscale[L];             // (w s / N)_t
-  float npart[4][DH];
-  float part[4][L];                          // dn partials
-  float partR[4][L], partK[4][L];
-  float scan[8];
-  float df_carry;
+  alignas(16) float npart[16][DH];           // S2 -> S3: per-warp partial column sums of Q^T (w s dn)
+  float partR[4][L], partK[4][L];            // q . dq, k . dk partials per 32-column block
+  alignas(16) float dbuf[2][2][L];           // [step parity][R - K | K][row]: handed to the gate warp for di, df
   uint64_t bar_q, bar_k, bar_v, bar_dh, bar_cs, bar_in[3], bar_out[3], bar_dc;
   uint32_t tmem_base;
 };
+
+static_assert(sizeof(SmemF128) <= 232448, "fused128 backward: shared memory budget (227 KB per CTA) exceeded");
 
 // 32 columns [32 cb, 32 cb + 32) of row `row` of a [128][128] swizzled bf16 operand (two sub-tiles) -> fp32
 __device__ __forceinline__ void tile_row32_128(const uint8_t* tile, int row, int cb, float (&out)[32]) {
@@ -90,7 +96,10 @@ __device__ __forceinline__ void tile_row32_128(const uint8_t* tile, int row, int
   }
 }
 // the same block scaled by s and rounded to packed bf16 pairs: the A operand layout tcgen05.st puts into TMEM
+// (one packed bf16 multiply per pair: the scale is rounded to bf16 first, a 2^-9 relative error common to the row —
+// the same order as the rounding of the scaled operand itself, which the MMA needs in bf16 anyway)
 __device__ __forceinline__ void scaled_block(const uint8_t* tile, int row, int cb, float s, uint32_t (&pk)[16]) {
+  const __nv_bfloat162 s2 = __float2bfloat162_rn(s);
 #pragma unroll
   for (int x = 0; x < 32; x += 8) {
     const int col = cb * 32 + x;
@@ -98,9 +107,22 @@ __device__ __forceinline__ void scaled_block(const uint8_t* tile, int row, int c
     const __nv_bfloat162* qq = reinterpret_cast<const __nv_bfloat162*>(&w);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float2 f2 = __bfloat1622float2(qq[e]);
-      pk[x / 2 + e] = pack_bf16x2(f2.x * s, f2.y * s);
+      const __nv_bfloat162 r = __hmul2(qq[e], s2);
+      pk[x / 2 + e] = *reinterpret_cast<const uint32_t*>(&r);
     }
+  }
+}
+// rows of a [128][128] swizzled bf16 operand scaled in place by rowscale[row], same arithmetic as scaled_block
+__device__ __forceinline__ void scale_rows_bf16(uint8_t* tile, const float* rowscale, int tid) {
+#pragma unroll
+  for (int it = 0; it < TILE2 / 16 / CT; ++it) {
+    const uint32_t o = (uint32_t)(tid + it * CT) * 16u;
+    const __nv_bfloat162 s2 = __float2bfloat162_rn(rowscale[(o >> 7) & (L - 1)]);
+    uint4 w = *reinterpret_cast<uint4*>(tile + o);
+    __nv_bfloat162* kk = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) kk[e] = __hmul2(kk[e], s2);
+    *reinterpret_cast<uint4*>(tile + o) = w;
   }
 }
 __device__ __forceinline__ void stage_block(uint8_t* tile, int row, int cb, const uint32_t (&pk)[16]) {
@@ -111,8 +133,8 @@ __device__ __forceinline__ void stage_block(uint8_t* tile, int row, int cb, cons
         make_uint4(pk[4 * x4], pk[4 * x4 + 1], pk[4 * x4 + 2], pk[4 * x4 + 3]);
   }
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// (18 warps are allocated as 20: 96 registers per thread is the ceiling, ptxas finds it from the launch bounds)
 __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_constant__ F128Maps maps, const mlstm_params p,
                                                                 const float scale) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -141,7 +163,6 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
     for (int x = 0; x < 3; ++x) { mbar_init(&sm.bar_in[x], 1); mbar_init(&sm.bar_out[x], 1); }
     mbar_init(&sm.bar_dc, 1);
     fence_mbar_init();
-    sm.df_carry = 0.f;
   }
   if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
   for (int e = tid; e < KT * TILE_C / 16; e += NT) reinterpret_cast<uint4*>(sm.dcb)[e] = make_uint4(0, 0, 0, 0);
@@ -159,12 +180,14 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
   auto tok0_of = [&](int c) { return mem_chunk(sc_of(c), NC, rev) * L; };
   auto load_act = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int c) {
     mbar_arrive_expect_tx(bar, TILE2);
-    for (int kt = 0; kt < KT; ++kt) tma_load_4d(dst + kt * TILE, map, bar, kt * 64, tok0_of(c), h, b);
+#pragma unroll
+    for (int r0 = 0; r0 < L; r0 += LB)
+      for (int kt = 0; kt < KT; ++kt) tma_load_4d(dst + kt * TILE + r0 * 128, map, bar, kt * 64, tok0_of(c) + r0, h, b);
   };
   auto load_cs = [&](int c) {
     mbar_arrive_expect_tx(&sm.bar_cs, KT * TILE_C);
     for (int kt = 0; kt < KT; ++kt) tma_load_2d(sm.cs + kt * TILE_C, &maps.cs, &sm.bar_cs, kt * 64, (bh * NC + sc_of(c)) * DH);
-  };
+  };   // (the state rows are contiguous in memory: one box per half)
   auto gates_of = [&](int c) {   // one warp
     const int slot = c % 3;
     gates_warp_bwd(sm.g[slot], p, b, h, bh, mem_chunk(sc_of(c), NC, rev), lane, nullptr);
@@ -235,13 +258,42 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
     issue_in(1);
   }
 
+  // di, df of processing step c (gate warp, one step behind the compute warps): di_j = K_j, df_j = sigmoid(-f_j) * (suffix
+  // sum in scan order of R - K, carried along the walk).  Lane l owns tile rows 4l..4l+3.
+  float df_carry = 0.f;
+  auto scan_of = [&](int c) {
+    const GateBuf& Gs = sm.g[c % 3];
+    const float4 d4 = *reinterpret_cast<const float4*>(&sm.dbuf[c & 1][0][lane * 4]);
+    const float4 k4 = *reinterpret_cast<const float4*>(&sm.dbuf[c & 1][1][lane * 4]);
+    const float dB[4] = {d4.x, d4.y, d4.z, d4.w}, Kj[4] = {k4.x, k4.y, k4.z, k4.w};
+    float pre[4], run = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { run += dB[e]; pre[e] = run; }
+    const float incl = warp_scan_add(run, lane);
+    const float excl = incl - run, tot = __shfl_sync(0xffffffffu, incl, 31);
+    const int tok0 = tok0_of(c);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = lane * 4 + e, tok = tok0 + r;
+      const float pin = excl + pre[e];
+      const float suf = rev ? pin : (tot - pin + dB[e]);
+      if (tok < S) {
+        const float i_raw = p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s];
+        p.di.ptr[(int64_t)b * p.di.stride_b + (int64_t)h * p.di.stride_h + (int64_t)tok * p.di.stride_s] = Kj[e] * igate_dlog(p, i_raw);
+        p.df.ptr[(int64_t)b * p.df.stride_b + (int64_t)h * p.df.stride_h + (int64_t)tok * p.df.stride_s] = (suf + df_carry) * Gs.sig[r];
+      }
+    }
+    df_carry += tot;
+  };
+
   float nstate = 0.f;   // thread dk < DH: decayed dn_state entering the step
   for (int c = 0; c < NC; ++c) {
     const uint32_t ph = c & 1;
     const bool last = (c + 1 == NC);
     if (gatew) {
+      if (c > 0) scan_of(c - 1);             // before gates_of(c + 2) reuses that chunk's ring slot
       if (c + 2 < NC) gates_of(c + 2);
-      named_sync(7, GT0);   // with the compute warps: gates two steps ahead are complete
+      named_sync(7, GT0);   // with the compute warps: gates two steps ahead are complete, step c's R - K, K rows are published
       continue;
     }
     const GateBuf& G = sm.g[c % 3];
@@ -257,43 +309,50 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
     float dn_row = 0.f;
     TLG(0);
 
-    // ---- P0: dn_t = dnf_t (dh_t . h_t); row coefficients of the state update -----------------------------------
+    // ---- S1: dn_t = dnf_t (dh_t . h_t) ; chain Q operands straight into TMEM ; chain V operands into registers.  The two
+    //      gated tiles have opposite orientations (rows = queries / rows = keys), so every scheduler (= TMEM lane quadrant)
+    //      gets three full and two diagonal 32x32 blocks between them.
     if (compute) {
+      // h rows for the row dots dh_t . h_t, read the way they lie in memory: a half-warp takes one 256-byte row (16 bytes per
+      // lane), warp w owns tile rows 8w .. 8w+7 — full cache lines per request (a thread reading its own row's 64 bytes, 32
+      // rows per request, serialises in the L1 and holds up the control warp's MMA / TMA issue behind it)
       uint4 hw[4];
-      if (row_ok) {
-        const uint4* src = reinterpret_cast<const uint4*>(h_base + (int64_t)tok * p.h.stride_s + cq * 32);
-#pragma unroll
-        for (int x = 0; x < 4; ++x) hw[x] = src[x];
-      } else {
-#pragma unroll
-        for (int x = 0; x < 4; ++x) hw[x] = make_uint4(0, 0, 0, 0);
-      }
-      mbar_wait(&sm.bar_dh, ph);
-      float part = 0.f;
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
-        const int col = cq * 32 + x * 8;
-        const uint4 wd = *reinterpret_cast<const uint4*>(sm.dh + (col >> 6) * TILE + swz128(row, col & 63));
+        const int t_ = tok0 + warp * 8 + 2 * x + (lane >> 4);
+        hw[x] = (t_ < S) ? *reinterpret_cast<const uint4*>(h_base + (int64_t)t_ * p.h.stride_s + (lane & 15) * 8) : make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait(&sm.bar_dh, ph);
+      TLG(1);
+      const float rs = G.w[row] * scale * G.invN[row];
+      scaled_block(sm.dh, row, cq, rs, ps);             // Ps = dHs = (w s / N) dH: the same rounding as the in-place copy in S4
+      // Pg / Ps are free: their last reader, out(K) of the previous step, was waited for in that step's S6
+      tmem_st16(tPs + lane_sel + cq * 16, ps);
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int r_ = warp * 8 + 2 * x + (lane >> 4), ch = lane & 15;
+        const uint4 wd = *reinterpret_cast<const uint4*>(sm.dh + (ch >> 3) * TILE + swz128(r_, (ch & 7) * 8));
         const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&hw[x]);
         const __nv_bfloat162* dd = reinterpret_cast<const __nv_bfloat162*>(&wd);
+        float part = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 a = __bfloat1622float2(hh[e]), c2 = __bfloat1622float2(dd[e]);
           part = fmaf(a.x, c2.x, fmaf(a.y, c2.y, part));
         }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (ch == 0) {
+          const float dn_ = G.dnf[r_] * part;
+          sm.g[c % 3].dn[r_] = dn_;                     // read by row (chain Q) and by column (chain K)
+          sm.ncoef[r_] = G.w[r_] * scale * dn_;
+          sm.rowscale[r_] = G.w[r_] * scale * G.invN[r_];
+        }
       }
-      sm.part[cq][row] = part;
       named_sync(3, CT);
-      dn_row = G.dnf[row] * ((sm.part[0][row] + sm.part[1][row]) + (sm.part[2][row] + sm.part[3][row]));
-      const float rs = G.w[row] * scale * G.invN[row];
-      if (cq == 0) {
-        sm.g[c % 3].dn[row] = dn_row;                 // chain K reads dn by column
-        sm.ncoef[row] = G.w[row] * scale * dn_row;
-        sm.rowscale[row] = rs;
-      }
-      TLG(1);
-      // ---- P1: chain Q.  Ps = dHs, Pg = dS'[t][j] = (Z invN_t + dn_t) 2^(u2_j + log2 s - M2_t), keep j <= t (reverse: j >= t)
-      scaled_block(sm.dh, row, cq, rs, ps);
+      dn_row = G.dn[row];
+      TLG(2);
+      // Pg = dS'[t][j] = (Z invN_t + dn_t) 2^(u2_j + log2 s - M2_t), keep j <= t (reverse: j >= t)
       mbar_wait(&sm.bar_in[0], ph);
       tc_fence_after();
       if (fullT || diag) {
@@ -318,24 +377,10 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
 #pragma unroll
         for (int x = 0; x < 16; ++x) pg[x] = 0u;
       }
-      // Pg / Ps are free: their last reader, out(K) of the previous step, was waited for in that step's P6
-      tmem_st16(tPs + lane_sel + cq * 16, ps);
       tmem_st16(tPg + lane_sel + cq * 16, pg);
-      tmem_st_wait();
-    }
-    tc_fence_before();
-    named_sync(2, GT0);
-    TLG(2);
-    if (issuer) {
-      tc_fence_after();
-      mbar_wait(&sm.bar_cs, ph);
-      mbar_wait(&sm.bar_k, ph);
-      tc_fence_after();
-      issue_out(0);
-    }
-
-    // ---- P2: chain V.  Ps = Ks = kw K, Pg = E^T[j][t] = S^T 2^(u2_j + log2 s - c2_t), keep t >= j (reverse: t <= j) ------
-    if (compute) {
+      TLG(3);
+      // chain V: Ps = Ks = kw K, Pg = E^T[j][t] = S^T 2^(u2_j + log2 s - c2_t), keep t >= j (reverse: t <= j) — kept in
+      // registers until out(Q) has consumed the chain Q operands
       mbar_wait(&sm.bar_k, ph);
       scaled_block(sm.k, row, cq, G.kw[row], ps);
       mbar_wait(&sm.bar_in[1], ph);
@@ -362,24 +407,70 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
 #pragma unroll
         for (int x = 0; x < 16; ++x) pg[x] = 0u;
       }
-      TLG(3);
-      mbar_wait(&sm.bar_out[0], ph);   // out(Q) complete: Pg / Ps free, X0 = dQ, the Cs tile is dead
-      tc_fence_after();
-      TLG(4);
-      tmem_st16(tPs + lane_sel + cq * 16, ps);
-      tmem_st16(tPg + lane_sel + cq * 16, pg);
       tmem_st_wait();
+      TLG(4);
     }
     tc_fence_before();
     named_sync(2, GT0);
     TLG(5);
     if (issuer) {
       tc_fence_after();
+      mbar_wait(&sm.bar_cs, ph);
+      mbar_wait(&sm.bar_k, ph);
+      tc_fence_after();
+      TLG(22);
+      issue_out(0);
+      // the next chunk's tiles towards L2 now: their TMA loads, issued as each tile dies later in this step, then find them
+      // there (191.5 -> 186.7 us at B32 NH4 S1600)
+      if (!last) {
+        for (int kt = 0; kt < KT; ++kt) {
+          tma_prefetch_4d(&maps.k, kt * 64, tok0_of(c + 1), h, b); tma_prefetch_4d(&maps.v, kt * 64, tok0_of(c + 1), h, b);
+          tma_prefetch_4d(&maps.dh, kt * 64, tok0_of(c + 1), h, b); tma_prefetch_4d(&maps.q, kt * 64, tok0_of(c + 1), h, b);
+          tma_prefetch_2d(&maps.cs, kt * 64, (bh * NC + sc_of(c + 1)) * DH);
+        }
+      }
+    }
+
+    // ---- S2 (in the shadow of out(Q)): dn_state column sums of Q ; then the chain V operands go to TMEM --------------------
+    if (compute) {
+      if (!last) {
+        mbar_wait(&sm.bar_q, ph);
+        // lane: 4 adjacent dk columns, warp: 8 rows -> per-warp partial sums, reduced in S3
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const int col = lane * 4;
+#pragma unroll
+        for (int t = warp * 8; t < warp * 8 + 8; ++t) {
+          const uint2 w = *reinterpret_cast<const uint2*>(sm.q + (col >> 6) * TILE + swz128(t, col & 63));
+          const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+          const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+          const float cf = sm.ncoef[t];
+          a0 = fmaf(cf, f0.x, a0); a1 = fmaf(cf, f0.y, a1); a2 = fmaf(cf, f1.x, a2); a3 = fmaf(cf, f1.y, a3);
+        }
+        *reinterpret_cast<float4*>(&sm.npart[warp][col]) = make_float4(a0, a1, a2, a3);
+      }
+      TLG(6);
+      mbar_wait(&sm.bar_out[0], ph);   // out(Q) complete: Pg / Ps free, X0 = dQ, the Cs tile is dead
+      tc_fence_after();
+      TLG(7);
+      tmem_st16(tPs + lane_sel + cq * 16, ps);
+      tmem_st16(tPg + lane_sel + cq * 16, pg);
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    named_sync(2, GT0);
+    TLG(8);
+    if (issuer) {
+      tc_fence_after();
       issue_out(1);   // dCb: written by the previous step's state pass (generic proxy, fenced); dh landed before in(Q)
     }
 
-    // ---- P3: epilogue of chain Q.  dq = X0 + s w dn n_prev ; R = q . dq ; staged in the (dead) Cs tile -----------------
+    // ---- S3: epilogue of chain Q.  dq = X0 + s w dn n_prev ; R = q . dq ; staged in the (dead) Cs tile -----------------
+    float nadd = 0.f;   // thread dk < DH: this chunk's contribution to dn_state (the partials' buffer is reused from here on)
     if (compute) {
+      if (!last && tid < DH) {
+#pragma unroll
+        for (int pt = 0; pt < 16; ++pt) nadd += sm.npart[pt][tid];
+      }
       float acc[32], qr[32];
       tmem_ld32(tX0 + lane_sel + cq * 32, acc);
       tmem_ld_wait();
@@ -400,7 +491,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
     fence_proxy_async_smem();
     tc_fence_before();
     named_sync(2, GT0);
-    TLG(6);
+    TLG(9);
     if (issuer) {
       tc_fence_after();
       for (int kt = 0; kt < KT; ++kt) tma_store_4d(&maps.dq, sm.cs + kt * TILE, kt * 64, tok0, h, b);
@@ -410,16 +501,14 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
       tma_store_wait_read<0>();   // dq has left the Cs tile before this warp joins the barrier that lets dv be staged there
     }
 
-    // ---- P4: chain K.  Ps = Vs = kw V, Pg = dS'^T[j][t] = (Z^T invN_t + dn_t) 2^(u2_j + log2 s - M2_t) ; dh <- dHs ------
+    // ---- S4: chain K.  Ps = Vs = kw V, Pg = dS'^T[j][t] = (Z^T invN_t + dn_t) 2^(u2_j + log2 s - M2_t) ; dh <- dHs ------
     if (compute) {
       mbar_wait(&sm.bar_v, ph);
       scaled_block(sm.v, row, cq, G.kw[row], ps);
-      if (!last) {   // next chunk's h rows towards L2 while there is slack
-        const int ntok = tok0_of(c + 1) + row;
-        if (ntok < S && cq == 0) { prefetch_l2(h_base + (int64_t)ntok * p.h.stride_s); prefetch_l2(h_base + (int64_t)ntok * p.h.stride_s + 64); }
-      }
+      TLG(10);
       mbar_wait(&sm.bar_in[2], ph);
       tc_fence_after();
+      TLG(11);
       if (fullJ || diag) {
         float z[32];
         tmem_ld32(tX0 + lane_sel + cq * 32, z);
@@ -445,33 +534,49 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
 #pragma unroll
         for (int x = 0; x < 16; ++x) pg[x] = 0u;
       }
-      TLG(7);
+      TLG(12);
       mbar_wait(&sm.bar_out[1], ph);   // out(V) complete: Pg / Ps free, X1 = dV, dh has no unscaled reader left (Z, Z^T done too)
       tc_fence_after();
-      TLG(8);
+      TLG(13);
       tmem_st16(tPs + lane_sel + cq * 16, ps);
       tmem_st16(tPg + lane_sel + cq * 16, pg);
-      if (!last) scale_rows<DH>(sm.dh, sm.rowscale, tid);   // dHs in place: the B operand of dC += Q^T dHs
+      if (!last) scale_rows_bf16(sm.dh, sm.rowscale, tid);   // dHs in place: the B operand of dC += Q^T dHs
       tmem_st_wait();
     }
     fence_proxy_async_smem();
     tc_fence_before();
     named_sync(2, GT0);
-    TLG(9);
+    TLG(14);
     if (issuer) {
       tc_fence_after();
-      if (!last) {   // state update first: it frees dh (and, with out(K), q) for the next chunk's loads as early as possible
+      if (!last) {   // state update first: it frees dh for the next chunk's load as early as possible
 #pragma unroll
         for (int ks = 0; ks < L / 16; ++ks) umma_bf16_ss(tdC, dQmn + mnstep(ks), dHmn + mnstep(ks), idMM, (ks > 0 || c > 0) ? 1u : 0u);
         umma_commit(&sm.bar_dc);
       }
       issue_out(2);
-      if (!last) load_act(sm.v, &maps.v, &sm.bar_v, c + 1);   // Z, Z^T complete and the Vs copies taken: v is dead
+      if (!last) {
+        load_act(sm.v, &maps.v, &sm.bar_v, c + 1);   // Z, Z^T complete and the Vs copies taken: v is dead
+        mbar_wait(&sm.bar_dc, ph);                    // state update complete: dh is dead
+        TLG(23);
+        load_act(sm.dh, &maps.dh, &sm.bar_dh, c + 1);
+      }
     }
 
-    // ---- P5: epilogue of chain V (dv = X1, staged in the Cs tile); dn_state column sums; k rows for K = k . dk ----------
+    // ---- S5: epilogue of chain V (dv = X1, staged in the Cs tile); k rows for K = k . dk on their way ----------------------
     uint4 kw4[4];
     if (compute) {
+      {
+        float acc[32];
+        tmem_ld32(tX1 + lane_sel + cq * 32, acc);
+        tmem_ld_wait();
+        TLG(15);
+#pragma unroll
+        for (int x = 0; x < 32; x += 2) pg[x / 2] = pack_bf16x2(acc[x], acc[x + 1]);
+        stage_block(sm.cs, row, cq, pg);
+      }
+      // k rows for K = k . dk (the k tile already holds the next chunk): this thread's 32-column block of its row, L2 hits,
+      // issued behind the staging so nothing is live across the TMEM read; in flight across the barrier and out(K)'s tail
       if (row_ok) {
         const uint4* src = reinterpret_cast<const uint4*>(k_base + (int64_t)tok * p.k.stride_s + cq * 32);
 #pragma unroll
@@ -480,48 +585,32 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
 #pragma unroll
         for (int x = 0; x < 4; ++x) kw4[x] = make_uint4(0, 0, 0, 0);
       }
-      float acc[32];
-      tmem_ld32(tX1 + lane_sel + cq * 32, acc);
-      tmem_ld_wait();
-#pragma unroll
-      for (int x = 0; x < 32; x += 2) pg[x / 2] = pack_bf16x2(acc[x], acc[x + 1]);
-      stage_block(sm.cs, row, cq, pg);
-      if (!last) {
-        const int dk = tid & (DH - 1), pt = tid >> 7;
-        float a = 0.f;
-#pragma unroll 4
-        for (int t = pt * 32; t < pt * 32 + 32; ++t)
-          a = fmaf(sm.ncoef[t], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm.q + (dk >> 6) * TILE + swz128(t, dk & 63))), a);
-        sm.npart[pt][dk] = a;
-      }
     }
     fence_proxy_async_smem();
     tc_fence_before();
     named_sync(2, GT0);
-    TLG(10);
+    TLG(16);
     if (issuer) {
       tc_fence_after();
       for (int kt = 0; kt < KT; ++kt) tma_store_4d(&maps.dv, sm.cs + kt * TILE, kt * 64, tok0, h, b);
       tma_store_commit();
-      if (!last) {
-        mbar_wait(&sm.bar_dc, ph);       // state update complete: dh is dead
-        load_act(sm.dh, &maps.dh, &sm.bar_dh, c + 1);
-      }
-      mbar_wait(&sm.bar_out[2], ph);     // out(K) complete: with the column sums above (before the barrier) q is dead
+      mbar_wait(&sm.bar_out[2], ph);     // out(K) complete (and dC, above): with the column sums and the R dots long done, q is dead
+      TLG(24);
       if (!last) load_act(sm.q, &maps.q, &sm.bar_q, c + 1);
       tma_store_wait_read<0>();          // dv has left the Cs tile
+      TLG(25);
     }
 
-    // ---- P6: epilogue of chain K.  dk = X0 + kw dn_state ; K = k . dk ; di, df ; state pass ----------------------------
+    // ---- S6: epilogue of chain K.  dk = X0 + kw dn_state ; K = k . dk ; state pass ; R - K and K rows for the gate warp ----
     if (compute) {
       mbar_wait(&sm.bar_out[2], ph);
       tc_fence_after();
-      TLG(11);
+      TLG(17);
       float acc[32];
       tmem_ld32(tX0 + lane_sel + cq * 32, acc);
       tmem_ld_wait();
       const float kwj = G.kw[row];
-      float psum = 0.f;
+      float psum = 0.f;   // fp32 products of the un-rounded dk, like R = q . dq: the rounding noise of the two cancels in df
 #pragma unroll
       for (int x = 0; x < 32; x += 2) {
         const float o0 = fmaf(kwj, sm.nvec[cq * 32 + x], acc[x]);
@@ -531,32 +620,18 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
         pg[x / 2] = pack_bf16x2(o0, o1);
       }
       sm.partK[cq][row] = psum;
+      TLG(18);
     }
     // the Cs tile takes the staged dk: the control warp has seen the dv store leave it (wait_read above) before this barrier
     named_sync(5, GT0);
     if (compute) {
+      TLG(19);
       stage_block(sm.cs, row, cq, pg);
       if (cq == 0) {
-        // di_j = K_j ; df_j = sigmoid(-f_j) (suffix sum in scan order of (R - K) + carry from the later chunks)
         const float Kj = (sm.partK[0][row] + sm.partK[1][row]) + (sm.partK[2][row] + sm.partK[3][row]);
         const float Rj = (sm.partR[0][row] + sm.partR[1][row]) + (sm.partR[2][row] + sm.partR[3][row]);
-        const float dB = row_ok ? (Rj - Kj) : 0.f;
-        float pre = warp_scan_add(dB, lane);
-        if (lane == 31) sm.scan[rg] = pre;
-        named_sync(4, 128);
-        float off = 0.f, tot = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) { off += (w < rg) ? sm.scan[w] : 0.f; tot += sm.scan[w]; }
-        pre += off;
-        const float carry = sm.df_carry;
-        const float suf = rev ? pre : (tot - pre + dB);
-        if (row_ok) {
-          const float i_raw = p.i.ptr[(int64_t)b * p.i.stride_b + (int64_t)h * p.i.stride_h + (int64_t)tok * p.i.stride_s];
-          p.di.ptr[(int64_t)b * p.di.stride_b + (int64_t)h * p.di.stride_h + (int64_t)tok * p.di.stride_s] = Kj * igate_dlog(p, i_raw);
-          p.df.ptr[(int64_t)b * p.df.stride_b + (int64_t)h * p.df.stride_h + (int64_t)tok * p.df.stride_s] = (suf + carry) * G.sig[row];
-        }
-        named_sync(4, 128);
-        if (tid == 0) sm.df_carry = carry + tot;
+        sm.dbuf[c & 1][0][row] = row_ok ? (Rj - Kj) : 0.f;
+        sm.dbuf[c & 1][1][row] = row_ok ? Kj : 0.f;
       }
       // state pass: dCb <- bf16(dC), dC <- decay_next dC ; dn_state likewise
       if (!last) {
@@ -578,18 +653,17 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
         tmem_st32(tdC + lane_sel + cq * 32, r);
         tmem_st_wait();
         if (tid < DH) {
-          float nv = nstate;
-#pragma unroll
-          for (int pt = 0; pt < 4; ++pt) nv += sm.npart[pt][tid];
+          const float nv = nstate + nadd;
           sm.nvec[tid] = nv;
           nstate = nv * dnext;
         }
       }
+      TLG(20);
     }
-    TLG(12);
     fence_proxy_async_smem();
     tc_fence_before();
     named_sync(2, GT0);
+    TLG(21);
     if (issuer) {
       tc_fence_after();
       for (int kt = 0; kt < KT; ++kt) tma_store_4d(&maps.dk, sm.cs + kt * TILE, kt * 64, tok0, h, b);
@@ -597,18 +671,21 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
       if (!last) {
         tma_store_wait_read<0>();        // dk has left the Cs tile
         load_cs(c + 1);
+        TLG(26);
         // input products of the next chunk: X0 (dK) and X1 (dV) were consumed by the epilogues above
         mbar_wait(&sm.bar_dh, ph ^ 1); mbar_wait(&sm.bar_v, ph ^ 1);
         tc_fence_after();
+        TLG(27);
         issue_in(0);
         mbar_wait(&sm.bar_q, ph ^ 1); mbar_wait(&sm.bar_k, ph ^ 1);
         tc_fence_after();
+        TLG(28);
         issue_in(1);
       }
     }
-    if (compute) named_sync(7, GT0);   // with the gate warp: gates two steps ahead are complete
-    TLG(13);
+    if (compute) named_sync(7, GT0);   // with the gate warp: gates two steps ahead are complete; it may now scan this step's rows
   }
+  if (gatew) scan_of(NC - 1);
   if (issuer) tma_store_wait_read<0>();   // the staged tiles have been read; the global writes complete on their own
   tc_fence_before();
   __syncthreads();
@@ -632,10 +709,10 @@ int tc_bwd_fused128(const mlstm_params& p, cudaStream_t st, int part) {
   }
   F128Maps m;
   int r = 0;
-  r |= make_act_tmap(&m.q, p.q.ptr, p.B, p.NH, p.S, DH, p.q.stride_b, p.q.stride_h, p.q.stride_s, L);
-  r |= make_act_tmap(&m.k, p.k.ptr, p.B, p.NH, p.S, DH, p.k.stride_b, p.k.stride_h, p.k.stride_s, L);
-  r |= make_act_tmap(&m.v, p.v.ptr, p.B, p.NH, p.S, DH, p.v.stride_b, p.v.stride_h, p.v.stride_s, L);
-  r |= make_act_tmap(&m.dh, p.dh.ptr, p.B, p.NH, p.S, DH, p.dh.stride_b, p.dh.stride_h, p.dh.stride_s, L);
+  r |= make_act_tmap(&m.q, p.q.ptr, p.B, p.NH, p.S, DH, p.q.stride_b, p.q.stride_h, p.q.stride_s, LB);
+  r |= make_act_tmap(&m.k, p.k.ptr, p.B, p.NH, p.S, DH, p.k.stride_b, p.k.stride_h, p.k.stride_s, LB);
+  r |= make_act_tmap(&m.v, p.v.ptr, p.B, p.NH, p.S, DH, p.v.stride_b, p.v.stride_h, p.v.stride_s, LB);
+  r |= make_act_tmap(&m.dh, p.dh.ptr, p.B, p.NH, p.S, DH, p.dh.stride_b, p.dh.stride_h, p.dh.stride_s, LB);
   r |= make_act_tmap(&m.dq, p.dq.ptr, p.B, p.NH, p.S, DH, p.dq.stride_b, p.dq.stride_h, p.dq.stride_s, L);
   r |= make_act_tmap(&m.dk, p.dk.ptr, p.B, p.NH, p.S, DH, p.dk.stride_b, p.dk.stride_h, p.dk.stride_s, L);
   r |= make_act_tmap(&m.dv, p.dv.ptr, p.B, p.NH, p.S, DH, p.dv.stride_b, p.dv.stride_h, p.dv.stride_s, L);

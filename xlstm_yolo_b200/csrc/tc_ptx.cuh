@@ -67,6 +67,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
                : "r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+// Tile towards L2 only (no shared-memory destination, no completion to wait for): a later load of the same box hits L2.
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+               :
+               : "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" : : "l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const void* tmap, const void* smem_src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                :
