@@ -9,6 +9,10 @@ workload (default: BASELINE.json configs[1]: B=32, NH=4, S=400, DH=64, bf16).  P
 line (see the repo contract).  Timing: CUDA events on the launching stream, >=3 warm-up
 steps, inputs rotate over enough independent sets that the working set exceeds L2, max over
 ranks for N>1 (one process per GPU, torchrun env).
+
+The same line carries an ``also`` block (N=1): the north-star shapes of BASELINE.json configs[2] (B32 NH4 DH128 at 1600
+and 6400 tokens) and the per-GPU shape of batch-64 DDP on 8 GPUs (B8), measured the same way in the same run, so the
+driver's clock covers them too.  The headline workload stays configs[1].
 """
 from __future__ import annotations
 
@@ -34,6 +38,7 @@ WORKLOADS = {
     "dev_B32_NH4_S1600_DH64": (32, 4, 1600, 64),
 }
 DEFAULT_WORKLOAD = "cfg2_B32_NH4_S400_DH64"
+ALSO_WORKLOADS = ["cfg3_B32_NH4_S1600_DH128", "cfg3_B32_NH4_S6400_DH128", "ddp_B8_NH4_S1600_DH128"]
 CHUNK = 64          # the config's chunk size (algorithmic FLOP formula; kernels tile on their own)
 L2_BYTES = 126e6
 
@@ -57,9 +62,9 @@ def algorithmic(B, NH, S, DH):
 # part, from the round-1 `ncu --set full` captures (profiles/r01_ncu_full_*_summary.csv).  Writes that
 # stay in the 126 MB L2 until after the kernel are not counted by ncu.
 NCU_TRAFFIC_BYTES = {
-    "cfg2_B32_NH4_S400_DH64": {"fwd": 20.14e6, "bwd_dq": None, "bwd_dkv": 38.03e6 + 0.25e6},   # fused backward: one kernel
-    "cfg3_B32_NH4_S1600_DH128": {"fwd": 159.12e6 + 70.35e6, "bwd_dq": 320.92e6 + 42.60e6,
-                                 "bwd_dkv": (160.54e6 + 33.21e6) + (271.65e6 + 88.60e6) + 7.39e6},
+    "cfg2_B32_NH4_S400_DH64": {"fwd": 20.14e6, "bwd_dq": None, "bwd_dkv": 38.03e6 + 0.25e6},   # fused backward: one kernel (r01)
+    # r02: the DH = 128 fused walk (profiles/r02_ncu_full_cfg3_S1600_fused128.csv): 322.9 MB read + 126.8 MB written
+    "cfg3_B32_NH4_S1600_DH128": {"fwd": 159.12e6 + 70.35e6, "bwd_dq": None, "bwd_dkv": 322.93e6 + 126.77e6},
 }
 
 
@@ -73,18 +78,21 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def make_inputs(torch, B, NH, S, DH, seed, device, dtype):
+def make_inputs(torch, B, NH, S, DH, seed, device, dtype, on_device=False):
     """SURVEY.md §8(d) synthetic inputs in the reference's memory layout: (B,S,NH,DH) storage
-    viewed as (B,NH,S,DH); gates (B,S,NH) viewed (B,NH,S).  q,k in the post-projection regime."""
-    g = torch.Generator(device="cpu").manual_seed(seed)
+    viewed as (B,NH,S,DH); gates (B,S,NH) viewed (B,NH,S).  q,k in the post-projection regime.
+    ``on_device``: draw them with the device's generator (the large `also` shapes; the device-resident arm only)."""
+    gdev = device if on_device else "cpu"
+    g = torch.Generator(device=gdev).manual_seed(seed)
     std = DH ** -0.5
-    q = (torch.randn(B, S, NH, DH, generator=g) * std).to(dtype)
-    k = (torch.randn(B, S, NH, DH, generator=g) * std).to(dtype)
-    v = torch.randn(B, S, NH, DH, generator=g).to(dtype)
-    dh = torch.randn(B, S, NH, DH, generator=g).to(dtype)
-    i = torch.randn(B, S, NH, generator=g)
-    f = torch.linspace(3.0, 6.0, NH).view(1, 1, NH) + torch.randn(B, S, NH, generator=g)
-    return [t.to(device) if device != "cpu" else t for t in (q, k, v, i, f, dh)]
+    rn = lambda *shape: torch.randn(*shape, generator=g, device=gdev)
+    q = (rn(B, S, NH, DH) * std).to(dtype)
+    k = (rn(B, S, NH, DH) * std).to(dtype)
+    v = rn(B, S, NH, DH).to(dtype)
+    dh = rn(B, S, NH, DH).to(dtype)
+    i = rn(B, S, NH)
+    f = torch.linspace(3.0, 6.0, NH, device=gdev).view(1, 1, NH) + rn(B, S, NH)
+    return [t.to(device) if (device != "cpu" and not on_device) else t for t in (q, k, v, i, f, dh)]
 
 
 def as_heads(ts):
@@ -141,35 +149,63 @@ def cpu_fwbw_step(torch, O, cpu_inputs):
     return O.mlstm_fwbw(q, k, v, i, f, dh, chunk_size=CHUNK, eps=1e-6)
 
 
+def ref_chunk(S):
+    """The reference's chunkwise_simple needs chunk_size | S (backends.py:164): the divisor of S nearest the config's 64."""
+    divs = [d for d in range(8, min(S, 256) + 1) if S % d == 0]
+    return min(divs, key=lambda d: (abs(d - CHUNK), d)) if divs else S
+
+
+def reference_step_fn(torch):
+    """(step(inputs) -> None, kind, what): the reference's own chunkwise_simple (oracle/_ref/backends.py, placed there by
+    oracle/make_ref.py) when present, else the oracle port."""
+    from oracle import make_ref
+    mod = make_ref.load()
+    if mod is not None:
+        def step(cin):
+            q, k, v, i, f, dh = cin
+            leaves = [t.detach().requires_grad_(True) for t in (q, k, v, i, f)]
+            h = mod.chunkwise_simple(*leaves, chunk_size=ref_chunk(q.shape[2]), eps=1e-6)
+            h.backward(dh)
+        return step, "reference", "reference chunkwise_simple (backends.py:149-263) + autograd"
+    from oracle import mlstm_oracle as O
+    return (lambda cin: cpu_fwbw_step(torch, O, cin)), "port", "oracle port of backends.py:149-263 + autograd"
+
+
+def cpu_inputs(torch, B, NH, S, DH):
+    # contiguous (B,NH,S,DH) fp32: what the reference's .view() calls need
+    return [t.float().transpose(1, 2).contiguous() for t in make_inputs(torch, B, NH, S, DH, 0, "cpu", torch.bfloat16)]
+
+
 def run_reference(args):
-    """Reference arm: the reference's CPU implementation of the path (oracle port of
-    backends.py:149-263, torch CPU ops, all host threads), same config/metric/unit."""
+    """Reference arm: the reference's CPU implementation of the path on the box's host cores (all threads), the FULL batch of
+    the same workload, same metric / unit, the same number of steps (capped so the run ends within minutes)."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import mlstm_oracle as O
     B, NH, S, DH = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # bounded sample: a slice of the batch sized for ~1 s per step on a few cores
-    Bs = max(1, min(B, int(args.cpu_sample_batch)))
-    inputs = as_heads([t.float() for t in make_inputs(torch, Bs, NH, S, DH, 0, "cpu", torch.bfloat16)])
-    for _ in range(max(1, min(args.warmup, 2))):
-        cpu_fwbw_step(torch, O, inputs)
-    steps = max(1, min(args.steps, 5))
+    step, kind, what = reference_step_fn(torch)
+    inputs = cpu_inputs(torch, B, NH, S, DH)
+    t0 = time.perf_counter()
+    step(inputs)                                   # warm-up (also sizes the run)
+    t_one = time.perf_counter() - t0
+    for _ in range(max(0, min(args.warmup, 3) - 1)):
+        step(inputs)
+    steps = max(1, min(args.steps, int(120.0 / max(t_one, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_fwbw_step(torch, O, inputs)
+        step(inputs)
     dt = (time.perf_counter() - t0) / steps
-    val = Bs * S / dt
-    sample = f"batch slice {Bs}/{B} of {args.workload}, {steps} steps, fp32 torch CPU ops"
+    val = B * S / dt
+    sample = f"full batch {B}/{B} of {args.workload}, {steps} steps, chunk_size {ref_chunk(S)}, fp32, {what}"
     out = {
         "impl": "reference", "metric": "mLSTM fwd+bwd tokens/s/GPU", "value": val, "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "B": B, "NH": NH, "S": S, "DH": DH, "chunk_size": CHUNK},
-        "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": args.workload, "B_per_gpu": B, "NH": NH, "S": S, "DH": DH, "chunk_size": CHUNK},
+        "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(out)
@@ -188,56 +224,33 @@ def emit(obj):
         os.write(_OUT_FD, line)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--reverse", type=int, default=0)
-    ap.add_argument("--cpu-sample-batch", type=int, default=8)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner under NCCL_DEBUG=VERSION,
-    # for one) is sent to stderr by pointing fd 1 at fd 2; emit() writes to the saved descriptor
-    global _OUT_FD
-    sys.stdout.flush()
-    _OUT_FD = os.dup(1)
-    os.dup2(2, 1)
-    if args.impl == "reference":
-        return run_reference(args)
+def launches_of(variant_fwd, variant_bwd, DH):
+    """kernels behind each timed part, per variant (csrc/mlstm_tc_*.cu)"""
+    return {
+        "fwd": {"single_pass": ["tc_fwd_kernel"], "two_phase": ["tc_state_fwd_kernel", "tc_fwd_par_kernel"],
+                "simt": ["simt_fwd_kernel"]}[variant_fwd],
+        "bwd_dq": {"single_pass": ["tc_bwd_dq_kernel"], "chunk_parallel": ["tc_bwd_par_kernel<A>"],
+                   "fused_walk": [], "simt": ["simt_bwd_dq_kernel"]}[variant_bwd],
+        "bwd_dkv": {"single_pass": ["tc_bwd_dkv12_kernel (dv and dk walks co-resident)" if DH == 64 else "tc_bwd_dkv_kernel<1>, <2>"],
+                    "chunk_parallel": ["tc_state_bwd_kernel", "tc_bwd_b12_kernel (B1 dv | B2 dk side by side)", "tc_dfscan_kernel"],
+                    "fused_walk": [("tc_bwd_fused_kernel" if DH == 64 else "tc_bwd_fused128_kernel") + " (dq, dk, dv, di, df in one reverse walk)"],
+                    "simt": ["simt_bwd_dkv_kernel"]}[variant_bwd],
+    }
 
-    import torch
-    import torch.distributed as dist
-    from xlstm_yolo_b200 import _lib, ops
-    from xlstm_yolo_b200.backend import mLSTMBackend, mLSTMBackendConfig
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.load()
-
-    B, NH, S, DH = WORKLOADS[args.workload]
+def measure_device(torch, dist, ops, _lib, name, K, W, dev, rank, world, reverse=False, on_device=False):
+    """Device-resident arm of one workload: K steps between two CUDA events (CUDA-graph replay of one round over the rotating
+    input sets), then the same K steps eager with an event pair around every launch for the per-kernel durations."""
+    B, NH, S, DH = WORKLOADS[name]
     alg = algorithmic(B, NH, S, DH)
     pk = peaks()
-    W = max(3, args.warmup)
-    K = max(1, args.steps)
-
-    # ---- device-resident arm ("value"): rotating input sets so the working set exceeds L2 ----
     set_bytes = alg["bytes_fwd"] + alg["bytes_bwd"]
     nsets = max(2, int(2.2 * L2_BYTES / set_bytes) + 1)
     plans = []
     for s_ in range(nsets):
-        q, k, v, i, f, dh = as_heads(make_inputs(torch, B, NH, S, DH, 1000 * rank + s_, dev, torch.bfloat16))
-        plans.append(ops.MLSTMPlan(q, k, v, i, f, dh, eps=1e-6, chunk_size=CHUNK, reverse=bool(args.reverse)))
-    family = plans[0].family
+        q, k, v, i, f, dh = as_heads(make_inputs(torch, B, NH, S, DH, 1000 * rank + s_, dev, torch.bfloat16, on_device=on_device))
+        plans.append(ops.MLSTMPlan(q, k, v, i, f, dh, eps=1e-6, chunk_size=CHUNK, reverse=bool(reverse)))
+    pl0 = plans[0]
 
     def step(pl, evs=None):
         if evs is not None:
@@ -261,9 +274,8 @@ def main():
     torch.cuda.synchronize()
 
     # The timed region replays a CUDA graph of one round over the input sets (nsets steps, so the L2 rotation is kept): the
-    # kernels are the same launches with the same arguments, without the ~20 us of Python / ctypes / tensor-map encoding per
-    # step that otherwise competes with a 70 us step (and with the other ranks' host threads at N > 1).  BENCH_NO_GRAPH=1
-    # times eager launches instead.
+    # kernels are the same launches with the same arguments, without the Python / ctypes time per step that otherwise competes
+    # with a 60 us step (and with the other ranks' host threads at N > 1).  BENCH_NO_GRAPH=1 times eager launches instead.
     graph = None
     if not os.environ.get("BENCH_NO_GRAPH"):
         try:
@@ -295,8 +307,6 @@ def main():
 
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     torch.cuda.synchronize()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
@@ -304,7 +314,6 @@ def main():
     run_steps(K, W)
     t_end.record()
     torch.cuda.synchronize()
-    launches = launches_per_step * K
     if world > 1:
         dist.barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
@@ -315,13 +324,6 @@ def main():
     for s_ in range(K):
         step(plans[(W + s_) % nsets], evs[s_])
     torch.cuda.synchronize()
-    # keep the sampler alive long enough for at least a few samples of a very short region
-    t_hold = time.time()
-    while len(sampler.samples) < 3 and time.time() - t_hold < 0.2:
-        step(plans[0])
-    torch.cuda.synchronize()
-    sampler.stop_flag = True
-    sampler.join(timeout=1.0)
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / K
     dq_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / K
     dkv_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / K
@@ -332,11 +334,37 @@ def main():
     ms_per_step = elapsed_ms / K
     value = world * B * S / (ms_per_step * 1e-3)
 
-    # ---- end-to-end arm: host buffers -> public API (mLSTMBackend + autograd) -> host --------
+    parts = {"fwd": (fwd_ms, alg["bytes_fwd"]), "bwd_dq": (dq_ms, alg["bytes_bwd_dq"]), "bwd_dkv": (dkv_ms, alg["bytes_bwd_dkv"])}
+    if pl0.variant_bwd == "fused_walk":   # one kernel does the whole backward (part 0 launches nothing): SURVEY.md §8(d)'s 14 DH + 24 B
+        parts["bwd_dkv"] = (dkv_ms, alg["bytes_bwd"])
+    dom = max(parts, key=lambda n: parts[n][0])
+    dom_ms, dom_bytes = parts[dom]
+    lo = launches_of(pl0.variant_fwd, pl0.variant_bwd, DH)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": f"{pl0.family}:{'bwd_fused' if (dom == 'bwd_dkv' and pl0.variant_bwd == 'fused_walk') else dom}",
+        "launches": lo[dom], "variants": {"fwd": pl0.variant_fwd, "bwd": pl0.variant_bwd}, "achieved": achieved,
+        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_BYTES.get(name, {}).get(dom),
+        "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r0*_ncu_full_*)",
+        "algorithmic_bytes": dom_bytes, "peak_source": pk["source"],
+        "per_kernel_ms": {"fwd": fwd_ms, "bwd_dq": dq_ms, "bwd_dkv": dkv_ms},
+        "step_hbm_frac": (alg["bytes_fwd"] + alg["bytes_bwd"]) / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+        "step_tensor_frac": alg["flops_fwdbwd"] / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+    }
+    return {
+        "value": value, "ms_per_step": ms_per_step, "roofline": roofline, "launches_per_step": int(launches_per_step),
+        "family": pl0.family, "nsets": nsets, "set_bytes": set_bytes, "graph": graph is not None, "plans": plans, "step": step,
+    }
+
+
+def measure_e2e(torch, dist, name, K, dev, rank, world, full_result):
+    """End-to-end arm: host buffers -> public API (mLSTMBackend + autograd) -> host, every copy inside the timed region.
+    Inputs come from pinned host memory on a copy stream (double-buffered, so step s+1's H2D overlaps step s's kernels — what a
+    training input pipeline does).  ``full_result``: the whole result (h, dq, dk, dv, di, df) is copied back to pinned host
+    memory on a third stream; otherwise a 4-float checksum of it (the round-1 variant, kept as the second number)."""
+    from xlstm_yolo_b200.backend import mLSTMBackend, mLSTMBackendConfig
+    B, NH, S, DH = WORKLOADS[name]
     be = mLSTMBackend(mLSTMBackendConfig(chunk_size=CHUNK, eps=1e-6, autocast_kernel_dtype="bfloat16"))
-    # Every step copies its own inputs from pinned host memory and reads its result back; the copies
-    # run on a second stream into a double-buffered device set, so step s+1's H2D overlaps step s's
-    # kernels (what a training input pipeline does).  All of it is inside the timed region.
     host = [t.pin_memory() for t in make_inputs(torch, B, NH, S, DH, 77 + rank, "cpu", torch.bfloat16)]
     NBUF = 2
     dev_in = [[torch.empty_like(t, device=dev) for t in host] for _ in range(NBUF)]
@@ -344,12 +372,15 @@ def main():
     # static device-side result slots: a non_blocking D2H copy from a freshly allocated tensor makes the
     # caching allocator cudaMalloc every step (measured: 2.7 mallocs/step, 1.4-35 ms of host time)
     res_dev = [torch.zeros(4, dtype=torch.float32, device=dev) for _ in range(NBUF)]
+    res_full = [None] * NBUF          # pinned host tensors with the strides of the results, made on first use
     h2d = sum(t.numel() * t.element_size() for t in host)
-    d2h = res_host[0].numel() * 4
+    d2h = [res_host[0].numel() * 4]
     main_stream = torch.cuda.current_stream(dev)
     copy_stream = main_stream if os.environ.get("BENCH_E2E_SERIAL") else torch.cuda.Stream(device=dev)
+    back_stream = main_stream if os.environ.get("BENCH_E2E_SERIAL") else torch.cuda.Stream(device=dev)
     ready = [torch.cuda.Event() for _ in range(NBUF)]
     freed = [torch.cuda.Event() for _ in range(NBUF)]
+    done = [torch.cuda.Event() for _ in range(NBUF)]
     for ev in freed:
         ev.record(main_stream)
 
@@ -368,11 +399,25 @@ def main():
         leaves = [t.detach().requires_grad_(True) for t in (q, k, v, i, f)]
         h = be(*leaves)
         h.backward(dh)
-        with torch.no_grad():
-            torch.stack([h.abs().mean(dtype=torch.float32), leaves[0].grad.abs().mean(dtype=torch.float32),
-                         leaves[3].grad.abs().mean(), leaves[4].grad.abs().mean()], out=res_dev[b_])
-        res_host[b_].copy_(res_dev[b_], non_blocking=True)
+        outs = [h.detach()] + [l.grad for l in leaves]
         freed[b_].record(main_stream)
+        if full_result:
+            if res_full[b_] is None:
+                # pinned host tensors with exactly the results' strides ((B,S,NH,DH) storage viewed (B,NH,S,DH)): each copy is
+                # then one plain DMA, not a transposing kernel plus a staged copy
+                res_full[b_] = [torch.empty(o.numel(), dtype=o.dtype, pin_memory=True).as_strided(o.shape, o.stride()) for o in outs]
+                d2h[0] = sum(o.numel() * o.element_size() for o in outs)
+            done[b_].record(main_stream)
+            with torch.cuda.stream(back_stream):
+                back_stream.wait_event(done[b_])
+                for o, r in zip(outs, res_full[b_]):
+                    r.copy_(o, non_blocking=True)
+                    o.record_stream(back_stream)
+        else:
+            with torch.no_grad():
+                torch.stack([outs[0].abs().mean(dtype=torch.float32), outs[1].abs().mean(dtype=torch.float32),
+                             outs[4].abs().mean(), outs[5].abs().mean()], out=res_dev[b_])
+            res_host[b_].copy_(res_dev[b_], non_blocking=True)
 
     def e2e_run(n):
         e2e_copy(0)
@@ -389,6 +434,8 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     e2e_run(Ke)
+    if back_stream is not main_stream:
+        main_stream.wait_stream(back_stream)     # the result's way back to the host is inside the timed region
     e1.record()
     torch.cuda.synchronize()
     e2e_ms = e0.elapsed_time(e1) / Ke
@@ -396,84 +443,118 @@ def main():
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    e2e_val = world * B * S / (e2e_ms * 1e-3)
-    if os.environ.get("BENCH_E2E_DEBUG"):
-        def timed(fn, n=20):
-            torch.cuda.synchronize()
-            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0 = time.perf_counter()
-            a_.record()
-            for j in range(n):
-                fn(j)
-            th = (time.perf_counter() - t0) / n * 1e3
-            b_.record()
-            torch.cuda.synchronize()
-            return th, a_.elapsed_time(b_) / n
-        print("debug copies  host/dev ms", timed(lambda j: e2e_copy(j)), file=sys.stderr)
-        print("debug compute host/dev ms", timed(lambda j: e2e_compute(j)), file=sys.stderr)
-        print("debug both    host/dev ms", timed(lambda j: (e2e_copy(j), e2e_compute(j))), file=sys.stderr)
-        print("debug run(20) host/dev ms", timed(lambda j: e2e_run(20), 1), file=sys.stderr)
+    return {"value": world * B * S / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h[0],
+            "ms_per_step": e2e_ms}
 
-    # ---- roofline of the dominant kernel --------------------------------------------------
-    pl0 = plans[0]
-    parts = {"fwd": (fwd_ms, alg["bytes_fwd"]), "bwd_dq": (dq_ms, alg["bytes_bwd_dq"]), "bwd_dkv": (dkv_ms, alg["bytes_bwd_dkv"])}
-    if pl0.variant_bwd == "fused_walk":   # one kernel does the whole backward (part 0 launches nothing): SURVEY.md §8(d)'s 14 DH + 24 B
-        parts["bwd_dkv"] = (dkv_ms, alg["bytes_bwd"])
-    dom = max(parts, key=lambda n: parts[n][0])
-    dom_ms, dom_bytes = parts[dom]
-    launches_of = {   # kernels behind each timed part, per variant (csrc/mlstm_tc_*.cu)
-        "fwd": {"single_pass": ["tc_fwd_kernel"], "two_phase": ["tc_state_fwd_kernel", "tc_fwd_par_kernel"],
-                "simt": ["simt_fwd_kernel"]}[pl0.variant_fwd],
-        "bwd_dq": {"single_pass": ["tc_bwd_dq_kernel"], "chunk_parallel": ["tc_bwd_par_kernel<A>"],
-                   "fused_walk": [], "simt": ["simt_bwd_dq_kernel"]}[pl0.variant_bwd],
-        "bwd_dkv": {"single_pass": ["tc_bwd_dkv12_kernel (dv and dk walks co-resident)" if DH == 64 else "tc_bwd_dkv_kernel<1>, <2>"],
-                    "chunk_parallel": ["tc_state_bwd_kernel", "tc_bwd_b12_kernel (B1 dv | B2 dk side by side)", "tc_dfscan_kernel"],
-                    "fused_walk": [("tc_bwd_fused_kernel" if DH == 64 else "tc_bwd_fused128_kernel") + " (dq, dk, dv, di, df in one reverse walk)"],
-                    "simt": ["simt_bwd_dkv_kernel"]}[pl0.variant_bwd],
-    }
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    roofline = {
-        "bound": "hbm", "kernel": f"{family}:{'bwd_fused' if (dom == 'bwd_dkv' and pl0.variant_bwd == 'fused_walk') else dom}", "launches": launches_of[dom],
-        "variants": {"fwd": pl0.variant_fwd, "bwd": pl0.variant_bwd}, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-        "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_BYTES.get(args.workload, {}).get(dom),
-        "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_full_*_summary.csv)",
-        "algorithmic_bytes": dom_bytes, "peak_source": pk["source"],
-        "per_kernel_ms": {"fwd": fwd_ms, "bwd_dq": dq_ms, "bwd_dkv": dkv_ms},
-        "step_hbm_frac": (alg["bytes_fwd"] + alg["bytes_bwd"]) / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
-        "step_tensor_frac": alg["flops_fwdbwd"] / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
-    }
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--reverse", type=int, default=0)
+    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the `also` block (the other BASELINE shapes)")
+    args = ap.parse_args()
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner under NCCL_DEBUG=VERSION,
+    # for one) is sent to stderr by pointing fd 1 at fd 2; emit() writes to the saved descriptor
+    global _OUT_FD
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)
+    os.dup2(2, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from xlstm_yolo_b200 import _lib, ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    B, NH, S, DH = WORKLOADS[args.workload]
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    # ---- device-resident arm ("value") of the headline workload, clocks sampled during it --------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    m = measure_device(torch, dist, ops, _lib, args.workload, K, W, dev, rank, world, reverse=bool(args.reverse))
+    # keep the sampler alive long enough for at least a few samples of a very short region
+    t_hold = time.time()
+    while len(sampler.samples) < 3 and time.time() - t_hold < 0.2:
+        m["step"](m["plans"][0])
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    del m["plans"]
+
+    # ---- end-to-end arm: the whole result comes back (headline); the checksum variant beside it --------
+    e2e = measure_e2e(torch, dist, args.workload, K, dev, rank, world, full_result=True)
+    e2e_ck = measure_e2e(torch, dist, args.workload, K, dev, rank, world, full_result=False)
+    e2e.update({"api": "xlstm_yolo_b200.mLSTMBackend + autograd",
+                "pipeline": "H2D of step s+1 on a copy stream overlaps step s; the full result (h, dq, dk, dv, di, df) goes back "
+                            "to pinned host memory on a third stream",
+                "checksum_variant": {"value": e2e_ck["value"], "ms_per_step": e2e_ck["ms_per_step"],
+                                     "d2h_bytes_per_step": e2e_ck["d2h_bytes_per_step"],
+                                     "what": "4-float checksum of the result reduced on the device and copied back (round-1 e2e)"}})
 
     out = {
-        "metric": "mLSTM fwd+bwd tokens/s/GPU", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K,
-        "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": "mLSTM fwd+bwd tokens/s/GPU", "value": m["value"], "unit": "tokens/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "B_per_gpu": B, "NH": NH, "S": S, "DH": DH, "chunk_size": CHUNK,
-                   "reverse": int(args.reverse), "kernel_family": family,
-                   "l2": f"inputs rotate over {nsets} sets x {set_bytes / 1e6:.0f} MB > 126 MB L2", "parallelism": f"dp{world}",
-                   "launch": (f"CUDA graph of {nsets} steps (one per input set) replayed" if graph is not None else "eager ctypes launches"),
+                   "reverse": int(args.reverse), "kernel_family": m["family"],
+                   "l2": f"inputs rotate over {m['nsets']} sets x {m['set_bytes'] / 1e6:.0f} MB > 126 MB L2", "parallelism": f"dp{world}",
+                   "launch": (f"CUDA graph of {m['nsets']} steps (one per input set) replayed" if m["graph"] else "eager ctypes launches"),
                    "per_kernel_ms": "second pass of the same K steps with an event pair around every launch"},
         "clocks": sampler.result(),
-        "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "api": "xlstm_yolo_b200.mLSTMBackend + autograd", "pipeline": "H2D of step s+1 on a copy stream overlaps step s"},
-        "gpu_launches": int(launches),
-        "roofline": roofline,
+        "e2e": e2e,
+        "gpu_launches": int(m["launches_per_step"] * K),
+        "roofline": m["roofline"],
     }
 
-    # ---- CPU baseline (rank 0, N=1): the oracle port on the host cores, bounded sample ------
+    # ---- the other BASELINE shapes, same method, same run (N = 1) --------------------------------------
+    if world == 1 and not args.no_also and args.workload == DEFAULT_WORKLOAD:
+        also = []
+        for name in ALSO_WORKLOADS:
+            torch.cuda.empty_cache()
+            Ka = max(4, min(K, 12))
+            ma = measure_device(torch, dist, ops, _lib, name, Ka, 3, dev, rank, world, on_device=True)
+            del ma["plans"]
+            Ba, NHa, Sa, DHa = WORKLOADS[name]
+            also.append({"workload": name, "B_per_gpu": Ba, "NH": NHa, "S": Sa, "DH": DHa, "value": ma["value"], "unit": "tokens/s",
+                         "steps": Ka, "warmup": 3, "ms_per_step": ma["ms_per_step"], "gpu_launches": int(ma["launches_per_step"] * Ka),
+                         "roofline": ma["roofline"], "data": "synthetic, drawn on the device"})
+        out["also"] = also
+
+    # ---- CPU baseline (rank 0, N=1): the reference's CPU path on the host cores, bounded sample ------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import mlstm_oracle as O
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        Bs = max(1, min(B, int(args.cpu_sample_batch)))
-        cin = as_heads([t.float() for t in make_inputs(torch, Bs, NH, S, DH, 0, "cpu", torch.bfloat16)])
-        cpu_fwbw_step(torch, O, cin)
-        n = 3
+        step_cpu, kind, what = reference_step_fn(torch)
+        cin = cpu_inputs(torch, B, NH, S, DH)
+        t0 = time.perf_counter()
+        step_cpu(cin)
+        t_one = time.perf_counter() - t0
+        n = max(1, min(10, int(15.0 / max(t_one, 1e-3))))
         t0 = time.perf_counter()
         for _ in range(n):
-            cpu_fwbw_step(torch, O, cin)
+            step_cpu(cin)
         dt = (time.perf_counter() - t0) / n
-        out["cpu_baseline"] = {"value": Bs * S / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
-                               "sample": f"batch slice {Bs}/{B} of {args.workload}, {n} steps, fp32 torch CPU ops"}
+        out["cpu_baseline"] = {"value": B * S / dt, "unit": "tokens/s", "cores": cores, "kind": kind,
+                               "sample": f"full batch {B}/{B} of {args.workload}, {n} steps, chunk_size {ref_chunk(S)}, fp32, {what}"}
     if rank == 0:
         emit(out)
     if world > 1:

@@ -11,7 +11,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
              "vs_baseline", "dtype", "data", "config", "e2e"}
 
 
-def run(*args, timeout=600):
+def run(*args, timeout=900):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], cwd=ROOT, capture_output=True, text=True,
                        timeout=timeout)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -25,7 +25,10 @@ def test_reference_arm_line_on_cpu():
     assert BASE_KEYS <= set(d) and d["impl"] == "reference"
     assert d["metric"] == "mLSTM fwd+bwd tokens/s/GPU" and d["unit"] == "tokens/s" and d["higher_is_better"] is True
     assert d["config"]["workload"].startswith("cfg2_") and d["vs_baseline"] is None and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference": the reference's own chunkwise_simple from oracle/_ref (placed by oracle/make_ref.py); "port" without it
+    want_kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "backends.py")) else "port"
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "full batch 32/32" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
@@ -45,7 +48,15 @@ def test_b200_arm_line():
     assert d["gpu_launches"] >= 2 * d["steps"]   # forward + the fused backward walk (3+ with the multi-kernel backward)
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and 0 < rf["frac"] < 1 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
-    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] < d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] < d["value"]
+    # the whole result comes back inside the timed region: h, dq, dk, dv (bf16) + di, df (fp32)
+    B, NH, S, DH = 32, 4, 400, 64
+    assert d["e2e"]["d2h_bytes_per_step"] == 4 * B * NH * S * DH * 2 + 2 * B * NH * S * 4
+    assert d["e2e"]["checksum_variant"]["d2h_bytes_per_step"] == 16 and d["e2e"]["checksum_variant"]["value"] > 0
+    also = {a["workload"]: a for a in d["also"]}
+    assert set(also) == {"cfg3_B32_NH4_S1600_DH128", "cfg3_B32_NH4_S6400_DH128", "ddp_B8_NH4_S1600_DH128"}
+    for a in also.values():
+        assert a["value"] > 0 and a["gpu_launches"] >= 2 * a["steps"] and 0 < a["roofline"]["step_hbm_frac"] < 1
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] > 0 and "sample" in cb
+    assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and "full batch" in cb["sample"]
