@@ -501,3 +501,90 @@ def test_zz_kink_report(capsys):
         for what, frac, flipped in KINK_STATS:
             if frac > 0:
                 print(f"[kink]   {what}: {100 * frac:.3f} % of rows within 2 % of the kink, {flipped} flipped")
+
+
+def test_cell_and_layer_trace_under_torch_compile():
+    """The reference compiles its model (debug.py:13).  The cell is registered with torch.library (xlstm_yolo_b200::mlstm_fwd /
+    ::mlstm_bwd, fake implementations + autograd formula), so Dynamo + AOT autograd trace a module that contains it into ONE
+    graph; results equal eager mode.  backend="aot_eager": tracing, functionalisation and the fake kernels are what is under
+    test, not a code generator."""
+    from xlstm_yolo_b200 import MatrixLSTMCell, ViLBlockPair
+    torch.manual_seed(0)
+    cell = MatrixLSTMCell(dim=256, num_heads=4, chunk_size=64)
+    with torch.no_grad():
+        cell.igate.weight.normal_(0, 0.05); cell.fgate.weight.normal_(0, 0.05); cell.igate.bias.normal_(0, 1.0)
+    cell = cell.cuda().to(torch.bfloat16)
+    cell.fused_gates = False      # eager and compiled then run the same decomposition (F.linear gates + the cell op)
+    comp = torch.compile(cell, backend="aot_eager", fullgraph=True)
+    g = torch.Generator().manual_seed(1)
+    base = [(torch.randn(2, 400, 256, generator=g) * s).bfloat16().cuda() for s in (0.1, 0.1, 1.0)]
+    dy = torch.randn(2, 400, 256, generator=g).bfloat16().cuda()
+    res = []
+    for m in (cell, comp):
+        leaves = [t.clone().requires_grad_(True) for t in base]
+        cell.zero_grad()
+        y = m(*leaves)
+        y.backward(dy)
+        res.append([y.detach()] + [t.grad for t in leaves] + [cell.fgate.bias.grad.clone()])
+    for a, b in zip(*res):
+        assert torch.isfinite(a).all() and torch.equal(a, b)
+    assert hasattr(torch.ops.xlstm_yolo_b200, "mlstm_fwd") and hasattr(torch.ops.xlstm_yolo_b200, "mlstm_bwd")
+    # the whole bidirectional pair (graph breaks allowed: the depthwise conv view tricks are the compiler's business)
+    pair = ViLBlockPair(dim=128, chunk_size=64, qkv_block_size=64).cuda()
+    cpair = torch.compile(pair, backend="aot_eager")
+    x = torch.randn(2, 400, 128, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ye, yc = pair(x), cpair(x)
+    assert rel(yc.float(), ye.float().cpu()) < 2e-2
+
+
+@pytest.mark.parametrize("dtype,DK,DV", [(torch.float32, 32, 64), (torch.bfloat16, 32, 64), (torch.bfloat16, 64, 128)])
+def test_unequal_head_dims_match_oracle(dtype, DK, DV):
+    """qk_dim_factor = 0.5 of the reference's mLSTMLayerVision (mlstm_large.py:46,186-187): q, k of head dim DHqk, v and h of
+    head dim DHv = 2 DHqk.  Runs on the fp32 SIMT family (the tcgen05 kernels take DHqk == DHv only); the reference's own
+    PyTorch chunkwise_simple cannot run this shape at all (it views q, k, v with one DH, backends.py:163-171), so the oracle
+    restatement is the pin."""
+    B, NH, S = 2, 2, 200
+    g = torch.Generator().manual_seed(5)
+    mk = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc)
+    q, k = mk(B, S, NH, DK, sc=DK ** -0.5).to(dtype).transpose(1, 2), mk(B, S, NH, DK, sc=DK ** -0.5).to(dtype).transpose(1, 2)
+    v, dh = mk(B, S, NH, DV).to(dtype).transpose(1, 2), mk(B, S, NH, DV).to(dtype).transpose(1, 2)
+    i, f = mk(B, S, NH).transpose(1, 2), (torch.linspace(3, 6, NH).view(1, 1, NH) + mk(B, S, NH)).transpose(1, 2)
+    inputs = [q, k, v, i, f, dh]
+    ref = O.mlstm_fwbw(*(x.double() for x in inputs), chunk_size=64, eps=1e-6)
+    got = run_cuda(inputs)
+    from xlstm_yolo_b200 import ops
+    assert ops.kernel_family(q.cuda(), v.cuda()) == "simt"
+    check(got, ref, torch.float32 if dtype == torch.float32 else torch.bfloat16, f"DHqk {DK} DHv {DV}")
+
+
+def test_reference_mlstm_layer_vision_runs_on_the_shim():
+    """The reference's own mLSTMLayerVision (mlstm_large.py:135-330: soft-capped gates, sigmoid output gate, DHqk = DHv / 2,
+    carried state) imported unmodified from baseline/_ref, its mLSTMBackend being this repo's through the import shim: CUDA
+    forward + backward against the same module on CPU tensors (the native-PyTorch branch of the backend)."""
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.isdir(os.path.join(root, "ultralytics")):
+        pytest.skip("baseline/_ref not present (made by baseline/make_ref.py where the reference tree exists)")
+    from xlstm_yolo_b200.compat import reference_loader as RL
+    RL.import_reference(root)
+    from ultralytics.nn.modules.vision_lstm import mlstm_large as ML
+    torch.manual_seed(0)
+    cfg = ML.mLSTMVisionBlockConfig(embedding_dim=128, num_heads=2, chunkwise_kernel="chunkwise--triton_xl_chunk",
+                                    sequence_kernel="native_sequence__triton", step_kernel="triton", autocast_kernel_dtype="float32")
+    layer = ML.mLSTMLayerVision(cfg, seqlens=[14, 14])
+    with torch.no_grad():
+        for n, p in layer.named_parameters():
+            if "gate" in n and p.dim() > 1:
+                p.normal_(0, 0.05)
+    x = torch.randn(2, 196, 128)
+    res = []
+    import copy
+    for dev in ("cpu", "cuda"):
+        m = copy.deepcopy(layer).to(dev)
+        xi = x.to(dev).requires_grad_(True)
+        y = m(xi)
+        y.square().mean().backward()
+        res.append((y.detach().cpu(), xi.grad.cpu(), m.igate_preact.weight.grad.cpu()))
+    for a, b in zip(res[1], res[0]):
+        assert torch.isfinite(a).all() and rel(a, b) < 2e-4

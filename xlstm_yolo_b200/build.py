@@ -45,8 +45,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in _sources():
-        if os.path.basename(src).startswith("probe_"):
-            continue  # stand-alone tools, built separately
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
@@ -78,8 +76,6 @@ def build_variant(tag: str, defines=(), sources=("mlstm_tc_bwd_fused128.cu",)) -
     objs = []
     for src in _sources():
         base = os.path.basename(src)
-        if base.startswith("probe_"):
-            continue
         obj = os.path.join(LIBDIR, base[:-3] + ".o")
         if base in sources:
             obj = os.path.join(LIBDIR, base[:-3] + f"_{tag}.o")

@@ -135,7 +135,8 @@ class MatrixLSTMCell(nn.Module):
             raise ValueError("All input tensors (q, k, v) must be on the same device.")
         backend = self.gpu_backend if self.training else self.gpu_backend_infer
         with torch.autograd.profiler.record_function("ViLLayer::mlstm_cell"):
-            if q.is_cuda and getattr(self, "fused_gates", True) and _fused_gates_ok(H):
+            # (under torch.compile the cell goes through the registered custom op and the gate projection stays with the compiler)
+            if q.is_cuda and getattr(self, "fused_gates", True) and not torch.compiler.is_compiling() and _fused_gates_ok(H):
                 # hand-written gate projection fused with the cell into one autograd node
                 h = backend.fused_cell(q, k, v, self.igate, self.fgate, self.num_heads, reverse=reverse)
             else:

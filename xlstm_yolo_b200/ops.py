@@ -213,6 +213,104 @@ class _MLSTMCellFn(torch.autograd.Function):
         return dq, dk, dv, di, df, None, None, None, None, None, None, None, None
 
 
+# ---------------------------------------------------------------------------------------------
+# torch.library registration: the same two C-ABI calls as ``xlstm_yolo_b200::mlstm_fwd`` / ``::mlstm_bwd`` custom ops with
+# fake (shape-only) implementations and an autograd formula, so Dynamo / AOT autograd can trace a model that contains the
+# cell (the reference compiles its model in debug.py:13).  ``mlstm`` takes this route while torch.compile is tracing and
+# the plain autograd.Function otherwise (same kernels, less dispatch overhead per call in eager mode).
+# ---------------------------------------------------------------------------------------------
+def _states_numel(B, NH, S, DK, DV, dtype, save_rows: bool) -> int:
+    """Bytes of the chunk-state buffer for these shapes (a host-side query: no device pointers involved)."""
+    p = Params()
+    p.abi_version = _lib.ABI_VERSION
+    p.B, p.NH, p.S, p.DHQK, p.DHV = B, NH, S, DK, DV
+    p.dtype = _DT[dtype]
+    if save_rows:
+        p.n_row = p.m_row = 0x1000      # "a backward will follow" (only tested for NULL by the query)
+    return int(_lib.load().mlstm_b200_state_bytes(C.byref(p)))
+
+
+@torch.library.custom_op("xlstm_yolo_b200::mlstm_fwd", mutates_args=(), device_types="cuda")
+def _mlstm_fwd_op(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, i: torch.Tensor, f: torch.Tensor,
+                  c_initial: Optional[torch.Tensor], n_initial: Optional[torch.Tensor], m_initial: Optional[torch.Tensor],
+                  eps: float, chunk_size: int, reverse: bool, save_rows: bool, return_last_states: bool,
+                  gate_mode: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    q, k, v = _prep_act(q), _prep_act(k), _prep_act(v)
+    h, n_row, m_row, last, states = mlstm_fwd_raw(q, k, v, i, f, c_initial, n_initial, m_initial, eps=eps, chunk_size=chunk_size,
+                                                  reverse=reverse, save_rows=save_rows, return_last_states=return_last_states,
+                                                  gate_mode=gate_mode)
+    e = lambda dt=torch.float32: torch.empty(0, dtype=dt, device=q.device)
+    c_l, n_l, m_l = last if last is not None else (e(), e(), e())
+    return (h, n_row if n_row is not None else e(), m_row if m_row is not None else e(),
+            states if states is not None else e(torch.uint8), c_l, n_l, m_l)
+
+
+@_mlstm_fwd_op.register_fake
+def _(q, k, v, i, f, c_initial, n_initial, m_initial, eps, chunk_size, reverse, save_rows, return_last_states, gate_mode):
+    B, NH, S, DK = q.shape
+    DV = v.shape[-1]
+    dev = q.device
+    e = lambda dt=torch.float32: torch.empty(0, dtype=dt, device=dev)
+    h = torch.empty((B, S, NH, DV), dtype=q.dtype, device=dev).transpose(1, 2)
+    rows = (lambda: torch.empty((B, NH, S), dtype=torch.float32, device=dev)) if save_rows else e
+    states = torch.empty(_states_numel(B, NH, S, DK, DV, q.dtype, save_rows), dtype=torch.uint8, device=dev)
+    if return_last_states:
+        last = (torch.empty((B, NH, DK, DV), dtype=torch.float32, device=dev), torch.empty((B, NH, DK), dtype=torch.float32, device=dev),
+                torch.empty((B, NH, 1), dtype=torch.float32, device=dev))
+    else:
+        last = (e(), e(), e())
+    return (h, rows(), rows(), states) + last
+
+
+@torch.library.custom_op("xlstm_yolo_b200::mlstm_bwd", mutates_args=(), device_types="cuda")
+def _mlstm_bwd_op(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, i: torch.Tensor, f: torch.Tensor, h: torch.Tensor,
+                  n_row: torch.Tensor, m_row: torch.Tensor, dh: torch.Tensor, c_initial: Optional[torch.Tensor],
+                  n_initial: Optional[torch.Tensor], m_initial: Optional[torch.Tensor], states: torch.Tensor, eps: float,
+                  chunk_size: int, reverse: bool,
+                  gate_mode: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    q, k, v = _prep_act(q), _prep_act(k), _prep_act(v)
+    if dh.dtype != q.dtype:
+        dh = dh.to(q.dtype)
+    return mlstm_bwd_raw(q, k, v, i, f, h, n_row, m_row, _prep_act(dh), c_initial, n_initial, m_initial, eps=eps,
+                         chunk_size=chunk_size, reverse=reverse, states=states if states.numel() else None, gate_mode=gate_mode)
+
+
+@_mlstm_bwd_op.register_fake
+def _(q, k, v, i, f, h, n_row, m_row, dh, c_initial, n_initial, m_initial, states, eps, chunk_size, reverse, gate_mode):
+    B, NH, S, DK = q.shape
+    DV = v.shape[-1]
+    act = lambda D: torch.empty((B, S, NH, D), dtype=q.dtype, device=q.device).transpose(1, 2)
+    gate = lambda: torch.empty((B, S, NH), dtype=torch.float32, device=q.device).transpose(1, 2)
+    return act(DK), act(DK), act(DV), gate(), gate()
+
+
+def _op_setup_context(ctx, inputs, output):
+    q, k, v, i, f, c0, n0, m0, eps, chunk_size, reverse, save_rows, return_last_states, gate_mode = inputs
+    h, n_row, m_row, states = output[:4]
+    ctx.save_for_backward(q, k, v, i, f, h, n_row, m_row, c0, n0, m0, states)
+    ctx.cfg = (eps, chunk_size, reverse, gate_mode)
+    ctx.set_materialize_grads(False)
+
+
+def _op_backward(ctx, dh, *_unused):
+    q, k, v, i, f, h, n_row, m_row, c0, n0, m0, states = ctx.saved_tensors
+    eps, chunk_size, reverse, gate_mode = ctx.cfg
+    if dh is None:
+        dh = torch.zeros_like(h)
+    dq, dk, dv, di, df = _mlstm_bwd_op(q, k, v, i, f, h, n_row, m_row, dh, c0, n0, m0, states, eps, chunk_size, reverse, gate_mode)
+    return dq, dk, dv, di, df, None, None, None, None, None, None, None, None, None
+
+
+_mlstm_fwd_op.register_autograd(_op_backward, setup_context=_op_setup_context)
+
+
+def _mlstm_traced(q, k, v, i, f, c0, n0, m0, eps, chunk_size, reverse, return_last_states, gate_mode):
+    need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (q, k, v, i, f))
+    h, _n, _m, _s, c_l, n_l, m_l = _mlstm_fwd_op(q, k, v, i, f, c0, n0, m0, eps, chunk_size, reverse, need_grad,
+                                                  return_last_states, gate_mode)
+    return (h, c_l, n_l, m_l) if return_last_states else h
+
+
 def mlstm(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, i: torch.Tensor, f: torch.Tensor,
           c_initial: Optional[torch.Tensor] = None, n_initial: Optional[torch.Tensor] = None,
           m_initial: Optional[torch.Tensor] = None, return_last_states: bool = False, *, eps: float = 1e-6,
@@ -234,13 +332,18 @@ def mlstm(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, i: torch.Tensor, f:
         kernel_dtype = torch.float32 if in_dtype == torch.float32 else torch.bfloat16
     if kernel_dtype not in _DT:
         raise ValueError(f"kernel_dtype must be float32 or bfloat16, got {kernel_dtype}")
-    q, k, v = (_prep_act(t.to(kernel_dtype)) for t in (q, k, v))
+    tracing = torch.compiler.is_compiling()
+    q, k, v = ((t.to(kernel_dtype) if tracing else _prep_act(t.to(kernel_dtype))) for t in (q, k, v))
     i, f = i.to(torch.float32), f.to(torch.float32)
     c0 = None if c_initial is None else c_initial.detach().to(torch.float32).contiguous()
     n0 = None if n_initial is None else n_initial.detach().to(torch.float32).contiguous()
     m0 = None if m_initial is None else m_initial.detach().to(torch.float32).reshape(q.shape[0], q.shape[1]).contiguous()
-    out = _MLSTMCellFn.apply(q, k, v, i, f, c0, n0, m0, float(eps), int(chunk_size), bool(reverse),
-                             bool(return_last_states), gate_mode_of(input_gate))
+    if tracing:   # torch.compile: the registered custom op (layout fix-ups happen inside it)
+        out = _mlstm_traced(q, k, v, i, f, c0, n0, m0, float(eps), int(chunk_size), bool(reverse), bool(return_last_states),
+                            gate_mode_of(input_gate))
+    else:
+        out = _MLSTMCellFn.apply(q, k, v, i, f, c0, n0, m0, float(eps), int(chunk_size), bool(reverse),
+                                 bool(return_last_states), gate_mode_of(input_gate))
     if return_last_states:
         h, C, n, m = out
         return h.to(in_dtype), (C, n, m)

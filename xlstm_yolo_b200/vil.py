@@ -233,7 +233,7 @@ class ViLLayer(nn.Module):
         cell = self.mlstm_cell
         q, k, v = self.q_proj(conv_act), self.k_proj(conv_act), self.v_proj(x_mlstm)
         y = None
-        if x.is_cuda and getattr(self, "fused_tail", True) and not cell.raw_output:
+        if x.is_cuda and getattr(self, "fused_tail", True) and not cell.raw_output and not torch.compiler.is_compiling():
             # out-norm + skip + SiLU(z) gate as one streaming kernel over the raw cell output
             # (vision_lstm2.py:950, :498-499 are four separate (B,S,inner) round trips).  Direction and output
             # form are call arguments: no module state is touched, so the forward is re-entrant.
