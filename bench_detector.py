@@ -72,11 +72,10 @@ def main():
     dev = torch.device("cuda", local_rank) if on_gpu else torch.device("cpu")
     if on_gpu:
         torch.cuda.set_device(local_rank)
+    out_fd = os.dup(1)          # stdout carries exactly one JSON line: library chatter (NCCL's banner, ...) goes to stderr
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl" if on_gpu else "gloo", **({"device_id": dev} if on_gpu else {}))
-
-    out_fd = os.dup(1)          # stdout carries exactly one JSON line: library chatter goes to stderr
-    os.dup2(2, 1)
 
     from xlstm_yolo_b200.compat import reference_loader as RL
     ref_root = os.path.join(ROOT, "baseline", "_ref")
@@ -108,7 +107,8 @@ def main():
         net = model
         if world > 1:   # engine/trainer.py:274
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank] if on_gpu else None, find_unused_parameters=True)
-        opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.937, nesterov=True, weight_decay=5e-4)
+        # lr as in the first iterations of the reference's warm-up ramp (engine/trainer.py:366-375: from 0 towards lr0 = 0.01)
+        opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.937, nesterov=True, weight_decay=5e-4)
         scaler = torch.amp.GradScaler("cuda", enabled=on_gpu)
         ema = ModelEMA(model)
         batches = [synthetic_batch(torch, b, args.imgsz, 100 * rank + j, pin=on_gpu) for j in range(2)]

@@ -580,6 +580,8 @@ def test_reference_mlstm_layer_vision_runs_on_the_shim():
     x = torch.randn(2, 196, 128)
     res = []
     import copy
+    torch.backends.cudnn.allow_tf32 = False          # the CPU run is plain fp32: keep the conv / linears of the CUDA run there too
+    torch.backends.cuda.matmul.allow_tf32 = False
     for dev in ("cpu", "cuda"):
         m = copy.deepcopy(layer).to(dev)
         xi = x.to(dev).requires_grad_(True)
