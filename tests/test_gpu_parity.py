@@ -584,7 +584,7 @@ def test_reference_mlstm_layer_vision_runs_on_the_shim():
     torch.backends.cuda.matmul.allow_tf32 = False
     for dev in ("cpu", "cuda"):
         m = copy.deepcopy(layer).to(dev)
-        xi = x.to(dev).requires_grad_(True)
+        xi = x.detach().clone().to(dev).requires_grad_(True)
         y = m(xi)
         y.square().mean().backward()
         res.append((y.detach().cpu(), xi.grad.cpu(), m.igate_preact.weight.grad.cpu()))
