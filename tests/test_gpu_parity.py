@@ -126,8 +126,12 @@ CASES = [
     (3, 2, 127, 128, torch.bfloat16, "rand", True, 1e-6),
     (2, 2, 1, 64, torch.bfloat16, "rand", False, 1e-6),
     (2, 2, 1, 16, torch.float32, "rand", False, 1e-6),
-    (1, 2, 200, 256, torch.bfloat16, "rand", False, 1e-6),      # secondary-reading head dim: value-sliced SIMT
+    (1, 2, 200, 256, torch.bfloat16, "rand", False, 1e-6),      # secondary-reading head dim: slice-streaming tcgen05 family
     (1, 2, 200, 256, torch.bfloat16, "refinit", True, 5e-5),
+    (2, 2, 400, 256, torch.bfloat16, "forget", True, 1e-6),
+    (3, 2, 129, 256, torch.bfloat16, "rand", True, 1e-6),
+    (1, 4, 1600, 256, torch.bfloat16, "rand", False, 1e-6),     # cfg3 secondary reading (d = 512, expansion 2 -> DH 256)
+    (1, 2, 3200, 256, torch.bfloat16, "rand", True, 1e-6),
     (1, 2, 70, 256, torch.float32, "rand", True, 1e-6),
     (1, 2, 96, 192, torch.float32, "forget", False, 1e-6),      # three slices
 ]
@@ -207,11 +211,12 @@ def test_kernel_family_dispatch():
     assert ops.kernel_family(bf(128), bf(128)) == "tcgen05"
     assert ops.kernel_family(bf(16), bf(16)) == "simt"
     assert ops.kernel_family(bf(128).float(), bf(128).float()) == "simt"
-    assert ops.kernel_family(bf(256), bf(256)) == "simt"
+    assert ops.kernel_family(bf(256), bf(256)) == "tcgen05"
+    assert ops.kernel_family(bf(256).float(), bf(256).float()) == "simt"
 
 
 @pytest.mark.parametrize("dtype,DH", [(torch.float32, 32), (torch.bfloat16, 64), (torch.bfloat16, 128),
-                                      (torch.float32, 256)])
+                                      (torch.float32, 256), (torch.bfloat16, 256)])
 @pytest.mark.parametrize("reverse", [False, True])
 def test_initial_and_last_states(dtype, DH, reverse):
     B, NH, S = 2, 2, 300

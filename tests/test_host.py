@@ -107,7 +107,12 @@ def test_kernel_family_and_workspace(lib):
     assert lib.mlstm_b200_state_bytes(C.byref(p)) == 0
     p = _params(dtype=_lib.MLSTM_F32, DHQK=128, DHV=128)
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
-    p = _params(DHQK=256, DHV=256)   # value-sliced SIMT kernels: dn per slice + R + fp32 dq/dk accumulators
+    p = _params(DHQK=256, DHV=256)   # bf16: the slice-streaming tcgen05 family (mlstm_tc_256.cu), always chunk-parallel
+    assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"tcgen05"
+    assert lib.mlstm_b200_kernel_variant(C.byref(p), 0) == b"two_phase" and lib.mlstm_b200_kernel_variant(C.byref(p), 1) == b"chunk_parallel"
+    assert lib.mlstm_b200_state_bytes(C.byref(p)) >= items * (256 * 256 * 2 + 256 * 4 + 4)
+    assert lib.mlstm_b200_workspace_bytes(C.byref(p), 1) >= 4 * rows * (1 + 2 * 8) + items * (256 * 256 * 2 + 256 * 4 + 4 * 4)
+    p = _params(dtype=_lib.MLSTM_F32, DHQK=256, DHV=256)   # fp32: value-sliced SIMT kernels: dn per slice + R + fp32 dq/dk accumulators
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
     assert lib.mlstm_b200_workspace_bytes(C.byref(p), 1) == 4 * (rows * 5 + 2 * rows * 256)
     p = _params(DHQK=512, DHV=512)

@@ -46,15 +46,18 @@ struct BwdMaps { CUtensorMap t0, t1, t2, st, t3, h, out; };   // t3: q (A) / k (
 // backward scratch (p.workspace)
 struct BwdLayout {
   size_t dn_off, rpart_off, kpart_off, dcs_off, dns_off, flow_off, total;
+  int nparts, nblk;   // 32-column partial slots of R / K per row; 128 x 128 state blocks per chunk (flow partials)
   __host__ __device__ BwdLayout(int B, int NH, int S, int DH) {
     const size_t rows = (size_t)B * NH * S, items = (size_t)B * NH * num_chunks(S);
+    nparts = DH > 128 ? DH / 32 : 4;
+    nblk = DH > 128 ? (DH / 128) * (DH / 128) : 1;
     dn_off = 0;
     rpart_off = dn_off + rows * 4;
-    kpart_off = rpart_off + 4 * rows * 4;
-    dcs_off = (kpart_off + 4 * rows * 4 + 255) & ~(size_t)255;
+    kpart_off = rpart_off + nparts * rows * 4;
+    dcs_off = (kpart_off + nparts * rows * 4 + 255) & ~(size_t)255;
     dns_off = dcs_off + items * DH * DH * 2;
-    flow_off = (dns_off + items * DH * 4 + 255) & ~(size_t)255;   // fp32 per chunk: <dC, C> + <dn, n> across its entry boundary
-    total = (flow_off + items * 4 + 255) & ~(size_t)255;
+    flow_off = (dns_off + items * DH * 4 + 255) & ~(size_t)255;   // fp32 per chunk (x nblk): <dC, C> + <dn, n> across its entry boundary
+    total = (flow_off + items * nblk * 4 + 255) & ~(size_t)255;
   }
 };
 
@@ -494,11 +497,15 @@ struct SmemSB {
 // not wait for the SIMT half: the per-chunk update U = Qtilde^T dH (and its n column) goes into one of two
 // alternating TMEM buffers with a fresh accumulation, the running state lives in a third TMEM region that only
 // the state pass touches.  U of step pc+1 is therefore computed while the state pass of step pc runs.
+// Head dims above the template's DH (DHF = p.DHQK = 256, DH = 128): gridDim.y = (DHF / DH)^2 independent blocks
+// dC[row0 .. +DH)[col0 .. +DH) = f(Q columns row0.., dH columns col0..); column block 0 also carries the dn state.
 template <int DH>
 __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_constant__ BwdMaps maps, const mlstm_params p,
                                                              const float scale) {
   constexpr int KT = DH / 64;
   constexpr int NB = DH / 32;
+  const int DHF = p.DHQK, ncb = DHF / DH, nblk = ncb * ncb;
+  const int row0 = ((int)blockIdx.y / ncb) * DH, col0 = ((int)blockIdx.y % ncb) * DH;
   constexpr uint32_t A_LBO = (DH == 128) ? TILE : 0;
   constexpr uint32_t TCOLS = 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -511,11 +518,11 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
   const int bh = blockIdx.x, b = bh / p.NH, h = bh % p.NH;
   const int S = p.S, NC = num_chunks(S);
   const bool rev = p.reverse != 0;
-  const BwdLayout blay(p.B, p.NH, S, DH);
+  const BwdLayout blay(p.B, p.NH, S, DHF);
   uint8_t* ws = reinterpret_cast<uint8_t*>(p.workspace);
   const float* ws_dn = reinterpret_cast<const float*>(ws + blay.dn_off);
-  __nv_bfloat16* dCs = reinterpret_cast<__nv_bfloat16*>(ws + blay.dcs_off) + (size_t)bh * NC * DH * DH;
-  float* dns = reinterpret_cast<float*>(ws + blay.dns_off) + (size_t)bh * NC * DH;
+  __nv_bfloat16* dCs = reinterpret_cast<__nv_bfloat16*>(ws + blay.dcs_off) + (size_t)bh * NC * DHF * DHF;
+  float* dns = reinterpret_cast<float*>(ws + blay.dns_off) + (size_t)bh * NC * DHF;
 
   if (issuer) {
     tma_prefetch_desc(&maps.t0); tma_prefetch_desc(&maps.t1);
@@ -530,12 +537,13 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
   // tU[b] = tm + b*DH (update of a step), tC = running state, tUn[b] / tN: their n columns (16 wide)
   const uint32_t tm = sm.tmem_base, tC = tm + 2 * DH, tUn0 = tm + 3 * DH, tN = tm + 3 * DH + 32;
   const uint32_t lane_sel = (uint32_t)(rg * 32) << 16;
-  const StateLayout slay(p.B, p.NH, S, DH);
-  const float* ns_f = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.states) + slay.ns_off) + (size_t)bh * NC * DH;
-  float* flow = reinterpret_cast<float*>(ws + blay.flow_off) + (size_t)bh * NC;
+  const StateLayout slay(p.B, p.NH, S, DHF);
+  const float* ns_f = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.states) + slay.ns_off) + (size_t)bh * NC * DHF;
+  float* flow = reinterpret_cast<float*>(ws + blay.flow_off) + (size_t)bh * NC * nblk;
   auto load_cs = [&](int sc) {   // forward entry state of chunk sc (t2 map = the Cs buffer)
     mbar_arrive_expect_tx(&sm.bar_cs, KT * DH * 128);
-    for (int kt = 0; kt < KT; ++kt) tma_load_2d(sm.cst + kt * (DH * 128), &maps.t2, &sm.bar_cs, kt * 64, (bh * NC + sc) * DH);
+    for (int kt = 0; kt < KT; ++kt)
+      tma_load_2d(sm.cst + kt * (DH * 128), &maps.t2, &sm.bar_cs, col0 + kt * 64, (bh * NC + sc) * DHF + row0);
   };
 
   // processing step pc = 0..NC-1 handles scan chunk sc = NC-1-pc
@@ -543,9 +551,9 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
   auto load_qd = [&](int pc) {
     const int buf = pc & 1, tok0 = mem_chunk(sc_of(pc), NC, rev) * L;
     mbar_arrive_expect_tx(&sm.bar_q[buf], KT * TILE);
-    for (int kt = 0; kt < KT; ++kt) tma_load_4d(sm.q[buf] + kt * TILE, &maps.t0, &sm.bar_q[buf], kt * 64, tok0, h, b);
+    for (int kt = 0; kt < KT; ++kt) tma_load_4d(sm.q[buf] + kt * TILE, &maps.t0, &sm.bar_q[buf], row0 + kt * 64, tok0, h, b);
     mbar_arrive_expect_tx(&sm.bar_dh[buf], KT * TILE);
-    for (int kt = 0; kt < KT; ++kt) tma_load_4d(sm.dh[buf] + kt * TILE, &maps.t1, &sm.bar_dh[buf], kt * 64, tok0, h, b);
+    for (int kt = 0; kt < KT; ++kt) tma_load_4d(sm.dh[buf] + kt * TILE, &maps.t1, &sm.bar_dh[buf], col0 + kt * 64, tok0, h, b);
   };
   auto gates_of = [&](int pc) {   // gate warp: G.w <- (w s / N)_t, row scale of the Q tile
     GateBuf& G = sm.g[pc % 3];
@@ -587,8 +595,8 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
     uint32_t z[16];
 #pragma unroll
     for (int x = 0; x < 16; ++x) z[x] = 0u;
-    store_row32(dCs + ((size_t)(NC - 1) * DH + row) * DH + cq * 32, z);
-    if (cq == 0) dns[(size_t)(NC - 1) * DH + row] = 0.f;
+    store_row32(dCs + ((size_t)(NC - 1) * DHF + row0 + row) * DHF + col0 + cq * 32, z);
+    if (cq == 0 && col0 == 0) dns[(size_t)(NC - 1) * DHF + row0 + row] = 0.f;
   }
   __syncthreads();
   if (!gatew) mbar_wait(&sm.bar_q[0], 0);
@@ -669,7 +677,7 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
         for (int x = 0; x < 32; ++x) r[x] *= dnext;
         tmem_st32(tC + lane_sel + cq * 32, r);
       }
-      if (cq == 0) {
+      if (cq == 0 && col0 == 0) {
         float rn[16], an[16];
         tmem_ld16(tUn0 + buf * 16 + lane_sel, rn);
         if (pc > 0) {
@@ -679,8 +687,8 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
         } else {
           tmem_ld_wait();
         }
-        dns[(size_t)(sc - 1) * DH + row] = rn[0];
-        fl = fmaf(rn[0], ns_f[(size_t)sc * DH + row], fl);
+        dns[(size_t)(sc - 1) * DHF + row0 + row] = rn[0];
+        fl = fmaf(rn[0], ns_f[(size_t)sc * DHF + row0 + row], fl);
         if (more) {
 #pragma unroll
           for (int x = 0; x < 32; ++x) r[x] = rn[0] * dnext;
@@ -700,12 +708,12 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
       float f_ = 0.f;
 #pragma unroll
       for (int w = 0; w < 16; ++w) f_ += sm.fpart[w];
-      flow[sc] = f_;
+      flow[sc * nblk + blockIdx.y] = f_;
     }
     if (issuer && sc - 1 > 0) load_cs(sc - 1);   // (the boundary before chunk 0 is the initial state: not needed)
     if (issuer) {   // dC_{sc-1} tile -> workspace; its shared-memory copy is rewritten one step later
       for (int kt = 0; kt < KT; ++kt)
-        tma_store_2d(&maps.st, sm.stage + kt * (DH * 128), kt * 64, (bh * NC + (sc - 1)) * DH);
+        tma_store_2d(&maps.st, sm.stage + kt * (DH * 128), col0 + kt * 64, (bh * NC + (sc - 1)) * DHF + row0);
       tma_store_commit();
     }
   }
@@ -735,7 +743,7 @@ __global__ void __launch_bounds__(L) tc_dfscan_kernel(const mlstm_params p, cons
   const uint8_t* ws = reinterpret_cast<const uint8_t*>(p.workspace);
   const float* rp = reinterpret_cast<const float*>(ws + blay.rpart_off);
   const float* kp = reinterpret_cast<const float*>(ws + blay.kpart_off);
-  const float* flow = reinterpret_cast<const float*>(ws + blay.flow_off) + (size_t)bh * NC;
+  const float* flow = reinterpret_cast<const float*>(ws + blay.flow_off) + (size_t)bh * NC * blay.nblk;
   const int nb = DH / 32;
   const int tok0 = mem_chunk(sc, NC, rev) * L, nvalid = min(L, S - tok0);
   const bool valid = t < nvalid;
@@ -756,7 +764,10 @@ __global__ void __launch_bounds__(L) tc_dfscan_kernel(const mlstm_params p, cons
 #pragma unroll
   for (int w = 0; w < L / 32; ++w) { before += (w < warp) ? wsum[w] : 0.f; all += wsum[w]; }
   // inclusive suffix sum inside the chunk + the exact flow across the boundary to the next chunk
-  const float suffix = all - (incl + before) + dB + ((sc + 1 < NC) ? flow[sc + 1] : 0.f);
+  float fnext = 0.f;
+  if (sc + 1 < NC)
+    for (int k = 0; k < blay.nblk; ++k) fnext += flow[(sc + 1) * blay.nblk + k];
+  const float suffix = all - (incl + before) + dB + fnext;
   if (valid) {
     const float fi = p.f.ptr[(int64_t)b * p.f.stride_b + (int64_t)h * p.f.stride_h + (int64_t)tok * p.f.stride_s];
     p.df.ptr[(int64_t)b * p.df.stride_b + (int64_t)h * p.df.stride_h + (int64_t)tok * p.df.stride_s] = suffix / (1.f + __expf(fi));
@@ -856,6 +867,29 @@ int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
 
 }  // namespace
 
+// Pieces shared with the head-dim-256 family (mlstm_tc_256.cu): the adjoint-state walk over (DHF/128)^2 independent
+// 128 x 128 blocks per (batch, head) (`mcs`, `mdcs`: state maps with a box of 128 rows), the di / df scan, the scratch layout.
+int tc_state_bwd_blocks(const mlstm_params& p, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mdh,
+                        const CUtensorMap& mcs, const CUtensorMap& mdcs) {
+  BwdMaps ms{mq, mdh, mcs, mdcs, mq, mq, mq};
+  int rc;
+  const size_t smSB = sizeof(SmemSB<128>);
+  if ((rc = prep(tc_state_bwd_kernel<128>, smSB, "tc_state_bwd"))) return rc;
+  const int ncb = p.DHQK / 128;
+  tc_state_bwd_kernel<128><<<dim3(p.B * p.NH, ncb * ncb), dim3(NT), smSB, st>>>(ms, p, resolve_scale(p));
+  return launched("tc_state_bwd");
+}
+int tc_dfscan_launch(const mlstm_params& p, cudaStream_t st) {
+  tc_dfscan_kernel<<<dim3(p.B * p.NH * num_chunks(p.S)), dim3(L), 0, st>>>(p, p.DHQK);
+  return launched("tc_dfscan");
+}
+void tc_bwd_layout(const mlstm_params& p, size_t* dn_off, size_t* rpart_off, size_t* kpart_off, size_t* dcs_off, size_t* dns_off,
+                   size_t* total) {
+  const BwdLayout b(p.B, p.NH, p.S, p.DHQK);
+  *dn_off = b.dn_off; *rpart_off = b.rpart_off; *kpart_off = b.kpart_off; *dcs_off = b.dcs_off; *dns_off = b.dns_off;
+  *total = b.total;
+}
+
 // Short sequences with enough (batch, head) pairs to fill the GPU keep the single-pass kernels
 // (mlstm_tc_bwd1p.cu): with <= 4 chunks per head the serial chain is short and the chunk-state
 // round trip through HBM does not pay.
@@ -873,7 +907,10 @@ size_t tc_bwd_workspace(const mlstm_params& p) {
   return tc_use_single_pass_bwd(p) ? tc_bwd1p_workspace(p) : BwdLayout(p.B, p.NH, p.S, p.DHQK).total;
 }
 
+int tc256_bwd(const mlstm_params& p, cudaStream_t st, int part);
+
 int tc_bwd(const mlstm_params& p, cudaStream_t st, int part) {
+  if (p.DHQK == 256) return tc256_bwd(p, st, part);
   if (tc_use_fused_bwd(p)) return p.DHQK == 64 ? tc_bwd_fused(p, st, part) : tc_bwd_fused128(p, st, part);
   if (tc_use_single_pass_bwd(p)) return tc_bwd1p(p, st, part);
   if (p.DHQK == 64) return launch_bwd<64>(p, st, part);

@@ -11,7 +11,9 @@
 namespace mlstm {
 
 bool tc_supported(const mlstm_params& p) {
-  return p.dtype == MLSTM_BF16 && p.DHQK == p.DHV && (p.DHQK == 64 || p.DHQK == 128);
+  static const bool no256 = getenv("MLSTM_NO_TC256") != nullptr;   // developer switch: head dim 256 on the SIMT family (A/B timing)
+  if (p.DHQK == 256 && no256) return false;
+  return p.dtype == MLSTM_BF16 && p.DHQK == p.DHV && (p.DHQK == 64 || p.DHQK == 128 || p.DHQK == 256);
 }
 
 // of the device that owns the tensors, not of whichever device is current when a size query is made
@@ -27,6 +29,7 @@ static int forced(int which) {
 }
 
 bool tc_use_two_phase(const mlstm_params& p) {          // forward
+  if (p.DHQK == 256) return true;                       // mlstm_tc_256.cu: chunk-parallel only
   if (forced(0)) return forced(0) == 2;
   return p.B * p.NH * 2 <= sm_count(p) && tc::num_chunks(p.S) >= 4;
 }
@@ -37,11 +40,12 @@ static bool short_and_wide(const mlstm_params& p) { return tc::num_chunks(p.S) <
 // kernels on long sequences (B32 NH4 DH64: 244 vs 135 M tok/s at S=800, 309 vs 180 at S=1600).  MLSTM_FORCE_VARIANT backward
 // digit 3 pins it (DH = 64 only).
 bool tc_use_fused_bwd(const mlstm_params& p) {
+  if (p.DHQK == 256) return false;
   if (forced(1)) return forced(1) == 3;
   return p.B * p.NH * 2 > sm_count(p);
 }
 bool tc_use_single_pass_bwd(const mlstm_params& p) {    // backward, two-walk single-pass kernels
-  if (tc_use_fused_bwd(p)) return false;
+  if (tc_use_fused_bwd(p) || p.DHQK == 256) return false;
   if (forced(1)) return forced(1) == 1;
   return short_and_wide(p);
 }

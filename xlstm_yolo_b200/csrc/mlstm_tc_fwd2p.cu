@@ -45,11 +45,15 @@ struct SmemS {
 // gridDim.y value slices: the state C [dk][dv] splits by dv columns into independent recurrences (same K, same
 // gates), so a small batch can still put a CTA on most SMs: a sequential kernel is bound by what ONE SM can pull
 // from HBM per step (K + V + Cs tiles), and a slice pulls less.  Slice 0 also carries n and m.
+// Head dims above the template's DH (DHF = p.DHQK = 256 with DH = 128): the state also splits by dk rows into
+// DHF / DH independent row blocks (same V, same gates): blockIdx.y = row_block * nsl + slice, the CTA owns
+// C[row0 .. row0 + DH)[col0 .. col0 + DVs) and reads the K columns [row0, row0 + DH) only.
 template <int DH>
 __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_constant__ FwdMaps maps, const mlstm_params p) {
   constexpr int KT = DH / 64;
-  const int nsl = gridDim.y, sl = blockIdx.y;
-  const int DVs = DH / nsl, col0 = sl * DVs;   // this CTA's value columns [col0, col0 + DVs)
+  const int DHF = p.DHQK, nrb = DHF / DH;
+  const int nsl = gridDim.y / nrb, sl = blockIdx.y % nsl, row0 = (blockIdx.y / nsl) * DH;
+  const int DVs = DHF / nsl, col0 = sl * DVs;   // this CTA's value columns [col0, col0 + DVs)
   const int NB = DVs / 32, KTV = DVs / 64;     // active 32-column blocks / 64-column tiles of V and of the state
   constexpr uint32_t A_LBO = (DH == 128) ? TILE : 0;   // DH=64: the 2nd 64-row M block aliases the 1st
   constexpr uint32_t TCOLS = 256;
@@ -63,9 +67,9 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
   const int bh = blockIdx.x, b = bh / p.NH, h = bh % p.NH;
   const int S = p.S, NC = num_chunks(S);
   const bool rev = p.reverse != 0, has_init = p.c_initial != nullptr;
-  const StateLayout lay(p.B, p.NH, S, DH);
-  __nv_bfloat16* Cs = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(p.states) + lay.cs_off) + (size_t)bh * NC * DH * DH;
-  float* ns = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.states) + lay.ns_off) + (size_t)bh * NC * DH;
+  const StateLayout lay(p.B, p.NH, S, DHF);
+  __nv_bfloat16* Cs = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(p.states) + lay.cs_off) + (size_t)bh * NC * DHF * DHF;
+  float* ns = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.states) + lay.ns_off) + (size_t)bh * NC * DHF;
   float* ms = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.states) + lay.ms_off) + (size_t)bh * NC;
 
   if (issuer) {
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
   auto load_kv = [&](int sc) {
     const int buf = sc & 1, tok0 = mem_chunk(sc, NC, rev) * L;
     mbar_arrive_expect_tx(&sm.bar_k[buf], KT * TILE);
-    for (int kt = 0; kt < KT; ++kt) tma_load_4d(sm.k[buf] + kt * TILE, &maps.k, &sm.bar_k[buf], kt * 64, tok0, h, b);
+    for (int kt = 0; kt < KT; ++kt) tma_load_4d(sm.k[buf] + kt * TILE, &maps.k, &sm.bar_k[buf], row0 + kt * 64, tok0, h, b);
     mbar_arrive_expect_tx(&sm.bar_v[buf], KTV * TILE);
     for (int kt = 0; kt < KTV; ++kt) tma_load_4d(sm.v[buf] + kt * TILE, &maps.v, &sm.bar_v[buf], col0 + kt * 64, tok0, h, b);
   };
@@ -103,13 +107,13 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
   // entry state of chunk 0 -> workspace; TMEM C <- decay_0 * C_0 when an initial state is given
   if (row < DH && cq < NB) {
     float r[32];
-    const float* crow = has_init ? p.c_initial + ((int64_t)bh * DH + row) * DH + col0 + cq * 32 : nullptr;
+    const float* crow = has_init ? p.c_initial + ((int64_t)bh * DHF + row0 + row) * DHF + col0 + cq * 32 : nullptr;
 #pragma unroll
     for (int x = 0; x < 32; ++x) r[x] = has_init ? crow[x] : 0.f;
     uint32_t pk[16];
 #pragma unroll
     for (int x = 0; x < 32; x += 2) pk[x / 2] = pack_bf16x2(r[x], r[x + 1]);
-    store_row32(Cs + (size_t)row * DH + col0 + cq * 32, pk);
+    store_row32(Cs + (size_t)(row0 + row) * DHF + col0 + cq * 32, pk);
     if (has_init) {
       const float d0 = sm.g[0].decay;
 #pragma unroll
@@ -117,8 +121,8 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
       tmem_st32(tC + lane_sel + cq * 32, r);
     }
     if (cq == 0 && sl == 0) {
-      const float n0 = has_init ? p.n_initial[(int64_t)bh * DH + row] : 0.f;
-      ns[row] = n0;
+      const float n0 = has_init ? p.n_initial[(int64_t)bh * DHF + row0 + row] : 0.f;
+      ns[row0 + row] = n0;
       if (has_init) {
 #pragma unroll
         for (int x = 0; x < 32; ++x) r[x] = n0 * sm.g[0].decay;
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
     }
     if (has_init) tmem_st_wait();
   }
-  if (issuer && sl == 0) ms[0] = sm.g[0].m_prev;
+  if (issuer && sl == 0 && row0 == 0) ms[0] = sm.g[0].m_prev;
   // Kbar(0) = kw * K(0), in place
   if (!gatew) mbar_wait(&sm.bar_k[0], 0);
   if (compute) scale_rows<DH>(sm.k[0], sm.g[0].kw, tid);
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
         for (int x = 0; x < 32; ++x) r[x] *= dnext;
         tmem_st32(tC + lane_sel + cq * 32, r);
       } else if (p.c_last) {
-        float* dst = p.c_last + ((int64_t)bh * DH + row) * DH + col0 + cq * 32;
+        float* dst = p.c_last + ((int64_t)bh * DHF + row0 + row) * DHF + col0 + cq * 32;
 #pragma unroll
         for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4*>(dst + x) = make_float4(r[x], r[x + 1], r[x + 2], r[x + 3]);
       }
@@ -197,17 +201,17 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
         tmem_ld16(tN + lane_sel, rn);
         tmem_ld_wait();
         if (!last) {
-          ns[(size_t)(sc + 1) * DH + row] = rn[0];
+          ns[(size_t)(sc + 1) * DHF + row0 + row] = rn[0];
 #pragma unroll
           for (int x = 0; x < 32; ++x) r[x] = rn[0] * dnext;
           tmem_st32(tN + lane_sel, r);
         } else if (p.n_last) {
-          p.n_last[(int64_t)bh * DH + row] = rn[0];
+          p.n_last[(int64_t)bh * DHF + row0 + row] = rn[0];
         }
       }
       if (!last) tmem_st_wait();
     }
-    if (issuer && sl == 0) {
+    if (issuer && sl == 0 && row0 == 0) {
       if (!last) ms[sc + 1] = sm.g[sc % 3].m_next;
       else if (p.m_last) p.m_last[bh] = sm.g[sc % 3].m_next;
     }
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
     __syncthreads();
     if (issuer && !last) {
       for (int kt = 0; kt < KTV; ++kt)
-        tma_store_2d(&maps.cs, sm.stage[buf] + kt * (DH * 128), col0 + kt * 64, (bh * NC + sc + 1) * DH);
+        tma_store_2d(&maps.cs, sm.stage[buf] + kt * (DH * 128), col0 + kt * 64, (bh * NC + sc + 1) * DHF + row0);
       tma_store_commit();
       tma_store_wait_read<1>();   // the other staging buffer (written again in the next step) has been read
     }
@@ -515,7 +519,23 @@ int launch_fwd(const mlstm_params& p, cudaStream_t st) {
 
 }  // namespace
 
+// State walk for head dims above 128 (mlstm_tc_256.cu): DHF / 128 row blocks x nsl value slices per (batch, head), each an
+// independent recurrence on a [128][DHF / nsl] block of C.  `cs_store` has a box of 128 rows.
+int tc_state_fwd_blocks(const mlstm_params& p, cudaStream_t st, const CUtensorMap& mk, const CUtensorMap& mv,
+                        const CUtensorMap& cs_store, int nsl) {
+  FwdMaps maps;
+  maps.q = mk; maps.k = mk; maps.v = mv; maps.cs = cs_store;
+  int rc;
+  const size_t smS = sizeof(SmemS<128>);
+  if ((rc = prep(tc_state_fwd_kernel<128>, smS, "tc_state_fwd"))) return rc;
+  tc_state_fwd_kernel<128><<<dim3(p.B * p.NH, (p.DHQK / 128) * nsl), dim3(NT), smS, st>>>(maps, p);
+  return launched("tc_state_fwd");
+}
+
+int tc256_fwd(const mlstm_params& p, cudaStream_t st);
+
 int tc_fwd_two_phase(const mlstm_params& p, cudaStream_t st) {
+  if (p.DHQK == 256) return tc256_fwd(p, st);
   if (p.DHQK == 64) return launch_fwd<64>(p, st);
   return launch_fwd<128>(p, st);
 }

@@ -249,16 +249,18 @@ __device__ __forceinline__ void load_row32(const __nv_bfloat16* src, float (&out
 }
 
 // 2-D tensor map over a [rows][DH] bf16 matrix stack (the Cs / dCs workspace): dims (DH, rows_total)
-inline int make_state_tmap(CUtensorMap* out, const void* ptr, size_t rows_total, int DH) {
+// (box = 64 columns x box_rows rows; box_rows = 0 means DH: one whole [DH][64] state tile per load)
+inline int make_state_tmap(CUtensorMap* out, const void* ptr, size_t rows_total, int DH, int box_rows = 0) {
+  if (box_rows == 0) box_rows = DH;
   TmapKey key;
   memset(&key, 0, sizeof(key));
-  key.ptr = ptr; key.s0 = (int64_t)rows_total; key.d0 = DH; key.kind = 2;
+  key.ptr = ptr; key.s0 = (int64_t)rows_total; key.d0 = DH; key.box_rows = box_rows; key.kind = 2;
   if (tmap_cache_lookup(key, out, false)) return 0;
   PFN_tmapEncodeTiled enc = get_tmap_encoder();
   if (!enc) return -1;
   cuuint64_t dims[2] = {(cuuint64_t)DH, (cuuint64_t)rows_total};
   cuuint64_t strides[1] = {(cuuint64_t)DH * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)DH};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   const int r = (int)enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
