@@ -46,7 +46,7 @@ constexpr int STAGE = 3 * TILE;   // T0 slice | T1 slice | state slice, 16 KB ea
 
 enum { MODE_F = 0, MODE_A = 1, MODE_B1 = 2, MODE_B2 = 3 };
 
-struct Maps256 { CUtensorMap t0, t1, t2, st, out; };
+struct Maps256 { CUtensorMap t0, t1, t2, st, out, t3; };   // t3: q (A) / k (B2), the rows of R = q.dq / K = k.dk
 
 struct Scratch256 {   // device pointers into p.workspace / p.states
   float* dn; float* rpart; float* kpart;
@@ -54,14 +54,17 @@ struct Scratch256 {   // device pointers into p.workspace / p.states
   size_t rows_total;
 };
 
+template <int MODE>
 struct Smem256 {
+  // F: nvec, K-major [16][256] tiles (row 0 = hi(n), row 1 = lo(n)), ring of 3 | A, B2: t3, the q / k half tile [128][128]
+  static constexpr int AUX = (MODE == MODE_F) ? 3 * NSL * 2048 : ((MODE == MODE_B1) ? 1024 : 2 * TILE);
   alignas(1024) uint8_t ring[NST][STAGE];
   alignas(1024) uint8_t t2[2 * TILE];              // resident MMA2 operand half [128][128]; then the output staging tile
-  alignas(1024) uint8_t nvec[3][NSL * 2048];       // F: K-major [16][256]: row 0 = hi(n), row 1 = lo(n); ring of 3
+  alignas(1024) uint8_t aux[AUX];
   GateBuf g[3];                                    // the gate warp runs two items ahead
   alignas(16) float vecf[3][HW];                   // ns half (A) / dns half (B2) of the item
   float part[4][L];
-  uint64_t full[NST], empty[NST], bar_t2, bar_m1, bar_m2;
+  uint64_t full[NST], empty[NST], bar_t2, bar_t3, bar_m1, bar_m2;
   uint32_t tmem_base;
 };
 
@@ -71,12 +74,18 @@ __global__ void __launch_bounds__(NT, 1) tc256_par_kernel(const __grid_constant_
   constexpr bool IS_F = (MODE == MODE_F), IS_A = (MODE == MODE_A), IS_B1 = (MODE == MODE_B1), IS_B2 = (MODE == MODE_B2);
   constexpr bool ROWQ = IS_F || IS_A;             // thread row = query t (else key j)
   constexpr bool ST_MN = IS_F || IS_B1;           // state slice: [64 streamed rows][128 half columns], MN-major B operand
+  // K-major state slices sit right behind the T1 slice and continue its row pattern: S and the state product are ONE
+  // N = 256 MMA per k-step (A, B2).  With an MN-major state slice (F, B1) the two products are separate instructions,
+  // issued from two lanes (a single lane issues ~100 cycles per MMA, the tensor pipe needs 64).
+  constexpr bool MERGED = !ST_MN;
+  constexpr bool HAS_T3 = IS_A || IS_B2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  Smem256& sm = *reinterpret_cast<Smem256*>(smem_raw);
+  Smem256<MODE>& sm = *reinterpret_cast<Smem256<MODE>*>(smem_raw);
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool compute = tid < CT, issuer = tid == CT, gatew = tid >= GT0;
+  const bool issuer2 = !MERGED && tid == 32;      // second MMA lane (lane 0 of compute warp 1): the state product
   const int rg = warp & 3, cq = compute ? (warp >> 2) : 4, row = rg * 32 + lane;
   const int S = p.S, NC = num_chunks(S);
   const bool rev = p.reverse != 0;
@@ -86,13 +95,13 @@ __global__ void __launch_bounds__(NT, 1) tc256_par_kernel(const __grid_constant_
   if (issuer) {
     tma_prefetch_desc(&maps.t0); tma_prefetch_desc(&maps.t1); tma_prefetch_desc(&maps.t2); tma_prefetch_desc(&maps.st);
     tma_prefetch_desc(&maps.out);
-    for (int i = 0; i < NST; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-    mbar_init(&sm.bar_t2, 1); mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_m2, 1);
+    for (int i = 0; i < NST; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], MERGED ? 1 : 2); }
+    mbar_init(&sm.bar_t2, 1); mbar_init(&sm.bar_t3, 1); mbar_init(&sm.bar_m1, MERGED ? 1 : 2); mbar_init(&sm.bar_m2, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
   if (IS_F)
-    for (int e = tid; e < 3 * NSL * 2048 / 16; e += NT) reinterpret_cast<uint4*>(sm.nvec)[e] = make_uint4(0, 0, 0, 0);
+    for (int e = tid; e < 3 * NSL * 2048 / 16; e += NT) reinterpret_cast<uint4*>(sm.aux)[e] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -125,6 +134,17 @@ __global__ void __launch_bounds__(NT, 1) tc256_par_kernel(const __grid_constant_
     } else {       // rows: the half's 128 dk rows; columns: streamed slice of dv
       tma_load_2d(dst + 2 * TILE, &maps.st, &sm.full[slot], s * 64, ci * DHF + hf * HW);
     }
+    if (s == NSL - 2) {   // the item's last slice can only land once its first one has been consumed (3-slot ring, 4 slices):
+      const int s1 = NSL - 1;   // pull it into L2 now, so that the late load is an L2 hit
+      tma_prefetch_4d(&maps.t0, s1 * 64, tok0, h, b);
+      tma_prefetch_4d(&maps.t1, s1 * 64, tok0, h, b);
+      if (ST_MN) {
+        tma_prefetch_2d(&maps.st, hf * HW, ci * DHF + s1 * 64);
+        tma_prefetch_2d(&maps.st, hf * HW + 64, ci * DHF + s1 * 64);
+      } else {
+        tma_prefetch_2d(&maps.st, s1 * 64, ci * DHF + hf * HW);
+      }
+    }
   };
   int next_load = 0;
   auto pump_loads = [&](int upto) {   // issue every load up to slice index `upto` (inclusive) that has not gone out yet
@@ -135,30 +155,39 @@ __global__ void __launch_bounds__(NT, 1) tc256_par_kernel(const __grid_constant_
     mbar_arrive_expect_tx(&sm.bar_t2, 2 * TILE);
     for (int kt = 0; kt < 2; ++kt) tma_load_4d(sm.t2 + kt * TILE, &maps.t2, &sm.bar_t2, hf * HW + kt * 64, tok0, h, b);
   };
-  // MMA1 of the CTA's n-th item, slice by slice as the ring fills
-  auto stream_mma1 = [&](int n) {
-    constexpr uint32_t idS = make_idesc_bf16(128, 128, 0, 0);
-    constexpr uint32_t idX = make_idesc_bf16(128, HW, 0, ST_MN ? 1 : 0);
+  auto load_t3 = [&](int it2) {
+    int ci, hf, b, h, tok0; coords(it2, ci, hf, b, h, tok0);
+    mbar_arrive_expect_tx(&sm.bar_t3, 2 * TILE);
+    for (int kt = 0; kt < 2; ++kt) tma_load_4d(sm.aux + kt * TILE, &maps.t3, &sm.bar_t3, hf * HW + kt * 64, tok0, h, b);
+  };
+  // MMA1 of the CTA's n-th item, slice by slice as the ring fills.  lane2 = false: the control lane (S, or S | state
+  // product merged; it also keeps the ring loads going); lane2 = true: the second lane (state product, F: q.n).
+  auto stream_mma1 = [&](int n, bool lane2) {
+    constexpr uint32_t idS = make_idesc_bf16(128, MERGED ? 256 : 128, 0, 0);
+    constexpr uint32_t idX = make_idesc_bf16(128, HW, 0, 1);
     constexpr uint32_t idN = make_idesc_bf16(128, 16, 0, 0);
     for (int s = 0; s < NSL; ++s) {
       const int g = n * NSL + s, slot = g % NST;
       mbar_wait(&sm.full[slot], (g / NST) & 1);
       tc_fence_after();
       const uint32_t base = smem_u32(sm.ring[slot]);
-      const uint64_t d0 = make_sdesc(base, 16, 1024), d1 = make_sdesc(base + TILE, 16, 1024);
-      const uint64_t dst_ = ST_MN ? make_sdesc(base + 2 * TILE, 8192, 1024) : make_sdesc(base + 2 * TILE, 16, 1024);
+      const uint64_t d0 = make_sdesc(base, 16, 1024);
+      if (!lane2) {
+        const uint64_t d1 = make_sdesc(base + TILE, 16, 1024);   // MERGED: 256 rows = T1 slice, then the K-major state slice
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(tS, d0 + kstep(ks), d1 + kstep(ks), idS, (s > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(tS, d0 + kstep(ks), d1 + kstep(ks), idS, (s > 0 || ks > 0) ? 1u : 0u);
+      } else {
+        const uint64_t dst_ = make_sdesc(base + 2 * TILE, 8192, 1024);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_bf16_ss(tX, d0 + kstep(ks), dst_ + (ST_MN ? mnstep(ks) : kstep(ks)), idX, (s > 0 || ks > 0) ? 1u : 0u);
-      if (IS_F) {
-        const uint64_t dNv = make_sdesc(smem_u32(sm.nvec[n % 3]) + s * 2048, 16, 1024);
+        for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(tX, d0 + kstep(ks), dst_ + mnstep(ks), idX, (s > 0 || ks > 0) ? 1u : 0u);
+        if (IS_F) {
+          const uint64_t dNv = make_sdesc(smem_u32(sm.aux) + (n % 3) * (NSL * 2048) + s * 2048, 16, 1024);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(tQN, d0 + kstep(ks), dNv + kstep(ks), idN, (s > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(tQN, d0 + kstep(ks), dNv + kstep(ks), idN, (s > 0 || ks > 0) ? 1u : 0u);
+        }
       }
       umma_commit(&sm.empty[slot]);
-      pump_loads(g + 2);
+      if (!lane2) pump_loads(g + 2);
     }
     umma_commit(&sm.bar_m1);
   };
@@ -172,7 +201,7 @@ __global__ void __launch_bounds__(NT, 1) tc256_par_kernel(const __grid_constant_
         const float nv = sx.ns[(size_t)ci * DHF + d];
         const __nv_bfloat16 hi = __float2bfloat16_rn(nv);
         const __nv_bfloat16 lo = __float2bfloat16_rn(nv - __bfloat162float(hi));
-        uint8_t* base = sm.nvec[slot] + (d >> 6) * 2048;
+        uint8_t* base = sm.aux + slot * (NSL * 2048) + (d >> 6) * 2048;
         *reinterpret_cast<__nv_bfloat16*>(base + swz128(0, d & 63)) = hi;
         *reinterpret_cast<__nv_bfloat16*>(base + swz128(1, d & 63)) = lo;
       }
@@ -185,13 +214,14 @@ __global__ void __launch_bounds__(NT, 1) tc256_par_kernel(const __grid_constant_
     __syncwarp();
   };
 
-  if (issuer) { pump_loads(NST - 1); load_t2(cta); }
+  if (issuer) { pump_loads(NST - 1); load_t2(cta); if (HAS_T3) load_t3(cta); }
   if (gatew) {
     prep_item(cta, 0);
     if (cta + ncta < n_items) prep_item(cta + ncta, 1);
   }
   __syncthreads();
-  if (issuer) stream_mma1(0);
+  if (issuer) stream_mma1(0, false);
+  if (issuer2) stream_mma1(0, true);
 
   int n = 0;
   for (int it2 = cta; it2 < n_items; it2 += ncta, ++n) {
@@ -213,30 +243,43 @@ __global__ void __launch_bounds__(NT, 1) tc256_par_kernel(const __grid_constant_
     // ---- A: dn_t = dnf_t (dh_t . h_t) over all 256 columns, rows read straight from global (L2) ----------------
     float dn_row = 0.f;
     if (IS_A) {
-      float part = 0.f;
-      if (row_ok) {
-        const __nv_bfloat16* hrow = reinterpret_cast<const __nv_bfloat16*>(p.h.ptr) + (int64_t)b * p.h.stride_b + (int64_t)h * p.h.stride_h +
-                                    (int64_t)tok * p.h.stride_s + cq * 64;
-        const __nv_bfloat16* drow = reinterpret_cast<const __nv_bfloat16*>(p.dh.ptr) + (int64_t)b * p.dh.stride_b + (int64_t)h * p.dh.stride_h +
-                                    (int64_t)tok * p.dh.stride_s + cq * 64;
+      // a warp per 512-byte row (16 bytes per lane: fully coalesced), 8 rows per warp, 4 at a time
+      if (compute) {
+        const __nv_bfloat16* hbase = reinterpret_cast<const __nv_bfloat16*>(p.h.ptr) + (int64_t)b * p.h.stride_b + (int64_t)h * p.h.stride_h + lane * 8;
+        const __nv_bfloat16* dbase = reinterpret_cast<const __nv_bfloat16*>(p.dh.ptr) + (int64_t)b * p.dh.stride_b + (int64_t)h * p.dh.stride_h + lane * 8;
 #pragma unroll
-        for (int x8 = 0; x8 < 64; x8 += 8) {
-          const uint4 wh = *reinterpret_cast<const uint4*>(hrow + x8);
-          const uint4 wd = *reinterpret_cast<const uint4*>(drow + x8);
-          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&wh);
-          const __nv_bfloat162* dd = reinterpret_cast<const __nv_bfloat162*>(&wd);
+        for (int r0 = 0; r0 < 8; r0 += 4) {
+          uint4 wh[4], wd[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 a = __bfloat1622float2(hh[e]), c2 = __bfloat1622float2(dd[e]);
-            part = fmaf(a.x, c2.x, fmaf(a.y, c2.y, part));
+          for (int r = 0; r < 4; ++r) {
+            const int t = tok0 + warp * 8 + r0 + r;
+            wh[r] = wd[r] = make_uint4(0, 0, 0, 0);
+            if (t < S) {
+              wh[r] = *reinterpret_cast<const uint4*>(hbase + (int64_t)t * p.h.stride_s);
+              wd[r] = *reinterpret_cast<const uint4*>(dbase + (int64_t)t * p.dh.stride_s);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&wh[r]);
+            const __nv_bfloat162* dd = reinterpret_cast<const __nv_bfloat162*>(&wd[r]);
+            float part = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 a = __bfloat1622float2(hh[e]), c2 = __bfloat1622float2(dd[e]);
+              part = fmaf(a.x, c2.x, fmaf(a.y, c2.y, part));
+            }
+            part = warp_sum(part);
+            const int rr = warp * 8 + r0 + r;
+            if (lane == 0) {
+              const float dnr = G.dnf[rr] * part;
+              sm.part[0][rr] = dnr;
+              if (hf == 0 && tok0 + rr < S) sx.dn[(size_t)bh * S + tok0 + rr] = dnr;
+            }
           }
         }
-      }
-      if (compute) sm.part[cq][row] = part;
-      if (compute) named_sync(3, CT);
-      if (compute) {
-        dn_row = G.dnf[row] * ((sm.part[0][row] + sm.part[1][row]) + (sm.part[2][row] + sm.part[3][row]));
-        if (cq == 0 && hf == 0 && row_ok) sx.dn[grow] = dn_row;
+        named_sync(3, CT);
+        dn_row = sm.part[0][row];
       }
     }
     mbar_wait(&sm.bar_m1, ph);
@@ -288,6 +331,7 @@ __global__ void __launch_bounds__(NT, 1) tc256_par_kernel(const __grid_constant_
         for (int x = 0; x < 16; ++x) packed[x] = 0u;
       }
       if (IS_F) sm.part[cq][row] = rowsum;
+      (void)rowsum;
       tmem_st16(tP + lane_sel + cq * 16, packed);
       tmem_st_wait();
     }
@@ -322,54 +366,58 @@ __global__ void __launch_bounds__(NT, 1) tc256_par_kernel(const __grid_constant_
     mbar_wait(&sm.bar_m2, ph);
     tc_fence_after();
 
-    // ---- epilogue: outputs packed in registers, staged in the dead T2 half ----------------------------------------
+    // ---- epilogue, 16 columns at a time: outputs staged in the dead T2 half ------------------------------------------
     if (compute) {
-      uint32_t opk[16];
       float psum = 0.f;
-      float acc[32], gg[32];
-      tmem_ld32(((IS_F || IS_A) ? tS : tO) + lane_sel + cq * 32, acc);
-      tmem_ld32(tX + lane_sel + cq * 32, gg);
-      tmem_ld_wait();
-      if (IS_F) {
+      const float wt = G.w[row], invN = G.invN[row], kwj = G.kw[row];
+      if (HAS_T3) mbar_wait(&sm.bar_t3, ph);
 #pragma unroll
-        for (int x = 0; x < 32; x += 2)
-          opk[x / 2] = pack_bf16x2((acc[x] + ws * gg[x]) * inv, (acc[x + 1] + ws * gg[x + 1]) * inv);
-      } else if (IS_B1) {   // dv = E^T dH + kw (K dC)
-        const float kwj = G.kw[row];
+      for (int hc = 0; hc < 2; ++hc) {
+        const int c0 = cq * 32 + hc * 16;   // first column (within the half) of this pass
+        float acc[16], gg[16];
+        tmem_ld16(((IS_F || IS_A) ? tS : tO) + lane_sel + c0, acc);
+        tmem_ld16(tX + lane_sel + c0, gg);
+        tmem_ld_wait();
+        uint32_t opk[8];
+        if (IS_F) {
 #pragma unroll
-        for (int x = 0; x < 32; x += 2) opk[x / 2] = pack_bf16x2(fmaf(kwj, gg[x], acc[x]), fmaf(kwj, gg[x + 1], acc[x + 1]));
-      } else {              // A: dq, R = q . dq   |   B2: dk, K = k . dk   (q / k rows from global: L2 hits)
-        float xr[32];
-        if (row_ok) {
-          const mlstm_act& src = IS_A ? p.q : p.k;
-          load_row32(reinterpret_cast<const __nv_bfloat16*>(src.ptr) + (int64_t)b * src.stride_b + (int64_t)h * src.stride_h +
-                         (int64_t)tok * src.stride_s + hf * HW + cq * 32, xr);
-        } else {
+          for (int x = 0; x < 16; x += 2)
+            opk[x / 2] = pack_bf16x2((acc[x] + ws * gg[x]) * inv, (acc[x + 1] + ws * gg[x + 1]) * inv);
+        } else if (IS_B1) {   // dv = E^T dH + kw (K dC)
 #pragma unroll
-          for (int x = 0; x < 32; ++x) xr[x] = 0.f;
-        }
-        const float wt = G.w[row], invN = G.invN[row], kwj = G.kw[row];
+          for (int x = 0; x < 16; x += 2) opk[x / 2] = pack_bf16x2(fmaf(kwj, gg[x], acc[x]), fmaf(kwj, gg[x + 1], acc[x + 1]));
+        } else {              // A: dq, R = q . dq   |   B2: dk, K = k . dk   (q / k rows from the T3 tile)
 #pragma unroll
-        for (int x = 0; x < 32; x += 2) {
-          float o0, o1;
-          if (IS_A) {
-            o0 = scale * (acc[x] + wt * fmaf(gg[x], invN, dn_row * vecf[cq * 32 + x]));
-            o1 = scale * (acc[x + 1] + wt * fmaf(gg[x + 1], invN, dn_row * vecf[cq * 32 + x + 1]));
-          } else {
-            o0 = fmaf(kwj, gg[x] + vecf[cq * 32 + x], scale * acc[x]);
-            o1 = fmaf(kwj, gg[x + 1] + vecf[cq * 32 + x + 1], scale * acc[x + 1]);
+          for (int x8 = 0; x8 < 16; x8 += 8) {
+            const int col = c0 + x8;
+            const uint4 w = *reinterpret_cast<const uint4*>(sm.aux + (col >> 6) * TILE + swz128(row, col & 63));
+            const __nv_bfloat162* qq = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int x = x8 + 2 * e;
+              const float2 xr = __bfloat1622float2(qq[e]);
+              float o0, o1;
+              if (IS_A) {
+                o0 = scale * (acc[x] + wt * fmaf(gg[x], invN, dn_row * vecf[c0 + x]));
+                o1 = scale * (acc[x + 1] + wt * fmaf(gg[x + 1], invN, dn_row * vecf[c0 + x + 1]));
+              } else {
+                o0 = fmaf(kwj, gg[x] + vecf[c0 + x], scale * acc[x]);
+                o1 = fmaf(kwj, gg[x + 1] + vecf[c0 + x + 1], scale * acc[x + 1]);
+              }
+              psum = fmaf(xr.x, o0, fmaf(xr.y, o1, psum));
+              opk[x / 2] = pack_bf16x2(o0, o1);
+            }
           }
-          psum = fmaf(xr[x], o0, fmaf(xr[x + 1], o1, psum));
-          opk[x / 2] = pack_bf16x2(o0, o1);
         }
-        if (row_ok) (IS_A ? sx.rpart : sx.kpart)[(size_t)(hf * 4 + cq) * sx.rows_total + grow] = psum;
-      }
 #pragma unroll
-      for (int x4 = 0; x4 < 4; ++x4) {
-        const int col = cq * 32 + x4 * 8;
-        *reinterpret_cast<uint4*>(sm.t2 + (col >> 6) * TILE + swz128(row, col & 63)) =
-            make_uint4(opk[4 * x4], opk[4 * x4 + 1], opk[4 * x4 + 2], opk[4 * x4 + 3]);
+        for (int x4 = 0; x4 < 2; ++x4) {
+          const int col = c0 + x4 * 8;
+          *reinterpret_cast<uint4*>(sm.t2 + (col >> 6) * TILE + swz128(row, col & 63)) =
+              make_uint4(opk[4 * x4], opk[4 * x4 + 1], opk[4 * x4 + 2], opk[4 * x4 + 3]);
+        }
       }
+      if (HAS_T3 && row_ok) (IS_A ? sx.rpart : sx.kpart)[(size_t)(hf * 4 + cq) * sx.rows_total + grow] = psum;
+      (void)wt; (void)invN; (void)kwj; (void)psum;
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -378,11 +426,13 @@ __global__ void __launch_bounds__(NT, 1) tc256_par_kernel(const __grid_constant_
       for (int kt = 0; kt < 2; ++kt) tma_store_4d(&maps.out, sm.t2 + kt * TILE, hf * HW + kt * 64, tok0, h, b);
       tma_store_commit();
       if (has_next) {
-        stream_mma1(n + 1);
+        if (HAS_T3) load_t3(it2 + ncta);   // consumed by the epilogue just finished
+        stream_mma1(n + 1, false);
         tma_store_wait_read<0>();     // the staged output has left shared memory: T2 of the next item may land
         load_t2(it2 + ncta);
       }
     }
+    if (issuer2 && has_next) stream_mma1(n + 1, true);
   }
   if (issuer) tma_store_wait_all<0>();
   tc_fence_before();
@@ -412,7 +462,7 @@ int launched(const char* name) {
 template <int MODE>
 int launch_par(const Maps256& m, const mlstm_params& p, const Scratch256& sx, cudaStream_t st, const char* name) {
   int rc;
-  const size_t smem = sizeof(Smem256);
+  const size_t smem = sizeof(Smem256<MODE>);
   if ((rc = prep(tc256_par_kernel<MODE>, smem, name))) return rc;
   const int n_items = p.B * p.NH * num_chunks(p.S) * 2;
   const int sms = sm_count_of(p.q.ptr);
@@ -444,6 +494,7 @@ int tc256_fwd(const mlstm_params& p, cudaStream_t st) {
   r |= make_act_tmap(&m.t1, p.k.ptr, p.B, p.NH, p.S, DHF, p.k.stride_b, p.k.stride_h, p.k.stride_s, L);
   r |= make_act_tmap(&m.t2, p.v.ptr, p.B, p.NH, p.S, DHF, p.v.stride_b, p.v.stride_h, p.v.stride_s, L);
   r |= make_act_tmap(&m.out, p.h.ptr, p.B, p.NH, p.S, DHF, p.h.stride_b, p.h.stride_h, p.h.stride_s, L);
+  m.t3 = m.t0;
   r |= make_state_tmap(&m.st, sb + lay.cs_off, (size_t)n_chunks * DHF, DHF, 64);
   r |= make_state_tmap(&cs128, sb + lay.cs_off, (size_t)n_chunks * DHF, DHF, 128);
   if (r) return tmap_fail(r);
@@ -490,14 +541,14 @@ int tc256_bwd(const mlstm_params& p, cudaStream_t st, int part) {
   sx.rows_total = (size_t)p.B * p.NH * p.S;
   int rc;
   if (part != 1) {
-    Maps256 m{mdh, mv, mk, cs128, mdq};
+    Maps256 m{mdh, mv, mk, cs128, mdq, mq};
     if ((rc = launch_par<MODE_A>(m, p, sx, st, "tc256_bwd_dq"))) return rc;
   }
   if (part != 0) {
     if ((rc = tc_state_bwd_blocks(p, st, mq, mdh, cs128, dcs128))) return rc;
-    Maps256 m1{mk, mq, mdh, dcs64, mdv};
+    Maps256 m1{mk, mq, mdh, dcs64, mdv, mq};
     if ((rc = launch_par<MODE_B1>(m1, p, sx, st, "tc256_bwd_dv"))) return rc;
-    Maps256 m2{mv, mdh, mq, dcs128, mdk};
+    Maps256 m2{mv, mdh, mq, dcs128, mdk, mk};
     if ((rc = launch_par<MODE_B2>(m2, p, sx, st, "tc256_bwd_dk"))) return rc;
     if ((rc = tc_dfscan_launch(p, st))) return rc;
   }
