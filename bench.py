@@ -33,12 +33,15 @@ WORKLOADS = {
     "cfg3_B32_NH4_S1600_DH128": (32, 4, 1600, 128),
     "cfg3_B32_NH4_S6400_DH128": (32, 4, 6400, 128),
     "ddp_B8_NH4_S1600_DH128": (8, 4, 1600, 128),
+    # BASELINE configs[2] read as d = 512 with the layer's expansion 2 (inner 1024 / 4 heads): head dim 256, the shape on which
+    # the north star's ">= 50 % of tensor peak" lies below the HBM roofline (csrc/mlstm_tc_256.cu)
+    "cfg3alt_B32_NH4_S1600_DH256": (32, 4, 1600, 256),
     # developer shapes (dispatch thresholds of the DH = 64 backward variants; not BASELINE configs)
     "dev_B32_NH4_S800_DH64": (32, 4, 800, 64),
     "dev_B32_NH4_S1600_DH64": (32, 4, 1600, 64),
 }
 DEFAULT_WORKLOAD = "cfg2_B32_NH4_S400_DH64"
-ALSO_WORKLOADS = ["cfg3_B32_NH4_S1600_DH128", "cfg3_B32_NH4_S6400_DH128", "ddp_B8_NH4_S1600_DH128"]
+ALSO_WORKLOADS = ["cfg3_B32_NH4_S1600_DH128", "cfg3_B32_NH4_S6400_DH128", "ddp_B8_NH4_S1600_DH128", "cfg3alt_B32_NH4_S1600_DH256"]
 CHUNK = 64          # the config's chunk size (algorithmic FLOP formula; kernels tile on their own)
 L2_BYTES = 126e6
 
@@ -226,6 +229,11 @@ def emit(obj):
 
 def launches_of(variant_fwd, variant_bwd, DH):
     """kernels behind each timed part, per variant (csrc/mlstm_tc_*.cu)"""
+    if DH == 256 and variant_fwd == "two_phase":   # the slice-streaming family (csrc/mlstm_tc_256.cu)
+        return {"fwd": ["tc_state_fwd_kernel<128> on 2x2 blocks of C", "tc256_par_kernel<F>"],
+                "bwd_dq": ["tc256_par_kernel<A>"],
+                "bwd_dkv": ["tc_state_bwd_kernel<128> on 2x2 blocks of dC", "tc256_par_kernel<B1> (dv)", "tc256_par_kernel<B2> (dk)",
+                            "tc_dfscan_kernel"]}
     return {
         "fwd": {"single_pass": ["tc_fwd_kernel"], "two_phase": ["tc_state_fwd_kernel", "tc_fwd_par_kernel"],
                 "simt": ["simt_fwd_kernel"]}[variant_fwd],
@@ -350,6 +358,9 @@ def measure_device(torch, dist, ops, _lib, name, K, W, dev, rank, world, reverse
         "per_kernel_ms": {"fwd": fwd_ms, "bwd_dq": dq_ms, "bwd_dkv": dkv_ms},
         "step_hbm_frac": (alg["bytes_fwd"] + alg["bytes_bwd"]) / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
         "step_tensor_frac": alg["flops_fwdbwd"] / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+        # the tensor fraction a step running exactly at the HBM roofline would show (0.41 at DH 128, 0.74 at DH 256)
+        "step_tensor_ceiling": min(1.0, alg["flops_fwdbwd"] / (alg["bytes_fwd"] + alg["bytes_bwd"]) * pk["hbm_gbs"] * 1e9 / 1e12
+                                   / pk["bf16_tflops_sustained"]),
     }
     return {
         "value": value, "ms_per_step": ms_per_step, "roofline": roofline, "launches_per_step": int(launches_per_step),
