@@ -316,7 +316,7 @@ def test_module_trains_under_fp16_autocast():
 
 # ---- size-independent properties at BASELINE.json sizes ---------------------------------------
 
-FULL = [(32, 4, 400, 64), (32, 4, 1600, 128)]
+FULL = [(32, 4, 400, 64), (32, 4, 1600, 128), (16, 4, 1600, 256)]
 
 
 @pytest.mark.parametrize("B,NH,S,DH", FULL)
@@ -357,7 +357,8 @@ def test_full_size_gradient_identities(B, NH, S, DH):
 
 
 @pytest.mark.parametrize("B,NH,S,DH,reverse", [(32, 4, 400, 64, False), (32, 4, 400, 64, True), (32, 4, 1600, 128, False),
-                                                (32, 4, 1600, 128, True), (8, 4, 1600, 128, False)])
+                                                (32, 4, 1600, 128, True), (8, 4, 1600, 128, False), (32, 4, 1600, 256, False),
+                                                (8, 4, 1600, 256, True)])
 def test_full_size_batch_rows_match_oracle(B, NH, S, DH, reverse):
     """The BASELINE-size launches themselves (the wide-batch kernels bench.py times, and the per-GPU DDP shape) against
     the fp64 oracle on batch rows 0, mid and last — h and all five gradients, north-star tolerances: a (batch, head)
@@ -466,6 +467,28 @@ def test_full_size_backward_is_deterministic_dh128(reverse):
     for t in want:
         assert torch.isfinite(t).all()
     for _ in range(10):
+        for t in (pl.h, pl.dq, pl.dk, pl.dv, pl.di, pl.df):
+            t.fill_(float("nan"))
+        pl.forward(); pl.backward()
+        torch.cuda.synchronize()
+        for a, b in zip((pl.h, pl.dq, pl.dk, pl.dv, pl.di, pl.df), want):
+            assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_full_size_dh256_family_is_deterministic(reverse):
+    """The slice-streaming DH = 256 family (mlstm_tc_256.cu): ring slots change hands between TMA, two MMA lanes and the
+    next item's prefetch; the staged output tile doubles as the MMA2 operand buffer.  Bit-identical NaN-poisoned reruns."""
+    from xlstm_yolo_b200 import ops
+    q, k, v, i, f, dh = (x.cuda() for x in make(16, 4, 1600, 256, torch.bfloat16, "rand", seed=9))
+    pl = ops.MLSTMPlan(q, k, v, i, f, dh, reverse=reverse)
+    assert pl.family == "tcgen05" and pl.variant_bwd == "chunk_parallel"
+    pl.forward(); pl.backward()
+    torch.cuda.synchronize()
+    want = [t.clone() for t in (pl.h, pl.dq, pl.dk, pl.dv, pl.di, pl.df)]
+    for t in want:
+        assert torch.isfinite(t).all()
+    for _ in range(8):
         for t in (pl.h, pl.dq, pl.dk, pl.dv, pl.di, pl.df):
             t.fill_(float("nan"))
         pl.forward(); pl.backward()
