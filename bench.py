@@ -384,6 +384,7 @@ def measure_e2e(torch, dist, name, K, dev, rank, world, full_result):
     # caching allocator cudaMalloc every step (measured: 2.7 mallocs/step, 1.4-35 ms of host time)
     res_dev = [torch.zeros(4, dtype=torch.float32, device=dev) for _ in range(NBUF)]
     res_full = [None] * NBUF          # pinned host tensors with the strides of the results, made on first use
+    res_slot = [None] * NBUF          # static device-side copies of the results (same strides)
     h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = [res_host[0].numel() * 4]
     main_stream = torch.cuda.current_stream(dev)
@@ -392,7 +393,8 @@ def measure_e2e(torch, dist, name, K, dev, rank, world, full_result):
     ready = [torch.cuda.Event() for _ in range(NBUF)]
     freed = [torch.cuda.Event() for _ in range(NBUF)]
     done = [torch.cuda.Event() for _ in range(NBUF)]
-    for ev in freed:
+    copied = [torch.cuda.Event() for _ in range(NBUF)]
+    for ev in freed + copied:
         ev.record(main_stream)
 
     def e2e_copy(sidx):
@@ -415,15 +417,23 @@ def measure_e2e(torch, dist, name, K, dev, rank, world, full_result):
         if full_result:
             if res_full[b_] is None:
                 # pinned host tensors with exactly the results' strides ((B,S,NH,DH) storage viewed (B,NH,S,DH)): each copy is
-                # then one plain DMA, not a transposing kernel plus a staged copy
+                # then one plain DMA, not a transposing kernel plus a staged copy.  Static device-side slots of the same
+                # layout in between: a D2H copy straight from the step's own (freshly allocated) tensors on another stream
+                # needs record_stream, which keeps their blocks out of the caching allocator for a step or two and makes
+                # it cudaMalloc inside the timed region (measured: 1.2-4.5 ms per step, erratic, against 0.7 ms here).
                 res_full[b_] = [torch.empty(o.numel(), dtype=o.dtype, pin_memory=True).as_strided(o.shape, o.stride()) for o in outs]
+                res_slot[b_] = [torch.empty_strided(o.shape, o.stride(), dtype=o.dtype, device=dev) for o in outs]
                 d2h[0] = sum(o.numel() * o.element_size() for o in outs)
+            main_stream.wait_event(copied[b_])          # the slot's previous content has reached the host
+            with torch.no_grad():
+                for o, r in zip(outs, res_slot[b_]):
+                    r.copy_(o)
             done[b_].record(main_stream)
             with torch.cuda.stream(back_stream):
                 back_stream.wait_event(done[b_])
-                for o, r in zip(outs, res_full[b_]):
+                for o, r in zip(res_slot[b_], res_full[b_]):
                     r.copy_(o, non_blocking=True)
-                    o.record_stream(back_stream)
+                copied[b_].record(back_stream)
         else:
             with torch.no_grad():
                 torch.stack([outs[0].abs().mean(dtype=torch.float32), outs[1].abs().mean(dtype=torch.float32),
