@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define MLSTM_B200_ABI_VERSION 4
+#define MLSTM_B200_ABI_VERSION 5
 
 typedef enum mlstm_status {
   MLSTM_OK = 0,
@@ -197,6 +197,39 @@ int mlstm_b200_glue_supported(int D, int NH);
 size_t mlstm_b200_glue_workspace_bytes(const mlstm_glue_params* p);
 int mlstm_b200_glue_fwd(const mlstm_glue_params* p, void* cuda_stream);
 int mlstm_b200_glue_bwd(const mlstm_glue_params* p, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Producer of the cell's operands (ABI 5).  Reference, four separate HBM round trips
+ * over (B,S,inner) in ViLLayer.forward (vision_lstm2.py:482-491):
+ *     x_conv = SequenceConv2d(x_mlstm)        vision_lstm_util.py:96-129  depthwise 3x3 over the H x W token grid, zero padded
+ *     c      = silu(x_conv)
+ *     q, k   = LinearHeadwiseExpand(c)        vision_lstm2.py:987-1022    block-diagonal: one (d, d) matrix per head + bias
+ *     v      = LinearHeadwiseExpand(x_mlstm)
+ * Here one kernel: a 128-token x d-channel tile of x (with its halo rows) is staged in shared memory once,
+ * the conv + SiLU runs on it, and the three projections are tcgen05 MMAs on the staged tiles; c, q, k, v
+ * leave through TMA stores.  Rows are tokens of a row-major (GH x GW) grid per batch element; x is (B*S, D)
+ * with row stride ld_x elements (a column slice of proj_up's output), outputs dense (ld = D).
+ * `rotate` = 1 convolves with the kernel rotated by 180 degrees (the ROWWISE_FROM_BOT_RIGHT layer on the
+ * un-flipped sequence).  x_dtype 0: bf16, 1: fp16 (the trainer's autocast dtype; wv then has to be fp16
+ * too: the v projection runs as an fp16 x fp16 MMA); outputs are always bf16, what the cell kernels read. */
+typedef struct mlstm_qkv_params {
+  int32_t abi_version;                  /* MLSTM_B200_ABI_VERSION */
+  int32_t B, GH, GW;                    /* batch, token grid (S = GH * GW) */
+  int32_t D, NH;                        /* inner dim, projection blocks; d = D / NH in {64, 128} */
+  int32_t rotate;
+  int32_t x_dtype;                      /* 0 bf16, 1 fp16 */
+  const void* x;   int64_t ld_x;
+  const float* conv_w;                  /* (D, 3, 3) fp32 */
+  const float* conv_b;                  /* (D) fp32 or NULL */
+  const void *wq, *wk, *wv;             /* (NH, d, d) [out][in]; wq, wk bf16; wv in x_dtype */
+  const float *bq, *bk, *bv;            /* (D) fp32, each may be NULL */
+  void *c, *q, *k, *v;                  /* (B*S, D) bf16, dense */
+} mlstm_qkv_params;
+
+/* 1 when the producer handles the shape: d = D / NH in {64, 128}, GW <= 80 (halo rows staged on chip),
+ * ld_x % 8 == 0. */
+int mlstm_b200_qkv_supported(int D, int NH, int GH, int GW, int64_t ld_x);
+int mlstm_b200_qkv_fwd(const mlstm_qkv_params* p, void* cuda_stream);
 
 /* Library / ABI identification. */
 int mlstm_b200_abi_version(void);

@@ -22,7 +22,11 @@ for (B, grid, dim, bs) in [(32, 20, 128, 64), (32, 40, 256, 128), (8, 80, 256, 1
     torch.manual_seed(0)
     pair = ViLBlockPair(dim=dim, chunk_size=64, qkv_block_size=bs).cuda().to(torch.bfloat16).train()
     plain = copy.deepcopy(pair)
+    noprod = copy.deepcopy(pair)     # everything but the conv + SiLU + q / k / v producer kernel
+    for blk in (noprod.rowwise_from_top_left, noprod.rowwise_from_bot_right):
+        blk.layer.fused_producer = False
     for blk in (plain.rowwise_from_top_left, plain.rowwise_from_bot_right):
+        blk.layer.fused_producer = False
         blk.layer.fused_tail = False
         blk.layer.flip_free = False
         blk.layer.mlstm_cell.fused_gates = False
@@ -32,6 +36,13 @@ for (B, grid, dim, bs) in [(32, 20, 128, 64), (32, 40, 256, 128), (8, 80, 256, 1
         def f():
             y = m(x); y.backward(dy)
         return f
-    tf, tp = timeit(run(pair)), timeit(run(plain))
+    def fwd_only(m):
+        def f():
+            with torch.no_grad():
+                m(x)
+        return f
+    tf, tn, tp = timeit(run(pair)), timeit(run(noprod)), timeit(run(plain))
+    ff, fn_ = timeit(fwd_only(pair)), timeit(fwd_only(noprod))
     print(f"ViLBlockPair dim={dim} inner={2*dim} DH={bs} B={B} S={S}: fused {tf:.3f} ms ({B*S/tf/1e3:.1f} M tok/s)  "
-          f"unfused+flips {tp:.3f} ms  speed-up {tp/tf:.2f}x", flush=True)
+          f"without the producer kernel {tn:.3f} ms  unfused+flips {tp:.3f} ms  speed-up {tp/tf:.2f}x | forward only: "
+          f"{ff:.3f} ms vs {fn_:.3f} ms without the producer", flush=True)

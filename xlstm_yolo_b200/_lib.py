@@ -13,7 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 # MLSTM_B200_LIB: developer override for A/B builds (build.build_variant); the product path is the in-tree library
 LIB_PATH = os.environ.get("MLSTM_B200_LIB") or os.path.join(_PKG, "lib", "libmlstm_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MLSTM_F32, MLSTM_BF16 = 0, 1
 
 STATUS = {0: "OK", -1: "INVALID_ARG", -2: "UNSUPPORTED", -3: "WORKSPACE", -4: "CUDA", -5: "NO_DEVICE"}
@@ -27,6 +27,8 @@ EXPORTS = (
     "mlstm_b200_bwd_part",
     "mlstm_b200_kernel_name",
     "mlstm_b200_kernel_variant",
+    "mlstm_b200_qkv_supported",
+    "mlstm_b200_qkv_fwd",
     "mlstm_b200_gates_supported",
     "mlstm_b200_gates_workspace_bytes",
     "mlstm_b200_gates_fwd",
@@ -99,6 +101,19 @@ class GlueParams(C.Structure):
     ]
 
 
+class QkvParams(C.Structure):
+    """ctypes mirror of ``mlstm_qkv_params`` (include/mlstm_b200.h)."""
+    _fields_ = [
+        ("abi_version", C.c_int32), ("B", C.c_int32), ("GH", C.c_int32), ("GW", C.c_int32), ("D", C.c_int32), ("NH", C.c_int32),
+        ("rotate", C.c_int32), ("x_dtype", C.c_int32),
+        ("x", C.c_void_p), ("ld_x", C.c_int64),
+        ("conv_w", C.c_void_p), ("conv_b", C.c_void_p),
+        ("wq", C.c_void_p), ("wk", C.c_void_p), ("wv", C.c_void_p),
+        ("bq", C.c_void_p), ("bk", C.c_void_p), ("bv", C.c_void_p),
+        ("c", C.c_void_p), ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+    ]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -140,6 +155,10 @@ def load() -> C.CDLL:
         lib.mlstm_b200_kernel_name.argtypes = [C.POINTER(Params), C.c_int]
         lib.mlstm_b200_gates_supported.restype = C.c_int
         lib.mlstm_b200_gates_supported.argtypes = [C.c_int, C.c_int64]
+        lib.mlstm_b200_qkv_supported.restype = C.c_int
+        lib.mlstm_b200_qkv_supported.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
+        lib.mlstm_b200_qkv_fwd.restype = C.c_int
+        lib.mlstm_b200_qkv_fwd.argtypes = [C.POINTER(QkvParams), C.c_void_p]
         lib.mlstm_b200_glue_supported.restype = C.c_int
         lib.mlstm_b200_glue_supported.argtypes = [C.c_int, C.c_int]
         lib.mlstm_b200_gates_workspace_bytes.restype = C.c_size_t

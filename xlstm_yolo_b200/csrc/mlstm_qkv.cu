@@ -1,0 +1,335 @@
+// Producer of the cell's operands: depthwise 3x3 conv + SiLU + the three block-diagonal projections of a ViL layer
+// in one kernel.
+//
+// Reference (ViLLayer.forward, vision_lstm2.py:482-491), four separate round trips over (B,S,inner):
+//     x_conv = SequenceConv2d(x_mlstm)     vision_lstm_util.py:96-129   depthwise 3x3 on the H x W token grid, zero padded
+//     c      = silu(x_conv)
+//     q, k   = LinearHeadwiseExpand(c)     vision_lstm2.py:987-1022     y[h, o] = sum_d x[h, d] W[h, o, d] + b
+//     v      = LinearHeadwiseExpand(x_mlstm)
+//
+// One persistent CTA per SM walks (128-token tile, projection block) pairs of ONE block h (its three d x d weight
+// matrices stay in shared memory for the whole launch):
+//   TMA    the x tile [128 + 2 HALO rows][d] (halo = one grid row + 1 on each side, rounded up to 8 rows so the centre
+//          rows are a legal MMA operand; rows outside the sequence arrive as zeros)
+//   SIMT   conv + bias + SiLU from the staged rows (column wrap masked by grid position) -> bf16 tile c, K-major
+//   TMA    store of c
+//   MMA    q = c Wq^T, k = c Wk^T, v = x_centre Wv^T       (tcgen05, fp32 accumulators in TMEM)
+//   SIMT   + bias -> bf16 -> staged in the dead x rows / the c tile -> TMA stores
+// x is read once (plus L2-resident halo rows), c, q, k, v are written once: 5 tensor passes instead of 10.
+#include <cuda_fp16.h>
+
+#include "tc_common.cuh"
+
+namespace mlstm {
+namespace {
+
+using namespace tc;
+
+constexpr int QK_NT = CT + 32;        // 16 compute warps + the control warp
+constexpr int RMAX = 304;             // staged rows: 128 + 2 * HALO, HALO <= 88 (grid width <= 80)
+
+struct QkvMaps { CUtensorMap x, w[3], out[4]; };   // out: c, q, k, v
+
+template <int DBLK>
+struct SmemQ {
+  static constexpr int KT = DBLK / 64;
+  alignas(1024) uint8_t xh[KT][RMAX * 128];       // x rows with halo, 128-byte swizzled lines of 64 channels
+  alignas(1024) uint8_t xc[KT * TILE];            // c tile (A operand of q, k); later the staging tile of v
+  alignas(1024) uint8_t w[3][KT * DBLK * 128];    // Wq, Wk, Wv of this CTA's block: [out][in] = K-major B operands
+  alignas(16) float cw[9][DBLK];                  // conv taps of the block's channels, tap-major
+  alignas(16) float cb[DBLK];
+  alignas(16) float pb[3][DBLK];                  // projection biases
+  uint64_t bar_w, bar_x, bar_mma;
+  uint32_t tmem_base;
+};
+
+template <bool FP16>
+__device__ __forceinline__ void cvt8(const uint4& w, float (&x)[8]) {
+  if (FP16) {
+    const __half2* h = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f2 = __half22float2(h[e]); x[2 * e] = f2.x; x[2 * e + 1] = f2.y; }
+  } else {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f2 = __bfloat1622float2(h[e]); x[2 * e] = f2.x; x[2 * e + 1] = f2.y; }
+  }
+}
+
+template <int DBLK, bool FP16>
+__global__ void __launch_bounds__(QK_NT, 1) qkv_fwd_kernel(const __grid_constant__ QkvMaps maps, const mlstm_qkv_params p,
+                                                           const int halo, const int tiles_per_batch) {
+  constexpr int KT = DBLK / 64;
+  constexpr int CH = DBLK / 8;                    // 16-byte channel groups per row
+  constexpr int RPT = 128 * CH / CT;              // conv row-items per thread
+  constexpr int NB = DBLK / 32;                   // 32-column blocks of an output tile
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SmemQ<DBLK>& sm = *reinterpret_cast<SmemQ<DBLK>*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool compute = tid < CT, issuer = tid == CT;
+  const int rg = warp & 3, cq = compute ? (warp >> 2) : NB, row = rg * 32 + lane;
+  const int S = p.GH * p.GW, GW = p.GW, GH = p.GH;
+  const int NHB = p.NH;
+  const int hb = blockIdx.x % NHB;                           // this CTA's projection block
+  const int n_tiles = p.B * tiles_per_batch;
+  const int tile0 = blockIdx.x / NHB, tstep = gridDim.x / NHB;
+  const int R = 128 + 2 * halo, RB = R / 2;                  // staged rows, rows per TMA box
+
+  if (issuer) {
+    tma_prefetch_desc(&maps.x);
+    for (int j = 0; j < 3; ++j) tma_prefetch_desc(&maps.w[j]);
+    for (int j = 0; j < 4; ++j) tma_prefetch_desc(&maps.out[j]);
+    mbar_init(&sm.bar_w, 1); mbar_init(&sm.bar_x, 1); mbar_init(&sm.bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
+  // conv taps (rotated by 180 degrees for the bottom-right layer), biases
+  for (int e = tid; e < 9 * DBLK; e += QK_NT) {
+    const int tap = e / DBLK, ch = e % DBLK;
+    sm.cw[tap][ch] = p.conv_w[(size_t)(hb * DBLK + ch) * 9 + (p.rotate ? 8 - tap : tap)];
+  }
+  for (int e = tid; e < DBLK; e += QK_NT) {
+    sm.cb[e] = p.conv_b ? p.conv_b[hb * DBLK + e] : 0.f;
+    sm.pb[0][e] = p.bq ? p.bq[hb * DBLK + e] : 0.f;
+    sm.pb[1][e] = p.bk ? p.bk[hb * DBLK + e] : 0.f;
+    sm.pb[2][e] = p.bv ? p.bv[hb * DBLK + e] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = sm.tmem_base;
+  const uint32_t lane_sel = (uint32_t)(rg * 32) << 16;
+
+  auto tile_coords = [&](int t, int& b, int& tok0) { b = t / tiles_per_batch; tok0 = (t % tiles_per_batch) * 128; };
+  auto load_x = [&](int t) {
+    int b, tok0; tile_coords(t, b, tok0);
+    mbar_arrive_expect_tx(&sm.bar_x, KT * R * 128);
+    for (int kt = 0; kt < KT; ++kt)
+      for (int hbx = 0; hbx < 2; ++hbx)
+        tma_load_4d(sm.xh[kt] + hbx * RB * 128, &maps.x, &sm.bar_x, hb * DBLK + kt * 64, tok0 - halo + hbx * RB, b, 0);
+  };
+  auto prefetch_x = [&](int t) {
+    int b, tok0; tile_coords(t, b, tok0);
+    for (int kt = 0; kt < KT; ++kt)
+      for (int hbx = 0; hbx < 2; ++hbx) tma_prefetch_4d(&maps.x, hb * DBLK + kt * 64, tok0 - halo + hbx * RB, b, 0);
+  };
+  if (issuer && tile0 < n_tiles) {
+    mbar_arrive_expect_tx(&sm.bar_w, 3 * KT * DBLK * 128);
+    for (int j = 0; j < 3; ++j)
+      for (int kt = 0; kt < KT; ++kt) tma_load_2d(sm.w[j] + kt * DBLK * 128, &maps.w[j], &sm.bar_w, kt * 64, hb * DBLK);
+    load_x(tile0);
+  }
+  // instruction descriptors: q, k are bf16 x bf16; v is x_dtype x x_dtype
+  constexpr uint32_t idQK = make_idesc_bf16(128, DBLK, 0, 0);
+  constexpr uint32_t idV = FP16 ? ((1u << 4) | ((uint32_t)(DBLK >> 3) << 17) | ((uint32_t)(128 >> 4) << 24)) : idQK;
+
+  int n = 0;
+  for (int t = tile0; t < n_tiles; t += tstep, ++n) {
+    const uint32_t ph = n & 1;
+    int b, tok0; tile_coords(t, b, tok0);
+    const bool has_next = t + tstep < n_tiles;
+    if (issuer && has_next) prefetch_x(t + tstep);   // towards L2: the next tile's load waits for this tile's stores
+    mbar_wait(&sm.bar_x, ph);
+
+    // ---- conv + bias + SiLU: thread = (8 channels, RPT rows) ----------------------------------------------
+    if (compute) {
+      const int c8 = tid % CH, ch0 = c8 * 8, kt = ch0 >> 6, cc = ch0 & 63;
+#pragma unroll
+      for (int it = 0; it < RPT; ++it) {
+        const int r = tid / CH + it * (CT / CH);
+        const int tok = tok0 + r;
+        const int gy = tok / GW, gx = tok - gy * GW;
+        float acc[8];
+        {
+          const float4 b0 = *reinterpret_cast<const float4*>(&sm.cb[ch0]), b1 = *reinterpret_cast<const float4*>(&sm.cb[ch0 + 4]);
+          acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+        }
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            if (gy + dy < 0 || gy + dy >= GH || gx + dx < 0 || gx + dx >= GW) continue;
+            const int rr = halo + r + dy * GW + dx;
+            const uint4 w = *reinterpret_cast<const uint4*>(sm.xh[kt] + swz128(rr, cc));
+            float xv[8];
+            cvt8<FP16>(w, xv);
+            const int tap = (dy + 1) * 3 + (dx + 1);
+            const float4 w0 = *reinterpret_cast<const float4*>(&sm.cw[tap][ch0]), w1 = *reinterpret_cast<const float4*>(&sm.cw[tap][ch0 + 4]);
+            acc[0] = fmaf(xv[0], w0.x, acc[0]); acc[1] = fmaf(xv[1], w0.y, acc[1]);
+            acc[2] = fmaf(xv[2], w0.z, acc[2]); acc[3] = fmaf(xv[3], w0.w, acc[3]);
+            acc[4] = fmaf(xv[4], w1.x, acc[4]); acc[5] = fmaf(xv[5], w1.y, acc[5]);
+            acc[6] = fmaf(xv[6], w1.z, acc[6]); acc[7] = fmaf(xv[7], w1.w, acc[7]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = acc[e] / (1.f + __expf(-acc[e]));   // silu
+        *reinterpret_cast<uint4*>(sm.xc + kt * TILE + swz128(r, cc)) =
+            make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    named_sync(2, QK_NT);
+
+    // ---- c leaves; q = c Wq^T, k = c Wk^T, v = x Wv^T ----------------------------------------------------------
+    if (issuer) {
+      for (int kt = 0; kt < KT; ++kt) tma_store_4d(&maps.out[0], sm.xc + kt * TILE, hb * DBLK + kt * 64, tok0, b, 0);
+      tma_store_commit();
+      if (n == 0) mbar_wait(&sm.bar_w, 0);
+      tc_fence_after();
+      const uint64_t dC = make_sdesc(smem_u32(sm.xc), 16, 1024);
+      const uint64_t dX = make_sdesc(smem_u32(sm.xh[0]) + halo * 128, 16, 1024);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const uint64_t dW = make_sdesc(smem_u32(sm.w[j]), 16, 1024);
+#pragma unroll
+        for (int ks = 0; ks < DBLK / 16; ++ks)
+          umma_bf16_ss(tm + j * DBLK, (j < 2 ? dC + kstep(ks) : dX + kstep(ks, RMAX * 128)), dW + kstep(ks, DBLK * 128),
+                       j < 2 ? idQK : idV, ks > 0);
+      }
+      umma_commit(&sm.bar_mma);
+      tma_store_wait_read<0>();   // c has left its tile: v may be staged there (barrier 3 below)
+    }
+    mbar_wait(&sm.bar_mma, ph);
+    tc_fence_after();
+
+    // ---- epilogue: + bias -> bf16, staged: q, k in the dead x rows, v in the c tile ---------------------------
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (j == 2) named_sync(3, QK_NT);   // the control lane has seen the c store read its tile
+      if (cq < NB) {
+        float a[32];
+        tmem_ld32(tm + j * DBLK + lane_sel + cq * 32, a);
+        tmem_ld_wait();
+        uint8_t* stage = (j == 0) ? sm.xh[0] : (j == 1 ? sm.xh[0] + KT * TILE : sm.xc);
+#pragma unroll
+        for (int x = 0; x < 32; x += 8) {
+          const int col = cq * 32 + x;
+          const float4 b0 = *reinterpret_cast<const float4*>(&sm.pb[j][col]), b1 = *reinterpret_cast<const float4*>(&sm.pb[j][col + 4]);
+          *reinterpret_cast<uint4*>(stage + (col >> 6) * TILE + swz128(row, col & 63)) =
+              make_uint4(pack_bf16x2(a[x] + b0.x, a[x + 1] + b0.y), pack_bf16x2(a[x + 2] + b0.z, a[x + 3] + b0.w),
+                         pack_bf16x2(a[x + 4] + b1.x, a[x + 5] + b1.y), pack_bf16x2(a[x + 6] + b1.z, a[x + 7] + b1.w));
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    named_sync(2, QK_NT);
+    if (issuer) {
+      for (int kt = 0; kt < KT; ++kt) {
+        tma_store_4d(&maps.out[1], sm.xh[0] + kt * TILE, hb * DBLK + kt * 64, tok0, b, 0);
+        tma_store_4d(&maps.out[2], sm.xh[0] + (KT + kt) * TILE, hb * DBLK + kt * 64, tok0, b, 0);
+        tma_store_4d(&maps.out[3], sm.xc + kt * TILE, hb * DBLK + kt * 64, tok0, b, 0);
+      }
+      tma_store_commit();
+      if (has_next) {
+        tma_store_wait_read<0>();   // the staged tiles have been read: the x rows of the next tile may land
+        load_x(t + tstep);
+      }
+    }
+  }
+  if (issuer) tma_store_wait_all<0>();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+// 3-D map (channels, tokens, batch) of a (B*S, D) bf16/fp16 matrix with row stride ld; box = 64 x box_rows x 1.  Encoded as a 4-D
+// map with a unit outer dimension so the kernels use the one 4-D load / store wrapper.
+int make_rows_tmap(CUtensorMap* out, const void* ptr, int D, int S, int B, int64_t ld, int box_rows) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.s0 = ld; key.d0 = D; key.d1 = S; key.d2 = B; key.box_rows = box_rows; key.kind = 7;
+  if (tmap_cache_lookup(key, out, false)) return 0;
+  PFN_tmapEncodeTiled enc = get_tmap_encoder();
+  if (!enc) return -1;
+  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)B, 1};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * S, (cuuint64_t)ld * 2 * S * B};
+  cuuint32_t box[4] = {64u, (cuuint32_t)box_rows, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const int r = (int)enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == 0) tmap_cache_lookup(key, out, true);
+  return r;
+}
+
+bool qkv_shape_ok(int D, int NH, int GH, int GW, int64_t ld_x) {
+  if (D <= 0 || NH <= 0 || D % NH != 0 || GH <= 0 || GW <= 0) return false;
+  const int d = D / NH;
+  return (d == 64 || d == 128) && GW <= 80 && ld_x >= D && ld_x % 8 == 0;
+}
+
+template <int DBLK, bool FP16>
+int launch_qkv(const mlstm_qkv_params& p, const QkvMaps& maps, int halo, cudaStream_t st) {
+  const size_t smem = sizeof(SmemQ<DBLK>);
+  cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(qkv_fwd_kernel<DBLK, FP16>), smem);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(qkv_fwd, %zu B): %s", smem, cudaGetErrorString(e));
+    return MLSTM_ERR_CUDA;
+  }
+  const int S = p.GH * p.GW, tiles_per_batch = (S + 127) / 128;
+  const int sms = sm_count_of(p.x);
+  int per_block = sms / p.NH;                       // CTAs per projection block
+  if (per_block < 1) per_block = 1;
+  if (per_block > p.B * tiles_per_batch) per_block = p.B * tiles_per_batch;
+  qkv_fwd_kernel<DBLK, FP16><<<dim3(per_block * p.NH), dim3(QK_NT), smem, st>>>(maps, p, halo, tiles_per_batch);
+  count_launch();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("qkv_fwd launch failed: %s", cudaGetErrorString(e));
+    return MLSTM_ERR_CUDA;
+  }
+  return MLSTM_OK;
+}
+
+}  // namespace
+}  // namespace mlstm
+
+using namespace mlstm;
+
+extern "C" {
+
+int mlstm_b200_qkv_supported(int D, int NH, int GH, int GW, int64_t ld_x) { return qkv_shape_ok(D, NH, GH, GW, ld_x) ? 1 : 0; }
+
+int mlstm_b200_qkv_fwd(const mlstm_qkv_params* p, void* cuda_stream) {
+  clear_error();
+  if (!p) { set_error("params is NULL"); return MLSTM_ERR_INVALID_ARG; }
+  if (p->abi_version != MLSTM_B200_ABI_VERSION) {
+    set_error("abi_version %d != %d", p->abi_version, MLSTM_B200_ABI_VERSION);
+    return MLSTM_ERR_INVALID_ARG;
+  }
+  if (p->B < 0 || p->x_dtype < 0 || p->x_dtype > 1) { set_error("bad B / x_dtype"); return MLSTM_ERR_INVALID_ARG; }
+  if (!qkv_shape_ok(p->D, p->NH, p->GH, p->GW, p->ld_x)) {
+    set_error("qkv producer: D / NH must be 64 or 128, grid width <= 80, ld_x a multiple of 8 and >= D (D=%d NH=%d GH=%d GW=%d ld_x=%lld)",
+              p->D, p->NH, p->GH, p->GW, (long long)p->ld_x);
+    return MLSTM_ERR_UNSUPPORTED;
+  }
+  if (p->B == 0) return MLSTM_OK;
+  if (!p->x || !p->conv_w || !p->wq || !p->wk || !p->wv || !p->c || !p->q || !p->k || !p->v) {
+    set_error("qkv producer: null pointer");
+    return MLSTM_ERR_INVALID_ARG;
+  }
+  int rc;
+  if ((rc = bind_device(p->x))) return rc;
+  const int S = p->GH * p->GW, d = p->D / p->NH;
+  const int halo = ((p->GW + 1 + 7) / 8) * 8;
+  QkvMaps maps;
+  int r = 0;
+  r |= make_rows_tmap(&maps.x, p->x, p->D, S, p->B, p->ld_x, (128 + 2 * halo) / 2);
+  const void* ws[3] = {p->wq, p->wk, p->wv};
+  for (int j = 0; j < 3; ++j) r |= tc::make_state_tmap(&maps.w[j], ws[j], (size_t)p->D, d, d);
+  void* outs[4] = {p->c, p->q, p->k, p->v};
+  for (int j = 0; j < 4; ++j) r |= make_rows_tmap(&maps.out[j], outs[j], p->D, S, p->B, p->D, 128);
+  if (r) {
+    set_error("cuTensorMapEncodeTiled failed (%d): pointers must be 16-byte aligned", r);
+    return r == -1 ? MLSTM_ERR_NO_DEVICE : MLSTM_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (d == 128) return p->x_dtype ? launch_qkv<128, true>(*p, maps, halo, st) : launch_qkv<128, false>(*p, maps, halo, st);
+  return p->x_dtype ? launch_qkv<64, true>(*p, maps, halo, st) : launch_qkv<64, false>(*p, maps, halo, st);
+}
+
+}  // extern "C"

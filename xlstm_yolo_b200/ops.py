@@ -18,7 +18,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import Act, Gate, GateProjParams, GlueParams, Params
+from ._lib import Act, Gate, GateProjParams, GlueParams, Params, QkvParams
 
 _DT = {torch.float32: _lib.MLSTM_F32, torch.bfloat16: _lib.MLSTM_BF16}
 
@@ -565,6 +565,126 @@ def layer_tail(h: torch.Tensor, conv_act: torch.Tensor, z: torch.Tensor, norm_we
     (B,NH,S,DH); check ``glue_supported`` first."""
     f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()
     return _GlueFn.apply(h, conv_act, z, f32(norm_weight), f32(norm_bias), f32(skip), float(eps))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Producer of the cell's operands: conv + SiLU + block-diagonal q / k / v (csrc/mlstm_qkv.cu; SURVEY.md 8 row f2)
+# ---------------------------------------------------------------------------------------------------------------
+
+def qkv_supported(x: torch.Tensor, D: int, NH: int, gh: int, gw: int) -> bool:
+    """x: (B,S,D) rows of proj_up's output (a column slice is fine), bf16 or fp16 on CUDA."""
+    if not x.is_cuda or x.dtype not in (torch.bfloat16, torch.float16) or x.dim() != 3 or x.shape[1] != gh * gw:
+        return False
+    if x.stride(2) != 1 or x.stride(0) != x.shape[1] * x.stride(1) or x.data_ptr() % 16:
+        return False
+    return bool(_lib.load().mlstm_b200_qkv_supported(int(D), int(NH), int(gh), int(gw), int(x.stride(1))))
+
+
+def qkv_reference(x, conv_w, conv_b, wq, bq, wk, bk, wv, bv, gh, gw, rotate=False):
+    """The four reference ops in plain PyTorch (any device / dtype): returns (c, q, k, v), each (B,S,D).
+    conv_w (D,1,3,3); w* (NH,d,d) [out][in]; ``rotate`` convolves with the kernel rotated by 180 degrees."""
+    B, S, D = x.shape
+    NH, d = wq.shape[0], wq.shape[1]
+    w = conv_w.flip(-1, -2) if rotate else conv_w
+    img = x.reshape(B, gh, gw, D).permute(0, 3, 1, 2)
+    u = torch.nn.functional.conv2d(img, w.to(x.dtype), None if conv_b is None else conv_b.to(x.dtype), padding=1, groups=D)
+    c = torch.nn.functional.silu(u).permute(0, 2, 3, 1).reshape(B, S, D)
+    hw = lambda t, wt, b: (torch.einsum("bshd,hod->bsho", t.reshape(B, S, NH, d), wt.to(t.dtype)).reshape(B, S, D)
+                           + (0 if b is None else b.to(t.dtype)))
+    return c, hw(c, wq, bq), hw(c, wk, bk), hw(x, wv, bv)
+
+
+def qkv_backward(x, c, conv_w, conv_b, wq, wk, wv, has_bias, dc, dq, dk, dv, gh, gw, rotate):
+    """Backward of the producer in PyTorch ops (cuBLAS batched GEMMs over the strided head views, cuDNN depthwise conv):
+    the saved c replaces everything but the conv pre-activation, which is recomputed.  Works on any device (the CPU
+    tests differentiate it against autograd of ``qkv_reference``).  Returns gradients for
+    (x, conv_w, conv_b, wq, bq, wk, bk, wv, bv); bias gradients are None where ``has_bias`` says so."""
+    B, S, D = x.shape
+    NH, d = wq.shape[0], wq.shape[1]
+    T = B * S
+    cd = dq.dtype                                            # compute dtype of the projections' gradients
+    heads = lambda t: t.reshape(T, NH, d).transpose(0, 1)   # (NH, T, d) strided view: no copy for evenly strided rows
+    dense = lambda t: t if t.is_contiguous() else t.contiguous()
+    dqh, dkh, dvh = heads(dense(dq)), heads(dense(dk)), heads(dense(dv))
+    ch, xh = heads(c if c.dtype == cd else c.to(cd)), heads(x if x.dtype == cd else x.to(cd))
+    # projections: dW = dy^T in, din = dy W
+    dwq, dwk, dwv = torch.bmm(dqh.transpose(1, 2), ch), torch.bmm(dkh.transpose(1, 2), ch), torch.bmm(dvh.transpose(1, 2), xh)
+    # dxc = dc + dq Wq + dk Wk accumulated by the GEMMs themselves (beta = 1 into the strided head views)
+    if dc is not None:
+        dxc = dc.reshape(T, D).to(cd, copy=True)
+        dxc_h = dxc.view(T, NH, d).transpose(0, 1)
+        torch.baddbmm(dxc_h, dqh, wq.to(cd), out=dxc_h)
+    else:
+        dxc = torch.empty((T, D), dtype=cd, device=x.device)
+        dxc_h = dxc.view(T, NH, d).transpose(0, 1)
+        torch.bmm(dqh, wq.to(cd), out=dxc_h)
+    torch.baddbmm(dxc_h, dkh, wk.to(cd), out=dxc_h)
+    # conv + SiLU: u recomputed, du = dxc * silu'(u), then the depthwise conv's own backward and dx = conv^T(du) + dv Wv
+    w = (conv_w.flip(-1, -2) if rotate else conv_w).to(x.dtype)
+    img = x.reshape(B, gh, gw, D).permute(0, 3, 1, 2)
+    u = torch.nn.functional.conv2d(img, w, None if conv_b is None else conv_b.to(x.dtype), padding=1, groups=D)
+    dxc_img = dxc.view(B, gh, gw, D).permute(0, 3, 1, 2)
+    du = torch.ops.aten.silu_backward(dxc_img if dxc_img.dtype == u.dtype else dxc_img.to(u.dtype), u)
+    dimg, dwc, dbc = torch.ops.aten.convolution_backward(du, img, w, [D] if conv_b is not None else None, [1, 1], [1, 1], [1, 1],
+                                                         False, [0, 0], D, [True, True, conv_b is not None])
+    if rotate:
+        dwc = dwc.flip(-1, -2)
+    dx = dimg.permute(0, 2, 3, 1).reshape(T, D)
+    if dx.dtype == cd and dx.is_contiguous():
+        dx_h = dx.view(T, NH, d).transpose(0, 1)
+        torch.baddbmm(dx_h, dvh, wv.to(cd), out=dx_h)
+    else:
+        dx = dx + torch.bmm(dvh, wv.to(cd)).transpose(0, 1).reshape(T, D).to(dx.dtype)
+    dx = dx.view(B, S, D)
+    sums = lambda t, on: t.reshape(T, D).sum(0, dtype=torch.float32) if on else None
+    return (dx, dwc, dbc, dwq, sums(dq, has_bias[0]), dwk, sums(dk, has_bias[1]), dwv, sums(dv, has_bias[2]))
+
+
+class _QkvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, conv_w, conv_b, wq, bq, wk, bk, wv, bv, gh, gw, rotate):
+        lib = _lib.load()
+        B, S, D = x.shape
+        NH = wq.shape[0]
+        dev = x.device
+        f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
+        cw, cb, fbq, fbk, fbv = f32(conv_w), f32(conv_b), f32(bq), f32(bk), f32(bv)
+        kq, kk = wq.detach().to(torch.bfloat16).contiguous(), wk.detach().to(torch.bfloat16).contiguous()
+        kv = wv.detach().to(x.dtype).contiguous()
+        c, q, k, v = (torch.empty((B, S, D), dtype=torch.bfloat16, device=dev) for _ in range(4))
+        g = QkvParams()
+        g.abi_version = _lib.ABI_VERSION
+        g.B, g.GH, g.GW, g.D, g.NH = B, gh, gw, D, NH
+        g.rotate, g.x_dtype = int(bool(rotate)), int(x.dtype == torch.float16)
+        g.x, g.ld_x = x.data_ptr(), x.stride(1)
+        g.conv_w, g.conv_b = cw.data_ptr(), _ptr(cb)
+        g.wq, g.wk, g.wv = kq.data_ptr(), kk.data_ptr(), kv.data_ptr()
+        g.bq, g.bk, g.bv = _ptr(fbq), _ptr(fbk), _ptr(fbv)
+        g.c, g.q, g.k, g.v = c.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr()
+        with torch.cuda.device(dev):
+            rc = lib.mlstm_b200_qkv_fwd(C.byref(g), _stream())
+        if rc:
+            _fail(rc, "qkv producer forward")
+        ctx.save_for_backward(x, c, conv_w, conv_b, wq, wk, wv)
+        ctx.meta = (gh, gw, bool(rotate), (bq is not None, bk is not None, bv is not None))
+        return c, q, k, v
+
+    @staticmethod
+    def backward(ctx, dc, dq, dk, dv):
+        x, c, conv_w, conv_b, wq, wk, wv = ctx.saved_tensors
+        gh, gw, rotate, has_bias = ctx.meta
+        z = lambda t: torch.zeros_like(c) if t is None else t
+        g = qkv_backward(x, c, conv_w, conv_b, wq, wk, wv, has_bias, dc, z(dq), z(dk), z(dv), gh, gw, rotate)
+        dx, dwc, dbc, dwq, dbq, dwk, dbk, dwv, dbv = g
+        cast = lambda t, like: None if (t is None or like is None) else t.to(like.dtype)
+        return (dx.to(x.dtype), cast(dwc, conv_w), cast(dbc, conv_b), cast(dwq, wq), dbq, cast(dwk, wk), dbk, cast(dwv, wv), dbv,
+                None, None, None)
+
+
+def qkv_producer(x, conv_w, conv_b, wq, bq, wk, bk, wv, bv, gh: int, gw: int, rotate: bool = False):
+    """(c, q, k, v) = (silu(conv(x)), c Wq^T + bq, c Wk^T + bk, x Wv^T + bv), all (B,S,D) bf16, from one kernel
+    (csrc/mlstm_qkv.cu).  Check ``qkv_supported`` first.  Backward: ``qkv_backward`` (cuBLAS / cuDNN through PyTorch)."""
+    return _QkvFn.apply(x, conv_w, conv_b, wq, bq, wk, bk, wv, bv, int(gh), int(gw), bool(rotate))
 
 
 class MLSTMPlan:

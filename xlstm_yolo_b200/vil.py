@@ -198,6 +198,7 @@ class ViLLayer(nn.Module):
         self.num_blocks = num_blocks
         self.flip_free = flip_free
         self.fused_tail = True    # CUDA: csrc/mlstm_glue.cu for out-norm + skip + SiLU(z)
+        self.fused_producer = True   # CUDA, bf16 / fp16 activations: csrc/mlstm_qkv.cu for conv + SiLU + q / k / v
 
         inner_dim = expansion * dim
         num_heads = inner_dim // qkv_block_size
@@ -229,9 +230,22 @@ class ViLLayer(nn.Module):
         if literal_flip:
             y = y.flip(dims=[1])
         x_mlstm, z = self.proj_up(y).chunk(2, dim=-1)
-        conv_act = F.silu(self.conv(x_mlstm, rotate=anti))
         cell = self.mlstm_cell
-        q, k, v = self.q_proj(conv_act), self.k_proj(conv_act), self.v_proj(x_mlstm)
+        conv_act = None
+        if (x.is_cuda and getattr(self, "fused_producer", True) and self.conv.kernel_size == (3, 3)
+                and not torch.compiler.is_compiling()):
+            # conv + SiLU + the three block-diagonal projections as one kernel (vision_lstm2.py:482-491 are four
+            # round trips over (B,S,inner)); bf16 outputs, which is what the cell kernels read
+            from . import ops
+            gh = _grid_height(x_mlstm.shape[1], self.conv.seqlens)
+            gw = x_mlstm.shape[1] // gh
+            if ops.qkv_supported(x_mlstm, x_mlstm.shape[2], self.q_proj.num_heads, gh, gw):
+                conv_act, q, k, v = ops.qkv_producer(x_mlstm, self.conv.weight, self.conv.bias, self.q_proj.weight, self.q_proj.bias,
+                                                     self.k_proj.weight, self.k_proj.bias, self.v_proj.weight, self.v_proj.bias,
+                                                     gh, gw, rotate=anti)
+        if conv_act is None:
+            conv_act = F.silu(self.conv(x_mlstm, rotate=anti))
+            q, k, v = self.q_proj(conv_act), self.k_proj(conv_act), self.v_proj(x_mlstm)
         y = None
         if x.is_cuda and getattr(self, "fused_tail", True) and not cell.raw_output and not torch.compiler.is_compiling():
             # out-norm + skip + SiLU(z) gate as one streaming kernel over the raw cell output
