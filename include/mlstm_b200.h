@@ -230,6 +230,12 @@ typedef struct mlstm_qkv_params {
  * ld_x % 8 == 0. */
 int mlstm_b200_qkv_supported(int D, int NH, int GH, int GW, int64_t ld_x);
 int mlstm_b200_qkv_fwd(const mlstm_qkv_params* p, void* cuda_stream);
+/* Bias gradients of the three projections (the backward of vision_lstm2.py:1016-1021's `+ bias`): out[j*D + col] = sum over
+ * the T rows of src[j] (bf16, row stride ld elements, D % 8 == 0), j = 0..n_src-1 (n_src <= 3), in one streaming pass with a
+ * fixed-order (deterministic) two-stage reduction.  workspace >= mlstm_b200_colsum_workspace_bytes(D, n_src) bytes. */
+size_t mlstm_b200_colsum_workspace_bytes(int D, int n_src);
+int mlstm_b200_colsum(const void* const* src, int n_src, int T, int D, int64_t ld, float* out, void* workspace,
+                      size_t workspace_bytes, void* cuda_stream);
 
 /* Library / ABI identification. */
 int mlstm_b200_abi_version(void);

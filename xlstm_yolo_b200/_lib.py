@@ -29,6 +29,8 @@ EXPORTS = (
     "mlstm_b200_kernel_variant",
     "mlstm_b200_qkv_supported",
     "mlstm_b200_qkv_fwd",
+    "mlstm_b200_colsum_workspace_bytes",
+    "mlstm_b200_colsum",
     "mlstm_b200_gates_supported",
     "mlstm_b200_gates_workspace_bytes",
     "mlstm_b200_gates_fwd",
@@ -157,6 +159,11 @@ def load() -> C.CDLL:
         lib.mlstm_b200_gates_supported.argtypes = [C.c_int, C.c_int64]
         lib.mlstm_b200_qkv_supported.restype = C.c_int
         lib.mlstm_b200_qkv_supported.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
+        lib.mlstm_b200_colsum_workspace_bytes.restype = C.c_size_t
+        lib.mlstm_b200_colsum_workspace_bytes.argtypes = [C.c_int, C.c_int]
+        lib.mlstm_b200_colsum.restype = C.c_int
+        lib.mlstm_b200_colsum.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_size_t, C.c_void_p]
         lib.mlstm_b200_qkv_fwd.restype = C.c_int
         lib.mlstm_b200_qkv_fwd.argtypes = [C.POINTER(QkvParams), C.c_void_p]
         lib.mlstm_b200_glue_supported.restype = C.c_int

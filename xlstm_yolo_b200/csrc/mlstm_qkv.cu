@@ -14,7 +14,7 @@
 //   SIMT   conv + bias + SiLU from the staged rows (column wrap masked by grid position) -> bf16 tile c, K-major
 //   TMA    store of c
 //   MMA    q = c Wq^T, k = c Wk^T, v = x_centre Wv^T       (tcgen05, fp32 accumulators in TMEM)
-//   SIMT   + bias -> bf16 -> staged in the dead x rows / the c tile -> TMA stores
+//   SIMT   + bias -> bf16 -> staged in the c tile, one output at a time -> TMA stores (the next tile's x rows stream in meanwhile)
 // x is read once (plus L2-resident halo rows), c, q, k, v are written once: 5 tensor passes instead of 10.
 #include <cuda_fp16.h>
 
@@ -26,6 +26,15 @@ namespace {
 using namespace tc;
 
 constexpr int QK_NT = CT + 32;        // 16 compute warps + the control warp
+
+// Developer aid (-DQKV_TIMELINE): CTA 0 keeps clock64() stamps of the phases of its first tiles (thread 0 and the control lane) in
+// shared memory and dumps them over the first bytes of v at the end (tests/gpu_tools/timeline_qkv.py).
+#ifdef QKV_TIMELINE
+#define QTL(k) do { if (blockIdx.x == 0 && n < 8 && (threadIdx.x == 0 || threadIdx.x == CT)) \
+    qtl[(threadIdx.x == 0 ? 0 : 64) + n * 8 + (k)] = clock64(); } while (0)
+#else
+#define QTL(k) do { } while (0)
+#endif
 constexpr int RMAX = 304;             // staged rows: 128 + 2 * HALO, HALO <= 88 (grid width <= 80)
 
 struct QkvMaps { CUtensorMap x, w[3], out[4]; };   // out: c, q, k, v
@@ -34,7 +43,7 @@ template <int DBLK>
 struct SmemQ {
   static constexpr int KT = DBLK / 64;
   alignas(1024) uint8_t xh[KT][RMAX * 128];       // x rows with halo, 128-byte swizzled lines of 64 channels
-  alignas(1024) uint8_t xc[KT * TILE];            // c tile (A operand of q, k); later the staging tile of v
+  alignas(1024) uint8_t xc[KT * TILE];            // c tile: A operand of q, k and source of the c store
   alignas(1024) uint8_t w[3][KT * DBLK * 128];    // Wq, Wk, Wv of this CTA's block: [out][in] = K-major B operands
   alignas(16) float cw[9][DBLK];                  // conv taps of the block's channels, tap-major
   alignas(16) float cb[DBLK];
@@ -125,53 +134,78 @@ __global__ void __launch_bounds__(QK_NT, 1) qkv_fwd_kernel(const __grid_constant
   constexpr uint32_t idQK = make_idesc_bf16(128, DBLK, 0, 0);
   constexpr uint32_t idV = FP16 ? ((1u << 4) | ((uint32_t)(DBLK >> 3) << 17) | ((uint32_t)(128 >> 4) << 24)) : idQK;
 
+#ifdef QKV_TIMELINE
+  __shared__ long long qtl[128];
+#endif
   int n = 0;
   for (int t = tile0; t < n_tiles; t += tstep, ++n) {
     const uint32_t ph = n & 1;
     int b, tok0; tile_coords(t, b, tok0);
     const bool has_next = t + tstep < n_tiles;
-    if (issuer && has_next) prefetch_x(t + tstep);   // towards L2: the next tile's load waits for this tile's stores
+    if (issuer && has_next) prefetch_x(t + tstep);   // towards L2: the next tile's load has to wait for this tile's MMAs
+    QTL(0);
     mbar_wait(&sm.bar_x, ph);
+    QTL(1);
 
-    // ---- conv + bias + SiLU: thread = (8 channels, RPT rows) ----------------------------------------------
+    // ---- conv + bias + SiLU: thread = 8 channels x RPT consecutive tokens.  Per grid row dy the RPT + 2 staged rows
+    //      t0 - 1 .. t0 + RPT are read once each and feed the three taps dx they belong to (sliding window). ----------------
     if (compute) {
       const int c8 = tid % CH, ch0 = c8 * 8, kt = ch0 >> 6, cc = ch0 & 63;
+      const int r0 = (tid / CH) * RPT;
+      float acc[RPT][8];
+      uint32_t ok[RPT];                 // bit (dy+1)*3 + (dx+1): the tap lies inside the grid for this token
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(&sm.cb[ch0]), b1 = *reinterpret_cast<const float4*>(&sm.cb[ch0 + 4]);
 #pragma unroll
-      for (int it = 0; it < RPT; ++it) {
-        const int r = tid / CH + it * (CT / CH);
-        const int tok = tok0 + r;
-        const int gy = tok / GW, gx = tok - gy * GW;
-        float acc[8];
-        {
-          const float4 b0 = *reinterpret_cast<const float4*>(&sm.cb[ch0]), b1 = *reinterpret_cast<const float4*>(&sm.cb[ch0 + 4]);
-          acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+        for (int it = 0; it < RPT; ++it) {
+          const int tok = tok0 + r0 + it;
+          const int gy = tok / GW, gx = tok - gy * GW;
+          const uint32_t my = (gy > 0 ? 1u : 0u) | 2u | (gy + 1 < GH ? 4u : 0u);       // dy = -1, 0, +1
+          const uint32_t mx = (gx > 0 ? 1u : 0u) | 2u | (gx + 1 < GW ? 4u : 0u);
+          ok[it] = (gy < GH) ? (((my & 1u) ? mx : 0u) | ((my & 2u) ? mx << 3 : 0u) | ((my & 4u) ? mx << 6 : 0u)) : 0u;
+          acc[it][0] = b0.x; acc[it][1] = b0.y; acc[it][2] = b0.z; acc[it][3] = b0.w;
+          acc[it][4] = b1.x; acc[it][5] = b1.y; acc[it][6] = b1.z; acc[it][7] = b1.w;
+        }
+      }
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        float wt[3][8];
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float4 w0 = *reinterpret_cast<const float4*>(&sm.cw[(dy + 1) * 3 + dx][ch0]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&sm.cw[(dy + 1) * 3 + dx][ch0 + 4]);
+          wt[dx][0] = w0.x; wt[dx][1] = w0.y; wt[dx][2] = w0.z; wt[dx][3] = w0.w;
+          wt[dx][4] = w1.x; wt[dx][5] = w1.y; wt[dx][6] = w1.z; wt[dx][7] = w1.w;
         }
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
+        for (int j = -1; j <= RPT; ++j) {
+          const uint4 w = *reinterpret_cast<const uint4*>(sm.xh[kt] + swz128(halo + r0 + dy * GW + j, cc));
+          float xv[8];
+          cvt8<FP16>(w, xv);
 #pragma unroll
           for (int dx = -1; dx <= 1; ++dx) {
-            if (gy + dy < 0 || gy + dy >= GH || gx + dx < 0 || gx + dx >= GW) continue;
-            const int rr = halo + r + dy * GW + dx;
-            const uint4 w = *reinterpret_cast<const uint4*>(sm.xh[kt] + swz128(rr, cc));
-            float xv[8];
-            cvt8<FP16>(w, xv);
-            const int tap = (dy + 1) * 3 + (dx + 1);
-            const float4 w0 = *reinterpret_cast<const float4*>(&sm.cw[tap][ch0]), w1 = *reinterpret_cast<const float4*>(&sm.cw[tap][ch0 + 4]);
-            acc[0] = fmaf(xv[0], w0.x, acc[0]); acc[1] = fmaf(xv[1], w0.y, acc[1]);
-            acc[2] = fmaf(xv[2], w0.z, acc[2]); acc[3] = fmaf(xv[3], w0.w, acc[3]);
-            acc[4] = fmaf(xv[4], w1.x, acc[4]); acc[5] = fmaf(xv[5], w1.y, acc[5]);
-            acc[6] = fmaf(xv[6], w1.z, acc[6]); acc[7] = fmaf(xv[7], w1.w, acc[7]);
+            const int it = j - dx;     // the token this staged row is the dx-neighbour of
+            if (it < 0 || it >= RPT) continue;
+            if (!((ok[it] >> ((dy + 1) * 3 + (dx + 1))) & 1u)) continue;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[it][e] = fmaf(xv[e], wt[dx + 1][e], acc[it][e]);
           }
         }
+      }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = acc[e] / (1.f + __expf(-acc[e]));   // silu
-        *reinterpret_cast<uint4*>(sm.xc + kt * TILE + swz128(r, cc)) =
-            make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+      for (int it = 0; it < RPT; ++it) {
+        float* a_ = acc[it];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a_[e] = __fdividef(a_[e], 1.f + __expf(-a_[e]));   // silu
+        *reinterpret_cast<uint4*>(sm.xc + kt * TILE + swz128(r0 + it, cc)) =
+            make_uint4(pack_bf16x2(a_[0], a_[1]), pack_bf16x2(a_[2], a_[3]), pack_bf16x2(a_[4], a_[5]), pack_bf16x2(a_[6], a_[7]));
       }
     }
+    QTL(2);
     fence_proxy_async_smem();
     tc_fence_before();
     named_sync(2, QK_NT);
+    QTL(3);
 
     // ---- c leaves; q = c Wq^T, k = c Wk^T, v = x Wv^T ----------------------------------------------------------
     if (issuer) {
@@ -190,50 +224,92 @@ __global__ void __launch_bounds__(QK_NT, 1) qkv_fwd_kernel(const __grid_constant
                        j < 2 ? idQK : idV, ks > 0);
       }
       umma_commit(&sm.bar_mma);
-      tma_store_wait_read<0>();   // c has left its tile: v may be staged there (barrier 3 below)
     }
+    QTL(4);
     mbar_wait(&sm.bar_mma, ph);
     tc_fence_after();
+    QTL(5);
+    if (issuer) {
+      tma_store_wait_read<0>();   // c has left its tile: it becomes the staging tile of q, k, v in turn
+      if (has_next) load_x(t + tstep);   // the x rows are dead: the next tile streams in under the epilogue
+    }
 
-    // ---- epilogue: + bias -> bf16, staged: q, k in the dead x rows, v in the c tile ---------------------------
+    // ---- epilogue: + bias -> bf16 -> staged in the c tile (conflict-free swizzled 16-byte stores) -> one TMA store per output ----
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      if (j == 2) named_sync(3, QK_NT);   // the control lane has seen the c store read its tile
+      named_sync(3, QK_NT);   // the staging tile is free (c / the previous output has been read by the TMA engine)
       if (cq < NB) {
         float a[32];
         tmem_ld32(tm + j * DBLK + lane_sel + cq * 32, a);
         tmem_ld_wait();
-        uint8_t* stage = (j == 0) ? sm.xh[0] : (j == 1 ? sm.xh[0] + KT * TILE : sm.xc);
 #pragma unroll
         for (int x = 0; x < 32; x += 8) {
           const int col = cq * 32 + x;
           const float4 b0 = *reinterpret_cast<const float4*>(&sm.pb[j][col]), b1 = *reinterpret_cast<const float4*>(&sm.pb[j][col + 4]);
-          *reinterpret_cast<uint4*>(stage + (col >> 6) * TILE + swz128(row, col & 63)) =
+          *reinterpret_cast<uint4*>(sm.xc + (col >> 6) * TILE + swz128(row, col & 63)) =
               make_uint4(pack_bf16x2(a[x] + b0.x, a[x + 1] + b0.y), pack_bf16x2(a[x + 2] + b0.z, a[x + 3] + b0.w),
                          pack_bf16x2(a[x + 4] + b1.x, a[x + 5] + b1.y), pack_bf16x2(a[x + 6] + b1.z, a[x + 7] + b1.w));
         }
       }
+      fence_proxy_async_smem();
+      named_sync(4, QK_NT);
+      if (issuer) {
+        for (int kt = 0; kt < KT; ++kt) tma_store_4d(&maps.out[1 + j], sm.xc + kt * TILE, hb * DBLK + kt * 64, tok0, b, 0);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+      }
     }
-    fence_proxy_async_smem();
+    QTL(6);
     tc_fence_before();
-    named_sync(2, QK_NT);
-    if (issuer) {
-      for (int kt = 0; kt < KT; ++kt) {
-        tma_store_4d(&maps.out[1], sm.xh[0] + kt * TILE, hb * DBLK + kt * 64, tok0, b, 0);
-        tma_store_4d(&maps.out[2], sm.xh[0] + (KT + kt) * TILE, hb * DBLK + kt * 64, tok0, b, 0);
-        tma_store_4d(&maps.out[3], sm.xc + kt * TILE, hb * DBLK + kt * 64, tok0, b, 0);
-      }
-      tma_store_commit();
-      if (has_next) {
-        tma_store_wait_read<0>();   // the staged tiles have been read: the x rows of the next tile may land
-        load_x(t + tstep);
-      }
-    }
+    named_sync(2, QK_NT);   // accumulators consumed: the next tile's MMAs may overwrite them
   }
   if (issuer) tma_store_wait_all<0>();
   tc_fence_before();
   __syncthreads();
+#ifdef QKV_TIMELINE
+  if (blockIdx.x == 0 && tid < 128) reinterpret_cast<long long*>(p.v)[tid] = qtl[tid];
+#endif
   if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+// ---- column sums of up to three (T, D) bf16 matrices: partials[range][j][D], then a fixed-order reduction ----------------
+constexpr int CS_NT = 256, CS_RANGES = 296;      // 2 CTAs per SM per 256-column slab and source
+struct ColsumArgs { const __nv_bfloat16* src[3]; };
+
+__global__ void __launch_bounds__(CS_NT) colsum_kernel(const ColsumArgs a, const int T, const int D, const int64_t ld,
+                                                       float* __restrict__ partials, const int n_src) {
+  __shared__ float red[8][256];
+  const int j = blockIdx.z, cg = threadIdx.x & 31, rl = threadIdx.x >> 5;   // 32 groups of 8 columns x 8 row lanes
+  const int col = blockIdx.y * 256 + cg * 8;
+  const int per = (T + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per, t1 = min(T, t0 + per);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < D) {
+    const __nv_bfloat16* base = a.src[j] + col;
+    for (int t = t0 + rl; t < t1; t += 8) {
+      const uint4 w = *reinterpret_cast<const uint4*>(base + (int64_t)t * ld);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f2 = __bfloat1622float2(h[e]); acc[2 * e] += f2.x; acc[2 * e + 1] += f2.y; }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[rl][cg * 8 + e] = acc[e];
+  __syncthreads();
+  const int c = threadIdx.x;   // one column per thread, row lanes summed in fixed order
+  if (blockIdx.y * 256 + c < D) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += red[r][c];
+    partials[((size_t)blockIdx.x * n_src + j) * D + blockIdx.y * 256 + c] = s;
+  }
+}
+__global__ void colsum_reduce_kernel(const float* __restrict__ partials, float* __restrict__ out, const int n, const int ranges) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float s = 0.f;
+  for (int r = 0; r < ranges; ++r) s += partials[(size_t)r * n + e];
+  out[e] = s;
 }
 
 // 3-D map (channels, tokens, batch) of a (B*S, D) bf16/fp16 matrix with row stride ld; box = 64 x box_rows x 1.  Encoded as a 4-D
@@ -293,6 +369,46 @@ using namespace mlstm;
 extern "C" {
 
 int mlstm_b200_qkv_supported(int D, int NH, int GH, int GW, int64_t ld_x) { return qkv_shape_ok(D, NH, GH, GW, ld_x) ? 1 : 0; }
+
+size_t mlstm_b200_colsum_workspace_bytes(int D, int n_src) {
+  return (D > 0 && n_src > 0) ? sizeof(float) * (size_t)CS_RANGES * (size_t)n_src * (size_t)D : 0;
+}
+
+int mlstm_b200_colsum(const void* const* src, int n_src, int T, int D, int64_t ld, float* out, void* workspace,
+                      size_t workspace_bytes, void* cuda_stream) {
+  clear_error();
+  if (!src || n_src < 1 || n_src > 3 || T < 0 || D < 8 || D % 8 != 0 || ld % 8 != 0 || ld < D || !out) {
+    set_error("colsum: needs 1..3 sources, D and ld multiples of 8, ld >= D (n_src=%d T=%d D=%d ld=%lld)", n_src, T, D, (long long)ld);
+    return MLSTM_ERR_INVALID_ARG;
+  }
+  ColsumArgs a{};
+  for (int j = 0; j < n_src; ++j) {
+    if (!src[j] || ((uintptr_t)src[j] & 15u)) { set_error("colsum: source %d null or not 16-byte aligned", j); return MLSTM_ERR_INVALID_ARG; }
+    a.src[j] = reinterpret_cast<const __nv_bfloat16*>(src[j]);
+  }
+  if (!workspace || workspace_bytes < mlstm_b200_colsum_workspace_bytes(D, n_src)) {
+    set_error("colsum: workspace too small (%zu < %zu)", workspace ? workspace_bytes : (size_t)0, mlstm_b200_colsum_workspace_bytes(D, n_src));
+    return MLSTM_ERR_WORKSPACE;
+  }
+  int rc;
+  if ((rc = bind_device(src[0]))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const int n = n_src * D;
+  if (T == 0) {
+    cudaMemsetAsync(out, 0, sizeof(float) * n, st);
+    return MLSTM_OK;
+  }
+  int ranges = (T + 63) / 64;
+  if (ranges > CS_RANGES) ranges = CS_RANGES;
+  float* partials = reinterpret_cast<float*>(workspace);
+  colsum_kernel<<<dim3(ranges, (D + 255) / 256, n_src), CS_NT, 0, st>>>(a, T, D, ld, partials, n_src);
+  count_launch();
+  colsum_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(partials, out, n, ranges);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("colsum launch failed: %s", cudaGetErrorString(e)); return MLSTM_ERR_CUDA; }
+  return MLSTM_OK;
+}
 
 int mlstm_b200_qkv_fwd(const mlstm_qkv_params* p, void* cuda_stream) {
   clear_error();

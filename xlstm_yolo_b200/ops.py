@@ -594,6 +594,25 @@ def qkv_reference(x, conv_w, conv_b, wq, bq, wk, bk, wv, bv, gh, gw, rotate=Fals
     return c, hw(c, wq, bq), hw(c, wk, bk), hw(x, wv, bv)
 
 
+def colsum(srcs) -> torch.Tensor:
+    """Column sums of up to three equally shaped (T, D) bf16 CUDA matrices (evenly strided rows, D % 8 == 0) in one pass:
+    (len(srcs), D) fp32, deterministic (csrc/mlstm_qkv.cu).  The projections' bias gradients."""
+    lib = _lib.load()
+    T, D = srcs[0].shape
+    ld = srcs[0].stride(0)
+    assert all(t.is_cuda and t.dtype == torch.bfloat16 and t.shape == (T, D) and t.stride() == (ld, 1) for t in srcs)
+    dev = srcs[0].device
+    out = torch.empty((len(srcs), D), dtype=torch.float32, device=dev)
+    need = lib.mlstm_b200_colsum_workspace_bytes(D, len(srcs))
+    ws = torch.empty(max(1, need // 4), dtype=torch.float32, device=dev)
+    ptrs = (C.c_void_p * len(srcs))(*[t.data_ptr() for t in srcs])
+    with torch.cuda.device(dev):
+        rc = lib.mlstm_b200_colsum(ptrs, len(srcs), T, D, ld, out.data_ptr(), ws.data_ptr(), ws.numel() * 4, _stream())
+    if rc:
+        _fail(rc, "column sums")
+    return out
+
+
 def qkv_backward(x, c, conv_w, conv_b, wq, wk, wv, has_bias, dc, dq, dk, dv, gh, gw, rotate):
     """Backward of the producer in PyTorch ops (cuBLAS batched GEMMs over the strided head views, cuDNN depthwise conv):
     the saved c replaces everything but the conv pre-activation, which is recomputed.  Works on any device (the CPU
@@ -636,8 +655,12 @@ def qkv_backward(x, c, conv_w, conv_b, wq, wk, wv, has_bias, dc, dq, dk, dv, gh,
     else:
         dx = dx + torch.bmm(dvh, wv.to(cd)).transpose(0, 1).reshape(T, D).to(dx.dtype)
     dx = dx.view(B, S, D)
-    sums = lambda t, on: t.reshape(T, D).sum(0, dtype=torch.float32) if on else None
-    return (dx, dwc, dbc, dwq, sums(dq, has_bias[0]), dwk, sums(dk, has_bias[1]), dwv, sums(dv, has_bias[2]))
+    if any(has_bias) and dq.is_cuda and cd == torch.bfloat16 and D % 8 == 0:
+        cs = colsum([dqh.transpose(0, 1).reshape(T, D), dkh.transpose(0, 1).reshape(T, D), dvh.transpose(0, 1).reshape(T, D)])
+        sums = [cs[j] if has_bias[j] else None for j in range(3)]
+    else:
+        sums = [t.reshape(T, D).sum(0, dtype=torch.float32) if on else None for t, on in zip((dq, dk, dv), has_bias)]
+    return (dx, dwc, dbc, dwq, sums[0], dwk, sums[1], dwv, sums[2])
 
 
 class _QkvFn(torch.autograd.Function):
