@@ -230,6 +230,33 @@ typedef struct mlstm_qkv_params {
  * ld_x % 8 == 0. */
 int mlstm_b200_qkv_supported(int D, int NH, int GH, int GW, int64_t ld_x);
 int mlstm_b200_qkv_fwd(const mlstm_qkv_params* p, void* cuda_stream);
+/* Backward of the three projections (ABI 5): the five GEMMs of LinearHeadwiseExpand's backward (vision_lstm2.py:1016-1021 under
+ * autograd) and the bias sums in one kernel,
+ *     dxc = dc + dq Wq + dk Wk            (gradient w.r.t. c = silu(conv(x)); dc: what reaches c from the layer tail's skip)
+ *     dxv = dv Wv                         (the v projection's share of the gradient w.r.t. x)
+ *     dWq = dq^T c,  dWk = dk^T c,  dWv = dv^T x            (per block, fp32, deterministic two-stage reduction over tiles)
+ *     db  = column sums of dq | dk | dv
+ * The depthwise conv's own backward (du = dxc * silu'(u), dx = conv^T(du) + dxv) stays with cuDNN.  All (T, D) operands dense
+ * except x (row stride ld_x); bf16 except x (x_dtype). */
+typedef struct mlstm_qkv_bwd_params {
+  int32_t abi_version;                  /* MLSTM_B200_ABI_VERSION */
+  int32_t T, D, NH;                     /* rows (B * S), inner dim, projection blocks; d = D / NH in {64, 128} */
+  int32_t x_dtype;                      /* 0 bf16, 1 fp16 */
+  int32_t reserved_;
+  const void* x;   int64_t ld_x;
+  const void* c;                        /* saved forward output c */
+  const void *dq, *dk, *dv;
+  const void* dc;                       /* or NULL */
+  const void *wq, *wk, *wv;             /* (NH, d, d) [out][in], bf16 */
+  void *dxc, *dxv;                      /* outputs (T, D) bf16 */
+  float *dwq, *dwk, *dwv;               /* outputs (NH, d, d) fp32 */
+  float* db;                            /* output (3, D) fp32, or NULL */
+  void* workspace;                      /* >= mlstm_b200_qkv_bwd_workspace_bytes() */
+  size_t workspace_bytes;
+} mlstm_qkv_bwd_params;
+size_t mlstm_b200_qkv_bwd_workspace_bytes(const mlstm_qkv_bwd_params* p);
+int mlstm_b200_qkv_bwd(const mlstm_qkv_bwd_params* p, void* cuda_stream);
+
 /* Bias gradients of the three projections (the backward of vision_lstm2.py:1016-1021's `+ bias`): out[j*D + col] = sum over
  * the T rows of src[j] (bf16, row stride ld elements, D % 8 == 0), j = 0..n_src-1 (n_src <= 3), in one streaming pass with a
  * fixed-order (deterministic) two-stage reduction.  workspace >= mlstm_b200_colsum_workspace_bytes(D, n_src) bytes. */

@@ -29,6 +29,8 @@ EXPORTS = (
     "mlstm_b200_kernel_variant",
     "mlstm_b200_qkv_supported",
     "mlstm_b200_qkv_fwd",
+    "mlstm_b200_qkv_bwd_workspace_bytes",
+    "mlstm_b200_qkv_bwd",
     "mlstm_b200_colsum_workspace_bytes",
     "mlstm_b200_colsum",
     "mlstm_b200_gates_supported",
@@ -116,6 +118,20 @@ class QkvParams(C.Structure):
     ]
 
 
+class QkvBwdParams(C.Structure):
+    """ctypes mirror of ``mlstm_qkv_bwd_params`` (include/mlstm_b200.h)."""
+    _fields_ = [
+        ("abi_version", C.c_int32), ("T", C.c_int32), ("D", C.c_int32), ("NH", C.c_int32), ("x_dtype", C.c_int32),
+        ("reserved_", C.c_int32),
+        ("x", C.c_void_p), ("ld_x", C.c_int64),
+        ("c", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("dc", C.c_void_p),
+        ("wq", C.c_void_p), ("wk", C.c_void_p), ("wv", C.c_void_p),
+        ("dxc", C.c_void_p), ("dxv", C.c_void_p),
+        ("dwq", C.c_void_p), ("dwk", C.c_void_p), ("dwv", C.c_void_p), ("db", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -159,6 +175,10 @@ def load() -> C.CDLL:
         lib.mlstm_b200_gates_supported.argtypes = [C.c_int, C.c_int64]
         lib.mlstm_b200_qkv_supported.restype = C.c_int
         lib.mlstm_b200_qkv_supported.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
+        lib.mlstm_b200_qkv_bwd_workspace_bytes.restype = C.c_size_t
+        lib.mlstm_b200_qkv_bwd_workspace_bytes.argtypes = [C.POINTER(QkvBwdParams)]
+        lib.mlstm_b200_qkv_bwd.restype = C.c_int
+        lib.mlstm_b200_qkv_bwd.argtypes = [C.POINTER(QkvBwdParams), C.c_void_p]
         lib.mlstm_b200_colsum_workspace_bytes.restype = C.c_size_t
         lib.mlstm_b200_colsum_workspace_bytes.argtypes = [C.c_int, C.c_int]
         lib.mlstm_b200_colsum.restype = C.c_int

@@ -449,3 +449,382 @@ int mlstm_b200_qkv_fwd(const mlstm_qkv_params* p, void* cuda_stream) {
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// Backward of the three projections: dxc = dc + dq Wq + dk Wk, dxv = dv Wv, dW* = dy^T in, db = column sums.
+// Same tiling as the forward (a persistent CTA per SM walks 128-row tiles of ONE block h, weights resident).  The weight
+// gradients accumulate in TMEM over all tiles of the CTA (three d x d fp32 accumulators) and leave once, as per-CTA partials
+// reduced in fixed order by a second kernel.  Two MMA phases per tile share the activation buffers:
+//   phase 1   acc  = dq Wq + dk Wk ;  dWq += dq^T c ;  dWk += dk^T c        buffers: dq | dk | c | stage <- dc
+//   phase 2   acc  = dv Wv ;          dWv += dv^T x                          buffers: dv (was dq) | x (was c)
+// =====================================================================================================================
+namespace mlstm {
+namespace {
+
+struct QkvBwdMaps { CUtensorMap x, c, dq, dk, dv, dc, w[3], dxc, dxv; };
+
+template <int DBLK>
+struct SmemQB {
+  static constexpr int KT = DBLK / 64;
+  alignas(1024) uint8_t w[3][KT * DBLK * 128];
+  alignas(1024) uint8_t a0[KT * TILE];            // dq, then dv
+  alignas(1024) uint8_t a1[KT * TILE];            // dk
+  alignas(1024) uint8_t a2[KT * TILE];            // c, then x
+  alignas(1024) uint8_t stage[KT * TILE];         // dc on the way in, dxc / dxv on the way out
+  uint64_t bar_w, bar_l1, bar_l2, bar_m1, bar_m2;
+  uint32_t tmem_base;
+};
+
+// column partial sums of a [128][DBLK] swizzled bf16 tile: thread = (8 columns, row lane of 32)
+template <int DBLK>
+__device__ __forceinline__ void tile_colsum(const uint8_t* tile, int tid, float (&acc)[8]) {
+  constexpr int CH = DBLK / 8;
+  const int c8 = tid % CH, ch0 = c8 * 8, kt = ch0 >> 6, cc = ch0 & 63;
+#pragma unroll
+  for (int r = tid / CH; r < 128; r += CT / CH) {
+    const uint4 w = *reinterpret_cast<const uint4*>(tile + kt * TILE + swz128(r, cc));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f2 = __bfloat1622float2(h[e]); acc[2 * e] += f2.x; acc[2 * e + 1] += f2.y; }
+  }
+}
+
+template <int DBLK, bool FP16>
+__global__ void __launch_bounds__(QK_NT, 1) qkv_bwd_kernel(const __grid_constant__ QkvBwdMaps maps, const mlstm_qkv_bwd_params p,
+                                                           const int n_tiles, float* __restrict__ ws) {
+  constexpr int KT = DBLK / 64;
+  constexpr int NB = DBLK / 32;
+  constexpr int CH = DBLK / 8;
+  constexpr uint32_t A_LBO = (DBLK == 128) ? TILE : 0;    // d = 64: the second 64-row M block of a d x d product aliases the first
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SmemQB<DBLK>& sm = *reinterpret_cast<SmemQB<DBLK>*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool compute = tid < CT, issuer = tid == CT;
+  const int rg = warp & 3, cq = compute ? (warp >> 2) : NB, row = rg * 32 + lane;
+  const int hb = blockIdx.x % p.NH;
+  const int tile0 = blockIdx.x / p.NH, tstep = gridDim.x / p.NH;
+  const bool has_dc = p.dc != nullptr;
+
+  if (issuer) {
+    mbar_init(&sm.bar_w, 1); mbar_init(&sm.bar_l1, 1); mbar_init(&sm.bar_l2, 1); mbar_init(&sm.bar_m1, 1); mbar_init(&sm.bar_m2, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = sm.tmem_base, tAcc = tm + 3 * DBLK;
+  const uint32_t lane_sel = (uint32_t)(rg * 32) << 16;
+
+  auto load_tile = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int t) {
+    for (int kt = 0; kt < KT; ++kt) tma_load_2d(dst + kt * TILE, map, bar, hb * DBLK + kt * 64, t * 128);
+  };
+  auto load_phase1 = [&](int t) {
+    mbar_arrive_expect_tx(&sm.bar_l1, (has_dc ? 4 : 3) * KT * TILE);
+    load_tile(sm.a0, &maps.dq, &sm.bar_l1, t);
+    load_tile(sm.a1, &maps.dk, &sm.bar_l1, t);
+    load_tile(sm.a2, &maps.c, &sm.bar_l1, t);
+    if (has_dc) load_tile(sm.stage, &maps.dc, &sm.bar_l1, t);
+  };
+  if (issuer && tile0 < n_tiles) {
+    mbar_arrive_expect_tx(&sm.bar_w, 3 * KT * DBLK * 128);
+    for (int j = 0; j < 3; ++j)
+      for (int kt = 0; kt < KT; ++kt) tma_load_2d(sm.w[j] + kt * DBLK * 128, &maps.w[j], &sm.bar_w, kt * 64, hb * DBLK);
+    load_phase1(tile0);
+  }
+  // dy W : A = dy tile, K-major (K = out); B = W [K = out rows][N = in contiguous], MN-major
+  constexpr uint32_t idX = make_idesc_bf16(128, DBLK, 0, 1);
+  // dy^T in : A = dy tile, MN-major (M = out); B = in tile, MN-major (N = in); K = the tile's 128 rows
+  constexpr uint32_t idW = make_idesc_bf16(128, DBLK, 1, 1);
+  auto mma_dx = [&](const uint8_t* a, const uint8_t* w, uint32_t acc_first) {
+    const uint64_t dA = make_sdesc(smem_u32(a), 16, 1024), dB = make_sdesc(smem_u32(w), DBLK * 128, 1024);
+#pragma unroll
+    for (int ks = 0; ks < DBLK / 16; ++ks) umma_bf16_ss(tAcc, dA + kstep(ks), dB + mnstep(ks), idX, ks > 0 ? 1u : acc_first);
+  };
+  auto mma_dw = [&](uint32_t d_tmem, const uint8_t* a, const uint8_t* b, uint32_t acc_first) {
+    const uint64_t dA = make_sdesc(smem_u32(a), A_LBO, 1024), dB = make_sdesc(smem_u32(b), TILE, 1024);
+#pragma unroll
+    for (int ks = 0; ks < 128 / 16; ++ks) umma_bf16_ss(d_tmem, dA + mnstep(ks), dB + mnstep(ks), idW, ks > 0 ? 1u : acc_first);
+  };
+  // + optional dc, -> bf16 -> stage (each thread rewrites exactly the 64 bytes it has just read)
+  auto epilogue = [&](bool add_dc) {
+    if (cq < NB) {
+      float a[32];
+      tmem_ld32(tAcc + lane_sel + cq * 32, a);
+      tmem_ld_wait();
+#pragma unroll
+      for (int x = 0; x < 32; x += 8) {
+        const int col = cq * 32 + x;
+        uint4* slot = reinterpret_cast<uint4*>(sm.stage + (col >> 6) * TILE + swz128(row, col & 63));
+        if (add_dc) {
+          const uint4 w = *slot;
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float2 f2 = __bfloat1622float2(h[e]); a[x + 2 * e] += f2.x; a[x + 2 * e + 1] += f2.y; }
+        }
+        *slot = make_uint4(pack_bf16x2(a[x], a[x + 1]), pack_bf16x2(a[x + 2], a[x + 3]), pack_bf16x2(a[x + 4], a[x + 5]),
+                           pack_bf16x2(a[x + 6], a[x + 7]));
+      }
+    }
+  };
+
+  float dbq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dbk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dbv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int n = 0;
+  for (int t = tile0; t < n_tiles; t += tstep, ++n) {
+    const uint32_t ph = n & 1;
+    const bool has_next = t + tstep < n_tiles;
+    const uint32_t accw = n > 0 ? 1u : 0u;
+    // ---- phase 1 ----------------------------------------------------------------------------------------------------
+    mbar_wait(&sm.bar_l1, ph);
+    if (issuer) {
+      if (n == 0) mbar_wait(&sm.bar_w, 0);
+      tc_fence_after();
+      mma_dx(sm.a0, sm.w[0], 0u);
+      mma_dx(sm.a1, sm.w[1], 1u);
+      mma_dw(tm, sm.a0, sm.a2, accw);
+      mma_dw(tm + DBLK, sm.a1, sm.a2, accw);
+      umma_commit(&sm.bar_m1);
+    }
+    if (compute && p.db) { tile_colsum<DBLK>(sm.a0, tid, dbq); tile_colsum<DBLK>(sm.a1, tid, dbk); }
+    mbar_wait(&sm.bar_m1, ph);
+    tc_fence_after();
+    named_sync(2, QK_NT);          // every warp is past its column sums: dq and c may be overwritten
+    if (issuer) {
+      mbar_arrive_expect_tx(&sm.bar_l2, 2 * KT * TILE);
+      load_tile(sm.a0, &maps.dv, &sm.bar_l2, t);
+      load_tile(sm.a2, &maps.x, &sm.bar_l2, t);
+    }
+    epilogue(has_dc);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    named_sync(3, QK_NT);          // dxc staged, acc consumed
+    if (issuer) {
+      for (int kt = 0; kt < KT; ++kt) tma_store_2d(&maps.dxc, sm.stage + kt * TILE, hb * DBLK + kt * 64, t * 128);
+      tma_store_commit();
+    }
+    // ---- phase 2 ----------------------------------------------------------------------------------------------------
+    mbar_wait(&sm.bar_l2, ph);
+    if (FP16) {                    // x arrives as fp16: bf16 in place (the MMAs of this kernel are bf16 x bf16)
+      if (compute) {
+#pragma unroll
+        for (int it = 0; it < KT * TILE / 16 / CT; ++it) {
+          uint4* q4 = reinterpret_cast<uint4*>(sm.a2) + tid + it * CT;
+          uint4 w = *q4;
+          const __half2* h = reinterpret_cast<const __half2*>(&w);
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float2 f2 = __half22float2(h[e]); o[e] = pack_bf16x2(f2.x, f2.y); }
+          *q4 = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      named_sync(2, QK_NT);
+    }
+    if (issuer) {
+      tc_fence_after();
+      mma_dx(sm.a0, sm.w[2], 0u);
+      mma_dw(tm + 2 * DBLK, sm.a0, sm.a2, accw);
+      umma_commit(&sm.bar_m2);
+      tma_store_wait_read<0>();    // dxc has left the staging tile
+    }
+    if (compute && p.db) tile_colsum<DBLK>(sm.a0, tid, dbv);
+    mbar_wait(&sm.bar_m2, ph);
+    tc_fence_after();
+    named_sync(2, QK_NT);          // staging tile free (the control lane waited for the store), dv and x dead
+    if (issuer && has_next) {      // the next tile's dq, dk, c stream in under the second epilogue; its dc after the store below
+      mbar_arrive_expect_tx(&sm.bar_l1, (has_dc ? 4 : 3) * KT * TILE);
+      load_tile(sm.a0, &maps.dq, &sm.bar_l1, t + tstep);
+      load_tile(sm.a1, &maps.dk, &sm.bar_l1, t + tstep);
+      load_tile(sm.a2, &maps.c, &sm.bar_l1, t + tstep);
+    }
+    epilogue(false);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    named_sync(3, QK_NT);
+    if (issuer) {
+      for (int kt = 0; kt < KT; ++kt) tma_store_2d(&maps.dxv, sm.stage + kt * TILE, hb * DBLK + kt * 64, t * 128);
+      tma_store_commit();
+      if (has_next) {
+        tma_store_wait_read<0>();   // the staging tile is rewritten by the next tile (its dc now, or its first epilogue)
+        if (has_dc) load_tile(sm.stage, &maps.dc, &sm.bar_l1, t + tstep);
+      }
+    }
+  }
+  if (issuer) tma_store_wait_all<0>();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // ---- weight-gradient partials of this CTA: [3][DBLK][DBLK] fp32, then the bias partials [3][DBLK] -----------------------
+  float* wsw = ws + (size_t)blockIdx.x * (3 * DBLK * DBLK + 3 * DBLK);
+  if (cq < NB && n > 0) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float a[32];
+      tmem_ld32(tm + j * DBLK + lane_sel + cq * 32, a);
+      tmem_ld_wait();
+      if (row < DBLK) {
+        float* dst = wsw + ((size_t)j * DBLK + row) * DBLK + cq * 32;
+#pragma unroll
+        for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4*>(dst + x) = make_float4(a[x], a[x + 1], a[x + 2], a[x + 3]);
+      }
+    }
+  }
+  if (p.db) {   // reduce the 32 row lanes in fixed order through shared memory (the activation buffers are dead)
+    float* red = reinterpret_cast<float*>(sm.a0);   // [32 row lanes][3][DBLK] floats <= a0 + a1
+    if (compute) {
+      const int c8 = tid % CH, rl = tid / CH;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        red[(rl * 3 + 0) * DBLK + c8 * 8 + e] = dbq[e];
+        red[(rl * 3 + 1) * DBLK + c8 * 8 + e] = dbk[e];
+        red[(rl * 3 + 2) * DBLK + c8 * 8 + e] = dbv[e];
+      }
+    }
+    __syncthreads();
+    if (tid < 3 * DBLK) {
+      float s = 0.f;
+      for (int rl = 0; rl < CT / CH; ++rl) s += red[rl * 3 * DBLK + tid];
+      wsw[3 * DBLK * DBLK + tid] = s;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+// out[j][h][o][i] = sum over the CTAs of block h, in launch order
+__global__ void qkv_bwd_reduce_kernel(const float* __restrict__ ws, const mlstm_qkv_bwd_params p, const int per_block, const int d) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = 3 * d * d + 3 * d;
+  if (e < 3 * p.NH * d * d) {
+    const int j = e / (p.NH * d * d), r = e % (p.NH * d * d), h = r / (d * d), oi = r % (d * d);
+    float s = 0.f;
+    for (int k = 0; k < per_block; ++k) s += ws[(size_t)(k * p.NH + h) * stride + (size_t)j * d * d + oi];
+    (j == 0 ? p.dwq : (j == 1 ? p.dwk : p.dwv))[(size_t)h * d * d + oi] = s;
+  }
+  if (p.db && e < 3 * p.D) {
+    const int j = e / p.D, col = e % p.D, h = col / d, c = col % d;
+    float s = 0.f;
+    for (int k = 0; k < per_block; ++k) s += ws[(size_t)(k * p.NH + h) * stride + 3 * d * d + j * d + c];
+    p.db[e] = s;
+  }
+}
+
+int qkv_bwd_ctas_per_block(const mlstm_qkv_bwd_params& p) {
+  int per_block = 148 / p.NH;    // fixed (not the device's SM count): the workspace size must not depend on the device
+  const int n_tiles = (p.T + 127) / 128;
+  if (per_block < 1) per_block = 1;
+  if (per_block > n_tiles) per_block = n_tiles;
+  return per_block;
+}
+
+// 2-D map (columns, rows) of a (T, D) 16-bit matrix with row stride ld; box 64 x 128
+int make_mat_tmap(CUtensorMap* out, const void* ptr, int D, int T, int64_t ld) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.s0 = ld; key.d0 = D; key.d1 = T; key.box_rows = 128; key.kind = 8;
+  if (tmap_cache_lookup(key, out, false)) return 0;
+  PFN_tmapEncodeTiled enc = get_tmap_encoder();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)T};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, 128u};
+  cuuint32_t estr[2] = {1u, 1u};
+  const int r = (int)enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == 0) tmap_cache_lookup(key, out, true);
+  return r;
+}
+
+template <int DBLK, bool FP16>
+int launch_qkv_bwd(const mlstm_qkv_bwd_params& p, const QkvBwdMaps& maps, cudaStream_t st) {
+  const size_t smem = sizeof(SmemQB<DBLK>);
+  cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(qkv_bwd_kernel<DBLK, FP16>), smem);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(qkv_bwd, %zu B): %s", smem, cudaGetErrorString(e));
+    return MLSTM_ERR_CUDA;
+  }
+  const int per_block = qkv_bwd_ctas_per_block(p), n_tiles = (p.T + 127) / 128;
+  float* ws = reinterpret_cast<float*>(p.workspace);
+  qkv_bwd_kernel<DBLK, FP16><<<dim3(per_block * p.NH), dim3(QK_NT), smem, st>>>(maps, p, n_tiles, ws);
+  count_launch();
+  const int n = 3 * p.NH * DBLK * DBLK;
+  qkv_bwd_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, p, per_block, DBLK);
+  count_launch();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("qkv_bwd launch failed: %s", cudaGetErrorString(e));
+    return MLSTM_ERR_CUDA;
+  }
+  return MLSTM_OK;
+}
+
+}  // namespace
+}  // namespace mlstm
+
+extern "C" {
+
+size_t mlstm_b200_qkv_bwd_workspace_bytes(const mlstm_qkv_bwd_params* p) {
+  if (!p || p->T <= 0 || p->NH <= 0 || p->D % p->NH != 0) return 0;
+  const size_t d = (size_t)(p->D / p->NH);
+  return sizeof(float) * (size_t)qkv_bwd_ctas_per_block(*p) * (size_t)p->NH * (3 * d * d + 3 * d);
+}
+
+int mlstm_b200_qkv_bwd(const mlstm_qkv_bwd_params* p, void* cuda_stream) {
+  clear_error();
+  if (!p) { set_error("params is NULL"); return MLSTM_ERR_INVALID_ARG; }
+  if (p->abi_version != MLSTM_B200_ABI_VERSION) {
+    set_error("abi_version %d != %d", p->abi_version, MLSTM_B200_ABI_VERSION);
+    return MLSTM_ERR_INVALID_ARG;
+  }
+  if (p->T < 0 || p->x_dtype < 0 || p->x_dtype > 1) { set_error("bad T / x_dtype"); return MLSTM_ERR_INVALID_ARG; }
+  if (!qkv_shape_ok(p->D, p->NH, 1, 1, p->ld_x)) {
+    set_error("qkv backward: D / NH must be 64 or 128, ld_x a multiple of 8 and >= D (D=%d NH=%d ld_x=%lld)", p->D, p->NH, (long long)p->ld_x);
+    return MLSTM_ERR_UNSUPPORTED;
+  }
+  if (!p->dwq || !p->dwk || !p->dwv) { set_error("qkv backward: null weight-gradient pointer"); return MLSTM_ERR_INVALID_ARG; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const int d = p->D / p->NH;
+  if (p->T == 0) {
+    int rc0 = bind_device(p->dwq);
+    if (rc0) return rc0;
+    for (float* w : {p->dwq, p->dwk, p->dwv}) cudaMemsetAsync(w, 0, sizeof(float) * (size_t)p->NH * d * d, st);
+    if (p->db) cudaMemsetAsync(p->db, 0, sizeof(float) * 3 * p->D, st);
+    return MLSTM_OK;
+  }
+  if (!p->x || !p->c || !p->dq || !p->dk || !p->dv || !p->wq || !p->wk || !p->wv || !p->dxc || !p->dxv) {
+    set_error("qkv backward: null pointer");
+    return MLSTM_ERR_INVALID_ARG;
+  }
+  if (!p->workspace || p->workspace_bytes < mlstm_b200_qkv_bwd_workspace_bytes(p)) {
+    set_error("qkv backward: workspace too small (%zu < %zu)", p->workspace ? p->workspace_bytes : (size_t)0,
+              mlstm_b200_qkv_bwd_workspace_bytes(p));
+    return MLSTM_ERR_WORKSPACE;
+  }
+  int rc;
+  if ((rc = bind_device(p->x))) return rc;
+  QkvBwdMaps maps;
+  int r = 0;
+  r |= make_mat_tmap(&maps.x, p->x, p->D, p->T, p->ld_x);
+  r |= make_mat_tmap(&maps.c, p->c, p->D, p->T, p->D);
+  r |= make_mat_tmap(&maps.dq, p->dq, p->D, p->T, p->D);
+  r |= make_mat_tmap(&maps.dk, p->dk, p->D, p->T, p->D);
+  r |= make_mat_tmap(&maps.dv, p->dv, p->D, p->T, p->D);
+  maps.dc = maps.c;
+  if (p->dc) r |= make_mat_tmap(&maps.dc, p->dc, p->D, p->T, p->D);
+  r |= make_mat_tmap(&maps.dxc, p->dxc, p->D, p->T, p->D);
+  r |= make_mat_tmap(&maps.dxv, p->dxv, p->D, p->T, p->D);
+  const void* wsrc[3] = {p->wq, p->wk, p->wv};
+  for (int j = 0; j < 3; ++j) r |= tc::make_state_tmap(&maps.w[j], wsrc[j], (size_t)p->D, d, d);
+  if (r) {
+    set_error("cuTensorMapEncodeTiled failed (%d): pointers must be 16-byte aligned", r);
+    return r == -1 ? MLSTM_ERR_NO_DEVICE : MLSTM_ERR_INVALID_ARG;
+  }
+  if (d == 128) return p->x_dtype ? launch_qkv_bwd<128, true>(*p, maps, st) : launch_qkv_bwd<128, false>(*p, maps, st);
+  return p->x_dtype ? launch_qkv_bwd<64, true>(*p, maps, st) : launch_qkv_bwd<64, false>(*p, maps, st);
+}
+
+}  // extern "C"

@@ -18,7 +18,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import Act, Gate, GateProjParams, GlueParams, Params, QkvParams
+from ._lib import Act, Gate, GateProjParams, GlueParams, Params, QkvBwdParams, QkvParams
 
 _DT = {torch.float32: _lib.MLSTM_F32, torch.bfloat16: _lib.MLSTM_BF16}
 
@@ -613,6 +613,57 @@ def colsum(srcs) -> torch.Tensor:
     return out
 
 
+def qkv_proj_backward(x, c, wq, wk, wv, dc, dq, dk, dv, need_db=True):
+    """The projections' share of the producer's backward as one kernel (csrc/mlstm_qkv.cu, qkv_bwd_kernel): returns
+    (dxc, dxv, dWq, dWk, dWv, db) with dxc = dc + dq Wq + dk Wk, dxv = dv Wv (both (B,S,D) bf16), dW* (NH,d,d) fp32,
+    db (3, D) fp32 column sums of dq | dk | dv.  x: (B,S,D) bf16 / fp16 rows (column slice allowed); the rest dense bf16."""
+    lib = _lib.load()
+    B, S, D = x.shape
+    NH, d = wq.shape[0], wq.shape[1]
+    T, dev = B * S, x.device
+    dense = lambda t: None if t is None else (t if (t.dtype == torch.bfloat16 and t.is_contiguous()) else t.to(torch.bfloat16).contiguous())
+    c, dq, dk, dv, dc = dense(c), dense(dq), dense(dk), dense(dv), dense(dc)
+    kw = [w.detach().to(torch.bfloat16).contiguous() for w in (wq, wk, wv)]
+    dxc = torch.empty((B, S, D), dtype=torch.bfloat16, device=dev)
+    dxv = torch.empty((B, S, D), dtype=torch.bfloat16, device=dev)
+    dws = [torch.empty((NH, d, d), dtype=torch.float32, device=dev) for _ in range(3)]
+    db = torch.empty((3, D), dtype=torch.float32, device=dev) if need_db else None
+    g = QkvBwdParams()
+    g.abi_version = _lib.ABI_VERSION
+    g.T, g.D, g.NH, g.x_dtype = T, D, NH, int(x.dtype == torch.float16)
+    g.x, g.ld_x = x.data_ptr(), x.stride(1)
+    g.c, g.dq, g.dk, g.dv, g.dc = c.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), _ptr(dc)
+    g.wq, g.wk, g.wv = (w.data_ptr() for w in kw)
+    g.dxc, g.dxv = dxc.data_ptr(), dxv.data_ptr()
+    g.dwq, g.dwk, g.dwv = (w.data_ptr() for w in dws)
+    g.db = _ptr(db)
+    need = lib.mlstm_b200_qkv_bwd_workspace_bytes(C.byref(g))
+    ws = torch.empty(max(1, (need + 3) // 4), dtype=torch.float32, device=dev)
+    g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    with torch.cuda.device(dev):
+        rc = lib.mlstm_b200_qkv_bwd(C.byref(g), _stream())
+    if rc:
+        _fail(rc, "qkv producer backward")
+    return dxc, dxv, dws[0], dws[1], dws[2], db
+
+
+def _conv_silu_backward(x, conv_w, conv_b, dxc, dxv, gh, gw, rotate):
+    """du = dxc * silu'(u) with u = conv(x) recomputed, then the depthwise conv's own backward; dx = conv^T(du) + dxv."""
+    B, S, D = x.shape
+    w = (conv_w.flip(-1, -2) if rotate else conv_w).to(x.dtype)
+    img = x.reshape(B, gh, gw, D).permute(0, 3, 1, 2)
+    u = torch.nn.functional.conv2d(img, w, None if conv_b is None else conv_b.to(x.dtype), padding=1, groups=D)
+    dxc_img = dxc.reshape(B, gh, gw, D).permute(0, 3, 1, 2)
+    du = torch.ops.aten.silu_backward(dxc_img if dxc_img.dtype == u.dtype else dxc_img.to(u.dtype), u)
+    dimg, dwc, dbc = torch.ops.aten.convolution_backward(du, img, w, [D] if conv_b is not None else None, [1, 1], [1, 1], [1, 1],
+                                                         False, [0, 0], D, [True, True, conv_b is not None])
+    if rotate:
+        dwc = dwc.flip(-1, -2)
+    dx = dimg.permute(0, 2, 3, 1).reshape(B, S, D)
+    dx = dx + (dxv if dxv.dtype == dx.dtype else dxv.to(dx.dtype)).reshape(B, S, D)
+    return dx, dwc, dbc
+
+
 def qkv_backward(x, c, conv_w, conv_b, wq, wk, wv, has_bias, dc, dq, dk, dv, gh, gw, rotate):
     """Backward of the producer in PyTorch ops (cuBLAS batched GEMMs over the strided head views, cuDNN depthwise conv):
     the saved c replaces everything but the conv pre-activation, which is recomputed.  Works on any device (the CPU
@@ -621,6 +672,14 @@ def qkv_backward(x, c, conv_w, conv_b, wq, wk, wv, has_bias, dc, dq, dk, dv, gh,
     B, S, D = x.shape
     NH, d = wq.shape[0], wq.shape[1]
     T = B * S
+    if (x.is_cuda and dq.dtype == torch.bfloat16 and c.dtype == torch.bfloat16 and x.dtype in (torch.bfloat16, torch.float16)
+            and x.stride(2) == 1 and x.stride(0) == S * x.stride(1) and x.data_ptr() % 16 == 0
+            and _lib.load().mlstm_b200_qkv_supported(D, NH, 1, 1, x.stride(1))):
+        # the five GEMMs and the bias sums as one tcgen05 kernel; the conv's own backward stays with cuDNN
+        dxc, dxv, dwq, dwk, dwv, db = qkv_proj_backward(x, c, wq, wk, wv, dc, dq, dk, dv, need_db=any(has_bias))
+        dx, dwc, dbc = _conv_silu_backward(x, conv_w, conv_b, dxc, dxv, gh, gw, rotate)
+        pick = lambda j: db[j] if has_bias[j] else None
+        return (dx, dwc, dbc, dwq, pick(0), dwk, pick(1), dwv, pick(2))
     cd = dq.dtype                                            # compute dtype of the projections' gradients
     heads = lambda t: t.reshape(T, NH, d).transpose(0, 1)   # (NH, T, d) strided view: no copy for evenly strided rows
     dense = lambda t: t if t.is_contiguous() else t.contiguous()
