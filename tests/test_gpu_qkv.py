@@ -128,3 +128,21 @@ def test_projection_backward_kernel_matches_fp64(B, S, NH, d, xdtype, with_dc):
     again = run()
     for a, b_ in zip(got, again):
         assert torch.equal(a, b_)
+
+
+def test_half_precision_inference_pair_runs_with_and_without_the_producer():
+    """engine/validator.py:117-119 runs the detector as model.half() without autocast: fp16 parameters and activations around
+    bf16 cell kernels.  The pair with the producer kernel agrees with the pair without it (regression: the tail used to assume
+    conv_act and z share a dtype)."""
+    from xlstm_yolo_b200 import ViLBlockPair
+    torch.manual_seed(0)
+    pair = ViLBlockPair(dim=128, chunk_size=64, qkv_block_size=64).cuda().half().eval()
+    x = torch.randn(2, 400, 128, device="cuda", dtype=torch.float16)
+    outs = []
+    for fused in (True, False):
+        for blk in (pair.rowwise_from_top_left, pair.rowwise_from_bot_right):
+            blk.layer.fused_producer = fused
+        with torch.no_grad():
+            outs.append(pair(x).float())
+    assert outs[0].dtype == torch.float32 and torch.isfinite(outs[0]).all()
+    assert rel(outs[0], outs[1]) < 1e-2

@@ -253,10 +253,9 @@ class ViLLayer(nn.Module):
             # form are call arguments: no module state is touched, so the forward is re-entrant.
             from . import ops
             h_raw = cell(q, k, v, reverse=anti, raw_output=True)                 # (B,NH,S,DH)
-            if conv_act.dtype != h_raw.dtype:
-                conv_act_k, z_k = conv_act.to(h_raw.dtype), z.to(h_raw.dtype)
-            else:
-                conv_act_k, z_k = conv_act, z
+            # (each on its own: the producer already hands conv_act over in the cell's dtype, z keeps the autocast / model dtype)
+            conv_act_k = conv_act if conv_act.dtype == h_raw.dtype else conv_act.to(h_raw.dtype)
+            z_k = z if z.dtype == h_raw.dtype else z.to(h_raw.dtype)
             if ops.glue_supported(h_raw, conv_act_k, z_k):
                 y = ops.layer_tail(h_raw, conv_act_k, z_k, cell.outnorm.weight, cell.outnorm.bias, self.learnable_skip,
                                    eps=cell.outnorm.eps)
@@ -266,6 +265,8 @@ class ViLLayer(nn.Module):
         if y is None:
             h = cell(q, k, v, reverse=anti)
             y = (h + self.learnable_skip * conv_act) * F.silu(z)
+        if y.dtype != self.proj_down.weight.dtype and not torch.is_autocast_enabled():
+            y = y.to(self.proj_down.weight.dtype)   # model.half() inference around the bf16 kernels (engine/validator.py:117-119)
         y = self.proj_down(y)
         if literal_flip:
             y = y.flip(dims=[1])
