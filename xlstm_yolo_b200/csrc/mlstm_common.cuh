@@ -65,6 +65,18 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// Fixed-order (deterministic) sum of n_part partials spaced `stride` floats apart, by a group of 8 adjacent lanes: lane l adds
+// partials l, l+8, ... , then the eight lane sums are added in lane order.  Every lane of the warp must call it (clamp the
+// element index instead of returning early); the total comes back in all eight lanes.
+__device__ __forceinline__ float ordered_sum8(const float* base, int n_part, size_t stride) {
+  const int l8 = threadIdx.x & 7;
+  float acc = 0.f;
+  for (int r = l8; r < n_part; r += 8) acc += base[(size_t)r * stride];
+  float tot = 0.f;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) tot += __shfl_sync(0xffffffffu, acc, l, 8);
+  return tot;
+}
 // inclusive scans across the 32 lanes of a warp
 __device__ __forceinline__ float warp_scan_add(float v, int lane) {
 #pragma unroll

@@ -245,19 +245,20 @@ __global__ void __launch_bounds__(BW_NT) gates_bwd_kernel(const mlstm_gate_proj_
 __global__ void gates_reduce_kernel(const mlstm_gate_proj_params p, const float* __restrict__ ws_w,
                                     const float* __restrict__ ws_b, const int ranges) {
   const int C3 = 3 * p.D, NO = 2 * p.NH;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < NO * C3) {
-    float acc = 0.f;
-    for (int r = 0; r < ranges; ++r) acc += ws_w[(size_t)r * NO * C3 + e];
+  const int e0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;   // eight lanes per output element
+  const bool lead = (threadIdx.x & 7) == 0;
+  {
+    const int e = min(e0, NO * C3 - 1);
+    const float acc = ordered_sum8(ws_w + e, ranges, (size_t)NO * C3);
     const int o = e / C3, c = e - o * C3;
     float* out = o < p.NH ? p.dw_i + (size_t)o * C3 + c : p.dw_f + (size_t)(o - p.NH) * C3 + c;
-    *out = acc;
+    if (lead && e0 < NO * C3) *out = acc;
   }
-  if (e < NO) {
-    float acc = 0.f;
-    for (int r = 0; r < ranges; ++r) acc += ws_b[(size_t)r * NO + e];
+  if (e0 < ((NO + 31) & ~31)) {   // warp-uniform (NO is rounded up to whole warps of element groups)
+    const int e = min(e0, NO - 1);
+    const float acc = ordered_sum8(ws_b + e, ranges, (size_t)NO);
     float* out = e < p.NH ? (p.db_i ? p.db_i + e : nullptr) : (p.db_f ? p.db_f + (e - p.NH) : nullptr);
-    if (out) *out = acc;
+    if (lead && e0 < NO && out) *out = acc;
   }
 }
 
@@ -374,7 +375,7 @@ int mlstm_b200_gates_bwd(const mlstm_gate_proj_params* p, void* cuda_stream) {
     if ((rc = finish("gates_bwd"))) return rc;
   }
   const int n = NO * C3;
-  gates_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(*p, ws_w, ws_b, ranges);
+  gates_reduce_kernel<<<(n * 8 + 255) / 256, 256, 0, st>>>(*p, ws_w, ws_b, ranges);
   return finish("gates_reduce");
 }
 

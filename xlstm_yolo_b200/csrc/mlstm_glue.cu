@@ -197,13 +197,12 @@ __global__ void __launch_bounds__(GL_NT, 2) glue_bwd_kernel(const mlstm_glue_par
 }
 
 __global__ void glue_reduce_kernel(const mlstm_glue_params p, const float* __restrict__ ws, const int ctas) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 3 * p.D) return;
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;   // eight lanes per output element
+  const int i = min(i0, 3 * p.D - 1);
   const int k = i / p.D, cd = i - k * p.D;
-  float acc = 0.f;
-  for (int c = 0; c < ctas; ++c) acc += ws[((size_t)c * 3 + k) * p.D + cd];
+  const float acc = ordered_sum8(ws + (size_t)k * p.D + cd, ctas, (size_t)3 * p.D);
   float* out = k == 0 ? p.dw : (k == 1 ? p.db : p.dskip);
-  if (out) out[cd] = acc;
+  if (out && i0 < 3 * p.D && (threadIdx.x & 7) == 0) out[cd] = acc;
 }
 
 int glue_grid(const mlstm_glue_params& p) {
@@ -298,7 +297,7 @@ int mlstm_b200_glue_bwd(const mlstm_glue_params* p, void* cuda_stream) {
   if (p->dtype == MLSTM_BF16) glue_bwd_kernel<__nv_bfloat16><<<grid, GL_NT, 0, st>>>(*p, ws);
   else glue_bwd_kernel<float><<<grid, GL_NT, 0, st>>>(*p, ws);
   if ((rc = done("glue_bwd"))) return rc;
-  glue_reduce_kernel<<<(3 * p->D + 255) / 256, 256, 0, st>>>(*p, ws, grid);
+  glue_reduce_kernel<<<(3 * p->D * 8 + 255) / 256, 256, 0, st>>>(*p, ws, grid);
   return done("glue_reduce");
 }
 

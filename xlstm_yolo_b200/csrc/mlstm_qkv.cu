@@ -305,11 +305,10 @@ __global__ void __launch_bounds__(CS_NT) colsum_kernel(const ColsumArgs a, const
   }
 }
 __global__ void colsum_reduce_kernel(const float* __restrict__ partials, float* __restrict__ out, const int n, const int ranges) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  float s = 0.f;
-  for (int r = 0; r < ranges; ++r) s += partials[(size_t)r * n + e];
-  out[e] = s;
+  const int e0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;   // eight lanes per output element
+  const int e = min(e0, n - 1);
+  const float s = ordered_sum8(partials + e, ranges, (size_t)n);
+  if (e0 < n && (threadIdx.x & 7) == 0) out[e] = s;
 }
 
 // 3-D map (channels, tokens, batch) of a (B*S, D) bf16/fp16 matrix with row stride ld; box = 64 x box_rows x 1.  Encoded as a 4-D
@@ -403,7 +402,7 @@ int mlstm_b200_colsum(const void* const* src, int n_src, int T, int D, int64_t l
   float* partials = reinterpret_cast<float*>(workspace);
   colsum_kernel<<<dim3(ranges, (D + 255) / 256, n_src), CS_NT, 0, st>>>(a, T, D, ld, partials, n_src);
   count_launch();
-  colsum_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(partials, out, n, ranges);
+  colsum_reduce_kernel<<<(n * 8 + 255) / 256, 256, 0, st>>>(partials, out, n, ranges);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("colsum launch failed: %s", cudaGetErrorString(e)); return MLSTM_ERR_CUDA; }

@@ -505,7 +505,10 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
   constexpr int KT = DH / 64;
   constexpr int NB = DH / 32;
   const int DHF = p.DHQK, ncb = DHF / DH, nblk = ncb * ncb;
-  const int row0 = ((int)blockIdx.y / ncb) * DH, col0 = ((int)blockIdx.y % ncb) * DH;
+  // block launches (DHF > DH): block index in blockIdx.x, so the CTAs sharing a Q or dH tile run side by side (L2 reuse)
+  const bool blocks = DHF != DH;
+  const int by = blocks ? (int)blockIdx.x : (int)blockIdx.y;
+  const int row0 = (by / ncb) * DH, col0 = (by % ncb) * DH;
   constexpr uint32_t A_LBO = (DH == 128) ? TILE : 0;
   constexpr uint32_t TCOLS = 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -515,7 +518,7 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool compute = tid < CT, issuer = tid == CT, gatew = tid >= GT0;
   const int rg = warp & 3, cq = compute ? (warp >> 2) : 4, row = rg * 32 + lane;
-  const int bh = blockIdx.x, b = bh / p.NH, h = bh % p.NH;
+  const int bh = blocks ? blockIdx.y : blockIdx.x, b = bh / p.NH, h = bh % p.NH;
   const int S = p.S, NC = num_chunks(S);
   const bool rev = p.reverse != 0;
   const BwdLayout blay(p.B, p.NH, S, DHF);
@@ -708,7 +711,7 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
       float f_ = 0.f;
 #pragma unroll
       for (int w = 0; w < 16; ++w) f_ += sm.fpart[w];
-      flow[sc * nblk + blockIdx.y] = f_;
+      flow[sc * nblk + by] = f_;
     }
     if (issuer && sc - 1 > 0) load_cs(sc - 1);   // (the boundary before chunk 0 is the initial state: not needed)
     if (issuer) {   // dC_{sc-1} tile -> workspace; its shared-memory copy is rewritten one step later
@@ -876,7 +879,7 @@ int tc_state_bwd_blocks(const mlstm_params& p, cudaStream_t st, const CUtensorMa
   const size_t smSB = sizeof(SmemSB<128>);
   if ((rc = prep(tc_state_bwd_kernel<128>, smSB, "tc_state_bwd"))) return rc;
   const int ncb = p.DHQK / 128;
-  tc_state_bwd_kernel<128><<<dim3(p.B * p.NH, ncb * ncb), dim3(NT), smSB, st>>>(ms, p, resolve_scale(p));
+  tc_state_bwd_kernel<128><<<dim3(ncb * ncb, p.B * p.NH), dim3(NT), smSB, st>>>(ms, p, resolve_scale(p));
   return launched("tc_state_bwd");
 }
 int tc_dfscan_launch(const mlstm_params& p, cudaStream_t st) {

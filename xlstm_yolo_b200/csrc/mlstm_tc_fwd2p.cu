@@ -52,7 +52,11 @@ template <int DH>
 __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_constant__ FwdMaps maps, const mlstm_params p) {
   constexpr int KT = DH / 64;
   const int DHF = p.DHQK, nrb = DHF / DH;
-  const int nsl = gridDim.y / nrb, sl = blockIdx.y % nsl, row0 = (blockIdx.y / nsl) * DH;
+  // block launches (DHF > DH) put the block index in blockIdx.x: the CTAs that share a K or V tile are neighbours in launch
+  // order, run in the same round and find each other's tiles in L2 (405 -> 210 MB DRAM reads at B32 NH4 S1600 DH256)
+  const bool blocks = DHF != DH;
+  const int by = blocks ? blockIdx.x : blockIdx.y, ny = blocks ? gridDim.x : gridDim.y;
+  const int nsl = ny / nrb, sl = by % nsl, row0 = (by / nsl) * DH;
   const int DVs = DHF / nsl, col0 = sl * DVs;   // this CTA's value columns [col0, col0 + DVs)
   const int NB = DVs / 32, KTV = DVs / 64;     // active 32-column blocks / 64-column tiles of V and of the state
   constexpr uint32_t A_LBO = (DH == 128) ? TILE : 0;   // DH=64: the 2nd 64-row M block aliases the 1st
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(NT, 1) tc_state_fwd_kernel(const __grid_consta
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool compute = tid < CT, issuer = tid == CT, gatew = tid >= GT0;
   const int rg = warp & 3, cq = compute ? (warp >> 2) : 4, row = rg * 32 + lane;
-  const int bh = blockIdx.x, b = bh / p.NH, h = bh % p.NH;
+  const int bh = blocks ? blockIdx.y : blockIdx.x, b = bh / p.NH, h = bh % p.NH;
   const int S = p.S, NC = num_chunks(S);
   const bool rev = p.reverse != 0, has_init = p.c_initial != nullptr;
   const StateLayout lay(p.B, p.NH, S, DHF);
@@ -528,7 +532,7 @@ int tc_state_fwd_blocks(const mlstm_params& p, cudaStream_t st, const CUtensorMa
   int rc;
   const size_t smS = sizeof(SmemS<128>);
   if ((rc = prep(tc_state_fwd_kernel<128>, smS, "tc_state_fwd"))) return rc;
-  tc_state_fwd_kernel<128><<<dim3(p.B * p.NH, (p.DHQK / 128) * nsl), dim3(NT), smS, st>>>(maps, p);
+  tc_state_fwd_kernel<128><<<dim3((p.DHQK / 128) * nsl, p.B * p.NH), dim3(NT), smS, st>>>(maps, p);
   return launched("tc_state_fwd");
 }
 
