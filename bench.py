@@ -62,12 +62,15 @@ def algorithmic(B, NH, S, DH):
 
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the kernels behind each timed
-# part, from the round-1 `ncu --set full` captures (profiles/r01_ncu_full_*_summary.csv).  Writes that
+# part, from the `ncu --set full` captures (profiles/r0*_ncu_full_*_summary.csv).  Writes that
 # stay in the 126 MB L2 until after the kernel are not counted by ncu.
 NCU_TRAFFIC_BYTES = {
-    "cfg2_B32_NH4_S400_DH64": {"fwd": 20.14e6, "bwd_dq": None, "bwd_dkv": 38.03e6 + 0.25e6},   # fused backward: one kernel (r01)
-    # r02: the DH = 128 fused walk (profiles/r02_ncu_full_cfg3_S1600_fused128.csv): 322.9 MB read + 126.8 MB written
-    "cfg3_B32_NH4_S1600_DH128": {"fwd": 159.12e6 + 70.35e6, "bwd_dq": None, "bwd_dkv": 322.93e6 + 126.77e6},
+    # round 2 captures (profiles/r02_ncu_full_<workload>_summary.csv)
+    "cfg2_B32_NH4_S400_DH64": {"fwd": 20.1e6, "bwd_dq": None, "bwd_dkv": 38.0e6 + 0.25e6},   # fused backward: one kernel; its outputs stay in L2
+    "cfg3_B32_NH4_S1600_DH128": {"fwd": 159.1e6 + 73.0e6, "bwd_dq": None, "bwd_dkv": 326.5e6 + 129.3e6},   # DH = 128 fused walk
+    # DH = 256 family: state walk + F | A | adjoint-state walk + B1 + B2 + scan
+    "cfg3alt_B32_NH4_S1600_DH256": {"fwd": (405.5 + 189.8 + 536.1 + 91.5) * 1e6, "bwd_dq": (747.5 + 100.4) * 1e6,
+                                    "bwd_dkv": (620.1 + 201.2 + 536.1 + 88.8 + 643.4 + 97.5 + 14.0) * 1e6},
 }
 
 
