@@ -224,6 +224,8 @@ typedef struct mlstm_qkv_params {
   const void *wq, *wk, *wv;             /* (NH, d, d) [out][in]; wq, wk bf16; wv in x_dtype */
   const float *bq, *bk, *bv;            /* (D) fp32, each may be NULL */
   void *c, *q, *k, *v;                  /* (B*S, D) bf16, dense */
+  void* sp;                             /* optional (B*S, D) bf16, dense: silu'(conv(x)), what mlstm_b200_conv_bwd needs (training);
+                                           NULL in inference */
 } mlstm_qkv_params;
 
 /* 1 when the producer handles the shape: d = D / NH in {64, 128}, GW <= 80 (halo rows staged on chip),
@@ -256,6 +258,32 @@ typedef struct mlstm_qkv_bwd_params {
 } mlstm_qkv_bwd_params;
 size_t mlstm_b200_qkv_bwd_workspace_bytes(const mlstm_qkv_bwd_params* p);
 int mlstm_b200_qkv_bwd(const mlstm_qkv_bwd_params* p, void* cuda_stream);
+
+/* Backward of the depthwise conv + SiLU in front of the projections (ABI 5): with du = dxc * sp (sp = silu'(conv(x)) saved by
+ * mlstm_b200_qkv_fwd),
+ *     dx  = conv^T(du) + dxv             (the transposed depthwise 3x3 conv; dxv from mlstm_b200_qkv_bwd)
+ *     dwc = sum over tokens of du (x) x  (per channel, 3 x 3),  dbc = sum over tokens of du
+ * in one kernel: a tile of x and of dxc with one grid row + 1 of halo on each side is staged once, du is formed in place,
+ * dx leaves in x's dtype; the weight gradients go through per-CTA partials reduced in fixed order (deterministic).
+ * Replaces cuDNN's dgrad / wgrad, the conv recompute, silu_backward and the final add (and the channels-last copies
+ * cuDNN makes of the strided x). */
+typedef struct mlstm_conv_bwd_params {
+  int32_t abi_version;                  /* MLSTM_B200_ABI_VERSION */
+  int32_t B, GH, GW;                    /* batch, token grid (S = GH * GW) */
+  int32_t D, NH;                        /* inner dim, channel blocks (d = D / NH in {64, 128}) */
+  int32_t rotate;                       /* as in the forward */
+  int32_t x_dtype;                      /* 0 bf16, 1 fp16: dtype of x and of dx */
+  const void* x;   int64_t ld_x;
+  const void *dxc, *dxv, *sp;           /* (B*S, D) bf16, dense */
+  const float* conv_w;                  /* (D, 3, 3) fp32 */
+  void* dx;                             /* output (B*S, D) in x_dtype, dense */
+  float* dwc;                           /* output (D, 3, 3) fp32 */
+  float* dbc;                           /* output (D) fp32, or NULL */
+  void* workspace;                      /* >= mlstm_b200_conv_bwd_workspace_bytes() */
+  size_t workspace_bytes;
+} mlstm_conv_bwd_params;
+size_t mlstm_b200_conv_bwd_workspace_bytes(const mlstm_conv_bwd_params* p);
+int mlstm_b200_conv_bwd(const mlstm_conv_bwd_params* p, void* cuda_stream);
 
 /* Bias gradients of the three projections (the backward of vision_lstm2.py:1016-1021's `+ bias`): out[j*D + col] = sum over
  * the T rows of src[j] (bf16, row stride ld elements, D % 8 == 0), j = 0..n_src-1 (n_src <= 3), in one streaming pass with a

@@ -146,3 +146,40 @@ def test_half_precision_inference_pair_runs_with_and_without_the_producer():
             outs.append(pair(x).float())
     assert outs[0].dtype == torch.float32 and torch.isfinite(outs[0]).all()
     assert rel(outs[0], outs[1]) < 1e-2
+
+
+@pytest.mark.parametrize("B,gh,gw,D,xdtype,rotate,bias", [(2, 20, 20, 256, torch.bfloat16, False, True), (2, 40, 40, 512, torch.bfloat16, True, True),
+                                                          (1, 80, 80, 128, torch.float16, False, False), (3, 7, 9, 64, torch.float16, True, True),
+                                                          (40, 20, 20, 256, torch.bfloat16, False, True)])
+def test_conv_silu_backward_kernel_matches_fp64(B, gh, gw, D, xdtype, rotate, bias):
+    """conv_bwd_kernel (du = dxc * silu'(u) in place over the staged rows, transposed depthwise conv, weight / bias gradients through
+    fixed-order partials) against autograd of silu(conv(x)) in fp64 with the same 16-bit inputs; bit-identical when repeated."""
+    from xlstm_yolo_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    S = gh * gw
+    up = torch.randn(B, S, 2 * D, generator=g).to(xdtype)
+    conv_w = torch.randn(D, 1, 3, 3, generator=g) * 0.3
+    conv_b = torch.randn(D, generator=g) * 0.1 if bias else None
+    dxc, dxv = (torch.randn(B, S, D, generator=g).bfloat16() for _ in range(2))
+    xd = up[..., :D].double().requires_grad_(True)
+    wd = conv_w.double().requires_grad_(True)
+    bd = conv_b.double().requires_grad_(True) if bias else None
+    w_used = wd.flip(-1, -2) if rotate else wd
+    u = torch.nn.functional.conv2d(xd.reshape(B, gh, gw, D).permute(0, 3, 1, 2), w_used, bd, padding=1, groups=D)
+    # the kernel's operands: sp rounded to bf16, du = dxc * sp rounded to bf16
+    sg = torch.sigmoid(u.detach())
+    sp = (sg * (1 + u.detach() * (1 - sg))).permute(0, 2, 3, 1).reshape(B, S, D).bfloat16()
+    du = (dxc.double() * sp.double()).bfloat16().double()
+    grads = torch.autograd.grad(u, [xd, wd] + ([bd] if bias else []), du.reshape(B, gh, gw, D).permute(0, 3, 1, 2))
+    want = [grads[0] + dxv.double(), grads[1]] + ([grads[2]] if bias else [])
+    x = up.cuda()[..., :D]
+    run = lambda: ops.conv_silu_backward(x, sp.cuda(), dxc.cuda(), dxv.cuda(), conv_w.cuda(), bias, gh, gw, rotate)
+    got = run()
+    torch.cuda.synchronize()
+    assert got[0].dtype == xdtype and (got[2] is None) == (not bias)
+    for name, a, b_ in zip(["dx", "dwc", "dbc"], got, want):
+        assert torch.isfinite(a).all(), name
+        assert rel(a, b_) < (1e-2 if name == "dx" else 2e-3), f"{name}: {rel(a, b_):.3e}"
+    again = run()
+    for a, b_ in zip(got, again):
+        assert a is None or torch.equal(a, b_)

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 @pytest.mark.parametrize("cname,ctype", [("mlstm_params", _lib.Params), ("mlstm_gate_proj_params", _lib.GateProjParams),
                                          ("mlstm_glue_params", _lib.GlueParams), ("mlstm_qkv_params", _lib.QkvParams),
-                                         ("mlstm_qkv_bwd_params", _lib.QkvBwdParams)])
+                                         ("mlstm_qkv_bwd_params", _lib.QkvBwdParams), ("mlstm_conv_bwd_params", _lib.ConvBwdParams)])
 def test_ctypes_struct_matches_c_layout(tmp_path, cname, ctype):
     fields = [n for n, _ in ctype._fields_]
     src = tmp_path / "layout.c"

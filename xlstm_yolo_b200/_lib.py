@@ -31,6 +31,8 @@ EXPORTS = (
     "mlstm_b200_qkv_fwd",
     "mlstm_b200_qkv_bwd_workspace_bytes",
     "mlstm_b200_qkv_bwd",
+    "mlstm_b200_conv_bwd_workspace_bytes",
+    "mlstm_b200_conv_bwd",
     "mlstm_b200_colsum_workspace_bytes",
     "mlstm_b200_colsum",
     "mlstm_b200_gates_supported",
@@ -114,7 +116,19 @@ class QkvParams(C.Structure):
         ("conv_w", C.c_void_p), ("conv_b", C.c_void_p),
         ("wq", C.c_void_p), ("wk", C.c_void_p), ("wv", C.c_void_p),
         ("bq", C.c_void_p), ("bk", C.c_void_p), ("bv", C.c_void_p),
-        ("c", C.c_void_p), ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+        ("c", C.c_void_p), ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("sp", C.c_void_p),
+    ]
+
+
+class ConvBwdParams(C.Structure):
+    """ctypes mirror of ``mlstm_conv_bwd_params`` (include/mlstm_b200.h)."""
+    _fields_ = [
+        ("abi_version", C.c_int32), ("B", C.c_int32), ("GH", C.c_int32), ("GW", C.c_int32), ("D", C.c_int32), ("NH", C.c_int32),
+        ("rotate", C.c_int32), ("x_dtype", C.c_int32),
+        ("x", C.c_void_p), ("ld_x", C.c_int64),
+        ("dxc", C.c_void_p), ("dxv", C.c_void_p), ("sp", C.c_void_p),
+        ("conv_w", C.c_void_p), ("dx", C.c_void_p), ("dwc", C.c_void_p), ("dbc", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -179,6 +193,10 @@ def load() -> C.CDLL:
         lib.mlstm_b200_qkv_bwd_workspace_bytes.argtypes = [C.POINTER(QkvBwdParams)]
         lib.mlstm_b200_qkv_bwd.restype = C.c_int
         lib.mlstm_b200_qkv_bwd.argtypes = [C.POINTER(QkvBwdParams), C.c_void_p]
+        lib.mlstm_b200_conv_bwd_workspace_bytes.restype = C.c_size_t
+        lib.mlstm_b200_conv_bwd_workspace_bytes.argtypes = [C.POINTER(ConvBwdParams)]
+        lib.mlstm_b200_conv_bwd.restype = C.c_int
+        lib.mlstm_b200_conv_bwd.argtypes = [C.POINTER(ConvBwdParams), C.c_void_p]
         lib.mlstm_b200_colsum_workspace_bytes.restype = C.c_size_t
         lib.mlstm_b200_colsum_workspace_bytes.argtypes = [C.c_int, C.c_int]
         lib.mlstm_b200_colsum.restype = C.c_int

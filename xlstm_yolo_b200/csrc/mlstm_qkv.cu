@@ -195,8 +195,21 @@ __global__ void __launch_bounds__(QK_NT, 1) qkv_fwd_kernel(const __grid_constant
 #pragma unroll
       for (int it = 0; it < RPT; ++it) {
         float* a_ = acc[it];
+        if (p.sp) {   // training: silu'(u) = sg (1 + u (1 - sg)) for the conv's backward, 16 bytes per thread and row
+          float d_[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) a_[e] = __fdividef(a_[e], 1.f + __expf(-a_[e]));   // silu
+          for (int e = 0; e < 8; ++e) {
+            const float sg = __fdividef(1.f, 1.f + __expf(-a_[e]));
+            d_[e] = sg * fmaf(a_[e], 1.f - sg, 1.f);
+            a_[e] *= sg;
+          }
+          if (tok0 + r0 + it < S)
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.sp) + ((size_t)b * S + tok0 + r0 + it) * p.D + hb * DBLK + ch0) =
+                make_uint4(pack_bf16x2(d_[0], d_[1]), pack_bf16x2(d_[2], d_[3]), pack_bf16x2(d_[4], d_[5]), pack_bf16x2(d_[6], d_[7]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) a_[e] = __fdividef(a_[e], 1.f + __expf(-a_[e]));   // silu
+        }
         *reinterpret_cast<uint4*>(sm.xc + kt * TILE + swz128(r0 + it, cc)) =
             make_uint4(pack_bf16x2(a_[0], a_[1]), pack_bf16x2(a_[2], a_[3]), pack_bf16x2(a_[4], a_[5]), pack_bf16x2(a_[6], a_[7]));
       }
@@ -824,6 +837,340 @@ int mlstm_b200_qkv_bwd(const mlstm_qkv_bwd_params* p, void* cuda_stream) {
   }
   if (d == 128) return p->x_dtype ? launch_qkv_bwd<128, true>(*p, maps, st) : launch_qkv_bwd<128, false>(*p, maps, st);
   return p->x_dtype ? launch_qkv_bwd<64, true>(*p, maps, st) : launch_qkv_bwd<64, false>(*p, maps, st);
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// Backward of the depthwise conv + SiLU: du = dxc * sp ; dx = conv^T(du) + dxv ; dwc, dbc.  SIMT (depthwise: nothing for the
+// tensor cores), same tiling and staging as the forward: x and dxc rows of a 128-token tile with a halo of one grid row + 1,
+// du formed in place over the staged dxc rows (sp read straight from global, 16 coalesced bytes per thread), dx written
+// straight to global.  Weight-gradient accumulators live in registers over all tiles of the CTA (thread = 4 channels x rows).
+// =====================================================================================================================
+namespace mlstm {
+namespace {
+
+struct ConvBwdMaps { CUtensorMap x, dxc; };
+
+template <int DBLK>
+struct SmemCB {
+  static constexpr int KT = DBLK / 64;
+  alignas(1024) uint8_t xh[KT][RMAX * 128];       // x rows with halo
+  alignas(1024) uint8_t dh[KT][RMAX * 128];       // dxc rows with halo -> du (bf16) in place
+  alignas(16) float cw[9][DBLK];                  // taps as the forward applied them (rotated for the bottom-right layer)
+  uint64_t bar_x;
+};
+
+template <int DBLK, bool FP16>
+__global__ void __launch_bounds__(CT, 1) conv_bwd_kernel(const __grid_constant__ ConvBwdMaps maps, const mlstm_conv_bwd_params p,
+                                                         const int halo, const int tiles_per_batch, float* __restrict__ ws) {
+  constexpr int KT = DBLK / 64;
+  constexpr int CH = DBLK / 8;                    // 16-byte channel groups per row (steps A, B)
+  constexpr int RPT = 128 * CH / CT;              // rows per thread in step B (consecutive tokens)
+  constexpr int CG = DBLK / 4;                    // 8-byte channel groups per row (step C)
+  constexpr int RL = CT / CG;                     // row lanes in step C
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SmemCB<DBLK>& sm = *reinterpret_cast<SmemCB<DBLK>*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+
+  const int tid = threadIdx.x;
+  const int S = p.GH * p.GW, GW = p.GW, GH = p.GH;
+  const int hb = blockIdx.x % p.NH;
+  const int n_tiles = p.B * tiles_per_batch;
+  const int tile0 = blockIdx.x / p.NH, tstep = gridDim.x / p.NH;
+  const int R = 128 + 2 * halo, RB = R / 2;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&maps.x); tma_prefetch_desc(&maps.dxc);
+    mbar_init(&sm.bar_x, 1);
+    fence_mbar_init();
+  }
+  for (int e = tid; e < 9 * DBLK; e += CT) {
+    const int tap = e / DBLK, ch = e % DBLK;
+    sm.cw[tap][ch] = p.conv_w[(size_t)(hb * DBLK + ch) * 9 + (p.rotate ? 8 - tap : tap)];
+  }
+  __syncthreads();
+
+  auto tile_coords = [&](int t, int& b, int& tok0) { b = t / tiles_per_batch; tok0 = (t % tiles_per_batch) * 128; };
+  auto load_tile = [&](int t) {
+    int b, tok0; tile_coords(t, b, tok0);
+    mbar_arrive_expect_tx(&sm.bar_x, 2 * KT * R * 128);
+    for (int kt = 0; kt < KT; ++kt)
+      for (int hbx = 0; hbx < 2; ++hbx) {
+        tma_load_4d(sm.xh[kt] + hbx * RB * 128, &maps.x, &sm.bar_x, hb * DBLK + kt * 64, tok0 - halo + hbx * RB, b, 0);
+        tma_load_4d(sm.dh[kt] + hbx * RB * 128, &maps.dxc, &sm.bar_x, hb * DBLK + kt * 64, tok0 - halo + hbx * RB, b, 0);
+      }
+  };
+  auto prefetch_tile = [&](int t) {
+    int b, tok0; tile_coords(t, b, tok0);
+    for (int kt = 0; kt < KT; ++kt)
+      for (int hbx = 0; hbx < 2; ++hbx) {
+        tma_prefetch_4d(&maps.x, hb * DBLK + kt * 64, tok0 - halo + hbx * RB, b, 0);
+        tma_prefetch_4d(&maps.dxc, hb * DBLK + kt * 64, tok0 - halo + hbx * RB, b, 0);
+      }
+  };
+  // bit (dy+1)*3 + (dx+1): token (gy, gx) has a neighbour at (gy+dy, gx+dx) inside the grid
+  auto tap_mask = [&](int tok) -> uint32_t {
+    const int gy = tok / GW, gx = tok - gy * GW;
+    if (gy >= GH) return 0u;
+    const uint32_t my = (gy > 0 ? 1u : 0u) | 2u | (gy + 1 < GH ? 4u : 0u);
+    const uint32_t mx = (gx > 0 ? 1u : 0u) | 2u | (gx + 1 < GW ? 4u : 0u);
+    return ((my & 1u) ? mx : 0u) | ((my & 2u) ? mx << 3 : 0u) | ((my & 4u) ? mx << 6 : 0u);
+  };
+  if (tid == 0 && tile0 < n_tiles) load_tile(tile0);
+
+  float wacc[9][4], bacc[4];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) wacc[k][e] = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) bacc[e] = 0.f;
+
+  int n = 0;
+  for (int t = tile0; t < n_tiles; t += tstep, ++n) {
+    int b, tok0; tile_coords(t, b, tok0);
+    const bool has_next = t + tstep < n_tiles;
+    if (tid == 0 && has_next) prefetch_tile(t + tstep);
+    mbar_wait(&sm.bar_x, n & 1);
+
+    // ---- A: du = dxc * sp over every staged row that is a token of this batch element (zero rows stay zero) -----------
+    {
+      const int c8 = tid % CH, ch0 = c8 * 8, kt = ch0 >> 6, cc = ch0 & 63;
+      for (int r = tid / CH; r < R; r += CT / CH) {
+        const int tok = tok0 - halo + r;
+        if (tok < 0 || tok >= S) continue;
+        uint4* slot = reinterpret_cast<uint4*>(sm.dh[kt] + swz128(r, cc));
+        const uint4 wd = *slot;
+        const uint4 wsp = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.sp) + ((size_t)b * S + tok) * p.D + hb * DBLK + ch0);
+        float d[8], s8[8];
+        cvt8<false>(wd, d);
+        cvt8<false>(wsp, s8);
+        *slot = make_uint4(pack_bf16x2(d[0] * s8[0], d[1] * s8[1]), pack_bf16x2(d[2] * s8[2], d[3] * s8[3]),
+                           pack_bf16x2(d[4] * s8[4], d[5] * s8[5]), pack_bf16x2(d[6] * s8[6], d[7] * s8[7]));
+      }
+    }
+    __syncthreads();
+
+    // ---- B: dx[t] = sum_taps w[tap] du[t - off(tap)] + dxv[t]: thread = 8 channels x RPT consecutive tokens, sliding window -------
+    {
+      const int c8 = tid % CH, ch0 = c8 * 8, kt = ch0 >> 6, cc = ch0 & 63;
+      const int r0 = (tid / CH) * RPT;
+      float acc[RPT][8];
+      uint32_t ok[RPT];
+#pragma unroll
+      for (int it = 0; it < RPT; ++it) {
+        ok[it] = tap_mask(tok0 + r0 + it);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[it][e] = 0.f;
+      }
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        float wt[3][8];
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float4 w0 = *reinterpret_cast<const float4*>(&sm.cw[(dy + 1) * 3 + dx][ch0]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&sm.cw[(dy + 1) * 3 + dx][ch0 + 4]);
+          wt[dx][0] = w0.x; wt[dx][1] = w0.y; wt[dx][2] = w0.z; wt[dx][3] = w0.w;
+          wt[dx][4] = w1.x; wt[dx][5] = w1.y; wt[dx][6] = w1.z; wt[dx][7] = w1.w;
+        }
+        // the source of tap (dy, dx) for output token it is the staged du row  it - dy*GW - dx ; j = it - dx
+#pragma unroll
+        for (int j = -1; j <= RPT; ++j) {
+          const uint4 w = *reinterpret_cast<const uint4*>(sm.dh[kt] + swz128(halo + r0 - dy * GW + j, cc));
+          float dv8[8];
+          cvt8<false>(w, dv8);
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int it = j + dx;
+            if (it < 0 || it >= RPT) continue;
+            // the source token's tap (dy, dx) lands on this token iff this token has a neighbour at (-dy, -dx)
+            if (!((ok[it] >> (8 - ((dy + 1) * 3 + (dx + 1)))) & 1u)) continue;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[it][e] = fmaf(dv8[e], wt[dx + 1][e], acc[it][e]);
+          }
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < RPT; ++it) {
+        const int tok = tok0 + r0 + it;
+        if (tok >= S) continue;
+        const size_t off = ((size_t)b * S + tok) * p.D + hb * DBLK + ch0;
+        float v8[8];
+        cvt8<false>(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dxv) + off), v8);
+        float* a_ = acc[it];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a_[e] += v8[e];
+        uint4 o;
+        if (FP16) {
+          __half2 h[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(a_[2 * e], a_[2 * e + 1]);
+          o = *reinterpret_cast<const uint4*>(h);
+        } else {
+          o = make_uint4(pack_bf16x2(a_[0], a_[1]), pack_bf16x2(a_[2], a_[3]), pack_bf16x2(a_[4], a_[5]), pack_bf16x2(a_[6], a_[7]));
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dx) + off) = o;
+      }
+    }
+
+    // ---- C: weight gradients: thread = 4 channels x strided rows; dwc[tap] += du[s] x[s + off(tap)], dbc += du[s] ----------------
+    {
+      const int c4 = tid % CG, ch0 = c4 * 4, kt = ch0 >> 6, cc = ch0 & 63;
+      for (int r = tid / CG; r < 128; r += RL) {
+        const int tok = tok0 + r;
+        if (tok >= S) break;
+        const uint32_t ok = tap_mask(tok);
+        const uint2 wd = *reinterpret_cast<const uint2*>(sm.dh[kt] + swz128(halo + r, cc));
+        const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&wd);
+        const float2 d01 = __bfloat1622float2(hd[0]), d23 = __bfloat1622float2(hd[1]);
+        bacc[0] += d01.x; bacc[1] += d01.y; bacc[2] += d23.x; bacc[3] += d23.y;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          if (!((ok >> tap) & 1u)) continue;
+          const int rr = halo + r + (tap / 3 - 1) * GW + (tap % 3 - 1);
+          const uint2 wx = *reinterpret_cast<const uint2*>(sm.xh[kt] + swz128(rr, cc));
+          float x0, x1, x2, x3;
+          if (FP16) {
+            const __half2* hx = reinterpret_cast<const __half2*>(&wx);
+            const float2 a = __half22float2(hx[0]), c2 = __half22float2(hx[1]);
+            x0 = a.x; x1 = a.y; x2 = c2.x; x3 = c2.y;
+          } else {
+            const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&wx);
+            const float2 a = __bfloat1622float2(hx[0]), c2 = __bfloat1622float2(hx[1]);
+            x0 = a.x; x1 = a.y; x2 = c2.x; x3 = c2.y;
+          }
+          wacc[tap][0] = fmaf(d01.x, x0, wacc[tap][0]); wacc[tap][1] = fmaf(d01.y, x1, wacc[tap][1]);
+          wacc[tap][2] = fmaf(d23.x, x2, wacc[tap][2]); wacc[tap][3] = fmaf(d23.y, x3, wacc[tap][3]);
+        }
+      }
+    }
+    __syncthreads();   // every read of the staged rows is done: the next tile may land
+    if (tid == 0 && has_next) load_tile(t + tstep);
+  }
+
+  // ---- per-CTA partials [10][DBLK] (9 taps in the forward's tap order + bias), row lanes summed in fixed order; two passes of
+  //      five rows each through the (dead) staging buffers ------------------------------------------------------------------
+  float* red = reinterpret_cast<float*>(sm.xh);   // [RL][5][DBLK] floats per pass
+  for (int k0 = 0; k0 < 10; k0 += 5) {
+    __syncthreads();
+    {
+      const int c4 = tid % CG, rl = tid / CG;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+#pragma unroll
+        for (int kk = 0; kk < 5; ++kk) {
+          const int k = k0 + kk;
+          red[(rl * 5 + kk) * DBLK + c4 * 4 + e] = (k < 9) ? wacc[k < 9 ? k : 0][e] : bacc[e];
+        }
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < 5 * DBLK; e += CT) {
+      float s = 0.f;
+      for (int rl = 0; rl < RL; ++rl) s += red[rl * 5 * DBLK + e];
+      ws[(size_t)blockIdx.x * 10 * DBLK + k0 * DBLK + e] = s;
+    }
+  }
+}
+
+// dwc[(h*d + ch)*9 + orig_tap], dbc[h*d + ch] = fixed-order sums over the CTAs of block h
+__global__ void conv_bwd_reduce_kernel(const float* __restrict__ ws, const mlstm_conv_bwd_params p, const int per_block, const int d) {
+  const int e0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;   // eight lanes per output element
+  const int n = 10 * p.D;
+  const int e = min(e0, n - 1);
+  const int k = e / p.D, col = e % p.D, h = col / d, ch = col % d;   // k: tap (0..8) or 9 = bias
+  const float s = ordered_sum8(ws + (size_t)h * 10 * d + (size_t)k * d + ch, per_block, (size_t)p.NH * 10 * d);
+  if (e0 < n && (threadIdx.x & 7) == 0) {
+    if (k < 9) p.dwc[(size_t)col * 9 + (p.rotate ? 8 - k : k)] = s;
+    else if (p.dbc) p.dbc[col] = s;
+  }
+}
+
+int conv_bwd_ctas_per_block(const mlstm_conv_bwd_params& p) {
+  int per_block = 148 / p.NH;    // fixed: the workspace size must not depend on the device
+  const int n_tiles = p.B * ((p.GH * p.GW + 127) / 128);
+  if (per_block < 1) per_block = 1;
+  if (per_block > n_tiles) per_block = n_tiles;
+  return per_block;
+}
+
+template <int DBLK, bool FP16>
+int launch_conv_bwd(const mlstm_conv_bwd_params& p, const ConvBwdMaps& maps, int halo, cudaStream_t st) {
+  const size_t smem = sizeof(SmemCB<DBLK>);
+  cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(conv_bwd_kernel<DBLK, FP16>), smem);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(conv_bwd, %zu B): %s", smem, cudaGetErrorString(e));
+    return MLSTM_ERR_CUDA;
+  }
+  const int S = p.GH * p.GW, tiles_per_batch = (S + 127) / 128;
+  const int per_block = conv_bwd_ctas_per_block(p);
+  float* ws = reinterpret_cast<float*>(p.workspace);
+  conv_bwd_kernel<DBLK, FP16><<<dim3(per_block * p.NH), dim3(CT), smem, st>>>(maps, p, halo, tiles_per_batch, ws);
+  count_launch();
+  const int n = 10 * p.D;
+  conv_bwd_reduce_kernel<<<(n * 8 + 255) / 256, 256, 0, st>>>(ws, p, per_block, DBLK);
+  count_launch();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("conv_bwd launch failed: %s", cudaGetErrorString(e));
+    return MLSTM_ERR_CUDA;
+  }
+  return MLSTM_OK;
+}
+
+}  // namespace
+}  // namespace mlstm
+
+extern "C" {
+
+size_t mlstm_b200_conv_bwd_workspace_bytes(const mlstm_conv_bwd_params* p) {
+  if (!p || p->B <= 0 || p->NH <= 0 || p->D % p->NH != 0 || p->GH <= 0 || p->GW <= 0) return 0;
+  return sizeof(float) * (size_t)conv_bwd_ctas_per_block(*p) * (size_t)p->NH * 10 * (size_t)(p->D / p->NH);
+}
+
+int mlstm_b200_conv_bwd(const mlstm_conv_bwd_params* p, void* cuda_stream) {
+  clear_error();
+  if (!p) { set_error("params is NULL"); return MLSTM_ERR_INVALID_ARG; }
+  if (p->abi_version != MLSTM_B200_ABI_VERSION) {
+    set_error("abi_version %d != %d", p->abi_version, MLSTM_B200_ABI_VERSION);
+    return MLSTM_ERR_INVALID_ARG;
+  }
+  if (p->B < 0 || p->x_dtype < 0 || p->x_dtype > 1) { set_error("bad B / x_dtype"); return MLSTM_ERR_INVALID_ARG; }
+  if (!qkv_shape_ok(p->D, p->NH, p->GH, p->GW, p->ld_x)) {
+    set_error("conv backward: D / NH must be 64 or 128, grid width <= 80, ld_x a multiple of 8 and >= D (D=%d NH=%d GH=%d GW=%d ld_x=%lld)",
+              p->D, p->NH, p->GH, p->GW, (long long)p->ld_x);
+    return MLSTM_ERR_UNSUPPORTED;
+  }
+  if (!p->dwc) { set_error("conv backward: dwc is NULL"); return MLSTM_ERR_INVALID_ARG; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (p->B == 0) {
+    int rc0 = bind_device(p->dwc);
+    if (rc0) return rc0;
+    cudaMemsetAsync(p->dwc, 0, sizeof(float) * 9 * (size_t)p->D, st);
+    if (p->dbc) cudaMemsetAsync(p->dbc, 0, sizeof(float) * (size_t)p->D, st);
+    return MLSTM_OK;
+  }
+  if (!p->x || !p->dxc || !p->dxv || !p->sp || !p->conv_w || !p->dx) { set_error("conv backward: null pointer"); return MLSTM_ERR_INVALID_ARG; }
+  if (!p->workspace || p->workspace_bytes < mlstm_b200_conv_bwd_workspace_bytes(p)) {
+    set_error("conv backward: workspace too small (%zu < %zu)", p->workspace ? p->workspace_bytes : (size_t)0,
+              mlstm_b200_conv_bwd_workspace_bytes(p));
+    return MLSTM_ERR_WORKSPACE;
+  }
+  int rc;
+  if ((rc = bind_device(p->x))) return rc;
+  const int S = p->GH * p->GW, d = p->D / p->NH;
+  const int halo = ((p->GW + 1 + 7) / 8) * 8;
+  ConvBwdMaps maps;
+  int r = 0;
+  r |= make_rows_tmap(&maps.x, p->x, p->D, S, p->B, p->ld_x, (128 + 2 * halo) / 2);
+  r |= make_rows_tmap(&maps.dxc, p->dxc, p->D, S, p->B, p->D, (128 + 2 * halo) / 2);
+  if (r) {
+    set_error("cuTensorMapEncodeTiled failed (%d): pointers must be 16-byte aligned", r);
+    return r == -1 ? MLSTM_ERR_NO_DEVICE : MLSTM_ERR_INVALID_ARG;
+  }
+  if (d == 128) return p->x_dtype ? launch_conv_bwd<128, true>(*p, maps, halo, st) : launch_conv_bwd<128, false>(*p, maps, halo, st);
+  return p->x_dtype ? launch_conv_bwd<64, true>(*p, maps, halo, st) : launch_conv_bwd<64, false>(*p, maps, halo, st);
 }
 
 }  // extern "C"

@@ -18,7 +18,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import Act, Gate, GateProjParams, GlueParams, Params, QkvBwdParams, QkvParams
+from ._lib import Act, ConvBwdParams, Gate, GateProjParams, GlueParams, Params, QkvBwdParams, QkvParams
 
 _DT = {torch.float32: _lib.MLSTM_F32, torch.bfloat16: _lib.MLSTM_BF16}
 
@@ -647,6 +647,37 @@ def qkv_proj_backward(x, c, wq, wk, wv, dc, dq, dk, dv, need_db=True):
     return dxc, dxv, dws[0], dws[1], dws[2], db
 
 
+def conv_silu_backward(x, sp, dxc, dxv, conv_w, need_bias, gh, gw, rotate):
+    """Backward of c = silu(conv3x3_depthwise(x)) as one kernel (csrc/mlstm_qkv.cu, conv_bwd_kernel): with du = dxc * sp
+    (sp = silu'(conv(x)), saved by the producer's forward) returns (dx, dwc, dbc): dx = conv^T(du) + dxv in x's dtype (B,S,D),
+    dwc (D,1,3,3) fp32, dbc (D) fp32 or None."""
+    lib = _lib.load()
+    B, S, D = x.shape
+    dev = x.device
+    dense = lambda t: t if (t.dtype == torch.bfloat16 and t.is_contiguous()) else t.to(torch.bfloat16).contiguous()
+    dxc, dxv, sp = dense(dxc), dense(dxv), dense(sp)
+    cw = conv_w.detach().to(torch.float32).contiguous()
+    dx = torch.empty((B, S, D), dtype=x.dtype, device=dev)
+    dwc = torch.empty((D, 1, 3, 3), dtype=torch.float32, device=dev)
+    dbc = torch.empty(D, dtype=torch.float32, device=dev) if need_bias else None
+    g = ConvBwdParams()
+    g.abi_version = _lib.ABI_VERSION
+    g.B, g.GH, g.GW, g.D = B, gh, gw, D
+    g.NH = D // 128 if D % 128 == 0 else D // 64           # channel blocks of the kernel's tiling (independent of the heads)
+    g.rotate, g.x_dtype = int(bool(rotate)), int(x.dtype == torch.float16)
+    g.x, g.ld_x = x.data_ptr(), x.stride(1)
+    g.dxc, g.dxv, g.sp = dxc.data_ptr(), dxv.data_ptr(), sp.data_ptr()
+    g.conv_w, g.dx, g.dwc, g.dbc = cw.data_ptr(), dx.data_ptr(), dwc.data_ptr(), _ptr(dbc)
+    need = lib.mlstm_b200_conv_bwd_workspace_bytes(C.byref(g))
+    ws = torch.empty(max(1, (need + 3) // 4), dtype=torch.float32, device=dev)
+    g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    with torch.cuda.device(dev):
+        rc = lib.mlstm_b200_conv_bwd(C.byref(g), _stream())
+    if rc:
+        _fail(rc, "conv + SiLU backward")
+    return dx, dwc, dbc
+
+
 def _conv_silu_backward(x, conv_w, conv_b, dxc, dxv, gh, gw, rotate):
     """du = dxc * silu'(u) with u = conv(x) recomputed, then the depthwise conv's own backward; dx = conv^T(du) + dxv."""
     B, S, D = x.shape
@@ -664,7 +695,7 @@ def _conv_silu_backward(x, conv_w, conv_b, dxc, dxv, gh, gw, rotate):
     return dx, dwc, dbc
 
 
-def qkv_backward(x, c, conv_w, conv_b, wq, wk, wv, has_bias, dc, dq, dk, dv, gh, gw, rotate):
+def qkv_backward(x, c, conv_w, conv_b, wq, wk, wv, has_bias, dc, dq, dk, dv, gh, gw, rotate, sp=None):
     """Backward of the producer in PyTorch ops (cuBLAS batched GEMMs over the strided head views, cuDNN depthwise conv):
     the saved c replaces everything but the conv pre-activation, which is recomputed.  Works on any device (the CPU
     tests differentiate it against autograd of ``qkv_reference``).  Returns gradients for
@@ -677,7 +708,10 @@ def qkv_backward(x, c, conv_w, conv_b, wq, wk, wv, has_bias, dc, dq, dk, dv, gh,
             and _lib.load().mlstm_b200_qkv_supported(D, NH, 1, 1, x.stride(1))):
         # the five GEMMs and the bias sums as one tcgen05 kernel; the conv's own backward stays with cuDNN
         dxc, dxv, dwq, dwk, dwv, db = qkv_proj_backward(x, c, wq, wk, wv, dc, dq, dk, dv, need_db=any(has_bias))
-        dx, dwc, dbc = _conv_silu_backward(x, conv_w, conv_b, dxc, dxv, gh, gw, rotate)
+        if sp is not None and _lib.load().mlstm_b200_qkv_supported(D, NH, gh, gw, x.stride(1)):
+            dx, dwc, dbc = conv_silu_backward(x, sp, dxc, dxv, conv_w, conv_b is not None, gh, gw, rotate)   # one kernel
+        else:
+            dx, dwc, dbc = _conv_silu_backward(x, conv_w, conv_b, dxc, dxv, gh, gw, rotate)                  # cuDNN
         pick = lambda j: db[j] if has_bias[j] else None
         return (dx, dwc, dbc, dwq, pick(0), dwk, pick(1), dwv, pick(2))
     cd = dq.dtype                                            # compute dtype of the projections' gradients
@@ -734,6 +768,8 @@ class _QkvFn(torch.autograd.Function):
         kq, kk = wq.detach().to(torch.bfloat16).contiguous(), wk.detach().to(torch.bfloat16).contiguous()
         kv = wv.detach().to(x.dtype).contiguous()
         c, q, k, v = (torch.empty((B, S, D), dtype=torch.bfloat16, device=dev) for _ in range(4))
+        # silu'(conv(x)) for the conv's backward kernel: only when a backward can follow
+        sp = torch.empty((B, S, D), dtype=torch.bfloat16, device=dev) if any(ctx.needs_input_grad[:9]) else None
         g = QkvParams()
         g.abi_version = _lib.ABI_VERSION
         g.B, g.GH, g.GW, g.D, g.NH = B, gh, gw, D, NH
@@ -743,20 +779,21 @@ class _QkvFn(torch.autograd.Function):
         g.wq, g.wk, g.wv = kq.data_ptr(), kk.data_ptr(), kv.data_ptr()
         g.bq, g.bk, g.bv = _ptr(fbq), _ptr(fbk), _ptr(fbv)
         g.c, g.q, g.k, g.v = c.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr()
+        g.sp = _ptr(sp)
         with torch.cuda.device(dev):
             rc = lib.mlstm_b200_qkv_fwd(C.byref(g), _stream())
         if rc:
             _fail(rc, "qkv producer forward")
-        ctx.save_for_backward(x, c, conv_w, conv_b, wq, wk, wv)
+        ctx.save_for_backward(x, c, conv_w, conv_b, wq, wk, wv, sp)
         ctx.meta = (gh, gw, bool(rotate), (bq is not None, bk is not None, bv is not None))
         return c, q, k, v
 
     @staticmethod
     def backward(ctx, dc, dq, dk, dv):
-        x, c, conv_w, conv_b, wq, wk, wv = ctx.saved_tensors
+        x, c, conv_w, conv_b, wq, wk, wv, sp = ctx.saved_tensors
         gh, gw, rotate, has_bias = ctx.meta
         z = lambda t: torch.zeros_like(c) if t is None else t
-        g = qkv_backward(x, c, conv_w, conv_b, wq, wk, wv, has_bias, dc, z(dq), z(dk), z(dv), gh, gw, rotate)
+        g = qkv_backward(x, c, conv_w, conv_b, wq, wk, wv, has_bias, dc, z(dq), z(dk), z(dv), gh, gw, rotate, sp=sp)
         dx, dwc, dbc, dwq, dbq, dwk, dbk, dwv, dbv = g
         cast = lambda t, like: None if (t is None or like is None) else t.to(like.dtype)
         return (dx.to(x.dtype), cast(dwc, conv_w), cast(dbc, conv_b), cast(dwq, wq), dbq, cast(dwk, wk), dbk, cast(dwv, wv), dbv,
