@@ -858,7 +858,7 @@ struct SmemCB {
   alignas(1024) uint8_t xh[KT][RMAX * 128];       // x rows with halo
   alignas(1024) uint8_t dh[KT][RMAX * 128];       // dxc rows with halo -> du (bf16) in place
   alignas(16) float cw[9][DBLK];                  // taps as the forward applied them (rotated for the bottom-right layer)
-  uint64_t bar_x;
+  uint64_t bar_x, bar_d;
 };
 
 template <int DBLK, bool FP16>
@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(CT, 1) conv_bwd_kernel(const __grid_constant__
 
   if (tid == 0) {
     tma_prefetch_desc(&maps.x); tma_prefetch_desc(&maps.dxc);
-    mbar_init(&sm.bar_x, 1);
+    mbar_init(&sm.bar_x, 1); mbar_init(&sm.bar_d, 1);
     fence_mbar_init();
   }
   for (int e = tid; e < 9 * DBLK; e += CT) {
@@ -892,14 +892,12 @@ __global__ void __launch_bounds__(CT, 1) conv_bwd_kernel(const __grid_constant__
   __syncthreads();
 
   auto tile_coords = [&](int t, int& b, int& tok0) { b = t / tiles_per_batch; tok0 = (t % tiles_per_batch) * 128; };
-  auto load_tile = [&](int t) {
+  auto load_rows = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int t) {   // dst: [KT][RMAX * 128]
     int b, tok0; tile_coords(t, b, tok0);
-    mbar_arrive_expect_tx(&sm.bar_x, 2 * KT * R * 128);
+    mbar_arrive_expect_tx(bar, KT * R * 128);
     for (int kt = 0; kt < KT; ++kt)
-      for (int hbx = 0; hbx < 2; ++hbx) {
-        tma_load_4d(sm.xh[kt] + hbx * RB * 128, &maps.x, &sm.bar_x, hb * DBLK + kt * 64, tok0 - halo + hbx * RB, b, 0);
-        tma_load_4d(sm.dh[kt] + hbx * RB * 128, &maps.dxc, &sm.bar_x, hb * DBLK + kt * 64, tok0 - halo + hbx * RB, b, 0);
-      }
+      for (int hbx = 0; hbx < 2; ++hbx)
+        tma_load_4d(dst + kt * (RMAX * 128) + hbx * RB * 128, map, bar, hb * DBLK + kt * 64, tok0 - halo + hbx * RB, b, 0);
   };
   auto prefetch_tile = [&](int t) {
     int b, tok0; tile_coords(t, b, tok0);
@@ -917,7 +915,10 @@ __global__ void __launch_bounds__(CT, 1) conv_bwd_kernel(const __grid_constant__
     const uint32_t mx = (gx > 0 ? 1u : 0u) | 2u | (gx + 1 < GW ? 4u : 0u);
     return ((my & 1u) ? mx : 0u) | ((my & 2u) ? mx << 3 : 0u) | ((my & 4u) ? mx << 6 : 0u);
   };
-  if (tid == 0 && tile0 < n_tiles) load_tile(tile0);
+  if (tid == 0 && tile0 < n_tiles) {
+    load_rows(&sm.dh[0][0], &maps.dxc, &sm.bar_d, tile0);
+    load_rows(&sm.xh[0][0], &maps.x, &sm.bar_x, tile0);
+  }
 
   float wacc[9][4], bacc[4];
 #pragma unroll
@@ -932,27 +933,73 @@ __global__ void __launch_bounds__(CT, 1) conv_bwd_kernel(const __grid_constant__
     int b, tok0; tile_coords(t, b, tok0);
     const bool has_next = t + tstep < n_tiles;
     if (tid == 0 && has_next) prefetch_tile(t + tstep);
-    mbar_wait(&sm.bar_x, n & 1);
+    mbar_wait(&sm.bar_d, n & 1);
 
-    // ---- A: du = dxc * sp over every staged row that is a token of this batch element (zero rows stay zero) -----------
+    // ---- A: du = dxc * sp over every staged row that is a token of this batch element (zero rows stay zero); four rows'
+    //      sp loads in flight per thread -----------------------------------------------------------------------------------
     {
       const int c8 = tid % CH, ch0 = c8 * 8, kt = ch0 >> 6, cc = ch0 & 63;
-      for (int r = tid / CH; r < R; r += CT / CH) {
-        const int tok = tok0 - halo + r;
-        if (tok < 0 || tok >= S) continue;
-        uint4* slot = reinterpret_cast<uint4*>(sm.dh[kt] + swz128(r, cc));
-        const uint4 wd = *slot;
-        const uint4 wsp = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.sp) + ((size_t)b * S + tok) * p.D + hb * DBLK + ch0);
-        float d[8], s8[8];
-        cvt8<false>(wd, d);
-        cvt8<false>(wsp, s8);
-        *slot = make_uint4(pack_bf16x2(d[0] * s8[0], d[1] * s8[1]), pack_bf16x2(d[2] * s8[2], d[3] * s8[3]),
-                           pack_bf16x2(d[4] * s8[4], d[5] * s8[5]), pack_bf16x2(d[6] * s8[6], d[7] * s8[7]));
+      const __nv_bfloat16* spb = reinterpret_cast<const __nv_bfloat16*>(p.sp) + (size_t)b * S * p.D + hb * DBLK + ch0;
+      for (int rb = tid / CH; rb < R; rb += 4 * (CT / CH)) {
+        uint4 wsp[4];
+        bool on[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = rb + u * (CT / CH), tok = tok0 - halo + r;
+          on[u] = r < R && tok >= 0 && tok < S;
+          wsp[u] = make_uint4(0, 0, 0, 0);
+          if (on[u]) wsp[u] = *reinterpret_cast<const uint4*>(spb + (size_t)tok * p.D);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!on[u]) continue;
+          uint4* slot = reinterpret_cast<uint4*>(sm.dh[kt] + swz128(rb + u * (CT / CH), cc));
+          float d[8], s8[8];
+          cvt8<false>(*slot, d);
+          cvt8<false>(wsp[u], s8);
+          *slot = make_uint4(pack_bf16x2(d[0] * s8[0], d[1] * s8[1]), pack_bf16x2(d[2] * s8[2], d[3] * s8[3]),
+                             pack_bf16x2(d[4] * s8[4], d[5] * s8[5]), pack_bf16x2(d[6] * s8[6], d[7] * s8[7]));
+        }
       }
     }
     __syncthreads();
+    mbar_wait(&sm.bar_x, n & 1);
 
-    // ---- B: dx[t] = sum_taps w[tap] du[t - off(tap)] + dxv[t]: thread = 8 channels x RPT consecutive tokens, sliding window -------
+    // ---- C: weight gradients: thread = 4 channels x strided rows; dwc[tap] += du[s] x[s + off(tap)], dbc += du[s] ----------------
+    {
+      const int c4 = tid % CG, ch0 = c4 * 4, kt = ch0 >> 6, cc = ch0 & 63;
+      for (int r = tid / CG; r < 128; r += RL) {
+        const int tok = tok0 + r;
+        if (tok >= S) break;
+        const uint32_t ok = tap_mask(tok);
+        const uint2 wd = *reinterpret_cast<const uint2*>(sm.dh[kt] + swz128(halo + r, cc));
+        const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&wd);
+        const float2 d01 = __bfloat1622float2(hd[0]), d23 = __bfloat1622float2(hd[1]);
+        bacc[0] += d01.x; bacc[1] += d01.y; bacc[2] += d23.x; bacc[3] += d23.y;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          if (!((ok >> tap) & 1u)) continue;
+          const int rr = halo + r + (tap / 3 - 1) * GW + (tap % 3 - 1);
+          const uint2 wx = *reinterpret_cast<const uint2*>(sm.xh[kt] + swz128(rr, cc));
+          float x0, x1, x2, x3;
+          if (FP16) {
+            const __half2* hx = reinterpret_cast<const __half2*>(&wx);
+            const float2 a = __half22float2(hx[0]), c2 = __half22float2(hx[1]);
+            x0 = a.x; x1 = a.y; x2 = c2.x; x3 = c2.y;
+          } else {
+            const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&wx);
+            const float2 a = __bfloat1622float2(hx[0]), c2 = __bfloat1622float2(hx[1]);
+            x0 = a.x; x1 = a.y; x2 = c2.x; x3 = c2.y;
+          }
+          wacc[tap][0] = fmaf(d01.x, x0, wacc[tap][0]); wacc[tap][1] = fmaf(d01.y, x1, wacc[tap][1]);
+          wacc[tap][2] = fmaf(d23.x, x2, wacc[tap][2]); wacc[tap][3] = fmaf(d23.y, x3, wacc[tap][3]);
+        }
+      }
+    }
+    __syncthreads();   // the x rows are dead: the next tile's stream in under step B
+    if (tid == 0 && has_next) load_rows(&sm.xh[0][0], &maps.x, &sm.bar_x, t + tstep);
+
+    // ---- B: dx[t] = dxv[t] + sum_taps w[tap] du[t - off(tap)]: thread = 8 channels x RPT consecutive tokens, sliding window -------
     {
       const int c8 = tid % CH, ch0 = c8 * 8, kt = ch0 >> 6, cc = ch0 & 63;
       const int r0 = (tid / CH) * RPT;
@@ -960,9 +1007,11 @@ __global__ void __launch_bounds__(CT, 1) conv_bwd_kernel(const __grid_constant__
       uint32_t ok[RPT];
 #pragma unroll
       for (int it = 0; it < RPT; ++it) {
-        ok[it] = tap_mask(tok0 + r0 + it);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[it][e] = 0.f;
+        const int tok = tok0 + r0 + it;
+        ok[it] = tap_mask(tok);
+        uint4 wv = make_uint4(0, 0, 0, 0);
+        if (tok < S) wv = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dxv) + ((size_t)b * S + tok) * p.D + hb * DBLK + ch0);
+        cvt8<false>(wv, acc[it]);
       }
 #pragma unroll
       for (int dy = -1; dy <= 1; ++dy) {
@@ -996,11 +1045,7 @@ __global__ void __launch_bounds__(CT, 1) conv_bwd_kernel(const __grid_constant__
         const int tok = tok0 + r0 + it;
         if (tok >= S) continue;
         const size_t off = ((size_t)b * S + tok) * p.D + hb * DBLK + ch0;
-        float v8[8];
-        cvt8<false>(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dxv) + off), v8);
         float* a_ = acc[it];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) a_[e] += v8[e];
         uint4 o;
         if (FP16) {
           __half2 h[4];
@@ -1013,40 +1058,8 @@ __global__ void __launch_bounds__(CT, 1) conv_bwd_kernel(const __grid_constant__
         *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dx) + off) = o;
       }
     }
-
-    // ---- C: weight gradients: thread = 4 channels x strided rows; dwc[tap] += du[s] x[s + off(tap)], dbc += du[s] ----------------
-    {
-      const int c4 = tid % CG, ch0 = c4 * 4, kt = ch0 >> 6, cc = ch0 & 63;
-      for (int r = tid / CG; r < 128; r += RL) {
-        const int tok = tok0 + r;
-        if (tok >= S) break;
-        const uint32_t ok = tap_mask(tok);
-        const uint2 wd = *reinterpret_cast<const uint2*>(sm.dh[kt] + swz128(halo + r, cc));
-        const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&wd);
-        const float2 d01 = __bfloat1622float2(hd[0]), d23 = __bfloat1622float2(hd[1]);
-        bacc[0] += d01.x; bacc[1] += d01.y; bacc[2] += d23.x; bacc[3] += d23.y;
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          if (!((ok >> tap) & 1u)) continue;
-          const int rr = halo + r + (tap / 3 - 1) * GW + (tap % 3 - 1);
-          const uint2 wx = *reinterpret_cast<const uint2*>(sm.xh[kt] + swz128(rr, cc));
-          float x0, x1, x2, x3;
-          if (FP16) {
-            const __half2* hx = reinterpret_cast<const __half2*>(&wx);
-            const float2 a = __half22float2(hx[0]), c2 = __half22float2(hx[1]);
-            x0 = a.x; x1 = a.y; x2 = c2.x; x3 = c2.y;
-          } else {
-            const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&wx);
-            const float2 a = __bfloat1622float2(hx[0]), c2 = __bfloat1622float2(hx[1]);
-            x0 = a.x; x1 = a.y; x2 = c2.x; x3 = c2.y;
-          }
-          wacc[tap][0] = fmaf(d01.x, x0, wacc[tap][0]); wacc[tap][1] = fmaf(d01.y, x1, wacc[tap][1]);
-          wacc[tap][2] = fmaf(d23.x, x2, wacc[tap][2]); wacc[tap][3] = fmaf(d23.y, x3, wacc[tap][3]);
-        }
-      }
-    }
-    __syncthreads();   // every read of the staged rows is done: the next tile may land
-    if (tid == 0 && has_next) load_tile(t + tstep);
+    __syncthreads();   // the du rows are dead
+    if (tid == 0 && has_next) load_rows(&sm.dh[0][0], &maps.dxc, &sm.bar_d, t + tstep);
   }
 
   // ---- per-CTA partials [10][DBLK] (9 taps in the forward's tap order + bias), row lanes summed in fixed order; two passes of
