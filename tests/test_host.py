@@ -136,6 +136,39 @@ def test_layer_tail_validation_needs_no_gpu(lib):
     assert lib.mlstm_b200_glue_fwd(C.byref(g), None) == 0
 
 
+def test_operand_producer_validation_needs_no_gpu(lib):
+    """Shape gates, error codes and workspace sizes of the producer entry points (ABI 5) without a device."""
+    assert lib.mlstm_b200_qkv_supported(512, 4, 40, 40, 1024) == 1 and lib.mlstm_b200_qkv_supported(256, 4, 20, 20, 256) == 1
+    assert lib.mlstm_b200_qkv_supported(512, 4, 100, 100, 1024) == 0      # grid wider than the staged halo
+    assert lib.mlstm_b200_qkv_supported(64, 4, 20, 20, 64) == 0           # block size 16
+    assert lib.mlstm_b200_qkv_supported(512, 4, 40, 40, 1020) == 0        # row stride not a multiple of 8
+    q = _lib.QkvParams()
+    assert lib.mlstm_b200_qkv_fwd(None, None) == -1
+    q.abi_version, q.B, q.GH, q.GW, q.D, q.NH, q.ld_x = _lib.ABI_VERSION, 2, 20, 20, 64, 4, 64
+    assert lib.mlstm_b200_qkv_fwd(C.byref(q), None) == -2 and b"64 or 128" in lib.mlstm_b200_last_error()
+    q.D = q.ld_x = 256
+    assert lib.mlstm_b200_qkv_fwd(C.byref(q), None) == -1                 # null pointers
+    q.B = 0
+    assert lib.mlstm_b200_qkv_fwd(C.byref(q), None) == 0                  # empty batch: nothing to do
+    q.abi_version = 4
+    assert lib.mlstm_b200_qkv_fwd(C.byref(q), None) == -1 and b"abi_version" in lib.mlstm_b200_last_error()
+    b = _lib.QkvBwdParams()
+    b.abi_version, b.T, b.D, b.NH, b.ld_x = _lib.ABI_VERSION, 51200, 512, 4, 1024
+    # 37 CTAs per block (148 / 4), per CTA three d x d fp32 weight-gradient partials + three bias rows
+    assert lib.mlstm_b200_qkv_bwd_workspace_bytes(C.byref(b)) == 4 * 37 * 4 * (3 * 128 * 128 + 3 * 128)
+    assert lib.mlstm_b200_qkv_bwd(C.byref(b), None) == -1                 # null pointers
+    b.T = 100
+    assert lib.mlstm_b200_qkv_bwd_workspace_bytes(C.byref(b)) == 4 * 1 * 4 * (3 * 128 * 128 + 3 * 128)   # one tile: one CTA per block
+    c = _lib.ConvBwdParams()
+    c.abi_version, c.B, c.GH, c.GW, c.D, c.NH, c.ld_x = _lib.ABI_VERSION, 32, 40, 40, 512, 4, 1024
+    assert lib.mlstm_b200_conv_bwd_workspace_bytes(C.byref(c)) == 4 * 37 * 4 * 10 * 128
+    assert lib.mlstm_b200_conv_bwd(C.byref(c), None) == -1
+    c.GW = 128
+    assert lib.mlstm_b200_conv_bwd(C.byref(c), None) == -2
+    assert lib.mlstm_b200_colsum_workspace_bytes(512, 3) == 4 * 296 * 3 * 512
+    assert lib.mlstm_b200_colsum(None, 3, 10, 512, 512, None, None, 0, None) == -1
+
+
 def test_cuda_op_refuses_cpu_tensors():
     from xlstm_yolo_b200 import ops
     x = torch.randn(1, 2, 8, 16)
