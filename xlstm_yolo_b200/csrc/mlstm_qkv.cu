@@ -440,6 +440,11 @@ int mlstm_b200_qkv_fwd(const mlstm_qkv_params* p, void* cuda_stream) {
     set_error("qkv producer: null pointer");
     return MLSTM_ERR_INVALID_ARG;
   }
+  if (((uintptr_t)p->x | (uintptr_t)p->wq | (uintptr_t)p->wk | (uintptr_t)p->wv | (uintptr_t)p->c | (uintptr_t)p->q | (uintptr_t)p->k |
+       (uintptr_t)p->v | (uintptr_t)p->sp) & 15u) {
+    set_error("qkv producer: x, weights and outputs must be 16-byte aligned (TMA)");
+    return MLSTM_ERR_INVALID_ARG;
+  }
   int rc;
   if ((rc = bind_device(p->x))) return rc;
   const int S = p->GH * p->GW, d = p->D / p->NH;
@@ -1165,6 +1170,10 @@ int mlstm_b200_conv_bwd(const mlstm_conv_bwd_params* p, void* cuda_stream) {
     return MLSTM_OK;
   }
   if (!p->x || !p->dxc || !p->dxv || !p->sp || !p->conv_w || !p->dx) { set_error("conv backward: null pointer"); return MLSTM_ERR_INVALID_ARG; }
+  if (((uintptr_t)p->x | (uintptr_t)p->dxc | (uintptr_t)p->dxv | (uintptr_t)p->sp | (uintptr_t)p->dx) & 15u) {
+    set_error("conv backward: x, dxc, dxv, sp, dx must be 16-byte aligned (16-byte vector and TMA accesses)");
+    return MLSTM_ERR_INVALID_ARG;
+  }
   if (!p->workspace || p->workspace_bytes < mlstm_b200_conv_bwd_workspace_bytes(p)) {
     set_error("conv backward: workspace too small (%zu < %zu)", p->workspace ? p->workspace_bytes : (size_t)0,
               mlstm_b200_conv_bwd_workspace_bytes(p));

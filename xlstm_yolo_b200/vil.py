@@ -232,8 +232,9 @@ class ViLLayer(nn.Module):
         x_mlstm, z = self.proj_up(y).chunk(2, dim=-1)
         cell = self.mlstm_cell
         conv_act = None
-        if (x.is_cuda and getattr(self, "fused_producer", True) and self.conv.kernel_size == (3, 3)
-                and not torch.compiler.is_compiling()):
+        if (x.is_cuda and getattr(self, "fused_producer", True) and not torch.compiler.is_compiling()
+                and self.conv.kernel_size == (3, 3) and self.conv.padding == (1, 1) and self.conv.stride == (1, 1)
+                and self.conv.dilation == (1, 1) and self.conv.groups == self.conv.in_channels == self.conv.out_channels):
             # conv + SiLU + the three block-diagonal projections as one kernel (vision_lstm2.py:482-491 are four
             # round trips over (B,S,inner)); bf16 outputs, which is what the cell kernels read
             from . import ops
