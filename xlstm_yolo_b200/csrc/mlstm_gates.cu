@@ -270,7 +270,9 @@ int sm_count() {
 
 int bwd_ranges(const mlstm_gate_proj_params& p) {
   const int slabs = (3 * p.D + BW_SLAB - 1) / BW_SLAB;
-  int r = (4 * 148 + slabs - 1) / slabs;          // ~4 CTAs per SM over the whole grid (fixed: keeps the
+  int r = (4 * 148) / slabs;                      // <= 4 CTAs per SM over the whole grid, rounded DOWN: one CTA beyond the resident
+                                                  // 592 would run as a second wave of its own (198 x 3 = 594 CTAs: 172 us; 197 x 3: one wave)
+                                                  // (fixed, not the device's SM count: keeps the
   const int max_r = (p.T + 4 * BW_TU - 1) / (4 * BW_TU);   // workspace size independent of the device)
   if (r > max_r) r = max_r;
   return r < 1 ? 1 : r;
