@@ -379,15 +379,35 @@ def measure_e2e(torch, dist, name, K, dev, rank, world, full_result):
     from xlstm_yolo_b200.backend import mLSTMBackend, mLSTMBackendConfig
     B, NH, S, DH = WORKLOADS[name]
     be = mLSTMBackend(mLSTMBackendConfig(chunk_size=CHUNK, eps=1e-6, autocast_kernel_dtype="bfloat16"))
-    host = [t.pin_memory() for t in make_inputs(torch, B, NH, S, DH, 77 + rank, "cpu", torch.bfloat16)]
     NBUF = 2
-    dev_in = [[torch.empty_like(t, device=dev) for t in host] for _ in range(NBUF)]
+
+    def flat_views(like, device, pinned=False):
+        """One flat byte buffer with a view per tensor of `like` (same dtype, shape, strides; 256-byte aligned offsets): the six
+        operands of a step travel as ONE copy instead of six (two of them 0.2 MB: per-copy latency, not bandwidth)."""
+        offs, total = [], 0
+        for t in like:
+            offs.append(total)
+            total += (t.numel() * t.element_size() + 255) // 256 * 256
+        flat = torch.empty(total, dtype=torch.uint8, device=device, pin_memory=pinned)
+        views = [flat[o:o + t.numel() * t.element_size()].view(t.dtype).as_strided(t.shape, t.stride()) for o, t in zip(offs, like)]
+        return flat, views
+
+    src = make_inputs(torch, B, NH, S, DH, 77 + rank, "cpu", torch.bfloat16)
+    host_flat, host = flat_views(src, "cpu", pinned=True)
+    for hv, t in zip(host, src):
+        hv.copy_(t)
+    dev_flat, dev_in = [], []
+    for _ in range(NBUF):
+        fl, vs = flat_views(src, dev)
+        dev_flat.append(fl)
+        dev_in.append(vs)
     res_host = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(NBUF)]
     # static device-side result slots: a non_blocking D2H copy from a freshly allocated tensor makes the
     # caching allocator cudaMalloc every step (measured: 2.7 mallocs/step, 1.4-35 ms of host time)
     res_dev = [torch.zeros(4, dtype=torch.float32, device=dev) for _ in range(NBUF)]
     res_full = [None] * NBUF          # pinned host tensors with the strides of the results, made on first use
     res_slot = [None] * NBUF          # static device-side copies of the results (same strides)
+    res_full_flat, res_slot_flat = [None] * NBUF, [None] * NBUF   # the flat buffers behind them: one copy each way per step
     h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = [res_host[0].numel() * 4]
     main_stream = torch.cuda.current_stream(dev)
@@ -404,8 +424,7 @@ def measure_e2e(torch, dist, name, K, dev, rank, world, full_result):
         b_ = sidx % NBUF
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[b_])
-            for d_, h_ in zip(dev_in[b_], host):
-                d_.copy_(h_, non_blocking=True)
+            dev_flat[b_].copy_(host_flat, non_blocking=True)     # q, k, v, i, f, dh in one DMA
             ready[b_].record(copy_stream)
 
     def e2e_compute(sidx):
@@ -424,8 +443,8 @@ def measure_e2e(torch, dist, name, K, dev, rank, world, full_result):
                 # layout in between: a D2H copy straight from the step's own (freshly allocated) tensors on another stream
                 # needs record_stream, which keeps their blocks out of the caching allocator for a step or two and makes
                 # it cudaMalloc inside the timed region (measured: 1.2-4.5 ms per step, erratic, against 0.7 ms here).
-                res_full[b_] = [torch.empty(o.numel(), dtype=o.dtype, pin_memory=True).as_strided(o.shape, o.stride()) for o in outs]
-                res_slot[b_] = [torch.empty_strided(o.shape, o.stride(), dtype=o.dtype, device=dev) for o in outs]
+                res_full_flat[b_], res_full[b_] = flat_views(outs, "cpu", pinned=True)
+                res_slot_flat[b_], res_slot[b_] = flat_views(outs, dev)
                 d2h[0] = sum(o.numel() * o.element_size() for o in outs)
             main_stream.wait_event(copied[b_])          # the slot's previous content has reached the host
             with torch.no_grad():
@@ -434,8 +453,7 @@ def measure_e2e(torch, dist, name, K, dev, rank, world, full_result):
             done[b_].record(main_stream)
             with torch.cuda.stream(back_stream):
                 back_stream.wait_event(done[b_])
-                for o, r in zip(res_slot[b_], res_full[b_]):
-                    r.copy_(o, non_blocking=True)
+                res_full_flat[b_].copy_(res_slot_flat[b_], non_blocking=True)     # h, dq, dk, dv, di, df in one DMA
                 copied[b_].record(back_stream)
         else:
             with torch.no_grad():
