@@ -132,6 +132,9 @@ CASES = [
     (3, 2, 129, 256, torch.bfloat16, "rand", True, 1e-6),
     (1, 4, 1600, 256, torch.bfloat16, "rand", False, 1e-6),     # cfg3 secondary reading (d = 512, expansion 2 -> DH 256)
     (1, 2, 3200, 256, torch.bfloat16, "rand", True, 1e-6),
+    (2, 2, 1, 256, torch.bfloat16, "rand", False, 1e-6),        # a single token: one item per output half, no state step
+    (1, 1, 128, 256, torch.bfloat16, "refinit", True, 5e-5),    # exactly one full chunk, one (batch, head): a 2-CTA grid
+    (1, 8, 300, 256, torch.bfloat16, "forget", False, 1e-6),
     (1, 2, 70, 256, torch.float32, "rand", True, 1e-6),
     (1, 2, 96, 192, torch.float32, "forget", False, 1e-6),      # three slices
 ]
