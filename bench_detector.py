@@ -57,6 +57,10 @@ def main():
     ap.add_argument("--imgsz", type=int, default=640)
     ap.add_argument("--device", default="cuda")
     ap.add_argument("--profile", default="", help="write a torch profiler table of one step to this file (rank 0)")
+    ap.add_argument("--graph", type=int, default=0,
+                    help="train mode: 1 = the network's forward and backward replayed from CUDA graphs (torch.cuda.make_graphed_callables "
+                         "over the model's tensor path; loss, optimizer, EMA and DDP's all-reduce stay eager).  At 8 GPUs the eager step is "
+                         "host-bound (60 ms of launches for 23 ms of device time at batch 8 per GPU)")
     args = ap.parse_args()
 
     import torch
@@ -105,8 +109,26 @@ def main():
         b = args.batch // world
         model.train()
         net = model
+        graphed = None
+        if args.graph and on_gpu:
+            # The tensor path of the model (images -> the Detect head's three maps) as two CUDA graphs (forward, backward).  Every op of
+            # this repo on that path is capturable (plain launches on the current stream, no host synchronisation, static shapes); the
+            # loss (data-dependent target assignment) stays eager and takes the maps as its input (nn/tasks.py:  loss(batch, preds)).
+            class TensorPath(torch.nn.Module):
+                def __init__(self, m):
+                    super().__init__()
+                    self.m = m
+
+                def forward(self, x):
+                    with torch.autocast("cuda", cache_enabled=False):
+                        return tuple(self.m.predict(x))
+            model.criterion = model.init_criterion()
+            sample = torch.rand(b, 3, args.imgsz, args.imgsz, device=dev)
+            graphed = torch.cuda.make_graphed_callables(TensorPath(model), (sample,), num_warmup_iters=11 if world > 1 else 3,
+                                                          allow_unused_input=True)   # the reference builds modules its forward never calls
+            net = graphed
         if world > 1:   # engine/trainer.py:274
-            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank] if on_gpu else None, find_unused_parameters=True)
+            net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank] if on_gpu else None, find_unused_parameters=True)
         # lr as in the first iterations of the reference's warm-up ramp (engine/trainer.py:366-375: from 0 towards lr0 = 0.01)
         opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.937, nesterov=True, weight_decay=5e-4)
         scaler = torch.amp.GradScaler("cuda", enabled=on_gpu)
@@ -117,9 +139,15 @@ def main():
             hb = batches[j % 2]
             batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
             batch["img"] = batch["img"].float() / 255          # models/yolo/detect/train.py:59
-            with torch.autocast(dev.type, enabled=on_gpu):
-                loss, _ = net(batch)
-                loss = loss.sum() * world                       # engine/trainer.py:382-383
+            if graphed is not None:
+                preds = list(net(batch["img"]))
+                with torch.autocast(dev.type, enabled=on_gpu):
+                    loss, _ = model.criterion(preds, batch)
+                    loss = loss.sum() * world
+            else:
+                with torch.autocast(dev.type, enabled=on_gpu):
+                    loss, _ = net(batch)
+                    loss = loss.sum() * world                   # engine/trainer.py:382-383
             scaler.scale(loss).backward()
             scaler.unscale_(opt)                                # engine/trainer.py:591-599
             torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=0.5)
@@ -186,7 +214,7 @@ def main():
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if args.mode == "train" else "weak", "vs_baseline": None,
             "dtype": "fp16 autocast (mLSTM kernels: bf16 operands, fp32 accumulation)" if on_gpu else "fp32", "data": "synthetic",
-            "config": {"model": f"xlstm-yolo-{args.scale}", "params": n_params, "imgsz": args.imgsz,
+            "config": {"model": f"xlstm-yolo-{args.scale}", "params": n_params, "imgsz": args.imgsz, "cuda_graph": int(bool(args.graph)),
                        "global_batch": args.batch if args.mode == "train" else b * world, "batch_per_gpu": b,
                        "parallelism": f"ddp{world}" if args.mode == "train" else f"replicas{world}", "mode": args.mode,
                        "vil": ("this repo's ViLBlockPair drop-in (BR(TL(x)), flip-free)" if args.impl == "b200" else
