@@ -328,6 +328,19 @@ def measure_device(torch, dist, ops, _lib, name, K, W, dev, rank, world, reverse
     if world > 1:
         dist.barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
+    # The same K steps as eager launches through the plan's C-ABI calls (no graph): what the step costs with the host in the loop
+    eager_value = None
+    if graph is not None and world == 1:
+        t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for s_ in range(3):
+            step(plans[s_ % nsets])
+        torch.cuda.synchronize()
+        t_a.record()
+        for s_ in range(K):
+            step(plans[(W + s_) % nsets])
+        t_b.record()
+        torch.cuda.synchronize()
+        eager_value = B * S / (t_a.elapsed_time(t_b) / K * 1e-3)
     # Second pass, same K steps, eager, with an event pair around every launch: the per-kernel durations the roofline uses.
     # Kept out of the headline region because the events themselves cost ~2.7 us per pair (the fused backward's empty
     # part 0 measures exactly that) and serialise consecutive launches.
@@ -368,6 +381,7 @@ def measure_device(torch, dist, ops, _lib, name, K, W, dev, rank, world, reverse
     return {
         "value": value, "ms_per_step": ms_per_step, "roofline": roofline, "launches_per_step": int(launches_per_step),
         "family": pl0.family, "nsets": nsets, "set_bytes": set_bytes, "graph": graph is not None, "plans": plans, "step": step,
+        "eager_value": eager_value,
     }
 
 
@@ -560,7 +574,8 @@ def main():
                    "reverse": int(args.reverse), "kernel_family": m["family"],
                    "l2": f"inputs rotate over {m['nsets']} sets x {m['set_bytes'] / 1e6:.0f} MB > 126 MB L2", "parallelism": f"dp{world}",
                    "launch": (f"CUDA graph of {m['nsets']} steps (one per input set) replayed" if m["graph"] else "eager ctypes launches"),
-                   "per_kernel_ms": "second pass of the same K steps with an event pair around every launch"},
+                   "per_kernel_ms": "second pass of the same K steps with an event pair around every launch",
+                   "eager_tokens_per_s": m["eager_value"]},   # the same steps launched eagerly through the C ABI (no graph)
         "clocks": sampler.result(),
         "e2e": e2e,
         "gpu_launches": int(m["launches_per_step"] * K),
