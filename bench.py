@@ -238,7 +238,7 @@ def launches_of(variant_fwd, variant_bwd, DH):
                 "bwd_dkv": ["tc_state_bwd_kernel<128> on 2x2 blocks of dC", "tc256_par_kernel<B1> (dv)", "tc256_par_kernel<B2> (dk)",
                             "tc_dfscan_kernel"]}
     return {
-        "fwd": {"single_pass": ["tc_fwd_kernel"], "two_phase": ["tc_state_fwd_kernel", "tc_fwd_par_kernel"],
+        "fwd": {"single_pass": ["tc_fwd_ws_kernel (warp-specialised walk; MLSTM_FWD_WS=0: tc_fwd_kernel)"], "two_phase": ["tc_state_fwd_kernel", "tc_fwd_par_kernel"],
                 "simt": ["simt_fwd_kernel"]}[variant_fwd],
         "bwd_dq": {"single_pass": ["tc_bwd_dq_kernel"], "chunk_parallel": ["tc_bwd_par_kernel<A>"],
                    "fused_walk": [], "simt": ["simt_bwd_dq_kernel"]}[variant_bwd],
