@@ -14,6 +14,8 @@
 #include "mlstm_common.cuh"
 
 namespace mlstm {
+bool gates_tc_ok(const mlstm_gate_proj_params& p);                     // mlstm_gates_tc.cu
+int gates_fwd_tc(const mlstm_gate_proj_params& p, cudaStream_t st);
 namespace {
 
 constexpr int OG = 8;            // gate outputs per pass (i_0..i_{NH-1}, f_0..f_{NH-1} in groups of 8)
@@ -344,6 +346,7 @@ int mlstm_b200_gates_fwd(const mlstm_gate_proj_params* p, void* cuda_stream) {
   if (rc || p->T == 0) return rc;
   if ((rc = bind_device(p->q))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (gates_tc_ok(*p)) return gates_fwd_tc(*p, st);   // bf16, D % 64 == 0, <= 16 gate outputs: the tensor-core streaming kernel
   const size_t smem = (size_t)OG * 3 * p->D * sizeof(float);
   const int tiles = (p->T + TT - 1) / TT, warps = FW_NT / 32;
   int grid = (tiles + warps - 1) / warps;

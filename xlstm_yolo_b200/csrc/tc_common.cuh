@@ -270,4 +270,24 @@ inline int make_state_tmap(CUtensorMap* out, const void* ptr, size_t rows_total,
 }
 
 }  // namespace tc
+
+// 2-D map (columns, rows) of a (T, D) 16-bit matrix with row stride ld; box 64 x 128
+inline int make_mat_tmap(CUtensorMap* out, const void* ptr, int D, int T, int64_t ld) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.s0 = ld; key.d0 = D; key.d1 = T; key.box_rows = 128; key.kind = 8;
+  if (tmap_cache_lookup(key, out, false)) return 0;
+  PFN_tmapEncodeTiled enc = get_tmap_encoder();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)T};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, 128u};
+  cuuint32_t estr[2] = {1u, 1u};
+  const int r = (int)enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == 0) tmap_cache_lookup(key, out, true);
+  return r;
+}
+
 }  // namespace mlstm
