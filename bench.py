@@ -240,7 +240,9 @@ def launches_of(variant_fwd, variant_bwd, DH):
     return {
         "fwd": {"single_pass": ["tc_fwd_ws_kernel (warp-specialised walk; MLSTM_FWD_WS=0: tc_fwd_kernel)"], "two_phase": ["tc_state_fwd_kernel", "tc_fwd_par_kernel"],
                 "simt": ["simt_fwd_kernel"]}[variant_fwd],
-        "bwd_dq": {"single_pass": ["tc_bwd_dq_kernel"], "chunk_parallel": ["tc_bwd_par_kernel<A>"],
+        "bwd_dq": {"single_pass": ["tc_bwd_dq_kernel"],
+                   "chunk_parallel": ["tc_bwd_par_kernel<A> (whole-backward calls with 2*B*NH <= #SM: tc_dn_kernel + tc_bwd_sa_kernel, "
+                                      "the state walk and A in one launch)"],
                    "fused_walk": [], "simt": ["simt_bwd_dq_kernel"]}[variant_bwd],
         "bwd_dkv": {"single_pass": ["tc_bwd_dkv12_kernel (dv and dk walks co-resident)" if DH == 64 else "tc_bwd_dkv_kernel<1>, <2>"],
                     "chunk_parallel": ["tc_state_bwd_kernel", "tc_bwd_b12_kernel (B1 dv | B2 dk side by side)", "tc_dfscan_kernel"],
@@ -264,17 +266,20 @@ def measure_device(torch, dist, ops, _lib, name, K, W, dev, rank, world, reverse
     pl0 = plans[0]
 
     def step(pl, evs=None):
-        if evs is not None:
-            evs[0].record()
+        # timed step: forward + the whole backward in one call, as mLSTMBackend's autograd node makes it (with few (batch, head)
+        # pairs the library then runs the adjoint-state walk and the dq kernel in one launch); the per-kernel pass (evs) calls
+        # the backward's two parts separately to put events between them
+        if evs is None:
+            pl.forward()
+            pl.backward()
+            return
+        evs[0].record()
         pl.forward()
-        if evs is not None:
-            evs[1].record()
+        evs[1].record()
         pl.backward(0)
-        if evs is not None:
-            evs[2].record()
+        evs[2].record()
         pl.backward(1)
-        if evs is not None:
-            evs[3].record()
+        evs[3].record()
 
     for w in range(W):
         step(plans[w % nsets])

@@ -115,7 +115,7 @@ struct SmemB {
 // in one launch, each on its own slice of the grid — see tc_bwd_b12_kernel)
 template <int DH, int MODE>
 __device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params& p, const float scale, const int n_items,
-                                         const int order, const int cta, const int ncta) {
+                                         const int order, const int cta, const int ncta, const bool write_dn = true) {
   constexpr int KT = DH / 64;
   constexpr int TILE_C = SmemB<DH>::TILE_C;
   constexpr int NB = DH / 32;
@@ -282,7 +282,7 @@ __device__ __forceinline__ void par_body(const BwdMaps& maps, const mlstm_params
       if (compute) named_sync(3, CT);
       if (compute) {
         dn_row = G.dnf[row] * ((sm.part[0][row] + sm.part[1][row]) + (sm.part[2][row] + sm.part[3][row]));
-        if (cq == 0 && row_ok) ws_dn[grow] = dn_row;
+        if (write_dn && cq == 0 && row_ok) ws_dn[grow] = dn_row;
       }
     }
     TLB(1);
@@ -499,15 +499,13 @@ struct SmemSB {
 // the state pass touches.  U of step pc+1 is therefore computed while the state pass of step pc runs.
 // Head dims above the template's DH (DHF = p.DHQK = 256, DH = 128): gridDim.y = (DHF / DH)^2 independent blocks
 // dC[row0 .. +DH)[col0 .. +DH) = f(Q columns row0.., dH columns col0..); column block 0 also carries the dn state.
+// bh: the (batch, head) pair of this CTA, by: its block of the state (0 unless DHF > DH)
 template <int DH>
-__global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_constant__ BwdMaps maps, const mlstm_params p,
-                                                             const float scale) {
+__device__ __forceinline__ void state_bwd_body(const BwdMaps& maps, const mlstm_params& p, const float scale, const int bh,
+                                               const int by) {
   constexpr int KT = DH / 64;
   constexpr int NB = DH / 32;
   const int DHF = p.DHQK, ncb = DHF / DH, nblk = ncb * ncb;
-  // block launches (DHF > DH): block index in blockIdx.x, so the CTAs sharing a Q or dH tile run side by side (L2 reuse)
-  const bool blocks = DHF != DH;
-  const int by = blocks ? (int)blockIdx.x : (int)blockIdx.y;
   const int row0 = (by / ncb) * DH, col0 = (by % ncb) * DH;
   constexpr uint32_t A_LBO = (DH == 128) ? TILE : 0;
   constexpr uint32_t TCOLS = 512;
@@ -518,7 +516,7 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool compute = tid < CT, issuer = tid == CT, gatew = tid >= GT0;
   const int rg = warp & 3, cq = compute ? (warp >> 2) : 4, row = rg * 32 + lane;
-  const int bh = blocks ? blockIdx.y : blockIdx.x, b = bh / p.NH, h = bh % p.NH;
+  const int b = bh / p.NH, h = bh % p.NH;
   const int S = p.S, NC = num_chunks(S);
   const bool rev = p.reverse != 0;
   const BwdLayout blay(p.B, p.NH, S, DHF);
@@ -727,6 +725,70 @@ __global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_consta
   if (warp == 0) tmem_dealloc(tm, TCOLS);
 }
 
+template <int DH>
+__global__ void __launch_bounds__(NT, 1) tc_state_bwd_kernel(const __grid_constant__ BwdMaps maps, const mlstm_params p,
+                                                             const float scale) {
+  // block launches (DHF > DH): block index in blockIdx.x, so the CTAs sharing a Q or dH tile run side by side (L2 reuse)
+  const bool blocks = p.DHQK != DH;
+  state_bwd_body<DH>(maps, p, scale, blocks ? blockIdx.y : blockIdx.x, blocks ? blockIdx.x : blockIdx.y);
+}
+
+// The adjoint-state walk occupies only B*NH SMs and kernel A (dq) does not depend on it: with few (batch, head) pairs
+// the two share ONE launch — CTAs [0, n_state) walk the states, the rest run A's item list — so the walk's 30-50 us
+// hide A entirely.  The walk's only input from A, dn_t, then comes from tc_dn_kernel (A keeps its own copy in
+// registers and does not write it).
+template <int DH>
+__global__ void __launch_bounds__(NT, 1) tc_bwd_sa_kernel(const __grid_constant__ BwdMaps maps_s, const __grid_constant__ BwdMaps maps_a,
+                                                          const mlstm_params p, const float scale, const int n_items,
+                                                          const int order, const int n_state) {
+  if ((int)blockIdx.x < n_state) state_bwd_body<DH>(maps_s, p, scale, blockIdx.x, 0);
+  else par_body<DH, MODE_A>(maps_a, p, scale, n_items, order, blockIdx.x - n_state, gridDim.x - n_state, false);
+}
+
+// dn_t = dnf_t (dh_t . h_t) for every row (the same formula as kernel A and gates_warp_bwd): DH / 8 lanes per row, one 16-byte
+// load per lane and operand, DN_U rows per lane group with all their loads in flight.
+constexpr int DN_U = 4;
+__global__ void __launch_bounds__(256) tc_dn_kernel(const mlstm_params p, float* __restrict__ ws_dn, const int DH) {
+  const int lpr = DH / 8, rpw = 32 / lpr;                 // lanes per row, rows per warp and pass
+  const int lane = threadIdx.x & 31, sub = lane / lpr, l = lane % lpr;
+  const int rows = p.B * p.NH * p.S;                      // < 2^31: checked by the launcher
+  const int r0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (rpw * DN_U) + sub;
+  const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(p.h.ptr) + l * 8;
+  const __nv_bfloat16* dp = reinterpret_cast<const __nv_bfloat16*>(p.dh.ptr) + l * 8;
+  uint4 wh[DN_U], wd[DN_U];
+  float nr[DN_U], mr[DN_U];
+#pragma unroll
+  for (int u = 0; u < DN_U; ++u) {
+    const int r = r0 + u * rpw;
+    wh[u] = wd[u] = make_uint4(0, 0, 0, 0);
+    nr[u] = mr[u] = 0.f;
+    if (r < rows) {
+      const int bh = r / p.S, t = r - bh * p.S, b = bh / p.NH, h = bh - b * p.NH;
+      wh[u] = *reinterpret_cast<const uint4*>(hp + (int64_t)b * p.h.stride_b + (int64_t)h * p.h.stride_h + (int64_t)t * p.h.stride_s);
+      wd[u] = *reinterpret_cast<const uint4*>(dp + (int64_t)b * p.dh.stride_b + (int64_t)h * p.dh.stride_h + (int64_t)t * p.dh.stride_s);
+      if (l == 0) { nr[u] = p.n_row[r]; mr[u] = p.m_row[r]; }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < DN_U; ++u) {
+    const int r = r0 + u * rpw;
+    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&wh[u]);
+    const __nv_bfloat162* dd = reinterpret_cast<const __nv_bfloat162*>(&wd[u]);
+    float part = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 a = __bfloat1622float2(hh[e]), c2 = __bfloat1622float2(dd[e]);
+      part = fmaf(a.x, c2.x, fmaf(a.y, c2.y, part));
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (r < rows && l == 0) {
+      const float floor_ = __expf(-mr[u]);
+      const float N = fmaxf(fabsf(nr[u]), floor_) + p.eps;
+      ws_dn[r] = (fabsf(nr[u]) >= floor_) ? (-copysignf(1.f, nr[u]) / N) * part : 0.f;
+    }
+  }
+}
+
 // =============================================================================================
 // DF: di = K, df = sigmoid(-f) * suffix_sum(R - K) in scan order.  One 128-thread CTA per chunk:
 // the suffix sum inside the chunk is re-anchored on flow[sc+1] = <dC, C> + <dn, n> across the
@@ -834,17 +896,37 @@ int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
   const float scale = resolve_scale(p);
   const size_t smB = sizeof(SmemB<DH>), smSB = sizeof(SmemSB<DH>);
   int rc;
-  if (part != 1) {
+  // whole backward in one call with few (batch, head) pairs: the state walk and kernel A share a launch (tc_bwd_sa_kernel)
+  static const bool merge_off = getenv("MLSTM_BWD_MERGE") != nullptr && getenv("MLSTM_BWD_MERGE")[0] == '0';
+  const int n_state = p.B * p.NH;
+  const bool merged = part != 0 && part != 1 && !merge_off && 2 * n_state <= sms && NC > 1 && (int64_t)n_state * p.S < (1ll << 31);
+  if (merged) {
+    const int64_t rows = (int64_t)n_state * p.S;
+    const int rows_per_cta = 8 * (32 / (DH / 8)) * DN_U;
+    tc_dn_kernel<<<dim3((unsigned)((rows + rows_per_cta - 1) / rows_per_cta)), dim3(256), 0, st>>>(
+        p, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + blay.dn_off), DH);
+    if ((rc = launched("tc_dn"))) return rc;
+    BwdMaps ma{mdh, mv, mk, mcs, mq, mh, mdq};
+    BwdMaps ms{mq, mdh, mcs, mdcs, mq, mh, mdq};
+    const size_t smSA = smB > smSB ? smB : smSB;
+    const int n_a = n_items < sms - n_state ? n_items : sms - n_state;
+    if ((rc = prep(tc_bwd_sa_kernel<DH>, smSA, "tc_bwd_state_dq"))) return rc;
+    tc_bwd_sa_kernel<DH><<<dim3(n_state + n_a), dim3(NT), smSA, st>>>(ms, ma, p, scale, n_items, order_of(0), n_state);
+    if ((rc = launched("tc_bwd_state_dq"))) return rc;
+  }
+  if (part != 1 && !merged) {
     BwdMaps m{mdh, mv, mk, mcs, mq, mh, mdq};
     if ((rc = prep(tc_bwd_par_kernel<DH, MODE_A>, smB, "tc_bwd_dq"))) return rc;
     tc_bwd_par_kernel<DH, MODE_A><<<dim3(grid), dim3(NT), smB, st>>>(m, p, scale, n_items, order_of(0));
     if ((rc = launched("tc_bwd_dq"))) return rc;
   }
   if (part != 0) {
-    BwdMaps ms{mq, mdh, mcs, mdcs, mq, mh, mdq};
-    if ((rc = prep(tc_state_bwd_kernel<DH>, smSB, "tc_state_bwd"))) return rc;
-    tc_state_bwd_kernel<DH><<<dim3(p.B * p.NH), dim3(NT), smSB, st>>>(ms, p, scale);
-    if ((rc = launched("tc_state_bwd"))) return rc;
+    if (!merged) {
+      BwdMaps ms{mq, mdh, mcs, mdcs, mq, mh, mdq};
+      if ((rc = prep(tc_state_bwd_kernel<DH>, smSB, "tc_state_bwd"))) return rc;
+      tc_state_bwd_kernel<DH><<<dim3(p.B * p.NH), dim3(NT), smSB, st>>>(ms, p, scale);
+      if ((rc = launched("tc_state_bwd"))) return rc;
+    }
     BwdMaps m1{mk, mq, mdh, mdcs, mq, mh, mdv};
     BwdMaps m2{mv, mdh, mq, mdcs, mk, mh, mdk};
     if (n_items < 4 * sms) {
