@@ -1,4 +1,4 @@
-"""Gate-projection kernels (csrc/mlstm_gates.cu) and the fused cell node vs PyTorch on the same inputs.
+"""Gate-projection kernels (csrc/mlstm_gates.cu, the tensor-core forward csrc/mlstm_gates_tc.cu) and the fused cell node vs PyTorch on the same inputs.
 
 Reference arithmetic: vision_lstm2.py:895-897 — ``cat[q,k,v]`` then two ``nn.Linear(3*dim, NH)``."""
 import pytest
@@ -33,6 +33,9 @@ SHAPES = [  # B, S, D, NH
     (1, 203, 1024, 4),     # two column slabs, ragged token tiles
     (2, 100, 512, 32),     # reference default qkv_block_size=16: eight output groups
     (1, 3, 64, 2),         # fewer tokens than a tile
+    (2, 300, 256, 8),      # 16 gate outputs: the N = 48 operand of the tensor-core forward (mlstm_gates_tc.cu)
+    (1, 129, 128, 6),      # 12 outputs padded to 16, one token past a tile
+    (1, 256, 64, 8),       # whole tiles, a single 64-column slice per tensor
 ]
 
 
