@@ -37,8 +37,13 @@ enum { MODE_A = 0, MODE_B1 = 1, MODE_B2 = 2 };
 #define TLB(k) do { if (MODE == MLSTM_TL_MODE && blockIdx.x == 0 && n < 8) { \
     if (threadIdx.x == 0) tlb[n * 32 + (k)] = clock64(); \
     if (threadIdx.x == CT) tlb[n * 32 + 16 + (k)] = clock64(); } } while (0)
+// state walk (tests/gpu_tools/timeline_state.py): CTA (bh 0, block 0) stamps its first 8 steps into the R partials
+#define TLS(k) do { if (bh == 0 && by == 0 && pc < 8) { \
+    if (threadIdx.x == 0) tls[pc * 32 + (k)] = clock64(); \
+    if (threadIdx.x == CT) tls[pc * 32 + 16 + (k)] = clock64(); } } while (0)
 #else
 #define TLB(k) do { } while (0)
+#define TLS(k) do { } while (0)
 #endif
 
 struct BwdMaps { CUtensorMap t0, t1, t2, st, t3, h, out; };   // t3: q (A) / k (B2) rows for R and K; h: A only
@@ -611,6 +616,9 @@ __device__ __forceinline__ void state_bwd_body(const BwdMaps& maps, const mlstm_
     issue_update(0);
   }
 
+#ifdef MLSTM_TIMELINE
+  long long* tls = reinterpret_cast<long long*>(ws + blay.rpart_off);
+#endif
   for (int pc = 0; pc < NC; ++pc) {
     const bool last = (pc + 1 == NC);
     const int buf = pc & 1, sc = sc_of(pc);
@@ -621,28 +629,34 @@ __device__ __forceinline__ void state_bwd_body(const BwdMaps& maps, const mlstm_
     }
     if (last) break;   // the state leaving chunk -1 is not needed (initial states carry no gradient)
     const bool more = pc + 2 < NC;   // step pc+1 still produces a state
+    TLS(0);
     // ---- operands and update of the next step, under this step's MMA / state pass --------------
     if (more) {
       mbar_wait(&sm.bar_q[buf ^ 1], ((pc + 1) >> 1) & 1);
       if (compute) prep_operands(pc + 1);
       fence_proxy_async_smem();
     }
+    TLS(1);
     if (issuer) tma_store_wait_read<0>();   // the previous step's staged dC tile has left shared memory
     tc_fence_before();
     named_sync(2, GT0);
+    TLS(2);
     if (issuer && more) {
       mbar_wait(&sm.bar_dh[buf ^ 1], ((pc + 1) >> 1) & 1);
       tc_fence_after();
       issue_update(pc + 1);
     }
+    TLS(3);
     mbar_wait(&sm.bar_mma[buf], (pc >> 1) & 1);
     tc_fence_after();
+    TLS(4);
     if (issuer && more) load_qd(pc + 2);   // q / dh of this step are free: U(pc) is complete
 
     // ---- state pass: dC_{sc-1} = (decayed running state) + U -> workspace (bf16), running state <- decay dC_{sc-1}
     const float dnext = sm.g[(pc + 1) % 3].decay;
     float fl = 0.f;   // partial of the boundary flow <dC_{sc-1}, Cs[sc]> + <dn_{sc-1}, ns[sc]>
     mbar_wait(&sm.bar_cs, pc & 1);
+    TLS(5);
     if (row < DH && cq < NB) {
       float r[32];
       tmem_ld32(tm + buf * DH + lane_sel + cq * 32, r);
@@ -698,6 +712,7 @@ __device__ __forceinline__ void state_bwd_body(const BwdMaps& maps, const mlstm_
       }
       if (more) tmem_st_wait();
     }
+    TLS(6);
     if (compute) {
       fl = warp_sum(fl);
       if (lane == 0) sm.fpart[warp] = fl;
@@ -705,6 +720,7 @@ __device__ __forceinline__ void state_bwd_body(const BwdMaps& maps, const mlstm_
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    TLS(7);
     if (tid == 0) {
       float f_ = 0.f;
 #pragma unroll
@@ -717,6 +733,7 @@ __device__ __forceinline__ void state_bwd_body(const BwdMaps& maps, const mlstm_
         tma_store_2d(&maps.st, sm.stage + kt * (DH * 128), col0 + kt * 64, (bh * NC + (sc - 1)) * DHF + row0);
       tma_store_commit();
     }
+    TLS(8);
   }
   if (issuer) tma_store_wait_all<0>();
   if (!gatew) { tc_fence_before(); __syncthreads(); }   // matches the gate warp's last in-loop barrier
