@@ -572,9 +572,9 @@ def test_cell_and_layer_trace_under_torch_compile():
 @pytest.mark.parametrize("dtype,DK,DV", [(torch.float32, 32, 64), (torch.bfloat16, 32, 64), (torch.bfloat16, 64, 128)])
 def test_unequal_head_dims_match_oracle(dtype, DK, DV):
     """qk_dim_factor = 0.5 of the reference's mLSTMLayerVision (mlstm_large.py:46,186-187): q, k of head dim DHqk, v and h of
-    head dim DHv = 2 DHqk.  Runs on the fp32 SIMT family (the tcgen05 kernels take DHqk == DHv only); the reference's own
-    PyTorch chunkwise_simple cannot run this shape at all (it views q, k, v with one DH, backends.py:163-171), so the oracle
-    restatement is the pin."""
+    head dim DHv = 2 DHqk.  bf16 runs the tcgen05 family on q, k zero-padded to DHv inside the library (mlstm_api.cu: every
+    q / k dependent quantity is an inner product over DHqk), fp32 the SIMT family; the reference's own PyTorch chunkwise_simple
+    cannot run this shape at all (it views q, k, v with one DH, backends.py:163-171), so the oracle restatement is the pin."""
     B, NH, S = 2, 2, 200
     g = torch.Generator().manual_seed(5)
     mk = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc)
@@ -585,8 +585,36 @@ def test_unequal_head_dims_match_oracle(dtype, DK, DV):
     ref = O.mlstm_fwbw(*(x.double() for x in inputs), chunk_size=64, eps=1e-6)
     got = run_cuda(inputs)
     from xlstm_yolo_b200 import ops
-    assert ops.kernel_family(q.cuda(), v.cuda()) == "simt"
+    assert ops.kernel_family(q.cuda(), v.cuda()) == ("simt" if dtype == torch.float32 else "tcgen05")
     check(got, ref, torch.float32 if dtype == torch.float32 else torch.bfloat16, f"DHqk {DK} DHv {DV}")
+
+
+@pytest.mark.parametrize("DK,DV,S,reverse", [(64, 128, 300, False), (32, 64, 700, True), (128, 256, 200, False)])
+def test_unequal_head_dims_with_states(DK, DV, S, reverse):
+    """The padded tensor-core path (bf16, DHqk < DHv) with carried state: c_initial (B, NH, DHqk, DHv) / n_initial are padded
+    with zero rows inside the library and the last states cropped back; both scan directions, single-pass and chunk-parallel
+    lengths, DHv = 256 (the slice-streaming family)."""
+    from xlstm_yolo_b200 import ops
+    B, NH = 2, 2
+    g = torch.Generator().manual_seed(9)
+    mk = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc)
+    bf = torch.bfloat16
+    q, k = mk(B, S, NH, DK, sc=DK ** -0.5).to(bf).transpose(1, 2), mk(B, S, NH, DK, sc=DK ** -0.5).to(bf).transpose(1, 2)
+    v, dh = mk(B, S, NH, DV).to(bf).transpose(1, 2), mk(B, S, NH, DV).to(bf).transpose(1, 2)
+    i, f = mk(B, S, NH).transpose(1, 2), (torch.linspace(3, 6, NH).view(1, 1, NH) + mk(B, S, NH)).transpose(1, 2)
+    inputs = [q, k, v, i, f, dh]
+    st = dict(c_initial=mk(B, NH, DK, DV), n_initial=mk(B, NH, DK), m_initial=mk(B, NH, 1))
+    assert ops.kernel_family(q.cuda(), v.cuda()) == "tcgen05"
+    ref = oracle_on_kernel_side(inputs, reverse=reverse, states=st, what=f"states DHqk{DK} DHv{DV} rev={reverse}")
+    got = run_cuda(inputs, reverse=reverse, states=st)
+    check(got, ref, bf, f"states DHqk {DK} DHv {DV}")
+    h, (C, n, m) = ops.mlstm(*(x.cuda() for x in inputs[:5]), *(s_.cuda() for s_ in st.values()), return_last_states=True,
+                             reverse=reverse)
+    _, (Cr, nr, mr) = O.mlstm_chunkwise(*(x.double() for x in inputs[:5]), *(s_.double() for s_ in st.values()),
+                                        chunk_size=64, return_last_states=True, reverse=reverse)
+    assert C.shape == (B, NH, DK, DV) and n.shape == (B, NH, DK)
+    th = TOL[bf][0]
+    assert rel(C, Cr) < th and rel(n, nr) < th and rel(m, mr) < 1e-4
 
 
 def test_reference_mlstm_layer_vision_runs_on_the_shim():

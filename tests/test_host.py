@@ -116,6 +116,19 @@ def test_kernel_family_and_workspace(lib):
     p = _params(dtype=_lib.MLSTM_F32, DHQK=256, DHV=256)   # fp32: value-sliced SIMT kernels: dn per slice + R + fp32 dq/dk accumulators
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
     assert lib.mlstm_b200_workspace_bytes(C.byref(p), 1) == 4 * (rows * 5 + 2 * rows * 256)
+    # DHqk < DHv (mLSTMLayerVision's qk_dim_factor = 0.5): bf16 runs the tcgen05 family on zero-padded q, k (mlstm_api.cu); the
+    # padded copies, padded initial / last states ride behind the chunk states, padded dq / dk behind the workspace
+    p = _params(DHQK=64, DHV=128)
+    assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"tcgen05"
+    assert lib.mlstm_b200_kernel_variant(C.byref(p), 0) in (b"single_pass", b"two_phase")
+    sq = _params(DHQK=128, DHV=128)
+    act = 2 * 64 * 2 * 128 * 2                                # B S NH DHv bf16
+    extra = 2 * act + 2 * (2 * 2 * 128 * 128 * 4) + 2 * (2 * 2 * 128 * 4)
+    assert lib.mlstm_b200_state_bytes(C.byref(p)) >= lib.mlstm_b200_state_bytes(C.byref(sq)) + extra
+    assert lib.mlstm_b200_workspace_bytes(C.byref(p), 1) >= lib.mlstm_b200_workspace_bytes(C.byref(sq), 1) + 2 * act
+    assert lib.mlstm_b200_kernel_name(C.byref(_params(DHQK=128, DHV=64)), 0) == b"simt"     # DHqk > DHv stays on SIMT
+    assert lib.mlstm_b200_kernel_name(C.byref(_params(DHQK=20, DHV=64)), 0) == b"simt"      # rows must be 16-byte multiples
+    assert lib.mlstm_b200_kernel_name(C.byref(_params(dtype=_lib.MLSTM_F32, DHQK=64, DHV=128)), 0) == b"simt"
     p = _params(DHQK=512, DHV=512)
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) is None
     assert lib.mlstm_b200_kernel_variant(C.byref(p), 1) is None

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "mlstm_common.cuh"
@@ -20,6 +21,197 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 void clear_error() { g_err[0] = 0; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// DHqk < DHv on the tensor cores (the reference's mLSTMLayerVision: qk_dim_factor = 0.5, mlstm_large.py:46,186-187).
+// Every q / k dependent quantity of the cell is an inner product over DHqk (S = Q K^T, q . C, q . n, the rows of C = K^T V
+// and of n = sum k), so q and k padded with zero columns to DHv give the same h, dv, di, df, the same first DHqk columns of
+// dq, dk and the same first DHqk rows of C, n — and DHqk = DHv is the shape the tcgen05 family runs.  The padded copies
+// (bf16, (B, S, NH, DHv)) live behind the chunk states in the caller's `states` buffer (written by the forward, read again
+// by the backward), dq / dk are produced padded in the workspace and copied out, initial / last states are padded / cropped
+// the same way; the 1 / sqrt(DHqk) scale is passed explicitly.  MLSTM_NO_TCPAD=1 keeps these shapes on the fp32 SIMT family.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct PadLayout {
+  size_t inner, act, cst, nst;             // bytes: padded problem's own states | one padded activation | C | n
+  size_t q_off, k_off, c0_off, n0_off, cl_off, nl_off, total;
+  size_t ws_inner, dq_off, dk_off, ws_total;
+};
+
+mlstm_params padded_params(const mlstm_params& p) {
+  mlstm_params pp = p;
+  pp.DHQK = p.DHV;
+  pp.qk_scale = resolve_scale(p);
+  return pp;
+}
+
+PadLayout pad_layout(const mlstm_params& p) {
+  const mlstm_params pp = padded_params(p);
+  PadLayout l;
+  l.inner = al256(tc_state_bytes(pp));
+  l.act = al256((size_t)p.B * p.S * p.NH * p.DHV * 2);
+  l.cst = al256((size_t)p.B * p.NH * p.DHV * p.DHV * 4);
+  l.nst = al256((size_t)p.B * p.NH * p.DHV * 4);
+  l.q_off = l.inner;
+  l.k_off = l.q_off + l.act;
+  l.c0_off = l.k_off + l.act;
+  l.n0_off = l.c0_off + l.cst;
+  l.cl_off = l.n0_off + l.nst;
+  l.nl_off = l.cl_off + l.cst;
+  l.total = l.nl_off + l.nst;
+  l.ws_inner = al256(tc_bwd_workspace(pp));
+  l.dq_off = l.ws_inner;
+  l.dk_off = l.dq_off + l.act;
+  l.ws_total = l.dk_off + l.act;
+  return l;
+}
+
+bool pad_path(const mlstm_params& p) {
+  static const bool off = getenv("MLSTM_NO_TCPAD") != nullptr && getenv("MLSTM_NO_TCPAD")[0] == '1';
+  if (off || p.dtype != MLSTM_BF16 || p.DHQK >= p.DHV || p.DHQK % 8 != 0) return false;
+  mlstm_params pp = p;
+  pp.DHQK = p.DHV;
+  return tc_supported(pp);
+}
+
+// rows (b, s, h) of a strided bf16 activation <-> rows of the dense padded copy, 16 bytes per thread
+__global__ void __launch_bounds__(256) pad_rows_kernel(const mlstm_act a0, const mlstm_act a1, __nv_bfloat16* __restrict__ d0,
+                                                       __nv_bfloat16* __restrict__ d1, const int B, const int S, const int NH,
+                                                       const int DK, const int DV, const int to_padded) {
+  const int cpr = DV / 8;                                    // 16-byte chunks per padded row
+  const int64_t n = (int64_t)B * S * NH * cpr;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % cpr);
+    const int64_t row = e / cpr;
+    const int h = (int)(row % NH);
+    const int64_t bs = row / NH;
+    const int s_ = (int)(bs % S), b = (int)(bs / S);
+    const bool live = c * 8 < DK;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const mlstm_act& a = w ? a1 : a0;
+      __nv_bfloat16* d = w ? d1 : d0;
+      if (!a.ptr) continue;
+      __nv_bfloat16* src = reinterpret_cast<__nv_bfloat16*>(a.ptr) + (int64_t)b * a.stride_b + (int64_t)h * a.stride_h +
+                           (int64_t)s_ * a.stride_s + c * 8;
+      uint4* pad = reinterpret_cast<uint4*>(d + row * DV + c * 8);
+      if (to_padded) *pad = live ? *reinterpret_cast<const uint4*>(src) : make_uint4(0, 0, 0, 0);
+      else if (live) *reinterpret_cast<uint4*>(src) = *pad;
+    }
+  }
+}
+
+// fp32 states: C (B*NH, DK, DV) <-> (B*NH, DV, DV), n (B*NH, DK) <-> (B*NH, DV)
+__global__ void __launch_bounds__(256) pad_states_kernel(float* __restrict__ c_small, float* __restrict__ n_small,
+                                                         float* __restrict__ c_pad, float* __restrict__ n_pad, const int BH,
+                                                         const int DK, const int DV, const int to_padded) {
+  const int64_t nc = (int64_t)BH * DV * DV, nn = (int64_t)BH * DV;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nc + nn; e += (int64_t)gridDim.x * blockDim.x) {
+    if (e < nc) {
+      const int col = (int)(e % DV), r = (int)((e / DV) % DV);
+      const int64_t bh = e / ((int64_t)DV * DV);
+      if (to_padded) c_pad[e] = r < DK ? c_small[(bh * DK + r) * DV + col] : 0.f;
+      else if (r < DK) c_small[(bh * DK + r) * DV + col] = c_pad[e];
+    } else {
+      const int64_t x = e - nc;
+      const int r = (int)(x % DV);
+      const int64_t bh = x / DV;
+      if (to_padded) n_pad[x] = r < DK ? n_small[bh * DK + r] : 0.f;
+      else if (r < DK) n_small[bh * DK + r] = n_pad[x];
+    }
+  }
+}
+
+int pad_launched(const char* what) {
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("%s launch failed: %s", what, cudaGetErrorString(e)); return MLSTM_ERR_CUDA; }
+  return MLSTM_OK;
+}
+
+mlstm_act dense_act(void* ptr, const mlstm_params& p) {
+  mlstm_act a;
+  a.ptr = ptr;
+  a.stride_b = (int64_t)p.S * p.NH * p.DHV;
+  a.stride_s = (int64_t)p.NH * p.DHV;
+  a.stride_h = p.DHV;
+  return a;
+}
+
+int grid_for(int64_t n) { return (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8); }
+
+// the padded problem of a forward or backward call: pointers into the caller's states / workspace buffers
+int make_padded(const mlstm_params& p, int is_bwd, mlstm_params* out, PadLayout* lay) {
+  const PadLayout l = pad_layout(p);
+  if (!p.states || p.states_bytes < l.total) {
+    set_error("DHqk < DHv on the tensor cores needs a states buffer of mlstm_b200_state_bytes() = %zu bytes (have %zu)", l.total,
+              p.states ? p.states_bytes : (size_t)0);
+    return MLSTM_ERR_WORKSPACE;
+  }
+  if ((reinterpret_cast<uintptr_t>(p.states) & 255u) != 0) { set_error("states buffer must be 256-byte aligned"); return MLSTM_ERR_INVALID_ARG; }
+  uint8_t* sb = reinterpret_cast<uint8_t*>(p.states);
+  mlstm_params pp = padded_params(p);
+  pp.states_bytes = l.inner;
+  if (l.inner == 0) pp.states = nullptr;   // forward-only single-pass call: the padded problem keeps its states on chip
+  pp.q = dense_act(sb + l.q_off, p);
+  pp.k = dense_act(sb + l.k_off, p);
+  if (p.c_initial) { pp.c_initial = reinterpret_cast<float*>(sb + l.c0_off); pp.n_initial = reinterpret_cast<float*>(sb + l.n0_off); }
+  if (p.c_last) { pp.c_last = reinterpret_cast<float*>(sb + l.cl_off); pp.n_last = reinterpret_cast<float*>(sb + l.nl_off); }
+  if (is_bwd) {
+    uint8_t* ws = reinterpret_cast<uint8_t*>(p.workspace);
+    pp.workspace_bytes = l.ws_inner;
+    pp.dq = dense_act(ws + l.dq_off, p);
+    pp.dk = dense_act(ws + l.dk_off, p);
+  }
+  *out = pp;
+  *lay = l;
+  return MLSTM_OK;
+}
+
+int tcpad_fwd(const mlstm_params& p, cudaStream_t st) {
+  mlstm_params pp;
+  PadLayout l;
+  int rc = make_padded(p, 0, &pp, &l);
+  if (rc) return rc;
+  const int64_t chunks = (int64_t)p.B * p.S * p.NH * (p.DHV / 8);
+  pad_rows_kernel<<<grid_for(chunks), 256, 0, st>>>(p.q, p.k, reinterpret_cast<__nv_bfloat16*>(pp.q.ptr),
+                                                    reinterpret_cast<__nv_bfloat16*>(pp.k.ptr), p.B, p.S, p.NH, p.DHQK, p.DHV, 1);
+  if ((rc = pad_launched("pad_rows"))) return rc;
+  if (p.c_initial) {
+    if (!p.n_initial) { set_error("c_initial without n_initial"); return MLSTM_ERR_INVALID_ARG; }
+    pad_states_kernel<<<grid_for((int64_t)p.B * p.NH * p.DHV * (p.DHV + 1)), 256, 0, st>>>(
+        const_cast<float*>(p.c_initial), const_cast<float*>(p.n_initial), const_cast<float*>(pp.c_initial),
+        const_cast<float*>(pp.n_initial), p.B * p.NH, p.DHQK, p.DHV, 1);
+    if ((rc = pad_launched("pad_states"))) return rc;
+  }
+  if ((rc = tc_fwd(pp, st))) return rc;
+  if (p.c_last) {
+    pad_states_kernel<<<grid_for((int64_t)p.B * p.NH * p.DHV * (p.DHV + 1)), 256, 0, st>>>(p.c_last, p.n_last, pp.c_last, pp.n_last,
+                                                                                        p.B * p.NH, p.DHQK, p.DHV, 0);
+    if ((rc = pad_launched("crop_states"))) return rc;
+  }
+  return MLSTM_OK;
+}
+
+int tcpad_bwd(const mlstm_params& p, cudaStream_t st, int part) {
+  mlstm_params pp;
+  PadLayout l;
+  int rc = make_padded(p, 1, &pp, &l);   // q, k, the initial states: the copies the forward left in the states buffer
+  if (rc) return rc;
+  if ((rc = tc_bwd(pp, st, part))) return rc;
+  mlstm_act none;
+  none.ptr = nullptr; none.stride_b = none.stride_h = none.stride_s = 0;
+  const int64_t chunks = (int64_t)p.B * p.S * p.NH * (p.DHV / 8);
+  pad_rows_kernel<<<grid_for(chunks), 256, 0, st>>>(part != 1 ? p.dq : none, part != 0 ? p.dk : none,
+                                                    reinterpret_cast<__nv_bfloat16*>(pp.dq.ptr),
+                                                    reinterpret_cast<__nv_bfloat16*>(pp.dk.ptr), p.B, p.S, p.NH, p.DHQK, p.DHV, 0);
+  return pad_launched("crop_rows");
+}
+
+}  // namespace
 
 namespace {
 
@@ -71,7 +263,7 @@ int validate(const mlstm_params* p, int is_bwd) {
   }
   if (p->B == 0 || p->S == 0) return MLSTM_OK;  // empty input: nothing to do
   int rc;
-  const bool tma = p->dtype == MLSTM_BF16 && tc_supported(*p);
+  const bool tma = p->dtype == MLSTM_BF16 && (tc_supported(*p) || pad_path(*p));
   if ((rc = check_act("q", p->q, true, tma, *p, p->DHQK)) || (rc = check_act("k", p->k, true, tma, *p, p->DHQK)) ||
       (rc = check_act("v", p->v, true, tma, *p, p->DHV)) || (rc = check_act("h", p->h, true, tma, *p, p->DHV)))
     return rc;
@@ -131,10 +323,11 @@ int bind_device(const void* dev_ptr) {
 
 namespace {
 
-enum Family { FAM_NONE = 0, FAM_SIMT = 1, FAM_TC = 2 };
+enum Family { FAM_NONE = 0, FAM_SIMT = 1, FAM_TC = 2, FAM_TCPAD = 3 };
 
 Family pick(const mlstm_params& p) {
   if (p.dtype == MLSTM_BF16 && tc_supported(p)) return FAM_TC;
+  if (pad_path(p)) return FAM_TCPAD;
   if (simt_supported(p)) return FAM_SIMT;
   return FAM_NONE;
 }
@@ -153,6 +346,7 @@ size_t mlstm_b200_workspace_bytes(const mlstm_params* p, int is_backward) {
   if (!is_backward) return 0;
   switch (pick(*p)) {
     case FAM_TC: return tc_bwd_workspace(*p);
+    case FAM_TCPAD: return pad_layout(*p).ws_total;
     case FAM_SIMT: return simt_bwd_workspace(*p);
     default: return 0;
   }
@@ -160,13 +354,15 @@ size_t mlstm_b200_workspace_bytes(const mlstm_params* p, int is_backward) {
 
 size_t mlstm_b200_state_bytes(const mlstm_params* p) {
   if (!p || p->B <= 0 || p->S <= 0) return 0;
-  return pick(*p) == FAM_TC ? tc_state_bytes(*p) : 0;
+  const Family fam = pick(*p);
+  return fam == FAM_TC ? tc_state_bytes(*p) : (fam == FAM_TCPAD ? pad_layout(*p).total : 0);
 }
 
 const char* mlstm_b200_kernel_name(const mlstm_params* p, int /*is_backward*/) {
   if (!p) return nullptr;
   switch (pick(*p)) {
     case FAM_TC: return "tcgen05";
+    case FAM_TCPAD: return "tcgen05";
     case FAM_SIMT: return "simt";
     default: return nullptr;
   }
@@ -174,6 +370,8 @@ const char* mlstm_b200_kernel_name(const mlstm_params* p, int /*is_backward*/) {
 
 const char* mlstm_b200_kernel_variant(const mlstm_params* p, int is_backward) {
   if (!p) return nullptr;
+  mlstm_params pp_;
+  if (pick(*p) == FAM_TCPAD) { pp_ = padded_params(*p); p = &pp_; }
   switch (pick(*p)) {
     case FAM_TC:
       if (is_backward) return tc_use_fused_bwd(*p) ? "fused_walk" : (tc_use_single_pass_bwd(*p) ? "single_pass" : "chunk_parallel");
@@ -192,6 +390,7 @@ int mlstm_b200_fwd(const mlstm_params* p, void* cuda_stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   switch (pick(*p)) {
     case FAM_TC: return tc_fwd(*p, st);
+    case FAM_TCPAD: return tcpad_fwd(*p, st);
     case FAM_SIMT: return simt_fwd(*p, st);
     default:
       set_error("no kernel for dtype=%d DHQK=%d DHV=%d", p->dtype, p->DHQK, p->DHV);
@@ -209,6 +408,7 @@ static int bwd_impl(const mlstm_params* p, int part, void* cuda_stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   switch (pick(*p)) {
     case FAM_TC: return tc_bwd(*p, st, part);
+    case FAM_TCPAD: return tcpad_bwd(*p, st, part);
     case FAM_SIMT: return simt_bwd(*p, st, part);
     default:
       set_error("no kernel for dtype=%d DHQK=%d DHV=%d", p->dtype, p->DHQK, p->DHV);

@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(GT_NT, 1) gates_fwd_tc_kernel(const __grid_con
 bool gates_tc_ok(const mlstm_gate_proj_params& p) {
   static const bool off = getenv("MLSTM_GATES_TC") != nullptr && getenv("MLSTM_GATES_TC")[0] == '0';
   if (off || p.dtype != MLSTM_BF16 || p.D % 64 != 0 || 2 * p.NH > 16 || p.ld % 8 != 0) return false;
+  // TMA needs 16-byte aligned base addresses; views that start mid-row at an odd offset stay on the SIMT kernel
+  if (((reinterpret_cast<uintptr_t>(p.q) | reinterpret_cast<uintptr_t>(p.k) | reinterpret_cast<uintptr_t>(p.v)) & 15u) != 0) return false;
   const size_t wbytes = (size_t)(3 * p.D / 64) * (2 * p.NH > 8 ? 48 : 32) * 128;
   return ((sizeof(SmemGT) + 1023) & ~(size_t)1023) + wbytes <= 220 * 1024;
 }
