@@ -112,9 +112,10 @@ typedef struct mlstm_params {
   /* Per-chunk entry states (bf16 C, fp32 n, m for every 128-token chunk), written by the
    * forward's state kernel and read by its chunk-parallel kernel and by the backward.  Size
    * mlstm_b200_state_bytes(); keep it with q,k,v,i,f,h,n_row,m_row until the backward has run.
-   * 0 bytes (NULL allowed) for the SIMT kernel family.  With DHQK < DHV (bf16) the buffer also holds
-   * the zero-padded copies of q, k and of the initial / last states the tensor-core kernels run on
-   * (the backward reads them back from here); 256-byte aligned in that case. */
+   * 0 bytes (NULL allowed) for the SIMT kernel family.  For bf16 head dims other than
+   * DHQK = DHV in {64, 128, 256} the buffer also holds the zero-padded copies of q, k, v, h and of the
+   * initial / last states the tensor-core kernels run on (the backward reads them back from here);
+   * 256-byte aligned in that case. */
   void* states;
   size_t states_bytes;
 

@@ -1,11 +1,13 @@
-"""Developer tool: forward + backward of the cell with DHqk = DHv / 2 (mLSTMLayerVision's qk_dim_factor = 0.5): the padded tensor-core
+"""Developer tool: forward + backward of the cell at head dims the tcgen05 kernels are not written for — DHqk = DHv / 2
+(mLSTMLayerVision's qk_dim_factor = 0.5), DH = 16 (the reference's default qkv_block_size), 32, 192: the zero-padded tensor-core
 path of mlstm_api.cu vs the fp32 SIMT family (MLSTM_NO_TCPAD=1)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from xlstm_yolo_b200 import ops
 
-for (B, NH, S, DK, DV) in [(32, 4, 1600, 64, 128), (32, 4, 400, 32, 64), (8, 4, 1600, 64, 128), (32, 4, 1600, 128, 256)]:
+for (B, NH, S, DK, DV) in [(32, 4, 1600, 64, 128), (32, 4, 400, 32, 64), (8, 4, 1600, 64, 128), (32, 4, 1600, 128, 256),
+                          (32, 32, 1600, 16, 16), (32, 16, 400, 16, 16), (32, 8, 1600, 32, 32), (16, 4, 1600, 192, 192)]:
     g = torch.Generator().manual_seed(0)
     act = lambda d: (torch.randn(B, S, NH, d, generator=g) * 0.3).to(torch.bfloat16).cuda().transpose(1, 2)
     q, k, v, dh = act(DK), act(DK), act(DV), act(DV)

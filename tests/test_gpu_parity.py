@@ -112,7 +112,7 @@ CASES = [
     (2, 2, 100, 16, torch.float32, "forget", True, 1e-6),
     (2, 4, 400, 64, torch.float32, "rand", True, 1e-6),
     (1, 2, 300, 128, torch.float32, "refinit", False, 5e-5),
-    (2, 8, 256, 16, torch.bfloat16, "rand", False, 1e-6),       # reference default qkv_block_size=16 -> SIMT
+    (2, 8, 256, 16, torch.bfloat16, "rand", False, 1e-6),       # reference default qkv_block_size=16 -> tcgen05, padded to 64
     (2, 4, 400, 64, torch.bfloat16, "rand", False, 1e-6),       # cfg2 shape (16-token tail)
     (2, 4, 400, 64, torch.bfloat16, "refinit", True, 5e-5),
     (2, 4, 400, 128, torch.bfloat16, "forget", True, 1e-6),
@@ -212,7 +212,10 @@ def test_kernel_family_dispatch():
     bf = lambda d: torch.empty(1, 1, 8, d, dtype=torch.bfloat16, device="cuda")
     assert ops.kernel_family(bf(64), bf(64)) == "tcgen05"
     assert ops.kernel_family(bf(128), bf(128)) == "tcgen05"
-    assert ops.kernel_family(bf(16), bf(16)) == "simt"
+    assert ops.kernel_family(bf(16), bf(16)) == "tcgen05"      # zero-padded to 64 inside the library (mlstm_api.cu)
+    assert ops.kernel_family(bf(192), bf(192)) == "tcgen05"    # ... to 256
+    assert ops.kernel_family(bf(8), bf(8)) == "simt"
+    assert ops.kernel_family(bf(16).float(), bf(16).float()) == "simt"
     assert ops.kernel_family(bf(128).float(), bf(128).float()) == "simt"
     assert ops.kernel_family(bf(256), bf(256)) == "tcgen05"
     assert ops.kernel_family(bf(256).float(), bf(256).float()) == "simt"

@@ -103,9 +103,11 @@ def test_kernel_family_and_workspace(lib):
     assert lib.mlstm_b200_state_bytes(C.byref(p)) == 0   # forward-only call (no saved rows): the single-pass forward keeps its states on chip
     p.n_row = p.m_row = 0x1000                             # a backward will follow
     assert lib.mlstm_b200_state_bytes(C.byref(p)) >= 2 * 2 * 1 * (64 * 64 * 2 + 64 * 4 + 4)   # per-chunk entry states
-    p = _params(DHQK=16, DHV=16)
+    p = _params(DHQK=8, DHV=8)
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
     assert lib.mlstm_b200_state_bytes(C.byref(p)) == 0
+    p = _params(dtype=_lib.MLSTM_F32, DHQK=16, DHV=16)
+    assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
     p = _params(dtype=_lib.MLSTM_F32, DHQK=128, DHV=128)
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
     p = _params(DHQK=256, DHV=256)   # bf16: the slice-streaming tcgen05 family (mlstm_tc_256.cu), always chunk-parallel
@@ -116,18 +118,22 @@ def test_kernel_family_and_workspace(lib):
     p = _params(dtype=_lib.MLSTM_F32, DHQK=256, DHV=256)   # fp32: value-sliced SIMT kernels: dn per slice + R + fp32 dq/dk accumulators
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"simt"
     assert lib.mlstm_b200_workspace_bytes(C.byref(p), 1) == 4 * (rows * 5 + 2 * rows * 256)
-    # DHqk < DHv (mLSTMLayerVision's qk_dim_factor = 0.5): bf16 runs the tcgen05 family on zero-padded q, k (mlstm_api.cu); the
-    # padded copies, padded initial / last states ride behind the chunk states, padded dq / dk behind the workspace
+    # bf16 head dims the tcgen05 kernels are not written for — DHqk != DHv (mLSTMLayerVision's qk_dim_factor = 0.5), DH = 16
+    # (the reference's default qkv_block_size), 32, 192 — run them zero-padded to 64 / 128 / 256 (mlstm_api.cu): the padded
+    # q, k, v, h and initial / last states ride behind the chunk states, padded dh, dq, dk, dv behind the workspace
     p = _params(DHQK=64, DHV=128)
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"tcgen05"
     assert lib.mlstm_b200_kernel_variant(C.byref(p), 0) in (b"single_pass", b"two_phase")
     sq = _params(DHQK=128, DHV=128)
-    act = 2 * 64 * 2 * 128 * 2                                # B S NH DHv bf16
-    extra = 2 * act + 2 * (2 * 2 * 128 * 128 * 4) + 2 * (2 * 2 * 128 * 4)
+    act = 2 * 64 * 2 * 128 * 2                                # B S NH DP bf16
+    extra = 4 * act + 2 * (2 * 2 * 128 * 128 * 4) + 2 * (2 * 2 * 128 * 4)
     assert lib.mlstm_b200_state_bytes(C.byref(p)) >= lib.mlstm_b200_state_bytes(C.byref(sq)) + extra
-    assert lib.mlstm_b200_workspace_bytes(C.byref(p), 1) >= lib.mlstm_b200_workspace_bytes(C.byref(sq), 1) + 2 * act
-    assert lib.mlstm_b200_kernel_name(C.byref(_params(DHQK=128, DHV=64)), 0) == b"simt"     # DHqk > DHv stays on SIMT
+    assert lib.mlstm_b200_workspace_bytes(C.byref(p), 1) >= lib.mlstm_b200_workspace_bytes(C.byref(sq), 1) + 4 * act
+    for dk, dv in ((16, 16), (32, 32), (192, 192), (128, 64), (24, 40)):
+        assert lib.mlstm_b200_kernel_name(C.byref(_params(DHQK=dk, DHV=dv)), 0) == b"tcgen05", (dk, dv)
+    assert lib.mlstm_b200_state_bytes(C.byref(_params(DHQK=16, DHV=16))) >= 4 * (2 * 64 * 2 * 64 * 2)
     assert lib.mlstm_b200_kernel_name(C.byref(_params(DHQK=20, DHV=64)), 0) == b"simt"      # rows must be 16-byte multiples
+    assert lib.mlstm_b200_kernel_name(C.byref(_params(DHQK=264, DHV=264)), 0) is None       # nothing to pad to, too wide for SIMT
     assert lib.mlstm_b200_kernel_name(C.byref(_params(dtype=_lib.MLSTM_F32, DHQK=64, DHV=128)), 0) == b"simt"
     p = _params(DHQK=512, DHV=512)
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) is None

@@ -23,65 +23,80 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 void clear_error() { g_err[0] = 0; }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// DHqk < DHv on the tensor cores (the reference's mLSTMLayerVision: qk_dim_factor = 0.5, mlstm_large.py:46,186-187).
+// Head dims the tcgen05 kernels are not written for, on the tensor cores anyway (bf16): DHqk != DHv (the reference's
+// mLSTMLayerVision: qk_dim_factor = 0.5, mlstm_large.py:46,186-187) and head dims below / between 64, 128, 256 (the
+// reference's default qkv_block_size = 16, vision_lstm2.py:416-417, gives DH = 16).
 // Every q / k dependent quantity of the cell is an inner product over DHqk (S = Q K^T, q . C, q . n, the rows of C = K^T V
-// and of n = sum k), so q and k padded with zero columns to DHv give the same h, dv, di, df, the same first DHqk columns of
-// dq, dk and the same first DHqk rows of C, n — and DHqk = DHv is the shape the tcgen05 family runs.  The padded copies
-// (bf16, (B, S, NH, DHv)) live behind the chunk states in the caller's `states` buffer (written by the forward, read again
-// by the backward), dq / dk are produced padded in the workspace and copied out, initial / last states are padded / cropped
-// the same way; the 1 / sqrt(DHqk) scale is passed explicitly.  MLSTM_NO_TCPAD=1 keeps these shapes on the fp32 SIMT family.
+// and of n = sum k) and every column of v only meets its own column of C, h and dh, so q, k, v, dh padded with zero columns
+// to a common DP in {64, 128, 256} give the same h, dq, dk, dv in the leading columns (zeros behind them), the same di, df
+// and the same leading block of the carried C, n.  The padded bf16 copies ((B, S, NH, DP), dense) of q, k, v and the padded h
+// live behind the chunk states in the caller's `states` buffer (written by the forward, read again by the backward); dh is
+// padded and dq, dk, dv are produced padded in the workspace and cropped out; initial / last states are padded / cropped the
+// same way; the 1 / sqrt(DHqk) scale is passed explicitly.  MLSTM_NO_TCPAD=1 keeps these shapes on the fp32 SIMT family.
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
 
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+int padded_dim(const mlstm_params& p) {
+  const int d = p.DHQK > p.DHV ? p.DHQK : p.DHV;
+  return d <= 64 ? 64 : (d <= 128 ? 128 : (d <= 256 ? 256 : 0));
+}
+
 struct PadLayout {
+  int DP;
   size_t inner, act, cst, nst;             // bytes: padded problem's own states | one padded activation | C | n
-  size_t q_off, k_off, c0_off, n0_off, cl_off, nl_off, total;
-  size_t ws_inner, dq_off, dk_off, ws_total;
+  size_t q_off, k_off, v_off, h_off, c0_off, n0_off, cl_off, nl_off, total;
+  size_t ws_inner, dh_off, dq_off, dk_off, dv_off, ws_total;
 };
 
 mlstm_params padded_params(const mlstm_params& p) {
   mlstm_params pp = p;
-  pp.DHQK = p.DHV;
   pp.qk_scale = resolve_scale(p);
+  pp.DHQK = pp.DHV = padded_dim(p);
   return pp;
 }
 
 PadLayout pad_layout(const mlstm_params& p) {
   const mlstm_params pp = padded_params(p);
   PadLayout l;
+  l.DP = pp.DHV;
   l.inner = al256(tc_state_bytes(pp));
-  l.act = al256((size_t)p.B * p.S * p.NH * p.DHV * 2);
-  l.cst = al256((size_t)p.B * p.NH * p.DHV * p.DHV * 4);
-  l.nst = al256((size_t)p.B * p.NH * p.DHV * 4);
+  l.act = al256((size_t)p.B * p.S * p.NH * l.DP * 2);
+  l.cst = al256((size_t)p.B * p.NH * l.DP * l.DP * 4);
+  l.nst = al256((size_t)p.B * p.NH * l.DP * 4);
   l.q_off = l.inner;
   l.k_off = l.q_off + l.act;
-  l.c0_off = l.k_off + l.act;
+  l.v_off = l.k_off + l.act;
+  l.h_off = l.v_off + l.act;
+  l.c0_off = l.h_off + l.act;
   l.n0_off = l.c0_off + l.cst;
   l.cl_off = l.n0_off + l.nst;
   l.nl_off = l.cl_off + l.cst;
   l.total = l.nl_off + l.nst;
   l.ws_inner = al256(tc_bwd_workspace(pp));
-  l.dq_off = l.ws_inner;
+  l.dh_off = l.ws_inner;
+  l.dq_off = l.dh_off + l.act;
   l.dk_off = l.dq_off + l.act;
-  l.ws_total = l.dk_off + l.act;
+  l.dv_off = l.dk_off + l.act;
+  l.ws_total = l.dv_off + l.act;
   return l;
 }
 
 bool pad_path(const mlstm_params& p) {
   static const bool off = getenv("MLSTM_NO_TCPAD") != nullptr && getenv("MLSTM_NO_TCPAD")[0] == '1';
-  if (off || p.dtype != MLSTM_BF16 || p.DHQK >= p.DHV || p.DHQK % 8 != 0) return false;
-  mlstm_params pp = p;
-  pp.DHQK = p.DHV;
-  return tc_supported(pp);
+  if (off || p.dtype != MLSTM_BF16 || p.DHQK % 8 != 0 || p.DHV % 8 != 0 || p.DHQK < 16 || p.DHV < 16) return false;
+  if (padded_dim(p) == 0 || tc_supported(p)) return false;
+  return tc_supported(padded_params(p));
 }
 
-// rows (b, s, h) of a strided bf16 activation <-> rows of the dense padded copy, 16 bytes per thread
-__global__ void __launch_bounds__(256) pad_rows_kernel(const mlstm_act a0, const mlstm_act a1, __nv_bfloat16* __restrict__ d0,
-                                                       __nv_bfloat16* __restrict__ d1, const int B, const int S, const int NH,
-                                                       const int DK, const int DV, const int to_padded) {
-  const int cpr = DV / 8;                                    // 16-byte chunks per padded row
+// rows (b, s, h) of up to three strided bf16 activations <-> rows of their dense padded copies, 16 bytes per thread
+struct PadJob { mlstm_act a; __nv_bfloat16* d; int D; };
+struct PadJobs { PadJob j[3]; };
+
+__global__ void __launch_bounds__(256) pad_rows_kernel(const PadJobs jobs, const int B, const int S, const int NH, const int DP,
+                                                       const int to_padded) {
+  const int cpr = DP / 8;                                    // 16-byte chunks per padded row
   const int64_t n = (int64_t)B * S * NH * cpr;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(e % cpr);
@@ -89,36 +104,36 @@ __global__ void __launch_bounds__(256) pad_rows_kernel(const mlstm_act a0, const
     const int h = (int)(row % NH);
     const int64_t bs = row / NH;
     const int s_ = (int)(bs % S), b = (int)(bs / S);
-    const bool live = c * 8 < DK;
 #pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      const mlstm_act& a = w ? a1 : a0;
-      __nv_bfloat16* d = w ? d1 : d0;
-      if (!a.ptr) continue;
-      __nv_bfloat16* src = reinterpret_cast<__nv_bfloat16*>(a.ptr) + (int64_t)b * a.stride_b + (int64_t)h * a.stride_h +
-                           (int64_t)s_ * a.stride_s + c * 8;
-      uint4* pad = reinterpret_cast<uint4*>(d + row * DV + c * 8);
+    for (int w = 0; w < 3; ++w) {
+      const PadJob& jb = jobs.j[w];
+      if (!jb.a.ptr) continue;
+      const bool live = c * 8 < jb.D;
+      __nv_bfloat16* src = reinterpret_cast<__nv_bfloat16*>(jb.a.ptr) + (int64_t)b * jb.a.stride_b + (int64_t)h * jb.a.stride_h +
+                           (int64_t)s_ * jb.a.stride_s + c * 8;
+      uint4* pad = reinterpret_cast<uint4*>(jb.d + row * DP + c * 8);
       if (to_padded) *pad = live ? *reinterpret_cast<const uint4*>(src) : make_uint4(0, 0, 0, 0);
       else if (live) *reinterpret_cast<uint4*>(src) = *pad;
     }
   }
 }
 
-// fp32 states: C (B*NH, DK, DV) <-> (B*NH, DV, DV), n (B*NH, DK) <-> (B*NH, DV)
+// fp32 states: C (B*NH, DK, DV) <-> (B*NH, DP, DP), n (B*NH, DK) <-> (B*NH, DP)
 __global__ void __launch_bounds__(256) pad_states_kernel(float* __restrict__ c_small, float* __restrict__ n_small,
                                                          float* __restrict__ c_pad, float* __restrict__ n_pad, const int BH,
-                                                         const int DK, const int DV, const int to_padded) {
-  const int64_t nc = (int64_t)BH * DV * DV, nn = (int64_t)BH * DV;
+                                                         const int DK, const int DV, const int DP, const int to_padded) {
+  const int64_t nc = (int64_t)BH * DP * DP, nn = (int64_t)BH * DP;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nc + nn; e += (int64_t)gridDim.x * blockDim.x) {
     if (e < nc) {
-      const int col = (int)(e % DV), r = (int)((e / DV) % DV);
-      const int64_t bh = e / ((int64_t)DV * DV);
-      if (to_padded) c_pad[e] = r < DK ? c_small[(bh * DK + r) * DV + col] : 0.f;
-      else if (r < DK) c_small[(bh * DK + r) * DV + col] = c_pad[e];
+      const int col = (int)(e % DP), r = (int)((e / DP) % DP);
+      const int64_t bh = e / ((int64_t)DP * DP);
+      const bool live = r < DK && col < DV;
+      if (to_padded) c_pad[e] = live ? c_small[(bh * DK + r) * DV + col] : 0.f;
+      else if (live) c_small[(bh * DK + r) * DV + col] = c_pad[e];
     } else {
       const int64_t x = e - nc;
-      const int r = (int)(x % DV);
-      const int64_t bh = x / DV;
+      const int r = (int)(x % DP);
+      const int64_t bh = x / DP;
       if (to_padded) n_pad[x] = r < DK ? n_small[bh * DK + r] : 0.f;
       else if (r < DK) n_small[bh * DK + r] = n_pad[x];
     }
@@ -132,23 +147,44 @@ int pad_launched(const char* what) {
   return MLSTM_OK;
 }
 
-mlstm_act dense_act(void* ptr, const mlstm_params& p) {
+mlstm_act dense_act(void* ptr, const mlstm_params& p, int DP) {
   mlstm_act a;
   a.ptr = ptr;
-  a.stride_b = (int64_t)p.S * p.NH * p.DHV;
-  a.stride_s = (int64_t)p.NH * p.DHV;
-  a.stride_h = p.DHV;
+  a.stride_b = (int64_t)p.S * p.NH * DP;
+  a.stride_s = (int64_t)p.NH * DP;
+  a.stride_h = DP;
   return a;
 }
 
+PadJob job(const mlstm_act& a, const mlstm_act& padded, int D) {
+  PadJob j;
+  j.a = a;
+  j.d = reinterpret_cast<__nv_bfloat16*>(padded.ptr);
+  j.D = D;
+  return j;
+}
+PadJob no_job() {
+  PadJob j;
+  j.a.ptr = nullptr; j.a.stride_b = j.a.stride_h = j.a.stride_s = 0;
+  j.d = nullptr; j.D = 0;
+  return j;
+}
+
 int grid_for(int64_t n) { return (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8); }
+
+int pad_rows(const mlstm_params& p, int DP, PadJob j0, PadJob j1, PadJob j2, int to_padded, cudaStream_t st, const char* what) {
+  PadJobs jobs;
+  jobs.j[0] = j0; jobs.j[1] = j1; jobs.j[2] = j2;
+  pad_rows_kernel<<<grid_for((int64_t)p.B * p.S * p.NH * (DP / 8)), 256, 0, st>>>(jobs, p.B, p.S, p.NH, DP, to_padded);
+  return pad_launched(what);
+}
 
 // the padded problem of a forward or backward call: pointers into the caller's states / workspace buffers
 int make_padded(const mlstm_params& p, int is_bwd, mlstm_params* out, PadLayout* lay) {
   const PadLayout l = pad_layout(p);
   if (!p.states || p.states_bytes < l.total) {
-    set_error("DHqk < DHv on the tensor cores needs a states buffer of mlstm_b200_state_bytes() = %zu bytes (have %zu)", l.total,
-              p.states ? p.states_bytes : (size_t)0);
+    set_error("head dims (%d, %d) run zero-padded to %d on the tensor cores: the states buffer must hold mlstm_b200_state_bytes() = "
+              "%zu bytes (have %zu)", p.DHQK, p.DHV, l.DP, l.total, p.states ? p.states_bytes : (size_t)0);
     return MLSTM_ERR_WORKSPACE;
   }
   if ((reinterpret_cast<uintptr_t>(p.states) & 255u) != 0) { set_error("states buffer must be 256-byte aligned"); return MLSTM_ERR_INVALID_ARG; }
@@ -156,15 +192,17 @@ int make_padded(const mlstm_params& p, int is_bwd, mlstm_params* out, PadLayout*
   mlstm_params pp = padded_params(p);
   pp.states_bytes = l.inner;
   if (l.inner == 0) pp.states = nullptr;   // forward-only single-pass call: the padded problem keeps its states on chip
-  pp.q = dense_act(sb + l.q_off, p);
-  pp.k = dense_act(sb + l.k_off, p);
+  // a side that already has the padded width runs on the caller's own tensors (DHqk < DHv = DP: only q, k are copied)
+  const bool pad_qk = p.DHQK != l.DP, pad_v = p.DHV != l.DP;
+  if (pad_qk) { pp.q = dense_act(sb + l.q_off, p, l.DP); pp.k = dense_act(sb + l.k_off, p, l.DP); }
+  if (pad_v) { pp.v = dense_act(sb + l.v_off, p, l.DP); pp.h = dense_act(sb + l.h_off, p, l.DP); }
   if (p.c_initial) { pp.c_initial = reinterpret_cast<float*>(sb + l.c0_off); pp.n_initial = reinterpret_cast<float*>(sb + l.n0_off); }
   if (p.c_last) { pp.c_last = reinterpret_cast<float*>(sb + l.cl_off); pp.n_last = reinterpret_cast<float*>(sb + l.nl_off); }
   if (is_bwd) {
     uint8_t* ws = reinterpret_cast<uint8_t*>(p.workspace);
     pp.workspace_bytes = l.ws_inner;
-    pp.dq = dense_act(ws + l.dq_off, p);
-    pp.dk = dense_act(ws + l.dk_off, p);
+    if (pad_qk) { pp.dq = dense_act(ws + l.dq_off, p, l.DP); pp.dk = dense_act(ws + l.dk_off, p, l.DP); }
+    if (pad_v) { pp.dh = dense_act(ws + l.dh_off, p, l.DP); pp.dv = dense_act(ws + l.dv_off, p, l.DP); }
   }
   *out = pp;
   *lay = l;
@@ -176,21 +214,22 @@ int tcpad_fwd(const mlstm_params& p, cudaStream_t st) {
   PadLayout l;
   int rc = make_padded(p, 0, &pp, &l);
   if (rc) return rc;
-  const int64_t chunks = (int64_t)p.B * p.S * p.NH * (p.DHV / 8);
-  pad_rows_kernel<<<grid_for(chunks), 256, 0, st>>>(p.q, p.k, reinterpret_cast<__nv_bfloat16*>(pp.q.ptr),
-                                                    reinterpret_cast<__nv_bfloat16*>(pp.k.ptr), p.B, p.S, p.NH, p.DHQK, p.DHV, 1);
-  if ((rc = pad_launched("pad_rows"))) return rc;
+  const bool pad_qk = p.DHQK != l.DP, pad_v = p.DHV != l.DP;
+  if ((rc = pad_rows(p, l.DP, pad_qk ? job(p.q, pp.q, p.DHQK) : no_job(), pad_qk ? job(p.k, pp.k, p.DHQK) : no_job(),
+                     pad_v ? job(p.v, pp.v, p.DHV) : no_job(), 1, st, "pad_rows")))
+    return rc;
+  const int64_t nst = (int64_t)p.B * p.NH * l.DP * (l.DP + 1);
   if (p.c_initial) {
     if (!p.n_initial) { set_error("c_initial without n_initial"); return MLSTM_ERR_INVALID_ARG; }
-    pad_states_kernel<<<grid_for((int64_t)p.B * p.NH * p.DHV * (p.DHV + 1)), 256, 0, st>>>(
-        const_cast<float*>(p.c_initial), const_cast<float*>(p.n_initial), const_cast<float*>(pp.c_initial),
-        const_cast<float*>(pp.n_initial), p.B * p.NH, p.DHQK, p.DHV, 1);
+    pad_states_kernel<<<grid_for(nst), 256, 0, st>>>(const_cast<float*>(p.c_initial), const_cast<float*>(p.n_initial),
+                                                     const_cast<float*>(pp.c_initial), const_cast<float*>(pp.n_initial),
+                                                     p.B * p.NH, p.DHQK, p.DHV, l.DP, 1);
     if ((rc = pad_launched("pad_states"))) return rc;
   }
   if ((rc = tc_fwd(pp, st))) return rc;
+  if (pad_v && (rc = pad_rows(p, l.DP, job(p.h, pp.h, p.DHV), no_job(), no_job(), 0, st, "crop_rows"))) return rc;
   if (p.c_last) {
-    pad_states_kernel<<<grid_for((int64_t)p.B * p.NH * p.DHV * (p.DHV + 1)), 256, 0, st>>>(p.c_last, p.n_last, pp.c_last, pp.n_last,
-                                                                                        p.B * p.NH, p.DHQK, p.DHV, 0);
+    pad_states_kernel<<<grid_for(nst), 256, 0, st>>>(p.c_last, p.n_last, pp.c_last, pp.n_last, p.B * p.NH, p.DHQK, p.DHV, l.DP, 0);
     if ((rc = pad_launched("crop_states"))) return rc;
   }
   return MLSTM_OK;
@@ -199,16 +238,14 @@ int tcpad_fwd(const mlstm_params& p, cudaStream_t st) {
 int tcpad_bwd(const mlstm_params& p, cudaStream_t st, int part) {
   mlstm_params pp;
   PadLayout l;
-  int rc = make_padded(p, 1, &pp, &l);   // q, k, the initial states: the copies the forward left in the states buffer
+  int rc = make_padded(p, 1, &pp, &l);   // q, k, v, h, the initial states: the copies the forward left in the states buffer
   if (rc) return rc;
+  const bool pad_qk = p.DHQK != l.DP, pad_v = p.DHV != l.DP;
+  if (pad_v && (rc = pad_rows(p, l.DP, job(p.dh, pp.dh, p.DHV), no_job(), no_job(), 1, st, "pad_rows"))) return rc;
   if ((rc = tc_bwd(pp, st, part))) return rc;
-  mlstm_act none;
-  none.ptr = nullptr; none.stride_b = none.stride_h = none.stride_s = 0;
-  const int64_t chunks = (int64_t)p.B * p.S * p.NH * (p.DHV / 8);
-  pad_rows_kernel<<<grid_for(chunks), 256, 0, st>>>(part != 1 ? p.dq : none, part != 0 ? p.dk : none,
-                                                    reinterpret_cast<__nv_bfloat16*>(pp.dq.ptr),
-                                                    reinterpret_cast<__nv_bfloat16*>(pp.dk.ptr), p.B, p.S, p.NH, p.DHQK, p.DHV, 0);
-  return pad_launched("crop_rows");
+  // all of them after either part: which part produces dq depends on the variant (the fused walk writes everything in part 1)
+  return pad_rows(p, l.DP, pad_qk ? job(p.dq, pp.dq, p.DHQK) : no_job(), pad_qk ? job(p.dk, pp.dk, p.DHQK) : no_job(),
+                  pad_v ? job(p.dv, pp.dv, p.DHV) : no_job(), 0, st, "crop_rows");
 }
 
 }  // namespace
