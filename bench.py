@@ -36,12 +36,16 @@ WORKLOADS = {
     # BASELINE configs[2] read as d = 512 with the layer's expansion 2 (inner 1024 / 4 heads): head dim 256, the shape on which
     # the north star's ">= 50 % of tensor peak" lies below the HBM roofline (csrc/mlstm_tc_256.cu)
     "cfg3alt_B32_NH4_S1600_DH256": (32, 4, 1600, 256),
+    # the reference's DEFAULT head dim: qkv_block_size = 16 (vision_lstm2.py:416-417) at inner 512 -> 32 heads of 16; runs the
+    # DH = 64 tcgen05 kernels on zero-padded copies made inside the library (csrc/mlstm_api.cu)
+    "refdefault_B32_NH32_S1600_DH16": (32, 32, 1600, 16),
     # developer shapes (dispatch thresholds of the DH = 64 backward variants; not BASELINE configs)
     "dev_B32_NH4_S800_DH64": (32, 4, 800, 64),
     "dev_B32_NH4_S1600_DH64": (32, 4, 1600, 64),
 }
 DEFAULT_WORKLOAD = "cfg2_B32_NH4_S400_DH64"
-ALSO_WORKLOADS = ["cfg3_B32_NH4_S1600_DH128", "cfg3_B32_NH4_S6400_DH128", "ddp_B8_NH4_S1600_DH128", "cfg3alt_B32_NH4_S1600_DH256"]
+ALSO_WORKLOADS = ["cfg3_B32_NH4_S1600_DH128", "cfg3_B32_NH4_S6400_DH128", "ddp_B8_NH4_S1600_DH128", "cfg3alt_B32_NH4_S1600_DH256",
+                  "refdefault_B32_NH32_S1600_DH16"]
 CHUNK = 64          # the config's chunk size (algorithmic FLOP formula; kernels tile on their own)
 L2_BYTES = 126e6
 
@@ -232,6 +236,12 @@ def emit(obj):
 
 def launches_of(variant_fwd, variant_bwd, DH):
     """kernels behind each timed part, per variant (csrc/mlstm_tc_*.cu)"""
+    if DH not in (64, 128, 256) and variant_fwd != "simt":   # zero-padded to the next kernel width inside the library (csrc/mlstm_api.cu)
+        DP = 64 if DH <= 64 else (128 if DH <= 128 else 256)
+        inner = launches_of(variant_fwd, variant_bwd, DP)
+        return {"fwd": ["pad_rows_kernel (q, k, v -> width %d)" % DP] + inner["fwd"] + ["pad_rows_kernel (crop h)"],
+                "bwd_dq": inner["bwd_dq"],
+                "bwd_dkv": ["pad_rows_kernel (dh)"] + inner["bwd_dkv"] + ["pad_rows_kernel (crop dq, dk, dv)"]}
     if DH == 256 and variant_fwd == "two_phase":   # the slice-streaming family (csrc/mlstm_tc_256.cu)
         return {"fwd": ["tc_state_fwd_kernel<128> on 2x2 blocks of C", "tc256_par_kernel<F>"],
                 "bwd_dq": ["tc256_par_kernel<A>"],

@@ -54,7 +54,9 @@ def test_b200_arm_line():
     assert d["e2e"]["d2h_bytes_per_step"] == 4 * B * NH * S * DH * 2 + 2 * B * NH * S * 4
     assert d["e2e"]["checksum_variant"]["d2h_bytes_per_step"] == 16 and d["e2e"]["checksum_variant"]["value"] > 0
     also = {a["workload"]: a for a in d["also"]}
-    assert set(also) == {"cfg3_B32_NH4_S1600_DH128", "cfg3_B32_NH4_S6400_DH128", "ddp_B8_NH4_S1600_DH128", "cfg3alt_B32_NH4_S1600_DH256"}
+    assert set(also) == {"cfg3_B32_NH4_S1600_DH128", "cfg3_B32_NH4_S6400_DH128", "ddp_B8_NH4_S1600_DH128", "cfg3alt_B32_NH4_S1600_DH256",
+                         "refdefault_B32_NH32_S1600_DH16"}
+    assert also["refdefault_B32_NH32_S1600_DH16"]["roofline"]["kernel"].startswith("tcgen05")   # zero-padded inside the library
     assert 0.7 < also["cfg3alt_B32_NH4_S1600_DH256"]["roofline"]["step_tensor_ceiling"] < 0.8
     for a in also.values():
         assert a["value"] > 0 and a["gpu_launches"] >= 2 * a["steps"] and 0 < a["roofline"]["step_hbm_frac"] < 1
