@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "mlstm_common.cuh"
+#include "tc_tmap.cuh"
 
 namespace mlstm {
 
@@ -179,6 +180,17 @@ int pad_rows(const mlstm_params& p, int DP, PadJob j0, PadJob j1, PadJob j2, int
   return pad_launched(what);
 }
 
+// Where every access of a kernel variant to q, k, v, h, dh, dq, dk, dv goes through TMA, the padding costs nothing: the tensor
+// maps are encoded with the true row length and TMA supplies / clips the rest (tc_tmap.cuh: ExtentOverride).  That holds for the
+// single-pass forward walks (mlstm_tc_fwd.cu, DP 64 and 128) and the DH = 64 fused backward walk (mlstm_tc_bwd_fused.cu); the
+// other variants read rows with plain loads somewhere and run on the copies.  MLSTM_TCPAD_COPY=1 forces the copies.
+bool zero_copy_off() {
+  static const bool off = getenv("MLSTM_TCPAD_COPY") != nullptr && getenv("MLSTM_TCPAD_COPY")[0] == '1';
+  return off;
+}
+bool zero_copy_fwd(const mlstm_params& pp) { return !zero_copy_off() && pp.DHV <= 128 && !tc_use_two_phase(pp); }
+bool zero_copy_bwd(const mlstm_params& pp) { return !zero_copy_off() && pp.DHV == 64 && tc_use_fused_bwd(pp); }
+
 // the padded problem of a forward or backward call: pointers into the caller's states / workspace buffers
 int make_padded(const mlstm_params& p, int is_bwd, mlstm_params* out, PadLayout* lay) {
   const PadLayout l = pad_layout(p);
@@ -192,8 +204,10 @@ int make_padded(const mlstm_params& p, int is_bwd, mlstm_params* out, PadLayout*
   mlstm_params pp = padded_params(p);
   pp.states_bytes = l.inner;
   if (l.inner == 0) pp.states = nullptr;   // forward-only single-pass call: the padded problem keeps its states on chip
-  // a side that already has the padded width runs on the caller's own tensors (DHqk < DHv = DP: only q, k are copied)
-  const bool pad_qk = p.DHQK != l.DP, pad_v = p.DHV != l.DP;
+  // a side that already has the padded width runs on the caller's own tensors (DHqk < DHv = DP: only q, k are copied);
+  // so does everything in the zero-copy variants
+  const bool zc = is_bwd ? zero_copy_bwd(pp) : zero_copy_fwd(pp);
+  const bool pad_qk = p.DHQK != l.DP && !zc, pad_v = p.DHV != l.DP && !zc;
   if (pad_qk) { pp.q = dense_act(sb + l.q_off, p, l.DP); pp.k = dense_act(sb + l.k_off, p, l.DP); }
   if (pad_v) { pp.v = dense_act(sb + l.v_off, p, l.DP); pp.h = dense_act(sb + l.h_off, p, l.DP); }
   if (p.c_initial) { pp.c_initial = reinterpret_cast<float*>(sb + l.c0_off); pp.n_initial = reinterpret_cast<float*>(sb + l.n0_off); }
@@ -214,8 +228,15 @@ int tcpad_fwd(const mlstm_params& p, cudaStream_t st) {
   PadLayout l;
   int rc = make_padded(p, 0, &pp, &l);
   if (rc) return rc;
-  const bool pad_qk = p.DHQK != l.DP, pad_v = p.DHV != l.DP;
-  if ((rc = pad_rows(p, l.DP, pad_qk ? job(p.q, pp.q, p.DHQK) : no_job(), pad_qk ? job(p.k, pp.k, p.DHQK) : no_job(),
+  const bool zc = zero_copy_fwd(pp);
+  const bool pad_qk = p.DHQK != l.DP && !zc, pad_v = p.DHV != l.DP && !zc;
+  ExtentScope ext;
+  if (zc) {
+    ext.add(p.q.ptr, p.DHQK); ext.add(p.k.ptr, p.DHQK);
+    ext.add(p.v.ptr, p.DHV); ext.add(p.h.ptr, p.DHV);
+  }
+  if ((pad_qk || pad_v) &&
+      (rc = pad_rows(p, l.DP, pad_qk ? job(p.q, pp.q, p.DHQK) : no_job(), pad_qk ? job(p.k, pp.k, p.DHQK) : no_job(),
                      pad_v ? job(p.v, pp.v, p.DHV) : no_job(), 1, st, "pad_rows")))
     return rc;
   const int64_t nst = (int64_t)p.B * p.NH * l.DP * (l.DP + 1);
@@ -240,7 +261,21 @@ int tcpad_bwd(const mlstm_params& p, cudaStream_t st, int part) {
   PadLayout l;
   int rc = make_padded(p, 1, &pp, &l);   // q, k, v, h, the initial states: the copies the forward left in the states buffer
   if (rc) return rc;
-  const bool pad_qk = p.DHQK != l.DP, pad_v = p.DHV != l.DP;
+  const bool zc = zero_copy_bwd(pp);
+  const bool pad_qk = p.DHQK != l.DP && !zc, pad_v = p.DHV != l.DP && !zc;
+  ExtentScope ext;
+  if (zc) {
+    ext.add(p.q.ptr, p.DHQK); ext.add(p.k.ptr, p.DHQK); ext.add(p.dq.ptr, p.DHQK); ext.add(p.dk.ptr, p.DHQK);
+    ext.add(p.v.ptr, p.DHV); ext.add(p.h.ptr, p.DHV); ext.add(p.dh.ptr, p.DHV); ext.add(p.dv.ptr, p.DHV);
+    return tc_bwd(pp, st, part);
+  }
+  if (zero_copy_fwd(pp)) {   // the forward ran on the caller's tensors and left no copies behind: make them now
+    if ((pad_qk || pad_v) &&
+        (rc = pad_rows(p, l.DP, pad_qk ? job(p.q, pp.q, p.DHQK) : no_job(), pad_qk ? job(p.k, pp.k, p.DHQK) : no_job(),
+                       pad_v ? job(p.v, pp.v, p.DHV) : no_job(), 1, st, "pad_rows")))
+      return rc;
+    if (pad_v && (rc = pad_rows(p, l.DP, job(p.h, pp.h, p.DHV), no_job(), no_job(), 1, st, "pad_rows"))) return rc;
+  }
   if (pad_v && (rc = pad_rows(p, l.DP, job(p.dh, pp.dh, p.DHV), no_job(), no_job(), 1, st, "pad_rows"))) return rc;
   if ((rc = tc_bwd(pp, st, part))) return rc;
   // all of them after either part: which part produces dq depends on the variant (the fused walk writes everything in part 1)

@@ -50,6 +50,36 @@ inline bool tmap_cache_lookup(const TmapKey& k, CUtensorMap* out, bool store) {
   return false;
 }
 
+// Narrow head dims without copies (mlstm_api.cu, zero-padded problems): the caller registers "this tensor's rows really hold
+// `extent` elements" for the duration of a launch sequence; make_act_tmap then encodes that extent as the innermost dimension
+// while the kernels keep asking for 64-column boxes — TMA reads the missing columns as zeros and clips them on store, which
+// is exactly the zero padding, at no HBM cost.  Per thread (the launch sequence runs on the calling thread).
+struct ExtentOverride { const void* ptr; int extent; };
+constexpr int MAX_EXTENT_OVERRIDES = 8;
+inline ExtentOverride* extent_overrides() {
+  static thread_local ExtentOverride t[MAX_EXTENT_OVERRIDES];
+  return t;
+}
+inline int true_extent(const void* ptr, int DH) {
+  const ExtentOverride* t = extent_overrides();
+  for (int i = 0; i < MAX_EXTENT_OVERRIDES; ++i)
+    if (t[i].ptr == ptr && ptr != nullptr) return t[i].extent;
+  return DH;
+}
+struct ExtentScope {   // RAII: the registrations of one padded call
+  ExtentScope() { clear(); }
+  ~ExtentScope() { clear(); }
+  void add(const void* ptr, int extent) {
+    ExtentOverride* t = extent_overrides();
+    for (int i = 0; i < MAX_EXTENT_OVERRIDES; ++i)
+      if (!t[i].ptr) { t[i].ptr = ptr; t[i].extent = extent; return; }
+  }
+  static void clear() {
+    ExtentOverride* t = extent_overrides();
+    for (int i = 0; i < MAX_EXTENT_OVERRIDES; ++i) { t[i].ptr = nullptr; t[i].extent = 0; }
+  }
+};
+
 // bf16 tensor (B, NH, S, DH); strides in elements.  Box = 64 (DH) x box_rows (S) x 1 x 1,
 // 128-byte swizzle, out-of-bounds rows read as zero / are clipped on store.
 // Returns 0 on success, else the CUresult (or -1 if the encoder is unavailable).
@@ -58,11 +88,12 @@ inline int make_act_tmap(CUtensorMap* out, const void* ptr, int B, int NH, int S
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.ptr = ptr; key.s0 = stride_s; key.s1 = stride_h; key.s2 = stride_b;
-  key.d0 = DH; key.d1 = S; key.d2 = NH; key.d3 = B; key.box_rows = box_rows; key.kind = 4;
+  const int ext = true_extent(ptr, DH);   // < DH: columns [ext, DH) are out of bounds = zeros (see ExtentOverride)
+  key.d0 = ext; key.d1 = S; key.d2 = NH; key.d3 = B; key.box_rows = box_rows; key.kind = 4;
   if (tmap_cache_lookup(key, out, false)) return 0;
   PFN_tmapEncodeTiled enc = get_tmap_encoder();
   if (!enc) return -1;
-  cuuint64_t dims[4] = {(cuuint64_t)DH, (cuuint64_t)S, (cuuint64_t)NH, (cuuint64_t)B};
+  cuuint64_t dims[4] = {(cuuint64_t)ext, (cuuint64_t)S, (cuuint64_t)NH, (cuuint64_t)B};
   // size-1 dimensions may come with arbitrary strides; give them a legal one
   int64_t ss = (S > 1) ? stride_s : (int64_t)DH;
   int64_t sh = (NH > 1) ? stride_h : (int64_t)DH * S;
