@@ -518,7 +518,7 @@ int tc256_bwd(const mlstm_params& p, cudaStream_t st, int part) {
   const int n_chunks = p.B * p.NH * num_chunks(p.S);
   uint8_t* sb = reinterpret_cast<uint8_t*>(p.states);
   uint8_t* ws = reinterpret_cast<uint8_t*>(p.workspace);
-  CUtensorMap mq, mk, mv, mdh, mdq, mdk, mdv, cs64, cs128, dcs64, dcs128;
+  CUtensorMap mq, mk, mv, mdh, mdq, mdk, mdv, cs128, dcs64, dcs128;
   int r = 0;
   r |= make_act_tmap(&mq, p.q.ptr, p.B, p.NH, p.S, DHF, p.q.stride_b, p.q.stride_h, p.q.stride_s, L);
   r |= make_act_tmap(&mk, p.k.ptr, p.B, p.NH, p.S, DHF, p.k.stride_b, p.k.stride_h, p.k.stride_s, L);
