@@ -182,14 +182,15 @@ int pad_rows(const mlstm_params& p, int DP, PadJob j0, PadJob j1, PadJob j2, int
 
 // Where every access of a kernel variant to q, k, v, h, dh, dq, dk, dv goes through TMA, the padding costs nothing: the tensor
 // maps are encoded with the true row length and TMA supplies / clips the rest (tc_tmap.cuh: ExtentOverride).  That holds for the
-// single-pass forward walks (mlstm_tc_fwd.cu, DP 64 and 128) and the DH = 64 fused backward walk (mlstm_tc_bwd_fused.cu); the
-// other variants read rows with plain loads somewhere and run on the copies.  MLSTM_TCPAD_COPY=1 forces the copies.
+// DP = 64 and 128 kernels except the two-walk single-pass backward (mlstm_tc_bwd1p.cu): where they touch rows with plain loads
+// or stores (the two-phase forward's h rows, tc_dn_kernel, two row reads of the DH = 128 fused walk) they take the true row
+// length as an argument; the DH = 256 family and the single-pass backward run on the copies.  MLSTM_TCPAD_COPY=1 forces the copies.
 bool zero_copy_off() {
   static const bool off = getenv("MLSTM_TCPAD_COPY") != nullptr && getenv("MLSTM_TCPAD_COPY")[0] == '1';
   return off;
 }
-bool zero_copy_fwd(const mlstm_params& pp) { return !zero_copy_off() && pp.DHV <= 128 && !tc_use_two_phase(pp); }
-bool zero_copy_bwd(const mlstm_params& pp) { return !zero_copy_off() && pp.DHV == 64 && tc_use_fused_bwd(pp); }
+bool zero_copy_fwd(const mlstm_params& pp) { return !zero_copy_off() && pp.DHV <= 128; }
+bool zero_copy_bwd(const mlstm_params& pp) { return !zero_copy_off() && pp.DHV <= 128 && !tc_use_single_pass_bwd(pp); }
 
 // the padded problem of a forward or backward call: pointers into the caller's states / workspace buffers
 int make_padded(const mlstm_params& p, int is_bwd, mlstm_params* out, PadLayout* lay) {

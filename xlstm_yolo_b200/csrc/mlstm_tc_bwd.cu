@@ -765,7 +765,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_sa_kernel(const __grid_constant_
 // dn_t = dnf_t (dh_t . h_t) for every row (the same formula as kernel A and gates_warp_bwd): DH / 8 lanes per row, one 16-byte
 // load per lane and operand, DN_U rows per lane group with all their loads in flight.
 constexpr int DN_U = 4;
-__global__ void __launch_bounds__(256) tc_dn_kernel(const mlstm_params p, float* __restrict__ ws_dn, const int DH) {
+__global__ void __launch_bounds__(256) tc_dn_kernel(const mlstm_params p, float* __restrict__ ws_dn, const int DH, const int dv_true) {
   const int lpr = DH / 8, rpw = 32 / lpr;                 // lanes per row, rows per warp and pass
   const int lane = threadIdx.x & 31, sub = lane / lpr, l = lane % lpr;
   const int rows = p.B * p.NH * p.S;                      // < 2^31: checked by the launcher
@@ -779,12 +779,12 @@ __global__ void __launch_bounds__(256) tc_dn_kernel(const mlstm_params p, float*
     const int r = r0 + u * rpw;
     wh[u] = wd[u] = make_uint4(0, 0, 0, 0);
     nr[u] = mr[u] = 0.f;
-    if (r < rows) {
+    if (r < rows && l * 8 < dv_true) {   // (columns past dv_true: a zero-padded problem on the caller's narrow rows)
       const int bh = r / p.S, t = r - bh * p.S, b = bh / p.NH, h = bh - b * p.NH;
       wh[u] = *reinterpret_cast<const uint4*>(hp + (int64_t)b * p.h.stride_b + (int64_t)h * p.h.stride_h + (int64_t)t * p.h.stride_s);
       wd[u] = *reinterpret_cast<const uint4*>(dp + (int64_t)b * p.dh.stride_b + (int64_t)h * p.dh.stride_h + (int64_t)t * p.dh.stride_s);
-      if (l == 0) { nr[u] = p.n_row[r]; mr[u] = p.m_row[r]; }
     }
+    if (r < rows && l == 0) { nr[u] = p.n_row[r]; mr[u] = p.m_row[r]; }
   }
 #pragma unroll
   for (int u = 0; u < DN_U; ++u) {
@@ -921,7 +921,7 @@ int launch_bwd(const mlstm_params& p, cudaStream_t st, int part) {
     const int64_t rows = (int64_t)n_state * p.S;
     const int rows_per_cta = 8 * (32 / (DH / 8)) * DN_U;
     tc_dn_kernel<<<dim3((unsigned)((rows + rows_per_cta - 1) / rows_per_cta)), dim3(256), 0, st>>>(
-        p, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + blay.dn_off), DH);
+        p, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + blay.dn_off), DH, true_extent(p.h.ptr, DH));
     if ((rc = launched("tc_dn"))) return rc;
     BwdMaps ma{mdh, mv, mk, mcs, mq, mh, mdq};
     BwdMaps ms{mq, mdh, mcs, mdcs, mq, mh, mdq};

@@ -135,8 +135,10 @@ __device__ __forceinline__ void stage_block(uint8_t* tile, int row, int cb, cons
 }
 
 // (18 warps are allocated as 20: 96 registers per thread is the ceiling, ptxas finds it from the launch bounds)
+// dk_true / dv_true: columns of a k / h row that exist in memory (< 128 for a zero-padded problem running on the caller's
+// narrow tensors, tc_tmap.cuh: ExtentOverride): the two places that read rows with plain loads supply the zeros themselves.
 __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_constant__ F128Maps maps, const mlstm_params p,
-                                                                const float scale) {
+                                                                const float scale, const int dk_true, const int dv_true) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   SmemF128& sm = *reinterpret_cast<SmemF128*>(smem_raw);
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -320,7 +322,8 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
         const int t_ = tok0 + warp * 8 + 2 * x + (lane >> 4);
-        hw[x] = (t_ < S) ? *reinterpret_cast<const uint4*>(h_base + (int64_t)t_ * p.h.stride_s + (lane & 15) * 8) : make_uint4(0, 0, 0, 0);
+        hw[x] = (t_ < S && (lane & 15) * 8 < dv_true) ? *reinterpret_cast<const uint4*>(h_base + (int64_t)t_ * p.h.stride_s + (lane & 15) * 8)
+                                                     : make_uint4(0, 0, 0, 0);
       }
       mbar_wait(&sm.bar_dh, ph);
       TLG(1);
@@ -580,7 +583,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
       if (row_ok) {
         const uint4* src = reinterpret_cast<const uint4*>(k_base + (int64_t)tok * p.k.stride_s + cq * 32);
 #pragma unroll
-        for (int x = 0; x < 4; ++x) kw4[x] = src[x];
+        for (int x = 0; x < 4; ++x) kw4[x] = (cq * 32 + x * 8 < dk_true) ? src[x] : make_uint4(0, 0, 0, 0);
       } else {
 #pragma unroll
         for (int x = 0; x < 4; ++x) kw4[x] = make_uint4(0, 0, 0, 0);
@@ -728,7 +731,8 @@ int tc_bwd_fused128(const mlstm_params& p, cudaStream_t st, int part) {
     set_error("cudaFuncSetAttribute(tc_bwd_fused128, %zu B): %s", smem, cudaGetErrorString(e));
     return MLSTM_ERR_CUDA;
   }
-  tc_bwd_fused128_kernel<<<dim3(p.B * p.NH), dim3(NT), smem, st>>>(m, p, resolve_scale(p));
+  tc_bwd_fused128_kernel<<<dim3(p.B * p.NH), dim3(NT), smem, st>>>(m, p, resolve_scale(p), true_extent(p.k.ptr, 128),
+                                                                   true_extent(p.h.ptr, 128));
   count_launch();
   e = cudaGetLastError();
   if (e != cudaSuccess) {

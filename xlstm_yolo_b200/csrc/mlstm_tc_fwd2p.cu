@@ -256,7 +256,9 @@ struct SmemP {
 
 template <int DH>
 __global__ void __launch_bounds__(NT, 1) tc_fwd_par_kernel(const __grid_constant__ FwdMaps maps, const mlstm_params p,
-                                                           const float scale, const int n_items) {
+                                                           const float scale, const int n_items, const int dv_true) {
+  // dv_true: columns of an h row that exist in memory (< DH for a zero-padded problem running on the caller's narrow
+  // tensors, tc_tmap.cuh: ExtentOverride) — the h rows leave through plain stores here, so the clipping TMA would do is explicit
   constexpr int KT = DH / 64;
   constexpr int TILE_C = SmemP<DH>::TILE_C;
   constexpr int NB = DH / 32;
@@ -459,7 +461,14 @@ __global__ void __launch_bounds__(NT, 1) tc_fwd_par_kernel(const __grid_constant
       if (tok < S) {
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.h.ptr) + (int64_t)b * p.h.stride_b + (int64_t)h * p.h.stride_h +
                              (int64_t)tok * p.h.stride_s + cq * 32;
-        store_row32(dst, hpk);
+        if (dv_true >= DH) {
+          store_row32(dst, hpk);
+        } else {
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            if (cq * 32 + x * 8 < dv_true)
+              *reinterpret_cast<uint4*>(dst + x * 8) = make_uint4(hpk[4 * x], hpk[4 * x + 1], hpk[4 * x + 2], hpk[4 * x + 3]);
+        }
       }
     }
   }
@@ -517,7 +526,7 @@ int launch_fwd(const mlstm_params& p, cudaStream_t st) {
   if ((rc = launched("tc_state_fwd"))) return rc;
   const int sms = sms_s;
   const int grid = n_items < sms ? n_items : sms;
-  tc_fwd_par_kernel<DH><<<dim3(grid), dim3(NT), smP, st>>>(maps, p, resolve_scale(p), n_items);
+  tc_fwd_par_kernel<DH><<<dim3(grid), dim3(NT), smP, st>>>(maps, p, resolve_scale(p), n_items, true_extent(p.h.ptr, DH));
   return launched("tc_fwd_par");
 }
 
