@@ -239,6 +239,9 @@ def launches_of(variant_fwd, variant_bwd, DH):
     if DH not in (64, 128, 256) and variant_fwd != "simt":   # zero-padded to the next kernel width inside the library (csrc/mlstm_api.cu)
         DP = 64 if DH <= 64 else (128 if DH <= 128 else 256)
         inner = launches_of(variant_fwd, variant_bwd, DP)
+        if DP <= 128:   # the tensor maps carry the true row length: TMA supplies the zero columns and clips the stores, no copies
+            note = "(width-%d kernel on %d-wide rows, zero columns from TMA)" % (DP, DH)
+            return {k_: [x + " " + note for x in v_] for k_, v_ in inner.items()}
         return {"fwd": ["pad_rows_kernel (q, k, v -> width %d)" % DP] + inner["fwd"] + ["pad_rows_kernel (crop h)"],
                 "bwd_dq": inner["bwd_dq"],
                 "bwd_dkv": ["pad_rows_kernel (dh)"] + inner["bwd_dkv"] + ["pad_rows_kernel (crop dq, dk, dv)"]}
