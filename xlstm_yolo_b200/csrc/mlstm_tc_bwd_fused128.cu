@@ -137,6 +137,8 @@ __device__ __forceinline__ void stage_block(uint8_t* tile, int row, int cb, cons
 // (18 warps are allocated as 20: 96 registers per thread is the ceiling, ptxas finds it from the launch bounds)
 // dk_true / dv_true: columns of a k / h row that exist in memory (< 128 for a zero-padded problem running on the caller's
 // narrow tensors, tc_tmap.cuh: ExtentOverride): the two places that read rows with plain loads supply the zeros themselves.
+// NARROW = false is the full-width kernel without those tests (the BASELINE shapes).
+template <bool NARROW>
 __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_constant__ F128Maps maps, const mlstm_params p,
                                                                 const float scale, const int dk_true, const int dv_true) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
         const int t_ = tok0 + warp * 8 + 2 * x + (lane >> 4);
-        hw[x] = (t_ < S && (lane & 15) * 8 < dv_true) ? *reinterpret_cast<const uint4*>(h_base + (int64_t)t_ * p.h.stride_s + (lane & 15) * 8)
+        hw[x] = (t_ < S && (!NARROW || (lane & 15) * 8 < dv_true)) ? *reinterpret_cast<const uint4*>(h_base + (int64_t)t_ * p.h.stride_s + (lane & 15) * 8)
                                                      : make_uint4(0, 0, 0, 0);
       }
       mbar_wait(&sm.bar_dh, ph);
@@ -583,7 +585,7 @@ __global__ void __launch_bounds__(NT, 1) tc_bwd_fused128_kernel(const __grid_con
       if (row_ok) {
         const uint4* src = reinterpret_cast<const uint4*>(k_base + (int64_t)tok * p.k.stride_s + cq * 32);
 #pragma unroll
-        for (int x = 0; x < 4; ++x) kw4[x] = (cq * 32 + x * 8 < dk_true) ? src[x] : make_uint4(0, 0, 0, 0);
+        for (int x = 0; x < 4; ++x) kw4[x] = (!NARROW || cq * 32 + x * 8 < dk_true) ? src[x] : make_uint4(0, 0, 0, 0);
       } else {
 #pragma unroll
         for (int x = 0; x < 4; ++x) kw4[x] = make_uint4(0, 0, 0, 0);
@@ -726,13 +728,16 @@ int tc_bwd_fused128(const mlstm_params& p, cudaStream_t st, int part) {
     return r == -1 ? MLSTM_ERR_NO_DEVICE : MLSTM_ERR_INVALID_ARG;
   }
   const size_t smem = sizeof(SmemF128);
-  cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(tc_bwd_fused128_kernel), smem);
+  const int dk_true = true_extent(p.k.ptr, 128), dv_true = true_extent(p.h.ptr, 128);
+  const bool narrow = dk_true < 128 || dv_true < 128;
+  cudaError_t e = narrow ? set_max_smem_once(reinterpret_cast<const void*>(tc_bwd_fused128_kernel<true>), smem)
+                         : set_max_smem_once(reinterpret_cast<const void*>(tc_bwd_fused128_kernel<false>), smem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(tc_bwd_fused128, %zu B): %s", smem, cudaGetErrorString(e));
     return MLSTM_ERR_CUDA;
   }
-  tc_bwd_fused128_kernel<<<dim3(p.B * p.NH), dim3(NT), smem, st>>>(m, p, resolve_scale(p), true_extent(p.k.ptr, 128),
-                                                                   true_extent(p.h.ptr, 128));
+  if (narrow) tc_bwd_fused128_kernel<true><<<dim3(p.B * p.NH), dim3(NT), smem, st>>>(m, p, resolve_scale(p), dk_true, dv_true);
+  else tc_bwd_fused128_kernel<false><<<dim3(p.B * p.NH), dim3(NT), smem, st>>>(m, p, resolve_scale(p), dk_true, dv_true);
   count_launch();
   e = cudaGetLastError();
   if (e != cudaSuccess) {
