@@ -125,13 +125,19 @@ def test_kernel_family_and_workspace(lib):
     assert lib.mlstm_b200_kernel_name(C.byref(p), 0) == b"tcgen05"
     assert lib.mlstm_b200_kernel_variant(C.byref(p), 0) in (b"single_pass", b"two_phase")
     sq = _params(DHQK=128, DHV=128)
-    act = 2 * 64 * 2 * 128 * 2                                # B S NH DP bf16
-    extra = 4 * act + 2 * (2 * 2 * 128 * 128 * 4) + 2 * (2 * 2 * 128 * 4)
-    assert lib.mlstm_b200_state_bytes(C.byref(p)) >= lib.mlstm_b200_state_bytes(C.byref(sq)) + extra
-    assert lib.mlstm_b200_workspace_bytes(C.byref(p), 1) >= lib.mlstm_b200_workspace_bytes(C.byref(sq), 1) + 4 * act
+    st_extra = 2 * (2 * 2 * 128 * 128 * 4) + 2 * (2 * 2 * 128 * 4)       # padded initial / last C and n
+    # padded width 64 / 128: the kernels run on the caller's narrow tensors (TMA supplies the zero columns): no room for copies
+    assert lib.mlstm_b200_state_bytes(C.byref(p)) >= lib.mlstm_b200_state_bytes(C.byref(sq)) + st_extra
+    assert lib.mlstm_b200_state_bytes(C.byref(p)) < lib.mlstm_b200_state_bytes(C.byref(sq)) + st_extra + 2 * 64 * 2 * 128 * 2
+    assert lib.mlstm_b200_workspace_bytes(C.byref(p), 1) < lib.mlstm_b200_workspace_bytes(C.byref(sq), 1) + 1024
     for dk, dv in ((16, 16), (32, 32), (192, 192), (128, 64), (24, 40)):
         assert lib.mlstm_b200_kernel_name(C.byref(_params(DHQK=dk, DHV=dv)), 0) == b"tcgen05", (dk, dv)
-    assert lib.mlstm_b200_state_bytes(C.byref(_params(DHQK=16, DHV=16))) >= 4 * (2 * 64 * 2 * 64 * 2)
+    # padded width 256 (the slice-streaming family reads rows with plain loads): four padded copies on either side
+    w, sq = _params(DHQK=192, DHV=192), _params(DHQK=256, DHV=256)
+    w.n_row = w.m_row = sq.n_row = sq.m_row = 0x1000
+    act = 2 * 64 * 2 * 256 * 2                                           # B S NH DP bf16
+    assert lib.mlstm_b200_state_bytes(C.byref(w)) >= lib.mlstm_b200_state_bytes(C.byref(sq)) + 4 * act
+    assert lib.mlstm_b200_workspace_bytes(C.byref(w), 1) >= lib.mlstm_b200_workspace_bytes(C.byref(sq), 1) + 4 * act
     assert lib.mlstm_b200_kernel_name(C.byref(_params(DHQK=20, DHV=64)), 0) == b"simt"      # rows must be 16-byte multiples
     assert lib.mlstm_b200_kernel_name(C.byref(_params(DHQK=264, DHV=264)), 0) is None       # nothing to pad to, too wide for SIMT
     assert lib.mlstm_b200_kernel_name(C.byref(_params(dtype=_lib.MLSTM_F32, DHQK=64, DHV=128)), 0) == b"simt"

@@ -47,6 +47,7 @@ int padded_dim(const mlstm_params& p) {
 struct PadLayout {
   int DP;
   size_t inner, act, cst, nst;             // bytes: padded problem's own states | one padded activation | C | n
+  size_t act_s, act_w;                     // room per copy in the states buffer / in the workspace (0 where no copies are made)
   size_t q_off, k_off, v_off, h_off, c0_off, n0_off, cl_off, nl_off, total;
   size_t ws_inner, dh_off, dq_off, dk_off, dv_off, ws_total;
 };
@@ -58,6 +59,18 @@ mlstm_params padded_params(const mlstm_params& p) {
   return pp;
 }
 
+// Where every access of a kernel variant to q, k, v, h, dh, dq, dk, dv goes through TMA, the padding costs nothing: the tensor
+// maps are encoded with the true row length and TMA supplies / clips the rest (tc_tmap.cuh: ExtentOverride).  That holds for the
+// DP = 64 and 128 kernels except the two-walk single-pass backward (mlstm_tc_bwd1p.cu): where they touch rows with plain loads
+// or stores (the two-phase forward's h rows, tc_dn_kernel, two row reads of the DH = 128 fused walk) they take the true row
+// length as an argument; the DH = 256 family and the single-pass backward run on the copies.  MLSTM_TCPAD_COPY=1 forces the copies.
+bool zero_copy_off() {
+  static const bool off = getenv("MLSTM_TCPAD_COPY") != nullptr && getenv("MLSTM_TCPAD_COPY")[0] == '1';
+  return off;
+}
+bool zero_copy_fwd(const mlstm_params& pp) { return !zero_copy_off() && pp.DHV <= 128; }
+bool zero_copy_bwd(const mlstm_params& pp) { return !zero_copy_off() && pp.DHV <= 128 && !tc_use_single_pass_bwd(pp); }
+
 PadLayout pad_layout(const mlstm_params& p) {
   const mlstm_params pp = padded_params(p);
   PadLayout l;
@@ -66,21 +79,25 @@ PadLayout pad_layout(const mlstm_params& p) {
   l.act = al256((size_t)p.B * p.S * p.NH * l.DP * 2);
   l.cst = al256((size_t)p.B * p.NH * l.DP * l.DP * 4);
   l.nst = al256((size_t)p.B * p.NH * l.DP * 4);
+  // copies of q, k, v, h: made by a forward that needs them, or by the backward that follows a copy-free forward (n_row set =
+  // a backward will follow; the backward itself always sees n_row, so both calls lay the buffer out the same way)
+  l.act_s = (!zero_copy_fwd(pp) || (p.n_row != nullptr && !zero_copy_bwd(pp))) ? l.act : 0;
+  l.act_w = !zero_copy_bwd(pp) ? l.act : 0;
   l.q_off = l.inner;
-  l.k_off = l.q_off + l.act;
-  l.v_off = l.k_off + l.act;
-  l.h_off = l.v_off + l.act;
-  l.c0_off = l.h_off + l.act;
+  l.k_off = l.q_off + l.act_s;
+  l.v_off = l.k_off + l.act_s;
+  l.h_off = l.v_off + l.act_s;
+  l.c0_off = l.h_off + l.act_s;
   l.n0_off = l.c0_off + l.cst;
   l.cl_off = l.n0_off + l.nst;
   l.nl_off = l.cl_off + l.cst;
   l.total = l.nl_off + l.nst;
   l.ws_inner = al256(tc_bwd_workspace(pp));
   l.dh_off = l.ws_inner;
-  l.dq_off = l.dh_off + l.act;
-  l.dk_off = l.dq_off + l.act;
-  l.dv_off = l.dk_off + l.act;
-  l.ws_total = l.dv_off + l.act;
+  l.dq_off = l.dh_off + l.act_w;
+  l.dk_off = l.dq_off + l.act_w;
+  l.dv_off = l.dk_off + l.act_w;
+  l.ws_total = l.dv_off + l.act_w;
   return l;
 }
 
@@ -179,18 +196,6 @@ int pad_rows(const mlstm_params& p, int DP, PadJob j0, PadJob j1, PadJob j2, int
   pad_rows_kernel<<<grid_for((int64_t)p.B * p.S * p.NH * (DP / 8)), 256, 0, st>>>(jobs, p.B, p.S, p.NH, DP, to_padded);
   return pad_launched(what);
 }
-
-// Where every access of a kernel variant to q, k, v, h, dh, dq, dk, dv goes through TMA, the padding costs nothing: the tensor
-// maps are encoded with the true row length and TMA supplies / clips the rest (tc_tmap.cuh: ExtentOverride).  That holds for the
-// DP = 64 and 128 kernels except the two-walk single-pass backward (mlstm_tc_bwd1p.cu): where they touch rows with plain loads
-// or stores (the two-phase forward's h rows, tc_dn_kernel, two row reads of the DH = 128 fused walk) they take the true row
-// length as an argument; the DH = 256 family and the single-pass backward run on the copies.  MLSTM_TCPAD_COPY=1 forces the copies.
-bool zero_copy_off() {
-  static const bool off = getenv("MLSTM_TCPAD_COPY") != nullptr && getenv("MLSTM_TCPAD_COPY")[0] == '1';
-  return off;
-}
-bool zero_copy_fwd(const mlstm_params& pp) { return !zero_copy_off() && pp.DHV <= 128; }
-bool zero_copy_bwd(const mlstm_params& pp) { return !zero_copy_off() && pp.DHV <= 128 && !tc_use_single_pass_bwd(pp); }
 
 // the padded problem of a forward or backward call: pointers into the caller's states / workspace buffers
 int make_padded(const mlstm_params& p, int is_bwd, mlstm_params* out, PadLayout* lay) {
