@@ -110,3 +110,35 @@ def test_cell_matches_vendored_cell():
 
 def test_golden_files_present():
     assert len(glob.glob(os.path.join(GOLD, "*.npz"))) >= 5
+
+
+@pytest.mark.parametrize("DK,DV,DP,reverse", [(8, 12, 16, False), (16, 16, 64, True), (24, 8, 32, False)])
+def test_zero_padded_head_dims_change_nothing(DK, DV, DP, reverse):
+    """The identity the library's padded tensor-core path rests on (csrc/mlstm_api.cu), pinned on the oracle in
+    fp64: q, k, v, dh padded with zero columns to a common DP — and the initial state with zero rows / columns — give the same
+    h, dq, dk, dv in the leading columns (zeros behind them), the same di, df and the same leading block of the last state,
+    provided the 1/sqrt(DHqk) scale of the ORIGINAL head dim is kept (here: folded into q, since the oracle, like the reference,
+    takes the scale from the tensor's last dimension, backends.py:168)."""
+    import torch.nn.functional as F
+    B, NH, S = 1, 2, 70
+    g = torch.Generator().manual_seed(3)
+    rn = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    q, k, v, dh = rn(B, NH, S, DK), rn(B, NH, S, DK), rn(B, NH, S, DV), rn(B, NH, S, DV)
+    i, f = rn(B, NH, S), rn(B, NH, S) + 3.0
+    st = dict(c_initial=rn(B, NH, DK, DV), n_initial=rn(B, NH, DK), m_initial=rn(B, NH, 1))
+    small = O.mlstm_fwbw(q, k, v, i, f, dh, chunk_size=32, eps=1e-6, reverse=reverse, **st)
+    r = (DP / DK) ** 0.5
+    pad = lambda t, d: F.pad(t, (0, DP - d))
+    stp = dict(c_initial=F.pad(st["c_initial"], (0, DP - DV, 0, DP - DK)), n_initial=pad(st["n_initial"], DK), m_initial=st["m_initial"])
+    big = O.mlstm_fwbw(pad(q, DK) * r, pad(k, DK), pad(v, DV), i, f, pad(dh, DV), chunk_size=32, eps=1e-6, reverse=reverse, **stp)
+    h, dq, dk, dv, di, df = small
+    hp, dqp, dkp, dvp, dip, dfp = big
+    tol = 1e-11
+    assert _rel(hp[..., :DV], h) < tol and hp[..., DV:].abs().max() == 0
+    assert _rel(dqp[..., :DK] * r, dq) < tol and _rel(dkp[..., :DK], dk) < tol and _rel(dvp[..., :DV], dv) < tol
+    assert dkp[..., DK:].abs().max() == 0 and _rel(dip, di) < tol and _rel(dfp, df) < tol
+    _, (C, n, m) = O.mlstm_chunkwise(q, k, v, i, f, **st, chunk_size=32, return_last_states=True, reverse=reverse)
+    _, (Cp, np_, mp) = O.mlstm_chunkwise(pad(q, DK) * r, pad(k, DK), pad(v, DV), i, f, **stp, chunk_size=32, return_last_states=True,
+                                         reverse=reverse)
+    assert _rel(Cp[:, :, :DK, :DV], C) < tol and _rel(np_[..., :DK], n) < tol and _rel(mp, m) < tol
+    assert Cp[:, :, DK:].abs().max() == 0 and Cp[..., DV:].abs().max() == 0
