@@ -307,3 +307,19 @@ def test_product_package_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, fn
+
+
+def test_three_way_bf16_split_reproduces_fp32_weights():
+    """Numerics claim of the tensor-core gate forward (csrc/mlstm_gates_tc.cu): an fp32 weight split as hi = bf16(w),
+    mid = bf16(w - hi), lo = bf16(w - hi - mid) is recovered by hi + mid + lo to fp32 rounding (each part carries 8 significant
+    bits, three of them cover the 24 of fp32), so one N = 3 x outputs MMA with fp32 accumulation computes the fp32-weight product."""
+    import torch
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(1 << 16, generator=g) * torch.logspace(-6, 3, 1 << 16)
+    hi = w.bfloat16().float()
+    mid = (w - hi).bfloat16().float()
+    lo = (w - hi - mid).bfloat16().float()
+    rec = hi.double() + mid.double() + lo.double()
+    assert float(((rec - w.double()).abs() / w.double().abs().clamp_min(1e-30)).max()) <= 2.0 ** -23
+    two = hi.double() + mid.double()     # two parts only: ~2^-16, the reason the third row block exists
+    assert float(((two - w.double()).abs() / w.double().abs().clamp_min(1e-30)).max()) > 2.0 ** -18
